@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- decoded Msamples/s of the usrp_nfc sample-rate path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A step = one pass of the hot path (envelope -> slicer -> Manchester/Miller -> frames) over one synthetic
+ISO 14443A capture that is already resident in HBM.  N=1 workload: BASELINE.json configs[2], 1e10 samples at
+13.56 MS/s (av_window=13560, max_len=339, hi_val=1.09).  N>1: weak scaling, every rank
+decodes its own 1e10-sample time shard of one endless capture (no data-path collective; frame counts are
+gathered).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE = 13.56e6
+HI_VAL = 1.09
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_schedule(rate, seed):
+    """Pulse schedule of one period of dense traffic: 12 Classic + 4 Ultralight sessions with idle gaps."""
+    from usrp_nfc_b200 import synth
+    rng = np.random.default_rng(seed)
+    sess = synth.load_sessions()
+    p = synth.rate_params(rate)
+    codes, lens = [], []
+    order = ["classic1k"] * 3 + ["ultralight"]
+    for i in range(16):
+        lead = float(rng.uniform(1000.0, 5000.0))
+        c, l = synth.schedule(sess[order[i % 4]], rate, rng, lead_us=lead, av_window=p["av_window"])
+        codes.append(c)
+        lens.append(l)
+    return np.concatenate(codes), np.concatenate(lens), p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(x_host_pieces, params, threads):
+    """The reference algorithm (oracle port, C) on the host cores: one independent piece per thread."""
+    from oracle import oracle
+    oracle.lib()
+    res = [None] * len(x_host_pieces)
+
+    def work(i):
+        res[i] = oracle.chain_run(x_host_pieces[i], RATE, 0.1, HI_VAL, params["av_window"], params["max_len"])
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(x_host_pieces))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    n = sum(len(p) for p in x_host_pieces)
+    return n / dt / 1e6, dt, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=float, default=1e10, help="samples per GPU per step")
+    ap.add_argument("--e2e-samples", type=float, default=float(1 << 30))
+    ap.add_argument("--cpu-piece", type=float, default=1.5e8, help="CPU-baseline samples per host thread")
+    ap.add_argument("--slab", type=float, default=float(1 << 30))
+    ap.add_argument("--seg-len", type=int, default=0)
+    ap.add_argument("--halo", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    codes, lens, params = build_schedule(RATE, 2024)
+    period = int(lens.sum())
+    chan = dict(carrier=0.5, pause=0.015, tag_high=1.07, noise=0.003, fade=0.05, fade_period=round(RATE * 0.02))
+    workload = "synthetic ISO 14443A reader+tag traffic, %.3g samples at 13.56 MS/s per GPU" % args.samples
+    config = {"workload": workload, "samp_rate": RATE, "hi_val": HI_VAL, "input": "float32 envelope resident in HBM",
+              "l2": "input (%.1f GB per step) is far larger than L2; no flush needed" % (args.samples * 4 / 1e9),
+              "schedule_period_samples": period, **params}
+
+    # ------------------------------------------------------------------ reference arm (host cores)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from usrp_nfc_b200 import synth
+        threads = max(1, cores)
+        piece = int(min(args.cpu_piece, (1 << 31) / threads))
+        rng = np.random.default_rng(5)
+        # same schedule, rendered on the host with the numpy generator (no GPU is used by this arm)
+        reps = int(np.ceil((piece + params["av_window"]) / period))
+        base = synth.render(np.tile(codes, reps), np.tile(lens, reps), RATE, rng,
+                            synth.Channel(pause=chan["pause"], tag_high=chan["tag_high"], noise=chan["noise"],
+                                          fade=chan["fade"], fade_period_us=20000.0))[:piece]
+        x = synth.envelope(synth.pcm_to_float(base))
+        pieces = [np.roll(x, 977 * i) for i in range(threads)]
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, dt, _ = cpu_baseline(pieces, params, threads)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([a for a, _ in vals]))
+        ms = float(np.mean([b for _, b in vals])) * 1e3
+        sample = "%d independent pieces of %d samples of the same schedule, one per host thread" % (threads, piece)
+        line = {"impl": "reference", "metric": "decoded_msamples_per_s", "value": v, "unit": "Msamples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(config, workload=workload + " (bounded CPU sample per step)"),
+                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    from usrp_nfc_b200 import _cabi
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = int(args.samples)
+    n -= n % 4
+    L = params["av_window"]
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    first_index = rank * n  # every rank renders and decodes its own time shard of one endless capture
+    _cabi.synth_render(x, codes, lens, seed=99, as_envelope=True, device=local_rank, first_index=first_index, **chan)
+    torch.cuda.synchronize()
+
+    s = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+    s.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(args.slab))
+
+    def step():
+        s.reset()
+        s.push_all(x)
+        fr, _ = s.drain_frames()
+        return len(fr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frames = 0
+    for _ in range(args.warmup):
+        frames = step()
+    s.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        frames = step()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    st = s.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    # device time of the step on the library's own stream (CUDA events inside the library bracket every slab)
+    dev_ms = st["kernel_ms"] / args.steps
+    wall_ms = wall * 1e3 / args.steps
+    t = torch.tensor([wall_ms, dev_ms, float(frames), float(st["launches"]), float(st["seam_mismatches"]),
+                      st["slicer_ms"] / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall_ms, dev_ms, slicer_ms = float(mx[0]), float(mx[1]), float(mx[5])
+        frames_total, launches, mism = int(sm[2]), int(sm[3]), int(sm[4])
+    else:
+        slicer_ms = float(t[5])
+        frames_total, launches, mism = frames, int(st["launches"]), int(st["seam_mismatches"])
+    value = world * n / (wall_ms * 1e-3) / 1e6  # whole job, wall clock around the synchronous ABI calls (>= device time)
+
+    # ---- e2e: host (pinned) buffers through the same ABI call, H2D inside the timed region
+    e2e = None
+    ne = int(min(args.e2e_samples, n))
+    try:
+        xh = torch.empty(ne, dtype=torch.float32, pin_memory=True)
+        xh.copy_(x[:ne])
+        torch.cuda.synchronize()
+        se = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+        se.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(min(args.slab, 1 << 27)))
+        xh_np = xh.numpy()
+        for _ in range(2):
+            se.reset()
+            se.push_all(xh_np)
+            se.drain_frames()
+        se.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(2, min(args.steps, 5))
+        for _ in range(esteps):
+            se.reset()
+            se.push_all(xh_np)
+            fr_e, _ = se.drain_frames()
+        barrier()
+        e_wall = (time.perf_counter() - t0) / esteps
+        est = se.stats()
+        tt = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ne / float(tt[0]) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(est["h2d_bytes"] / esteps), "d2h_bytes_per_step": int(est["d2h_bytes"] / esteps),
+               "samples_per_step_per_gpu": ne, "ms_per_step": float(tt[0]) * 1e3}
+        se.close()
+        del xh
+    except Exception as exc:  # pinned allocation can fail on small hosts
+        e2e = {"value": None, "unit": "Msamples/s", "error": str(exc)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    slic_launches = max(1, st["slicer_launches"])
+    alg_bytes_per_launch = 4.0 * n * args.steps / slic_launches
+    achieved = 4.0 * n / (slicer_ms * 1e-3) / 1e9 if slicer_ms > 0 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None,
+                "kernel": "nfc::slicer_kernel<256,4>", "peak_source": peak_src,
+                "algorithmic_bytes_per_sample": 4, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "avg_launch_ms": slicer_ms * args.steps / slic_launches,
+                "note": "achieved = 4 B x samples / CUDA-event time of the slicer launches (incl. seam checks) per step"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = max(1, cores)
+        piece = int(min(args.cpu_piece, (1 << 31) / threads, n // max(1, threads)))
+        piece -= piece % 4
+        host = x[: piece * threads].cpu().numpy()
+        pieces = [host[i * piece: (i + 1) * piece] for i in range(threads)]
+        v, dt, _ = cpu_baseline(pieces, params, threads)
+        cpu = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
+               "sample": "%d consecutive pieces of %d samples of rank 0's capture, one per host thread, %.1f s" % (
+                   threads, piece, dt)}
+
+    line = {"metric": "decoded_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

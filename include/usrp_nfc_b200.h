@@ -1,0 +1,164 @@
+/*
+ * usrp_nfc_b200.h -- C ABI of the B200 sample-rate decode path of usrp_nfc.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Each entry
+ * point names the reference interface it stands in for (paths relative to the reference's
+ * code/ directory).  INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions: every function returns 0 (or a non-negative count) on success and a negative
+ * value on failure, never throws; nfc_last_error() describes the last failure on the calling
+ * thread.  The caller owns every buffer it passes in.  One handle = one sample stream; a handle
+ * is not thread-safe, distinct handles are independent.  All decoding runs on the GPU: there is
+ * no CPU fallback, creation fails when no CUDA device is usable.
+ */
+#ifndef USRP_NFC_B200_H
+#define USRP_NFC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFC_ABI_VERSION 1
+
+/* what a pushed item is */
+enum {
+    NFC_IN_ENVELOPE_F32 = 0, /* float32 |z|^2 -- transition_sink's in_sig (transition_sink.py:16)             */
+    NFC_IN_REAL_F32 = 1,     /* float32 WAV samples; envelope = x*x on device (decoder.py:25-28)             */
+    NFC_IN_IQ_F32 = 2,       /* complex64 from UHD; envelope = re^2+im^2 on device (usrp_src.py:31)          */
+    NFC_IN_PCM_S16 = 3       /* int16 PCM; /pcm_scale, then x*x on device (blocks.wavfile_source, unpinned)  */
+};
+enum { NFC_MEM_HOST = 0, NFC_MEM_DEVICE = 1 };
+/* which outputs a stream materialises */
+enum { NFC_OUT_EVENTS = 1, NFC_OUT_SYMBOLS = 2, NFC_OUT_FRAMES = 4, NFC_OUT_DROPPED_EVENTS = 8 };
+
+typedef struct nfc_stream nfc_stream;
+
+/* Constructor parameters of transition_sink (transition_sink.py:12) and of background / decoder
+ * (background.py:17-21, decoder.py:16): same names, meaning and defaults. */
+typedef struct {
+    double samp_rate; /* 2e6 */
+    double lo_val;    /* 0.1 */
+    double hi_val;    /* 1.1 (decoder.py picks 1.1 for uhd, 1.09 for WAV) */
+    int32_t av_window; /* 2000, in samples */
+    int32_t max_len;   /* 50, in samples   */
+    int32_t decode_reader; /* background(reader=...) */
+    int32_t decode_tag;    /* background(tag=...)    */
+    int32_t input_kind;    /* NFC_IN_*  */
+    int32_t outputs;       /* NFC_OUT_* bit mask; NFC_OUT_DROPPED_EVENTS keeps the type -1 events too */
+    int32_t device;        /* CUDA device ordinal */
+    float pcm_scale;       /* divisor for NFC_IN_PCM_S16, 32767 = GNU Radio's 16-bit WAV normalisation */
+} nfc_params;
+
+/* One element of the list handed to transition_sink's callback (transition_sink.py:89-90,97):
+ * ((v, d*factor), type).  dur_us = d * (1e6 / samp_rate). */
+typedef struct {
+    int64_t pos;  /* stream index of the sample that emitted it */
+    int32_t d;
+    int8_t v;
+    int8_t type;
+    int16_t pad;
+} nfc_event;
+
+/* One CombinedPacketProcessor.append_bit(val, type) call (packets.py:94). */
+typedef struct {
+    int64_t pos;
+    int8_t type;
+    int8_t val;
+    int16_t pad;
+    int32_t pad2;
+} nfc_symbol;
+
+/* One fsm.process_bits(bits, packet_type) hand-off (packets.py:97-98). */
+typedef struct {
+    int64_t pos;     /* stream index of the event that closed the frame */
+    int64_t bit_off; /* into the buffer filled by nfc_stream_drain_frames */
+    int32_t nbits;
+    int32_t type;    /* PacketType: 0 TAG_TO_READER, 1 READER_TO_TAG (packets.py:19-20) */
+} nfc_frame;
+
+/* Filled with the defaults of the reference's constructors. */
+void nfc_default_params(nfc_params *p);
+
+/* transition_sink.__init__ + background.__init__ (transition_sink.py:12-34, background.py:17-25). */
+int nfc_stream_create(const nfc_params *p, nfc_stream **out);
+int nfc_stream_destroy(nfc_stream *s);
+/* Back to the state right after creation (a fresh transition_sink / background pair); keeps device buffers. */
+int nfc_stream_reset(nfc_stream *s);
+
+/* transition_sink.work (transition_sink.py:37-125): offers n items, returns how many were consumed.
+ * Like the reference, the call that completes the warm-up consumes only the warm-up part and
+ * reports *called_back = 0; afterwards every call consumes everything and reports 1 (the reference
+ * invokes its callback exactly once per work_stable call, even with an empty list).  The samples are
+ * copied (or fully processed) before the call returns.  mem = NFC_MEM_HOST or NFC_MEM_DEVICE. */
+int64_t nfc_stream_push(nfc_stream *s, const void *items, int64_t n, int mem, int *called_back);
+
+/* Results accumulated since the last drain, in stream order.  Each call copies up to cap records
+ * and removes them from the stream.  Pass cap = 0 to query the number available. */
+int64_t nfc_stream_drain_events(nfc_stream *s, nfc_event *out, int64_t cap);
+int64_t nfc_stream_drain_symbols(nfc_stream *s, nfc_symbol *out, int64_t cap);
+/* Frames whose bits fit: writes records to out (bit_off relative to bits) and one byte per bit. */
+int64_t nfc_stream_drain_frames(nfc_stream *s, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap);
+int64_t nfc_stream_pending_frame_bits(nfc_stream *s); /* bytes the next full drain needs */
+
+/* Implicit streaming state of the reference objects (transition_sink.py:20-34,102-106; decoder and
+ * PacketProcessor attributes), for checkpointing and for stitching time-sharded captures. */
+typedef struct {
+    int64_t pos;           /* items consumed so far */
+    double ss;             /* _sum */
+    int32_t cur_state, last_bit, dur; /* _current_state, _last_bit, _dur */
+    int32_t index;         /* _index */
+    int32_t stable;        /* work is work_stable */
+    int32_t miller_state, manch_state;
+    int32_t started[2];    /* PacketProcessor._started per type */
+    int32_t pending[2];    /* len(PacketProcessor._cur) per type */
+    int32_t serial_mode;   /* 1 once the stream left the exactly-summable regime */
+    int64_t lastL, lrun_start; /* position of the last LOW sample / start of its run (hysteresis carry) */
+} nfc_state;
+/* ring: av_window floats (the _ar list), may be NULL.  pending_bits: pending[0]+pending[1] bytes, may be NULL. */
+int nfc_stream_get_state(nfc_stream *s, nfc_state *st, float *ring, uint8_t *pending_bits);
+int nfc_stream_set_state(nfc_stream *s, const nfc_state *st, const float *ring, const uint8_t *pending_bits);
+
+/* Execution knobs (not part of the reference's interface).  seg_len / halo in samples (rounded up to
+ * tiles; 0 = automatic), slab_len = samples processed per kernel wave, force_serial = use the strictly
+ * sequential kernel for everything (the on-device cross-check). */
+int nfc_stream_set_tuning(nfc_stream *s, int64_t seg_len, int64_t halo, int64_t slab_len, int force_serial);
+
+/* Counters since creation: kernel time measured with CUDA events on the stream's CUDA stream. */
+typedef struct {
+    double kernel_ms;        /* device time spent in this library's kernels */
+    double slicer_ms;        /* of which the slicer kernel */
+    int64_t launches;        /* kernels launched */
+    int64_t slicer_launches;
+    int64_t samples;         /* items decoded on the device */
+    int64_t segments, seam_mismatches, serial_segments, overflow_retries;
+    int64_t h2d_bytes, d2h_bytes;
+} nfc_stats;
+int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
+int nfc_stream_reset_stats(nfc_stream *s);
+/* The CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events. */
+void *nfc_stream_cuda_stream(nfc_stream *s);
+
+/* The line-code tables the device uses (built on the host from the decoder rules, csrc/tables.cpp), for
+ * inspection and host-side tests; needs no GPU.  dclass[d] for d = 0..max_len, then
+ * table[dclass][v+1][state] entries (bits 0-3 next state, 4-5 number of outputs, 6-8 out0, 9-11 out1).
+ * which: 0 Manchester (8 states), 1 Miller (16 states).  Returns the number of table entries. */
+int nfc_build_tables(double samp_rate, int32_t max_len, int which, uint8_t *dclass, int32_t dclass_cap,
+                     uint16_t *table, int32_t table_cap, int32_t *n_dclass);
+
+/* Device-side synthetic traffic (binary_src.work, binary_src.py:64-103, rendered from a pulse schedule):
+ * level codes 0 carrier / 1 reader pause / 2 tag high with run lengths in samples; the schedule repeats.
+ * dev_out[k] is sample first_index + k of the endless capture (time shards render their own part). */
+int nfc_synth_render(void *dev_out_f32, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens,
+                     int64_t n_runs, float carrier, float pause, float tag_high, float noise, float fade,
+                     double fade_period, uint64_t seed, int as_envelope, int device);
+
+const char *nfc_last_error(void);
+int nfc_abi_version(void);
+int nfc_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

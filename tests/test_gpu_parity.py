@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-derived fixtures.
+Bit-exact on events, symbols and frames; the float envelope is compared where it is materialised."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import helpers as H
+from usrp_nfc_b200 import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+
+CAPTURES = [
+    ("surrogate_classic1k", 2e6, dict(hi_val=1.09)),
+    ("surrogate_ultralight", 2e6, dict(hi_val=1.09)),
+    ("rate_1356", 13.56e6, dict(hi_val=1.09, av_window=13560, max_len=339)),
+    ("rate_2000", 20e6, dict(hi_val=1.09, av_window=20000, max_len=500)),
+]
+
+
+def gpu_decode(x, rate, chunk=None, kind=_cabi.IN_ENVELOPE_F32, tuning=None, outputs=_cabi.OUT_ALL, **kw):
+    s = _cabi.Stream(rate, input_kind=kind, outputs=outputs, **kw)
+    if tuning:
+        s.set_tuning(**tuning)
+    n = len(x)
+    off = 0
+    step = chunk or max(n, 1)
+    while off < n:
+        used, _ = s.push(x[off: off + step])
+        off += used
+        assert used > 0
+    ev, sym = s.drain_events(), s.drain_symbols()
+    fr, bits = s.drain_frames()
+    return dict(events=ev, symbols=sym, frames=fr, frame_bits=bits, stream=s)
+
+
+def check_against_oracle(got, want):
+    H.assert_events_equal(got["events"], want["events"])
+    H.assert_symbols_equal(got["symbols"], want["symbols"])
+    assert len(got["frames"]) == len(want["frames"])
+    for f in ("pos", "nbits", "type"):
+        assert np.array_equal(got["frames"][f], want["frames"][f]), f
+    for a, b in zip(got["frame_bits"], want["frame_bits"]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,rate,kw", CAPTURES)
+@pytest.mark.parametrize("chunk", [None, 8192])
+def test_capture_matches_reference(name, rate, kw, chunk):
+    case = H.load_case(name)
+    got = gpu_decode(H.case_input(case), rate, chunk=chunk, **kw)
+    H.assert_events_equal(got["events"], case["ev"])
+    H.assert_symbols_equal(got["symbols"], case["sym"])
+    H.assert_frames_equal(got["frames"], got["frame_bits"], case)
+    st, ring, _ = got["stream"].state()
+    assert st.ss == float(case["state_ss"])
+    assert (st.cur_state, st.dur, st.last_bit, st.index) == tuple(
+        int(case["state_" + k]) for k in ("cur_state", "dur", "last_bit", "index"))
+    assert np.array_equal(ring.astype(np.float64), case["state_ring"])
+    assert not st.serial_mode
+
+
+@pytest.mark.parametrize("name,rate,kw", CAPTURES[:3])
+def test_capture_from_pcm_on_device_envelope(name, rate, kw):
+    """int16 PCM in, normalise + square on the device (decoder.py:25-28 chain)."""
+    case = H.load_case(name)
+    got = gpu_decode(case["pcm"], rate, kind=_cabi.IN_PCM_S16, **kw)
+    H.assert_events_equal(got["events"], case["ev"])
+    H.assert_frames_equal(got["frames"], got["frame_bits"], case)
+    real = gpu_decode(synth.pcm_to_float(case["pcm"]), rate, kind=_cabi.IN_REAL_F32, **kw)
+    H.assert_events_equal(real["events"], case["ev"])
+    # the float envelope itself (north star: 1e-5 relative; here it is bit-identical by construction)
+    _, ring, _ = real["stream"].state()
+    assert np.array_equal(ring.astype(np.float64), case["state_ring"])
+
+
+@pytest.mark.parametrize("name,rate,kw", CAPTURES[:2])
+def test_sequential_kernel_matches_reference(name, rate, kw):
+    case = H.load_case(name)
+    got = gpu_decode(H.case_input(case), rate, tuning=dict(force_serial=True), **kw)
+    H.assert_events_equal(got["events"], case["ev"])
+    H.assert_frames_equal(got["frames"], got["frame_bits"], case)
+    assert got["stream"].stats()["serial_segments"] > 0
+
+
+@pytest.mark.parametrize("seg,halo", [(8192, 2048), (16384, 16384), (65536, 32768)])
+def test_segment_seams_and_repairs(seg, halo):
+    """Small segments and short halos force speculative starts that do not converge: the seam
+    check must catch them and the repair must restore the exact stream."""
+    case = H.load_case("surrogate_classic1k")
+    got = gpu_decode(H.case_input(case), 2e6, tuning=dict(seg_len=seg, halo=halo), hi_val=1.09)
+    H.assert_events_equal(got["events"], case["ev"])
+    H.assert_symbols_equal(got["symbols"], case["sym"])
+    H.assert_frames_equal(got["frames"], got["frame_bits"], case)
+    st = got["stream"].stats()
+    assert st["segments"] > 4
+    print("segments %d, seam mismatches repaired %d" % (st["segments"], st["seam_mismatches"]))
+
+
+def test_slabs_and_chunked_pushes_agree():
+    case = H.load_case("surrogate_classic1k")
+    x = H.case_input(case)
+    got = gpu_decode(x, 2e6, chunk=100003, tuning=dict(slab_len=30011, seg_len=8192, halo=4096), hi_val=1.09)
+    H.assert_events_equal(got["events"], case["ev"])
+    H.assert_frames_equal(got["frames"], got["frame_bits"], case)
+
+
+def test_slicer_known_answers_small_windows():
+    z = H.load_case("slicer_kat")
+    meta = json.loads(bytes(z["meta"]).decode())
+    for ci, m in enumerate(meta):
+        x = z["x%d" % ci]
+        s = _cabi.Stream(2e6, m["lo"], m["hi"], m["L"], m["mx"], outputs=_cabi.OUT_EVENTS | _cabi.OUT_DROPPED_EVENTS)
+        off, k, evs, nb = 0, 0, [], []
+        while off < x.size:
+            n = m["chunks"][k % len(m["chunks"])]
+            k += 1
+            used, cb = s.push(x[off: off + n])
+            if cb:
+                ev = s.drain_events()
+                evs.append(ev)
+                nb.append(len(ev))
+            off += used
+        ev = np.concatenate(evs) if evs else np.zeros(0, _cabi.EVENT_DTYPE)
+        assert nb == z["nb%d" % ci].tolist(), "case %d: per-callback batch sizes" % ci
+        got = np.stack([ev["v"], ev["d"], ev["type"]], 1).astype(np.int32) if len(ev) else np.zeros((0, 3), np.int32)
+        assert np.array_equal(got, z["ev%d" % ci]), "case %d: events" % ci
+        st, ring, _ = s.state()
+        assert bool(st.stable) == m["stable"]
+        if m["stable"]:
+            assert st.ss == m["ss"] or (np.isnan(st.ss) and np.isnan(m["ss"])), "case %d: ss" % ci
+            assert (st.cur_state, st.dur, st.last_bit, st.index) == (m["cur_state"], m["dur"], m["last_bit"], m["index"]), ci
+            assert np.array_equal(ring.astype(np.float64), z["ring%d" % ci], equal_nan=True), "case %d: ring" % ci
+
+
+@pytest.mark.parametrize("L,mx", [(256, 7), (300, 50), (1024, 50), (1000, 33), (2002, 50), (4096, 13)])
+def test_parallel_kernel_small_windows_and_corner_cases(L, mx):
+    """Windows at the tile-size boundaries, windows that are not a multiple of 4 (scalar kernel),
+    long pauses (timeouts inside a LOW run) and spikes right after a pause (hysteresis)."""
+    rng = np.random.default_rng(L * 131 + mx)
+    n = 60000
+    x = (0.25 * (1 + 0.01 * rng.standard_normal(n))).astype(np.float32)
+    i = L + 10
+    while i < n - 4 * mx - 10:
+        kind = rng.integers(0, 4)
+        ln = int(rng.choice([1, 2, mx - 1, mx, mx + 1, 2 * mx, 2 * mx + 1, 3 * mx + 1, 6]))
+        if kind == 0:
+            x[i:i + ln] = 1e-4
+            i += ln
+            if rng.random() < 0.7:
+                k = int(rng.integers(0, mx + 4))
+                x[i + k: i + k + int(rng.integers(1, 4))] = 0.4
+        elif kind == 1:
+            x[i:i + ln] = 0.3 * (1 + 0.01 * rng.standard_normal(ln))
+            i += ln
+        elif kind == 2:
+            x[i:i + ln] = 0.2725 * (1 + 0.002 * rng.standard_normal(ln))  # hovering around hi = 1.09
+            i += ln
+        i += int(rng.integers(1, 4 * mx))
+    want = oracle.decode_capture(x, 2e6, hi_val=1.09, av_window=L, max_len=mx)
+    got = gpu_decode(x, 2e6, hi_val=1.09, av_window=L, max_len=mx, tuning=dict(seg_len=8192, halo=4096))
+    check_against_oracle(got, want)
+    assert not got["stream"].state()[0].serial_mode
+
+
+def test_inexact_sums_fall_back_to_sequential_kernel():
+    """Samples spanning 40 binades: double sums round, order matters, only the sequential recurrence
+    reproduces the reference.  The stream must notice and switch."""
+    rng = np.random.default_rng(9)
+    n = 20000
+    x = (np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-6, 6, n)).astype(np.float32)
+    want = oracle.decode_capture(x, 2e6, av_window=512, max_len=20)
+    got = gpu_decode(x, 2e6, av_window=512, max_len=20)
+    check_against_oracle(got, want)
+    assert got["stream"].state()[0].serial_mode
+
+
+def test_zeros_and_negative_input():
+    x = np.zeros(5000, np.float32)
+    x[3000:] = 0.25
+    x[4000:4010] = -1.0
+    want = oracle.decode_capture(x, 2e6, av_window=256, max_len=10)
+    got = gpu_decode(x, 2e6, av_window=256, max_len=10)
+    check_against_oracle(got, want)
+
+
+def test_empty_and_tiny_pushes():
+    s = _cabi.Stream(2e6)
+    assert s.push(np.zeros(0, np.float32)) == (0, False)
+    assert s.push(np.ones(1999, np.float32)) == (1999, False)
+    assert s.push(np.ones(10, np.float32)) == (1, False)
+    assert s.push(np.zeros(0, np.float32)) == (0, True)
+    assert len(s.drain_events()) == 0
+    assert s.push(np.ones(3, np.float32)) == (3, True)
+
+
+def test_state_roundtrip_between_handles():
+    case = H.load_case("surrogate_classic1k")
+    x = H.case_input(case)
+    cut = 201234
+    a = _cabi.Stream(2e6, hi_val=1.09)
+    a.push_all(x[:cut])
+    st, ring, pend = a.state()
+    b = _cabi.Stream(2e6, hi_val=1.09)
+    b.set_state(st, ring, pend)
+    b.push_all(x[cut:])
+    ev = np.concatenate([a.drain_events(), b.drain_events()])
+    H.assert_events_equal(ev, case["ev"])
+    fa, ba = a.drain_frames()
+    fb, bb = b.drain_frames()
+    H.assert_frames_equal(np.concatenate([fa, fb]), ba + bb, case)
+
+
+def test_reader_only_and_tag_only():
+    case = H.load_case("surrogate_ultralight")
+    x = H.case_input(case)
+    for reader, tag, keep in ((True, False, 1), (False, True, 0)):
+        got = gpu_decode(x, 2e6, hi_val=1.09, reader=reader, tag=tag)
+        want = case["sym"][case["sym"]["type"] == keep]
+        H.assert_symbols_equal(got["symbols"], want)
+
+
+def test_device_resident_input_torch():
+    import torch
+    case = H.load_case("rate_1356")
+    x = torch.from_numpy(H.case_input(case)).cuda()
+    got = gpu_decode(x, 13.56e6, hi_val=1.09, av_window=13560, max_len=339)
+    H.assert_events_equal(got["events"], case["ev"])
+    got2 = gpu_decode(x[3:], 13.56e6, hi_val=1.09, av_window=13560, max_len=339)  # misaligned device pointer
+    want = oracle.decode_capture(H.case_input(case)[3:], 13.56e6, hi_val=1.09, av_window=13560, max_len=339)
+    check_against_oracle(got2, want)
+
+
+@pytest.mark.parametrize("rate,n_sessions", [(13.56e6, 3), (2e6, 6)])
+def test_large_synthetic_stream(rate, n_sessions):
+    p = synth.rate_params(rate)
+    frames = synth.load_sessions()["classic1k"]
+    pcm = synth.capture(frames, rate, 4242, channel=synth.Channel(pause=0.03, tag_high=1.07, fade=0.08),
+                        av_window=p["av_window"], sessions=n_sessions)
+    x = synth.envelope(synth.pcm_to_float(pcm))
+    want = oracle.decode_capture(x, rate, hi_val=1.09, **p)
+    got = gpu_decode(x, rate, hi_val=1.09, **p)
+    check_against_oracle(got, want)
+    assert len(want["frames"]) >= 200 * n_sessions
+    print("samples %d frames %d stats %s" % (x.size, len(want["frames"]), got["stream"].stats()))

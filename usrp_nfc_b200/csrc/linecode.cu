@@ -1,0 +1,336 @@
+// linecode.cu -- events -> symbols -> frames: Manchester / modified-Miller decoding and framing.
+//
+// Replaces background.run's dispatch (background.py:30-52), manchester_decoder.process_transition
+// (manchester.py:30-61), miller_decoder.process_transition (miller.py:153-197) and
+// PacketProcessor.append_bit (packets.py:67-79).
+//
+// Both directions are finite transducers over the event stream:
+//   reader machine R = miller state (16) x PacketProcessor._started (2)   fed by type-1 events
+//   tag machine    G = manchester state (8) x _started (2)                fed by type-0 events
+// (type -1 events and disabled directions are dropped, background.py:30-35).  The stream is cut
+// into chunks of CHUNK events; pass A computes each chunk's transfer function (state at the chunk
+// start -> state at its end) for every possible start state, an order-preserving scan composes
+// them, and passes B/C re-run each chunk from its now known start state to count and to write
+// symbols, frame bits and frame-closing records.  How many bits a frame holds (len(self._cur),
+// packets.py:64) crosses chunks as a (has_emission, tail) pair combined by the same scan.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace nfc {
+
+static const int CHUNK = 128;
+static const int RSTATES = 32, GSTATES = 16;
+
+struct __align__(16) ChunkMap {
+    uint8_t r[RSTATES];
+    uint8_t g[GSTATES];
+};
+struct ComposeMap {  // (a then b)
+    __device__ __forceinline__ ChunkMap operator()(const ChunkMap &a, const ChunkMap &b) const {
+        ChunkMap c;
+#pragma unroll
+        for (int s = 0; s < RSTATES; s++) c.r[s] = b.r[a.r[s] & 31];
+#pragma unroll
+        for (int s = 0; s < GSTATES; s++) c.g[s] = b.g[a.g[s] & 15];
+        return c;
+    }
+};
+
+struct __align__(16) ChunkCnt {
+    uint32_t nsym, nbit0, nbit1, nemit;
+    uint32_t has0, tail0, has1, tail1;  // bits appended after the chunk's last emission (or all, if none)
+};
+struct CombineCnt {
+    __device__ __forceinline__ ChunkCnt operator()(const ChunkCnt &a, const ChunkCnt &b) const {
+        ChunkCnt c;
+        c.nsym = a.nsym + b.nsym;
+        c.nbit0 = a.nbit0 + b.nbit0;
+        c.nbit1 = a.nbit1 + b.nbit1;
+        c.nemit = a.nemit + b.nemit;
+        c.has0 = a.has0 | b.has0;
+        c.tail0 = b.has0 ? b.tail0 : a.tail0 + b.tail0;
+        c.has1 = a.has1 | b.has1;
+        c.tail1 = b.has1 ? b.tail1 : a.tail1 + b.tail1;
+        return c;
+    }
+};
+
+struct TabView {
+    const uint8_t *dcm, *dcg;       // duration classes (global)
+    const TabEntry *tm, *tg;        // tables (shared memory copies)
+    int use_reader, use_tag;
+};
+
+// one symbol into a PacketProcessor (packets.py:67-79); returns 1 when a frame is closed
+template <class Sink>
+__device__ __forceinline__ void framer_put(int &started, int o, int type, uint32_t pos, Sink &sink) {
+    const int start_bit = type == 0 ? 1 : 0;  // packets.py:24-30
+    sink.symbol(pos, type, o);
+    if (o >= 2) {
+        if (started) {
+            sink.emission(pos, type);
+            started = 0;
+        }
+    } else if (!started && o == start_bit) {
+        started = 1;
+    } else {
+        sink.bit(type, o);
+    }
+}
+
+// one event through the machine it belongs to; rs/gs are the R and G machine states
+template <class Sink>
+__device__ __forceinline__ void step_event(const EventRec &ev, const TabView &tv, int &rs, int &gs, Sink &sink) {
+    if (ev.type == 1 && tv.use_reader) {
+        const TabEntry e = tv.tm[((int)tv.dcm[ev.d] * 4 + (ev.v + 1)) * MILLER_STATES + (rs & 15)];
+        int started = rs >> 4;
+        const int n = tab_nout(e);
+        if (n > 0) framer_put(started, tab_out0(e), 1, ev.rel_pos, sink);
+        if (n > 1) framer_put(started, tab_out1(e), 1, ev.rel_pos, sink);
+        rs = tab_next(e) | (started << 4);
+    } else if (ev.type == 0 && tv.use_tag) {
+        const TabEntry e = tv.tg[((int)tv.dcg[ev.d] * 4 + (ev.v + 1)) * MANCH_STATES + (gs & 7)];
+        int started = gs >> 3;
+        if (tab_nout(e) > 0) framer_put(started, tab_out0(e), 0, ev.rel_pos, sink);
+        gs = (tab_next(e) & 7) | (started << 3);
+    }
+}
+
+struct NullSink {
+    __device__ __forceinline__ void symbol(uint32_t, int, int) {}
+    __device__ __forceinline__ void emission(uint32_t, int) {}
+    __device__ __forceinline__ void bit(int, int) {}
+};
+
+__device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, TabEntry *sg) {
+    for (int i = threadIdx.x; i < lt.n_dclass_miller * 4 * MILLER_STATES; i += blockDim.x) sm[i] = lt.miller[i];
+    for (int i = threadIdx.x; i < lt.n_dclass_manch * 4 * MANCH_STATES; i += blockDim.x) sg[i] = lt.manch[i];
+    __syncthreads();
+}
+
+#define NFC_TABLE_SMEM                                              \
+    __shared__ TabEntry s_tm[MAX_DCLASS * 4 * MILLER_STATES];       \
+    __shared__ TabEntry s_tg[MAX_DCLASS * 4 * MANCH_STATES];        \
+    load_tables(lt, s_tm, s_tg);                                    \
+    TabView tv;                                                     \
+    tv.dcm = lt.dclass_miller; tv.dcg = lt.dclass_manch;            \
+    tv.tm = s_tm; tv.tg = s_tg;                                     \
+    tv.use_reader = lt.decode_reader; tv.use_tag = lt.decode_tag;
+
+// ---- pass A: transfer function of every chunk -------------------------------------------------
+__global__ void chunk_map_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+                                 ChunkMap *__restrict__ maps, uint32_t n_chunks) {
+    NFC_TABLE_SMEM
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    uint8_t r[RSTATES], g[GSTATES];
+    for (int s = 0; s < RSTATES; s++) r[s] = (uint8_t)s;
+    for (int s = 0; s < GSTATES; s++) g[s] = (uint8_t)s;
+    bool r_flat = false, g_flat = false;  // all start states already lead to the same state
+    NullSink sink;
+    for (uint32_t i = i0; i < i1; i++) {
+        const EventRec e = ev[i];
+        if (e.type == 1 && tv.use_reader) {
+            if (r_flat) {
+                int rs = r[0], gs = 0;
+                step_event(e, tv, rs, gs, sink);
+                r[0] = (uint8_t)rs;
+            } else {
+                bool same = true;
+                int first = 0;
+                for (int s = 0; s < RSTATES; s++) {
+                    int rs = r[s], gs = 0;
+                    step_event(e, tv, rs, gs, sink);
+                    r[s] = (uint8_t)rs;
+                    if (s == 0) first = rs;
+                    same = same && (rs == first);
+                }
+                r_flat = same;
+            }
+        } else if (e.type == 0 && tv.use_tag) {
+            if (g_flat) {
+                int rs = 0, gs = g[0];
+                step_event(e, tv, rs, gs, sink);
+                g[0] = (uint8_t)gs;
+            } else {
+                bool same = true;
+                int first = 0;
+                for (int s = 0; s < GSTATES; s++) {
+                    int rs = 0, gs = g[s];
+                    step_event(e, tv, rs, gs, sink);
+                    g[s] = (uint8_t)gs;
+                    if (s == 0) first = gs;
+                    same = same && (gs == first);
+                }
+                g_flat = same;
+            }
+        }
+    }
+    ChunkMap m;
+    for (int s = 0; s < RSTATES; s++) m.r[s] = r_flat ? r[0] : r[s];
+    for (int s = 0; s < GSTATES; s++) m.g[s] = g_flat ? g[0] : g[s];
+    maps[c] = m;
+}
+
+// ---- pass B: counts per chunk from the true start state -------------------------------------
+struct CountSink {
+    ChunkCnt c;
+    __device__ __forceinline__ void symbol(uint32_t, int, int) { c.nsym++; }
+    __device__ __forceinline__ void emission(uint32_t, int type) {
+        c.nemit++;
+        if (type == 0) { c.has0 = 1; c.tail0 = 0; } else { c.has1 = 1; c.tail1 = 0; }
+    }
+    __device__ __forceinline__ void bit(int type, int) {
+        if (type == 0) { c.nbit0++; c.tail0++; } else { c.nbit1++; c.tail1++; }
+    }
+};
+
+__device__ __forceinline__ void chunk_start_state(const ChunkMap *prefix, uint32_t c, const DecCarry &carry, int &rs, int &gs) {
+    const int rs0 = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
+    const int gs0 = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
+    rs = prefix[c].r[rs0];
+    gs = prefix[c].g[gs0];
+}
+
+__global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+                                   const ChunkMap *__restrict__ prefix, DecCarry carry,
+                                   ChunkCnt *__restrict__ cnts, uint32_t n_chunks) {
+    NFC_TABLE_SMEM
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int rs, gs;
+    chunk_start_state(prefix, c, carry, rs, gs);
+    CountSink sink;
+    sink.c = ChunkCnt{0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    for (uint32_t i = i0; i < i1; i++) step_event(ev[i], tv, rs, gs, sink);
+    cnts[c] = sink.c;
+}
+
+// ---- pass C: write symbols, frame bits and frame-closing records --------------------------------
+struct EmissionRec {
+    uint32_t rel_pos;   // closing event
+    int32_t type;
+    uint32_t nbits;     // len(self._cur) when the frame closed; 0 = nothing forwarded (packets.py:97)
+    uint32_t bit_end;   // bits of this type appended in this slab before the frame closed
+};
+
+struct WriteSink {
+    SymbolRec *sym;
+    uint8_t *bits0, *bits1;
+    EmissionRec *em;
+    uint32_t isym, ib0, ib1, iem;
+    uint32_t pend0, pend1;
+    uint32_t cap_sym, cap_b0, cap_b1, cap_em;
+    __device__ __forceinline__ void symbol(uint32_t pos, int type, int o) {
+        if (sym && isym < cap_sym) {
+            SymbolRec s;
+            s.rel_pos = pos; s.type = (int8_t)type; s.val = (int8_t)o; s.pad = 0;
+            sym[isym] = s;
+        }
+        isym++;
+    }
+    __device__ __forceinline__ void emission(uint32_t pos, int type) {
+        if (iem < cap_em) {
+            EmissionRec e;
+            e.rel_pos = pos; e.type = type;
+            e.nbits = type == 0 ? pend0 : pend1;
+            e.bit_end = type == 0 ? ib0 : ib1;
+            em[iem] = e;
+        }
+        iem++;
+        if (type == 0) pend0 = 0; else pend1 = 0;
+    }
+    __device__ __forceinline__ void bit(int type, int o) {
+        if (type == 0) { if (ib0 < cap_b0) bits0[ib0] = (uint8_t)o; ib0++; pend0++; }
+        else { if (ib1 < cap_b1) bits1[ib1] = (uint8_t)o; ib1++; pend1++; }
+    }
+};
+
+struct LineOut {
+    SymbolRec *sym;
+    uint8_t *bits0, *bits1;
+    EmissionRec *em;
+    uint32_t cap_sym, cap_b0, cap_b1, cap_em;
+    uint32_t pending0, pending1;  // len(_cur) of each PacketProcessor at the slab start
+};
+
+__global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+                                   const ChunkMap *__restrict__ prefix, DecCarry carry,
+                                   const ChunkCnt *__restrict__ cnt_prefix, LineOut out, uint32_t n_chunks,
+                                   DecCarry *__restrict__ carry_out, uint32_t *__restrict__ pending_out) {
+    NFC_TABLE_SMEM
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int rs, gs;
+    chunk_start_state(prefix, c, carry, rs, gs);
+    const ChunkCnt pc = cnt_prefix[c];
+    WriteSink sink;
+    sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.em = out.em;
+    sink.cap_sym = out.cap_sym; sink.cap_b0 = out.cap_b0; sink.cap_b1 = out.cap_b1; sink.cap_em = out.cap_em;
+    sink.isym = pc.nsym; sink.ib0 = pc.nbit0; sink.ib1 = pc.nbit1; sink.iem = pc.nemit;
+    sink.pend0 = pc.has0 ? pc.tail0 : out.pending0 + pc.tail0;
+    sink.pend1 = pc.has1 ? pc.tail1 : out.pending1 + pc.tail1;
+    const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    for (uint32_t i = i0; i < i1; i++) step_event(ev[i], tv, rs, gs, sink);
+    if (c == n_chunks - 1) {
+        DecCarry co;
+        co.miller_state = rs & 15; co.started[1] = rs >> 4;
+        co.manch_state = gs & 7; co.started[0] = gs >> 3;
+        *carry_out = co;
+        pending_out[0] = sink.pend0;
+        pending_out[1] = sink.pend1;
+    }
+}
+
+// ---- host launchers ------------------------------------------------------------------------------
+uint32_t linecode_chunks(uint32_t n_ev) { return (n_ev + CHUNK - 1) / CHUNK; }
+size_t linecode_map_bytes() { return sizeof(ChunkMap); }
+size_t linecode_cnt_bytes() { return sizeof(ChunkCnt); }
+size_t linecode_emission_bytes() { return sizeof(EmissionRec); }
+size_t linecode_scratch_bytes(uint32_t n_chunks) {
+    return scan_scratch_elems(n_chunks) * sizeof(ChunkMap) + scan_scratch_elems(n_chunks) * sizeof(ChunkCnt);
+}
+
+// Passes A + B.  Leaves chunk start maps in d_prefix, count prefixes in d_cnt_prefix and the totals in *d_total.
+int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
+                          void *d_prefix, void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total,
+                          cudaStream_t stream) {
+    const uint32_t nc = linecode_chunks(n_ev);
+    if (nc == 0) return 0;
+    ChunkMap *maps = (ChunkMap *)d_maps, *prefix = (ChunkMap *)d_prefix;
+    ChunkCnt *cnts = (ChunkCnt *)d_cnts, *cprefix = (ChunkCnt *)d_cnt_prefix;
+    const unsigned nb = (nc + 127) / 128;
+    chunk_map_kernel<<<nb, 128, 0, stream>>>(d_ev, n_ev, lt, maps, nc);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    ChunkMap ident;
+    for (int s = 0; s < RSTATES; s++) ident.r[s] = (uint8_t)s;
+    for (int s = 0; s < GSTATES; s++) ident.g[s] = (uint8_t)s;
+    ChunkMap *scr_m = (ChunkMap *)d_scratch;
+    if (device_exclusive_scan<ChunkMap, ComposeMap>(maps, prefix, nc, ident, ComposeMap(), scr_m, nullptr, stream)) return -1;
+    chunk_count_kernel<<<nb, 128, 0, stream>>>(d_ev, n_ev, lt, prefix, carry, cnts, nc);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    ChunkCnt zero = {0, 0, 0, 0, 0, 0, 0, 0};
+    ChunkCnt *scr_c = (ChunkCnt *)((char *)d_scratch + scan_scratch_elems(nc) * sizeof(ChunkMap));
+    return device_exclusive_scan<ChunkCnt, CombineCnt>(cnts, cprefix, nc, zero, CombineCnt(), scr_c, (ChunkCnt *)d_total, stream);
+}
+
+int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, const void *d_prefix,
+                          const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
+                          uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
+    const uint32_t nc = linecode_chunks(n_ev);
+    if (nc == 0) return 0;
+    LineOut out;
+    out.sym = d_sym; out.bits0 = d_bits0; out.bits1 = d_bits1; out.em = (EmissionRec *)d_em;
+    out.cap_sym = cap_sym; out.cap_b0 = cap_b0; out.cap_b1 = cap_b1; out.cap_em = cap_em;
+    out.pending0 = pending0; out.pending1 = pending1;
+    chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, (const ChunkMap *)d_prefix, carry,
+                                                             (const ChunkCnt *)d_cnt_prefix, out, nc, d_carry_out,
+                                                             d_pending_out);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nfc

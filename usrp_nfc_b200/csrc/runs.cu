@@ -1,0 +1,191 @@
+// runs.cu -- val transitions -> the reference's event list, one thread per run.
+//
+// Replaces the run-length / timeout / emit part of transition_sink.work_stable
+// (transition_sink.py:84-99).  The reference carries (cur_state, last_bit, dur) from sample to
+// sample; here every field of every event is a closed-form function of the run it closes, the
+// run before it and the carry at the window start (derivation and CPU proof: tests/algomodel.py,
+// events_from_transitions).  Events are written in stream order (count -> scan -> write).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace nfc {
+
+// ---- segment lists -> one dense, ordered transition array ---------------------------------
+__global__ void seg_offsets_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, int n) {
+    // n is small (number of segments in a slab): one block, chunked
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        uint32_t v = i < n ? counts[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t a = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += a;
+            __syncthreads();
+        }
+        if (i < n) offsets[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+__global__ void gather_trans_kernel(const SegWork *__restrict__ works, const uint32_t *__restrict__ counts,
+                                    const uint32_t *__restrict__ offsets, TransRec *__restrict__ dense) {
+    const SegWork w = works[blockIdx.x];
+    const uint32_t n = min(counts[blockIdx.x], w.trans_cap), off = offsets[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dense[off + i] = w.trans[i];
+}
+
+// ---- per-run event derivation ---------------------------------------------------------------
+struct RunView {
+    const TransRec *tr;  // dense transitions of the window, ascending
+    uint32_t R;          // number of transitions (runs = R + 1; run 0 is the carried-in run)
+    int64_t w0, w1;      // window, relative to the slab origin
+    int st0, lb0, dur0;  // reference's (cur_state, last_bit, dur) at w0
+    int mx;
+
+    __device__ __forceinline__ int u(uint32_t r) const { return r == 0 ? lb0 : trans_val(tr[r - 1]); }
+    __device__ __forceinline__ int64_t p(uint32_t r) const { return r == 0 ? w0 - dur0 : (int64_t)trans_pos(tr[r - 1]); }
+    __device__ __forceinline__ int64_t e(uint32_t r) const { return r < R ? (int64_t)trans_pos(tr[r]) : w1; }
+
+    __device__ __forceinline__ bool tmo_at_last(int64_t pp, int64_t ee) const {
+        const int64_t ell = ee - pp;
+        return (ell - 1) >= mx && ((ell - 1) % mx) == 0;
+    }
+    // first timeout position q = p + k*mx (k >= 1), q >= w0, or -1 when none falls before e
+    __device__ __forceinline__ int64_t first_tmo(uint32_t r, int64_t pp, int64_t ee) const {
+        int64_t k = 1;
+        if (r == 0) {
+            const int64_t need = w0 - pp;  // = dur0
+            k = (need + mx - 1) / mx;
+            if (k < 1) k = 1;
+        }
+        const int64_t q = pp + k * mx;
+        return q < ee ? q : -1;
+    }
+    // cur_state after the last sample of a run with val != 0
+    __device__ __forceinline__ int s_end_nz(uint32_t r, int uu, int64_t pp, int64_t ee) const {
+        if (r == 0 && ee == w0) return st0;
+        return tmo_at_last(pp, ee) ? 0 : (uu == -1 ? 2 : 1);
+    }
+    __device__ int s_end(uint32_t r) const {
+        const int uu = u(r);
+        const int64_t pp = p(r), ee = e(r);
+        if (r == 0 && ee == w0) return st0;
+        if (uu != 0) return s_end_nz(r, uu, pp, ee);
+        if (first_tmo(r, pp, ee) >= 0) return 0;
+        if (r == 0) return st0;
+        return s_end_nz(r - 1, u(r - 1), p(r - 1), e(r - 1));  // adjacent runs differ, so run r-1 has val != 0
+    }
+};
+
+// Enumerate the events of run r in order; Emit(rel_pos, v, d, type).
+template <class Emit>
+__device__ __forceinline__ void run_events(const RunView &V, uint32_t r, bool keep_dropped, Emit emit) {
+    const int uu = V.u(r);
+    const int64_t pp = V.p(r), ee = V.e(r);
+    const int s_begin = r == 0 ? V.st0 : V.s_end(r - 1);
+    int64_t q = V.first_tmo(r, pp, ee);
+    bool first = true;
+    bool any_tmo = false;
+    while (q >= 0 && q < ee) {  // timeouts (transition_sink.py:95-99)
+        const int st_q = uu == -1 ? 2 : (uu == 1 ? 1 : (first ? s_begin : 0));
+        first = false;
+        any_tmo = true;
+        if (keep_dropped || st_q != 0) emit((uint32_t)q, uu + (st_q == 2 ? 1 : 0), V.mx, st_q - 1);
+        if (!keep_dropped && uu == 0) break;  // later timeouts of a 0-run all have cur_state 0 (dropped)
+        q += V.mx;
+    }
+    if (r < V.R) {  // the transition that closes the run (transition_sink.py:86-92)
+        int se;
+        if (r == 0 && ee == V.w0) se = V.st0;
+        else if (uu != 0) se = V.s_end_nz(r, uu, pp, ee);
+        else se = any_tmo ? 0 : s_begin;
+        const int un = trans_val(V.tr[r]);
+        const int st_after = un == -1 ? 2 : (un == 1 ? 1 : se);
+        const int64_t ell = ee - pp;
+        const int d = se == 0 ? V.mx : (int)((ell - 1) % V.mx) + 1;
+        if (keep_dropped || st_after != 0) emit((uint32_t)ee, uu + (st_after == 2 ? 1 : 0), d, st_after - 1);
+    }
+}
+
+__global__ void run_count_kernel(RunView V, int keep_dropped, uint32_t *__restrict__ counts) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > V.R) return;
+    uint32_t c = 0;
+    run_events(V, r, keep_dropped != 0, [&](uint32_t, int, int, int) { c++; });
+    counts[r] = c;
+}
+
+__global__ void run_write_kernel(RunView V, int keep_dropped, const uint32_t *__restrict__ offsets,
+                                 EventRec *__restrict__ out, uint32_t cap, RunCarry *__restrict__ carry_out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > V.R) return;
+    uint32_t idx = offsets[r];
+    run_events(V, r, keep_dropped != 0, [&](uint32_t pos, int v, int d, int type) {
+        if (idx < cap) {
+            EventRec ev;
+            ev.rel_pos = pos;
+            ev.d = (uint16_t)d;
+            ev.v = (int8_t)v;
+            ev.type = (int8_t)type;
+            out[idx] = ev;
+        }
+        idx++;
+    });
+    if (r == V.R && carry_out) {  // (cur_state, last_bit, dur) at w1
+        RunCarry c;
+        if (V.w1 > V.w0) {
+            c.st = V.s_end(r);
+            c.last_bit = V.u(r);
+            c.dur = (int)((V.w1 - 1 - V.p(r)) % V.mx) + 1;
+        } else {
+            c.st = V.st0; c.last_bit = V.lb0; c.dur = V.dur0;
+        }
+        c.pad = 0;
+        *carry_out = c;
+    }
+}
+
+// ---- host launchers ------------------------------------------------------------------------------
+int launch_gather_transitions(const SegWork *d_works, const uint32_t *d_counts, uint32_t *d_offsets, int n_segs,
+                              TransRec *d_dense, cudaStream_t stream) {
+    if (n_segs <= 0) return 0;
+    seg_offsets_kernel<<<1, 1024, 0, stream>>>(d_counts, d_offsets, n_segs);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    gather_trans_kernel<<<n_segs, 256, 0, stream>>>(d_works, d_counts, d_offsets, d_dense);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Counts the events of every run into d_counts[0..R] and scans them into d_offsets; *d_total = number of events.
+int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
+                     uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total,
+                     cudaStream_t stream) {
+    RunView V;
+    V.tr = d_tr; V.R = R; V.w0 = w0; V.w1 = w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
+    const uint32_t nrun = R + 1;
+    run_count_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_counts);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return device_exclusive_scan<uint32_t, AddU32>(d_counts, d_offsets, nrun, 0u, AddU32(), d_scratch, d_total, stream);
+}
+
+int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
+                     const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, RunCarry *d_carry_out,
+                     cudaStream_t stream) {
+    RunView V;
+    V.tr = d_tr; V.R = R; V.w0 = w0; V.w1 = w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
+    const uint32_t nrun = R + 1;
+    run_write_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_offsets, d_events, cap, d_carry_out);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nfc

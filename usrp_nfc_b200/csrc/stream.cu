@@ -1,0 +1,978 @@
+// stream.cu -- host driver of one sample stream and the extern "C" boundary (include/usrp_nfc_b200.h).
+//
+// A push is cut into slabs; a slab into time segments (one CTA each, slicer.cu).  Segment 0 starts
+// from the stream's true state, the others start cold `halo` samples early and are verified at the
+// seam against their predecessor's final state, then redone from the true state if they differ.
+// The ordered transitions of the slab go through runs.cu (events) and linecode.cu (symbols, frames);
+// only records leave the device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/usrp_nfc_b200.h"
+#include "common.cuh"
+#include "tables.h"
+
+namespace nfc {
+
+// ---- launchers implemented in the kernel files
+int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok, cudaStream_t);
+int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,
+                         size_t ring_stride, cudaStream_t);
+int launch_seam_compare(const SlicerHdr *const *d_truth, const SlicerHdr *const *d_assumed, const int *d_param_idx,
+                        const SlicerParams *d_params, int *d_mismatch, int n, cudaStream_t);
+int launch_gather_transitions(const SegWork *d_works, const uint32_t *d_counts, uint32_t *d_offsets, int n_segs,
+                              TransRec *d_dense, cudaStream_t);
+int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
+                     uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total, cudaStream_t);
+int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
+                     const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, RunCarry *d_carry_out, cudaStream_t);
+uint32_t linecode_chunks(uint32_t n_ev);
+size_t linecode_map_bytes();
+size_t linecode_cnt_bytes();
+size_t linecode_emission_bytes();
+size_t linecode_scratch_bytes(uint32_t n_chunks);
+int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
+                          void *d_prefix, void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t);
+int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, const void *d_prefix,
+                          const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
+                          uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t);
+int synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens, int64_t n_runs,
+                 float carrier, float pause, float tag_high, float noise, float fade, double fade_period, uint64_t seed,
+                 int as_envelope, cudaStream_t);
+
+// ---- error reporting
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        NFC_CUDA_CHECK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct EmissionHost {
+    uint32_t rel_pos;
+    int32_t type;
+    uint32_t nbits;
+    uint32_t bit_end;
+};
+
+static size_t item_bytes(int kind) {
+    switch (kind) {
+        case IN_IQ_F32: return 8;
+        case IN_PCM_S16: return 2;
+        default: return 4;
+    }
+}
+
+static int ceil_log2(int v) {
+    int l = 0;
+    while ((1LL << l) < v) l++;
+    return l;
+}
+
+static int classify_ratio_host(double ratio, double lo, double hi) {  // transition_sink.py:67-71
+    if (lo > ratio) return -1;
+    if (ratio > hi) return 1;
+    return 0;
+}
+
+struct Stream {
+    nfc_params prm;
+    SlicerParams sp;
+    HostTables ht;
+    LineTables lt;
+    double factor;
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+
+    // stream state
+    int64_t pos = 0;
+    bool stable = false;
+    bool serial_mode = false;
+    std::vector<float> warm;
+    DevBuf state;   // current true state block (hdr + ring)
+    RunCarry run_carry{0, 0, 0, 0};
+    DecCarry dec_carry{0, 0, {0, 0}};
+    uint32_t pending[2] = {0, 0};
+    std::vector<uint8_t> hbits[2];  // bits appended and not yet forwarded, per type
+
+    // tuning
+    int64_t seg_len = 0, halo = 0, slab_len = 0;
+    int force_serial = 0;
+
+    // device scratch
+    DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
+        seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
+        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    // results
+    std::vector<nfc_event> out_events;
+    std::vector<nfc_symbol> out_symbols;
+    std::vector<nfc_frame> out_frames;
+    std::vector<uint8_t> out_bits;
+    size_t ev_head = 0, sym_head = 0, fr_head = 0;
+
+    nfc_stats stats;
+
+    int tile() const { return (vec_ok() && sp.L >= 1024) ? 1024 : 256; }
+    bool vec_ok() const { return (sp.L % 4) == 0; }
+    bool parallel_ok() const { return sp.L >= 256 && sp.L <= 56000 && !force_serial && !serial_mode; }
+
+    int init(const nfc_params *p);
+    void destroy();
+    int ensure_pinned(size_t bytes);
+    int64_t push(const void *items, int64_t n, int mem, int *called_back);
+    int finish_warmup();
+    int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b);
+    int run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial, uint32_t *R_out,
+                   bool *fell_back);
+};
+
+int Stream::ensure_pinned(size_t bytes) {
+    if (bytes <= pinned_cap) return 0;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_cap = 0;
+    NFC_CUDA_CHECK(cudaMallocHost(&pinned, bytes + bytes / 4 + 4096));
+    pinned_cap = bytes + bytes / 4 + 4096;
+    return 0;
+}
+
+int Stream::init(const nfc_params *p) {
+    prm = *p;
+    memset(&stats, 0, sizeof(stats));
+    if (!(p->samp_rate > 0) || p->av_window < 1 || p->max_len < 1 || p->max_len > 65535) {
+        set_error("bad parameters: samp_rate=%g av_window=%d max_len=%d", p->samp_rate, p->av_window, p->max_len);
+        return -1;
+    }
+    if (p->av_window >= (1 << 28)) {
+        set_error("av_window too large");
+        return -1;
+    }
+    NFC_CUDA_CHECK(cudaSetDevice(p->device));
+    NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    NFC_CUDA_CHECK(cudaEventCreate(&ev_a));
+    NFC_CUDA_CHECK(cudaEventCreate(&ev_b));
+    NFC_CUDA_CHECK(cudaEventCreate(&ev_c));
+    factor = 1e6 / p->samp_rate;  // transition_sink.py:21
+    sp.lo = p->lo_val;
+    sp.hi = p->hi_val;
+    sp.L = p->av_window;
+    sp.Ld = (double)p->av_window;
+    sp.mx = p->max_len;
+    sp.cls_ss0_x0 = classify_ratio_host(1.0, sp.lo, sp.hi);            // transition_sink.py:60-61
+    sp.cls_ss0_xn = classify_ratio_host(sp.hi + 0.1, sp.lo, sp.hi);    // transition_sink.py:62-63
+    sp.span_limit = std::max(0, 28 - ceil_log2(sp.L) - 1);
+    sp.input_kind = p->input_kind;
+    sp.pcm_scale = p->pcm_scale > 0 ? p->pcm_scale : 32767.0f;
+    if (params_d.ensure(sizeof(SlicerParams))) return -1;
+    NFC_CUDA_CHECK(cudaMemcpy(params_d.p, &sp, sizeof(sp), cudaMemcpyHostToDevice));
+
+    if (!build_tables(sp.mx, factor, ht)) {
+        set_error("line-code tables need more than %d duration classes", MAX_DCLASS);
+        return -1;
+    }
+    const size_t dcm = ht.dclass_miller.size(), dcg = ht.dclass_manch.size();
+    const size_t tm = ht.miller.size() * sizeof(TabEntry), tg = ht.manch.size() * sizeof(TabEntry);
+    const size_t o1 = (dcm + 255) / 256 * 256, o2 = o1 + (dcg + 255) / 256 * 256, o3 = o2 + (tm + 255) / 256 * 256;
+    if (tab_d.ensure(o3 + tg)) return -1;
+    char *base = tab_d.as<char>();
+    NFC_CUDA_CHECK(cudaMemcpy(base, ht.dclass_miller.data(), dcm, cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpy(base + o1, ht.dclass_manch.data(), dcg, cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpy(base + o2, ht.miller.data(), tm, cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpy(base + o3, ht.manch.data(), tg, cudaMemcpyHostToDevice));
+    lt.dclass_miller = (const uint8_t *)base;
+    lt.dclass_manch = (const uint8_t *)(base + o1);
+    lt.miller = (const TabEntry *)(base + o2);
+    lt.manch = (const TabEntry *)(base + o3);
+    lt.n_dclass_miller = ht.n_dclass_miller;
+    lt.n_dclass_manch = ht.n_dclass_manch;
+    lt.decode_reader = p->decode_reader;
+    lt.decode_tag = p->decode_tag;
+
+    warm.reserve((size_t)sp.L);
+    if (state.ensure(state_block_bytes(sp.L))) return -1;
+    if (carry_d.ensure(256)) return -1;
+    if (totals_d.ensure(256)) return -1;
+    return 0;
+}
+
+void Stream::destroy() {
+    DevBuf *all[] = {&params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
+                     &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
+                     &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
+                     &serial_ring, &state};
+    for (DevBuf *b : all) b->release();
+    if (pinned) cudaFreeHost(pinned);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_c) cudaEventDestroy(ev_c);
+    if (cs) cudaStreamDestroy(cs);
+}
+
+// host-side envelope of the few warm-up samples (same float operations as the device path)
+static float host_env(const void *items, int64_t i, int kind, float pcm_scale) {
+    switch (kind) {
+        case IN_ENVELOPE_F32: return ((const float *)items)[i];
+        case IN_REAL_F32: {
+            volatile float s = ((const float *)items)[i];
+            volatile float r = s * s;
+            return r;
+        }
+        case IN_IQ_F32: {
+            volatile float re = ((const float *)items)[2 * i], im = ((const float *)items)[2 * i + 1];
+            volatile float a = re * re, b = im * im;
+            volatile float r = a + b;
+            return r;
+        }
+        default: {
+            volatile float s = (float)((const int16_t *)items)[i] / pcm_scale;
+            volatile float r = s * s;
+            return r;
+        }
+    }
+}
+
+int Stream::finish_warmup() {
+    // transition_sink.py:121-124: _sum = sum(ar) (left to right, double), _dur = length % max
+    double s = 0;
+    for (int i = 0; i < sp.L; i++) s += (double)warm[(size_t)i];
+    std::vector<char> blk(state_block_bytes(sp.L), 0);
+    SlicerHdr *h = reinterpret_cast<SlicerHdr *>(blk.data());
+    h->ss = s;
+    h->pos = sp.L;
+    h->lastL = NO_POS;
+    h->lrun_start = NO_POS;
+    h->last_val = 0;
+    memcpy(state_ring(h), warm.data(), (size_t)sp.L * 4);
+    NFC_CUDA_CHECK(cudaMemcpy(state.p, blk.data(), blk.size(), cudaMemcpyHostToDevice));
+    run_carry.st = 0;
+    run_carry.last_bit = 0;
+    run_carry.dur = sp.L % sp.mx;
+    stable = true;
+    return 0;
+}
+
+int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
+    if (called_back) *called_back = 0;
+    if (n < 0) {
+        set_error("negative item count");
+        return -1;
+    }
+    NFC_CUDA_CHECK(cudaSetDevice(prm.device));
+    const size_t ib = item_bytes(sp.input_kind);
+    if (!stable) {  // transition_sink.py:109-125
+        const int64_t need = sp.L - (int64_t)warm.size();
+        const int64_t can = std::min(n, need);
+        if (can > 0) {
+            std::vector<char> tmp;
+            const void *src = items;
+            if (mem == NFC_MEM_DEVICE) {
+                tmp.resize((size_t)can * ib);
+                NFC_CUDA_CHECK(cudaMemcpy(tmp.data(), items, (size_t)can * ib, cudaMemcpyDeviceToHost));
+                src = tmp.data();
+            }
+            for (int64_t i = 0; i < can; i++) warm.push_back(host_env(src, i, sp.input_kind, sp.pcm_scale));
+        }
+        pos += can;
+        if (can == need && finish_warmup()) return -1;
+        return can;
+    }
+    if (called_back) *called_back = 1;
+    int64_t done = 0;
+    const int64_t slab = slab_len > 0 ? slab_len : (int64_t)1 << 28;
+    while (done < n) {
+        const int64_t m = std::min(slab, n - done);
+        const int64_t a = pos, b = pos + m;
+        const int64_t in_pos0 = a - (a & 3);
+        const void *d_in = nullptr;
+        int64_t in_begin = in_pos0;
+        const char *src = (const char *)items + (size_t)done * ib;
+        const size_t padb = (size_t)(a - in_pos0) * ib;
+        if (mem == NFC_MEM_DEVICE && (((uintptr_t)src - padb) & 15) == 0) {
+            d_in = src - padb;  // usable in place: item with stream index in_pos0 would sit 16-byte aligned
+            in_begin = a;       // ... but nothing before the caller's pointer is read
+        } else {
+            if (staging.ensure(padb + (size_t)m * ib + 64)) return -1;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(staging.as<char>() + padb, src, (size_t)m * ib,
+                                           mem == NFC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+            if (mem == NFC_MEM_HOST) stats.h2d_bytes += (int64_t)((size_t)m * ib);
+            d_in = staging.p;
+        }
+        if (process_slab(d_in, in_pos0, in_begin, b, a, b)) return -1;
+        pos = b;
+        done += m;
+        stats.samples += m;
+    }
+    return n;
+}
+
+// Runs the slicer over [a, b) and leaves the dense ordered transitions in trans_dense (count in *R_out) and the
+// true final state in `state`.
+int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial,
+                       uint32_t *R_out, bool *fell_back) {
+    const int L = sp.L;
+    const int T = tile();
+    *fell_back = false;
+    // ---- plan segments
+    std::vector<int64_t> begins;  // first emitted sample of each segment
+    begins.push_back(a);
+    int64_t H = 0;
+    if (!serial) {
+        int64_t Hs = halo > 0 ? halo : (int64_t)16 * L;
+        H = (Hs + T - 1) / T * T;
+        int64_t S = seg_len;
+        if (S <= 0) {
+            S = (b - a) / 600;
+            S = std::max<int64_t>(S, 4 * H);
+            S = std::min<int64_t>(S, (int64_t)256 * L);
+            S = std::max<int64_t>(S, 4 * H);
+        }
+        S = (S + T - 1) / T * T;
+        int64_t b1 = a + std::max<int64_t>(S, (int64_t)L + H);
+        b1 = (b1 + T - 1) / T * T;
+        while (b1 + S / 2 <= b && b1 < b) {
+            begins.push_back(b1);
+            b1 += S;
+        }
+    }
+    const int nseg = (int)begins.size();
+    const size_t sblk = state_block_bytes(L);
+    // state blocks: [seam_in k][state_out k] per segment
+    if (states_d.ensure(sblk * 2 * (size_t)nseg)) return -1;
+    if (seg_counts.ensure(sizeof(uint32_t) * (size_t)nseg) || seg_offsets.ensure(sizeof(uint32_t) * ((size_t)nseg + 1)) ||
+        seg_status.ensure(sizeof(int32_t) * (size_t)nseg) || works_d.ensure(sizeof(SegWork) * (size_t)nseg) ||
+        mismatch_d.ensure(sizeof(int) * (size_t)nseg) || seam_ptrs.ensure((sizeof(void *) * 2 + sizeof(int)) * (size_t)nseg))
+        return -1;
+    if (serial && serial_ring.ensure((size_t)L * 4 + 64)) return -1;
+
+    std::vector<uint32_t> caps((size_t)nseg);
+    for (int k = 0; k < nseg; k++) {
+        const int64_t e = k + 1 < nseg ? begins[(size_t)k + 1] : b;
+        caps[(size_t)k] = (uint32_t)std::min<int64_t>((e - begins[(size_t)k]) / 8 + 1024, (e - begins[(size_t)k]) + 16);
+    }
+    std::vector<SegWork> works((size_t)nseg);
+    std::vector<uint32_t> counts((size_t)nseg);
+    std::vector<int32_t> status((size_t)nseg);
+
+    for (int attempt = 0; attempt < 4; attempt++) {
+        size_t total_cap = 0;
+        std::vector<size_t> toff((size_t)nseg);
+        for (int k = 0; k < nseg; k++) {
+            toff[(size_t)k] = total_cap;
+            total_cap += caps[(size_t)k];
+        }
+        if (trans_seg.ensure(total_cap * sizeof(TransRec) + 16)) return -1;
+        auto seam_in = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k)); };
+        auto st_out = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k + 1)); };
+        for (int k = 0; k < nseg; k++) {
+            SegWork &w = works[(size_t)k];
+            w.in = d_in;
+            w.in_pos0 = in_pos0;
+            w.in_begin = in_begin;
+            w.in_end = in_end;
+            w.begin = begins[(size_t)k];
+            w.end = k + 1 < nseg ? begins[(size_t)k + 1] : b;
+            w.warm_begin = k == 0 ? a : w.begin - H;
+            w.slab_pos0 = a;
+            w.state_in = k == 0 ? state.as<SlicerHdr>() : nullptr;
+            w.seam_in = k == 0 ? nullptr : seam_in(k);
+            w.state_out = st_out(k);
+            w.trans = trans_seg.as<TransRec>() + toff[(size_t)k];
+            w.trans_cap = caps[(size_t)k];
+            w.trans_count = seg_counts.as<uint32_t>() + k;
+            w.status = seg_status.as<int32_t>() + k;
+            w.param_idx = 0;
+            w.pad = 0;
+        }
+        NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+        if (serial) {
+            if (launch_slicer_serial(works_d.as<SegWork>(), nseg, params_d.as<SlicerParams>(), serial_ring.as<float>(),
+                                     (size_t)L + 16, cs))
+                return -1;
+            stats.serial_segments += nseg;
+        } else {
+            if (launch_slicer(works_d.as<SegWork>(), nseg, params_d.as<SlicerParams>(), L, vec_ok(), cs)) return -1;
+        }
+        stats.launches++;
+        stats.slicer_launches++;
+        stats.segments += nseg;
+
+        // ---- seams: verify and repair
+        if (nseg > 1) {
+            std::vector<const SlicerHdr *> truth((size_t)nseg), assumed((size_t)nseg);
+            std::vector<int> pidx((size_t)nseg, 0);
+            for (int k = 0; k < nseg; k++) {
+                truth[(size_t)k] = k == 0 ? nullptr : st_out(k - 1);
+                assumed[(size_t)k] = k == 0 ? nullptr : seam_in(k);
+            }
+            char *sp_base = seam_ptrs.as<char>();
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base, truth.data(), sizeof(void *) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(), sizeof(void *) * (size_t)nseg,
+                                           cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + 2 * sizeof(void *) * (size_t)nseg, pidx.data(), sizeof(int) * (size_t)nseg,
+                                           cudaMemcpyHostToDevice, cs));
+            std::vector<int> mism((size_t)nseg, 0);
+            std::vector<char> fixed((size_t)nseg, 0);  // segment was redone from a true state: its seam is settled
+            for (int round = 0; round < nseg + 1; round++) {
+                NFC_CUDA_CHECK(cudaMemsetAsync(mismatch_d.p, 0, sizeof(int) * (size_t)nseg, cs));
+                if (launch_seam_compare((const SlicerHdr *const *)sp_base,
+                                        (const SlicerHdr *const *)(sp_base + sizeof(void *) * (size_t)nseg),
+                                        (const int *)(sp_base + 2 * sizeof(void *) * (size_t)nseg),
+                                        params_d.as<SlicerParams>(), mismatch_d.as<int>(), nseg, cs))
+                    return -1;
+                stats.launches++;
+                NFC_CUDA_CHECK(cudaMemcpyAsync(mism.data(), mismatch_d.p, sizeof(int) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
+                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+                // redo, from their predecessor's final state, the flagged segments whose predecessor is settled
+                std::vector<SegWork> redo;
+                std::vector<int> redo_k;
+                bool prev_pending = false;
+                for (int k = 1; k < nseg; k++) {
+                    const bool bad = mism[(size_t)k] && !fixed[(size_t)k];
+                    if (bad && !prev_pending) {
+                        SegWork w = works[(size_t)k];
+                        w.warm_begin = w.begin;
+                        w.state_in = st_out(k - 1);
+                        w.seam_in = nullptr;
+                        redo.push_back(w);
+                        redo_k.push_back(k);
+                    }
+                    prev_pending = bad;
+                }
+                if (redo.empty()) break;
+                stats.seam_mismatches += (int64_t)redo.size();
+                if (works_d.ensure(sizeof(SegWork) * ((size_t)nseg + redo.size()))) return -1;
+                // works_d may have been reallocated: re-upload everything
+                NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+                SegWork *d_redo = works_d.as<SegWork>() + nseg;
+                NFC_CUDA_CHECK(cudaMemcpyAsync(d_redo, redo.data(), sizeof(SegWork) * redo.size(), cudaMemcpyHostToDevice, cs));
+                if (launch_slicer(d_redo, (int)redo.size(), params_d.as<SlicerParams>(), L, vec_ok(), cs)) return -1;
+                stats.launches++;
+                stats.slicer_launches++;
+                for (int k : redo_k) {
+                    fixed[(size_t)k] = 1;
+                    // the redone segment now starts from the truth: make its seam compare equal to itself
+                    assumed[(size_t)k] = truth[(size_t)k];
+                }
+                NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(),
+                                               sizeof(void *) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+            }
+        }
+        NFC_CUDA_CHECK(cudaMemcpyAsync(counts.data(), seg_counts.p, sizeof(uint32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        int st_all = 0;
+        bool over = false;
+        for (int k = 0; k < nseg; k++) {
+            st_all |= status[(size_t)k];
+            if (counts[(size_t)k] > caps[(size_t)k]) {
+                over = true;
+                caps[(size_t)k] = counts[(size_t)k] + 16;
+            }
+        }
+        if (!serial && (st_all & (SEG_INEXACT | SEG_NOT_SANE))) {
+            *fell_back = true;  // caller redoes the slab with the sequential kernel
+            return 0;
+        }
+        if (over) {
+            stats.overflow_retries++;
+            continue;
+        }
+        // ---- dense ordered transitions
+        size_t R = 0;
+        for (int k = 0; k < nseg; k++) R += counts[(size_t)k];
+        if (trans_dense.ensure((R + 16) * sizeof(TransRec))) return -1;
+        if (launch_gather_transitions(works_d.as<SegWork>(), seg_counts.as<uint32_t>(), seg_offsets.as<uint32_t>(), nseg,
+                                      trans_dense.as<TransRec>(), cs))
+            return -1;
+        stats.launches += 2;
+        // the slab's final state becomes the stream's state
+        NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
+        *R_out = (uint32_t)R;
+        return 0;
+    }
+    set_error("transition buffers kept overflowing");
+    return -1;
+}
+
+int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b) {
+    NFC_CUDA_CHECK(cudaEventRecord(ev_a, cs));
+    uint32_t R = 0;
+    bool fell_back = false;
+    const bool par = parallel_ok();
+    if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) return -1;
+    if (fell_back) {
+        serial_mode = true;  // sums are no longer exactly representable: stay on the sequential kernel
+        if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, true, &R, &fell_back)) return -1;
+    }
+    NFC_CUDA_CHECK(cudaEventRecord(ev_b, cs));
+
+    // ---- runs -> events
+    const int keep_dropped = (prm.outputs & NFC_OUT_DROPPED_EVENTS) ? 1 : 0;
+    const size_t nrun = (size_t)R + 1;
+    if (run_counts.ensure(nrun * 4) || run_offsets.ensure(nrun * 4) || scan_scr.ensure((nrun / 256 + 1024) * 4 * 4)) return -1;
+    if (launch_run_count(trans_dense.as<TransRec>(), R, 0, b - a, run_carry, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
+                         run_offsets.as<uint32_t>(), scan_scr.as<uint32_t>(), totals_d.as<uint32_t>(), cs))
+        return -1;
+    stats.launches += 3;
+    uint32_t M = 0;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(&M, totals_d.p, 4, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if (events_d.ensure(((size_t)M + 16) * sizeof(EventRec))) return -1;
+    RunCarry *d_rc = carry_d.as<RunCarry>();
+    if (launch_run_write(trans_dense.as<TransRec>(), R, 0, b - a, run_carry, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
+                         events_d.as<EventRec>(), M, d_rc, cs))
+        return -1;
+    stats.launches++;
+
+    // ---- events -> symbols, frame bits, frame closings
+    const uint32_t nc = linecode_chunks(M);
+    struct Totals {
+        uint32_t nsym, nbit0, nbit1, nemit, has0, tail0, has1, tail1;
+    } tot = {0, 0, 0, 0, 0, 0, 0, 0};
+    DecCarry *d_dc = reinterpret_cast<DecCarry *>(carry_d.as<char>() + 64);
+    uint32_t *d_pend = reinterpret_cast<uint32_t *>(carry_d.as<char>() + 128);
+    const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
+    if (nc > 0 && want_line) {
+        if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes()) ||
+            cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) || cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
+            line_scr.ensure(linecode_scratch_bytes(nc) + 256))
+            return -1;
+        if (launch_linecode_count(events_d.as<EventRec>(), M, lt, dec_carry, maps_d.p, prefix_d.p, cnts_d.p, cprefix_d.p,
+                                  line_scr.p, totals_d.as<char>() + 64, cs))
+            return -1;
+        stats.launches += 8;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
+        if ((want_sym && sym_d.ensure(((size_t)tot.nsym + 16) * sizeof(SymbolRec))) || bits0_d.ensure((size_t)tot.nbit0 + 16) ||
+            bits1_d.ensure((size_t)tot.nbit1 + 16) || em_d.ensure(((size_t)tot.nemit + 16) * linecode_emission_bytes()))
+            return -1;
+        if (launch_linecode_write(events_d.as<EventRec>(), M, lt, dec_carry, prefix_d.p, cprefix_d.p,
+                                  want_sym ? sym_d.as<SymbolRec>() : nullptr, want_sym ? tot.nsym : 0, bits0_d.as<uint8_t>(),
+                                  tot.nbit0, bits1_d.as<uint8_t>(), tot.nbit1, em_d.p, tot.nemit, pending[0], pending[1], d_dc,
+                                  d_pend, cs))
+            return -1;
+        stats.launches++;
+    }
+    NFC_CUDA_CHECK(cudaEventRecord(ev_c, cs));
+
+    // ---- records back to the host
+    const bool want_ev = (prm.outputs & NFC_OUT_EVENTS) != 0;
+    const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0 && nc > 0;
+    const bool want_fr = (prm.outputs & NFC_OUT_FRAMES) != 0 && nc > 0;
+    size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, off_c = 0, total = 0;
+    auto place = [&](size_t bytes) {
+        size_t o = total;
+        total += (bytes + 63) / 64 * 64;
+        return o;
+    };
+    off_c = place(256);
+    if (want_ev) off_ev = place((size_t)M * sizeof(EventRec));
+    if (want_sym) off_sym = place((size_t)tot.nsym * sizeof(SymbolRec));
+    if (want_fr) {
+        off_em = place((size_t)tot.nemit * sizeof(EmissionHost));
+        off_b0 = place(tot.nbit0);
+        off_b1 = place(tot.nbit1);
+    }
+    if (ensure_pinned(total)) return -1;
+    char *hp = (char *)pinned;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_c, carry_d.p, 256, cudaMemcpyDeviceToHost, cs));
+    if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d.p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs));
+    if (want_sym && tot.nsym)
+        NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d.p, (size_t)tot.nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs));
+    if (want_fr) {
+        if (tot.nemit)
+            NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d.p, (size_t)tot.nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs));
+        if (tot.nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d.p, tot.nbit0, cudaMemcpyDeviceToHost, cs));
+        if (tot.nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d.p, tot.nbit1, cudaMemcpyDeviceToHost, cs));
+    }
+    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    stats.d2h_bytes += (int64_t)total;
+    float ms_ab = 0, ms_ac = 0;
+    cudaEventElapsedTime(&ms_ab, ev_a, ev_b);
+    cudaEventElapsedTime(&ms_ac, ev_a, ev_c);
+    stats.slicer_ms += ms_ab;
+    stats.kernel_ms += ms_ac;
+
+    // ---- carries
+    run_carry = *reinterpret_cast<RunCarry *>(hp + off_c);
+    if (nc > 0 && want_line) {
+        dec_carry = *reinterpret_cast<DecCarry *>(hp + off_c + 64);
+        pending[0] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[0];
+        pending[1] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[1];
+    }
+    // ---- marshal records (absolute positions)
+    if (want_ev) {
+        const EventRec *e = reinterpret_cast<const EventRec *>(hp + off_ev);
+        out_events.reserve(out_events.size() + M);
+        for (uint32_t i = 0; i < M; i++) {
+            nfc_event o;
+            o.pos = a + (int64_t)e[i].rel_pos;
+            o.d = e[i].d;
+            o.v = e[i].v;
+            o.type = e[i].type;
+            o.pad = 0;
+            out_events.push_back(o);
+        }
+    }
+    if (want_sym) {
+        const SymbolRec *s = reinterpret_cast<const SymbolRec *>(hp + off_sym);
+        for (uint32_t i = 0; i < tot.nsym; i++) {
+            nfc_symbol o;
+            o.pos = a + (int64_t)s[i].rel_pos;
+            o.type = s[i].type;
+            o.val = s[i].val;
+            o.pad = 0;
+            o.pad2 = 0;
+            out_symbols.push_back(o);
+        }
+    }
+    if (want_fr) {
+        const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
+        const uint8_t *nb[2] = {(const uint8_t *)(hp + off_b0), (const uint8_t *)(hp + off_b1)};
+        const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
+        const size_t old[2] = {hbits[0].size(), hbits[1].size()};
+        for (int t = 0; t < 2; t++) hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
+        size_t last_end[2] = {0, 0};
+        bool any[2] = {false, false};
+        for (uint32_t i = 0; i < tot.nemit; i++) {
+            const int t = em[i].type;
+            const size_t end = old[t] + em[i].bit_end;  // index into hbits[t]
+            any[t] = true;
+            last_end[t] = end;
+            if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
+            if (em[i].nbits > end) {
+                set_error("internal: frame longer than the retained bits");
+                return -1;
+            }
+            nfc_frame f;
+            f.pos = a + (int64_t)em[i].rel_pos;
+            f.bit_off = (int64_t)out_bits.size();
+            f.nbits = (int32_t)em[i].nbits;
+            f.type = t;
+            out_bits.insert(out_bits.end(), hbits[t].begin() + (long)(end - em[i].nbits), hbits[t].begin() + (long)end);
+            out_frames.push_back(f);
+        }
+        for (int t = 0; t < 2; t++)
+            if (any[t]) hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+    }
+    return 0;
+}
+
+}  // namespace nfc
+
+// =================================================================================== extern "C"
+using nfc::Stream;
+struct nfc_stream {
+    Stream s;
+};
+
+template <class T>
+static int64_t drain_vec(std::vector<T> &v, size_t &head, T *out, int64_t cap) {
+    const int64_t avail = (int64_t)(v.size() - head);
+    if (cap <= 0 || !out) return avail;
+    const int64_t n = std::min(avail, cap);
+    memcpy(out, v.data() + head, (size_t)n * sizeof(T));
+    head += (size_t)n;
+    if (head == v.size()) {
+        v.clear();
+        head = 0;
+    }
+    return n;
+}
+
+extern "C" {
+
+void nfc_default_params(nfc_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->samp_rate = 2e6;
+    p->lo_val = 0.1;
+    p->hi_val = 1.1;
+    p->av_window = 2000;
+    p->max_len = 50;
+    p->decode_reader = 1;
+    p->decode_tag = 1;
+    p->input_kind = NFC_IN_ENVELOPE_F32;
+    p->outputs = NFC_OUT_EVENTS | NFC_OUT_SYMBOLS | NFC_OUT_FRAMES | NFC_OUT_DROPPED_EVENTS;
+    p->device = 0;
+    p->pcm_scale = 32767.0f;
+}
+
+int nfc_stream_create(const nfc_params *p, nfc_stream **out) {
+    if (!p || !out) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        nfc::set_error("no CUDA device: this library has no CPU path");
+        return -1;
+    }
+    nfc_stream *h = new (std::nothrow) nfc_stream();
+    if (!h) {
+        nfc::set_error("out of memory");
+        return -1;
+    }
+    if (h->s.init(p)) {
+        h->s.destroy();
+        delete h;
+        return -1;
+    }
+    *out = h;
+    return 0;
+}
+
+int nfc_stream_destroy(nfc_stream *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->s.prm.device);
+    h->s.destroy();
+    delete h;
+    return 0;
+}
+
+int nfc_stream_reset(nfc_stream *h) {
+    if (!h) return -1;
+    Stream &s = h->s;
+    s.pos = 0;
+    s.stable = false;
+    s.serial_mode = false;
+    s.warm.clear();
+    s.run_carry = nfc::RunCarry{0, 0, 0, 0};
+    s.dec_carry = nfc::DecCarry{0, 0, {0, 0}};
+    s.pending[0] = s.pending[1] = 0;
+    s.hbits[0].clear();
+    s.hbits[1].clear();
+    s.out_events.clear();
+    s.out_symbols.clear();
+    s.out_frames.clear();
+    s.out_bits.clear();
+    s.ev_head = s.sym_head = s.fr_head = 0;
+    return 0;
+}
+
+int64_t nfc_stream_push(nfc_stream *h, const void *items, int64_t n, int mem, int *called_back) {
+    if (!h || (n > 0 && !items)) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    return h->s.push(items, n, mem, called_back);
+}
+
+int64_t nfc_stream_drain_events(nfc_stream *h, nfc_event *out, int64_t cap) {
+    if (!h) return -1;
+    return drain_vec(h->s.out_events, h->s.ev_head, out, cap);
+}
+
+int64_t nfc_stream_drain_symbols(nfc_stream *h, nfc_symbol *out, int64_t cap) {
+    if (!h) return -1;
+    return drain_vec(h->s.out_symbols, h->s.sym_head, out, cap);
+}
+
+int64_t nfc_stream_pending_frame_bits(nfc_stream *h) {
+    if (!h) return -1;
+    int64_t n = 0;
+    for (size_t i = h->s.fr_head; i < h->s.out_frames.size(); i++) n += h->s.out_frames[i].nbits;
+    return n;
+}
+
+int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap) {
+    if (!h) return -1;
+    Stream &s = h->s;
+    const int64_t avail = (int64_t)(s.out_frames.size() - s.fr_head);
+    if (cap <= 0 || !out) return avail;
+    int64_t n = 0, used = 0;
+    while (n < cap && s.fr_head < s.out_frames.size()) {
+        const nfc_frame &f = s.out_frames[s.fr_head];
+        if (used + f.nbits > bits_cap) break;
+        out[n] = f;
+        out[n].bit_off = used;
+        if (f.nbits) memcpy(bits + used, s.out_bits.data() + f.bit_off, (size_t)f.nbits);
+        used += f.nbits;
+        n++;
+        s.fr_head++;
+    }
+    if (s.fr_head == s.out_frames.size()) {
+        s.out_frames.clear();
+        s.out_bits.clear();
+        s.fr_head = 0;
+    }
+    return n;
+}
+
+int nfc_stream_get_state(nfc_stream *h, nfc_state *st, float *ring, uint8_t *pending_bits) {
+    if (!h || !st) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    Stream &s = h->s;
+    memset(st, 0, sizeof(*st));
+    st->pos = s.pos;
+    st->stable = s.stable ? 1 : 0;
+    st->serial_mode = s.serial_mode ? 1 : 0;
+    st->lastL = nfc::NO_POS;
+    st->lrun_start = nfc::NO_POS;
+    if (s.stable) {
+        cudaSetDevice(s.prm.device);
+        std::vector<char> blk(nfc::state_block_bytes(s.sp.L));
+        NFC_CUDA_CHECK(cudaMemcpy(blk.data(), s.state.p, blk.size(), cudaMemcpyDeviceToHost));
+        const nfc::SlicerHdr *hd = reinterpret_cast<const nfc::SlicerHdr *>(blk.data());
+        st->ss = hd->ss;
+        st->lastL = hd->lastL;
+        st->lrun_start = hd->lrun_start;
+        st->index = (int32_t)(s.pos % s.sp.L);
+        if (ring) memcpy(ring, nfc::state_ring(hd), (size_t)s.sp.L * 4);
+        st->cur_state = s.run_carry.st;
+        st->last_bit = s.run_carry.last_bit;
+        st->dur = s.run_carry.dur;
+    } else {
+        st->dur = 1;  // transition_sink.py:22
+        if (ring) {
+            memset(ring, 0, (size_t)s.sp.L * 4);
+            if (!s.warm.empty()) memcpy(ring, s.warm.data(), s.warm.size() * 4);
+        }
+    }
+    st->miller_state = s.dec_carry.miller_state;
+    st->manch_state = s.dec_carry.manch_state;
+    for (int t = 0; t < 2; t++) {
+        st->started[t] = s.dec_carry.started[t];
+        st->pending[t] = (int32_t)s.pending[t];
+    }
+    if (pending_bits) {
+        size_t o = 0;
+        for (int t = 0; t < 2; t++) {
+            if (s.hbits[t].size()) memcpy(pending_bits + o, s.hbits[t].data(), s.hbits[t].size());
+            o += s.hbits[t].size();
+        }
+    }
+    return 0;
+}
+
+int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, const uint8_t *pending_bits) {
+    if (!h || !st) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    Stream &s = h->s;
+    if (!st->stable || !ring) {
+        nfc::set_error("set_state needs a stable state with its ring");
+        return -1;
+    }
+    cudaSetDevice(s.prm.device);
+    std::vector<char> blk(nfc::state_block_bytes(s.sp.L), 0);
+    nfc::SlicerHdr *hd = reinterpret_cast<nfc::SlicerHdr *>(blk.data());
+    hd->ss = st->ss;
+    hd->pos = st->pos;
+    hd->lastL = st->lastL;
+    hd->lrun_start = st->lrun_start;
+    hd->last_val = st->last_bit;
+    memcpy(nfc::state_ring(hd), ring, (size_t)s.sp.L * 4);
+    NFC_CUDA_CHECK(cudaMemcpy(s.state.p, blk.data(), blk.size(), cudaMemcpyHostToDevice));
+    s.pos = st->pos;
+    s.stable = true;
+    s.serial_mode = st->serial_mode != 0;
+    s.run_carry.st = st->cur_state;
+    s.run_carry.last_bit = st->last_bit;
+    s.run_carry.dur = st->dur;
+    s.dec_carry.miller_state = st->miller_state;
+    s.dec_carry.manch_state = st->manch_state;
+    size_t o = 0;
+    for (int t = 0; t < 2; t++) {
+        s.dec_carry.started[t] = st->started[t];
+        s.pending[t] = (uint32_t)st->pending[t];
+        s.hbits[t].clear();
+        if (pending_bits) s.hbits[t].assign(pending_bits + o, pending_bits + o + st->pending[t]);
+        else s.hbits[t].assign((size_t)st->pending[t], 0);
+        o += (size_t)st->pending[t];
+    }
+    return 0;
+}
+
+int nfc_stream_set_tuning(nfc_stream *h, int64_t seg_len, int64_t halo, int64_t slab_len, int force_serial) {
+    if (!h) return -1;
+    h->s.seg_len = seg_len;
+    h->s.halo = halo;
+    h->s.slab_len = slab_len;
+    h->s.force_serial = force_serial;
+    return 0;
+}
+
+int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
+    if (!h || !st) return -1;
+    *st = h->s.stats;
+    return 0;
+}
+
+int nfc_stream_reset_stats(nfc_stream *h) {
+    if (!h) return -1;
+    memset(&h->s.stats, 0, sizeof(h->s.stats));
+    return 0;
+}
+
+void *nfc_stream_cuda_stream(nfc_stream *h) { return h ? (void *)h->s.cs : nullptr; }
+
+int nfc_build_tables(double samp_rate, int32_t max_len, int which, uint8_t *dclass, int32_t dclass_cap, uint16_t *table,
+                     int32_t table_cap, int32_t *n_dclass) {
+    nfc::HostTables t;
+    if (!(samp_rate > 0) || max_len < 1 || !nfc::build_tables(max_len, 1e6 / samp_rate, t)) {
+        nfc::set_error("cannot build line-code tables for samp_rate=%g max_len=%d", samp_rate, max_len);
+        return -1;
+    }
+    const std::vector<uint8_t> &dc = which ? t.dclass_miller : t.dclass_manch;
+    const std::vector<nfc::TabEntry> &tb = which ? t.miller : t.manch;
+    if (n_dclass) *n_dclass = which ? t.n_dclass_miller : t.n_dclass_manch;
+    if (dclass && dclass_cap >= (int32_t)dc.size()) memcpy(dclass, dc.data(), dc.size());
+    if (table && table_cap >= (int32_t)tb.size()) memcpy(table, tb.data(), tb.size() * sizeof(uint16_t));
+    return (int)tb.size();
+}
+
+int nfc_synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens,
+                     int64_t n_runs, float carrier, float pause, float tag_high, float noise, float fade,
+                     double fade_period, uint64_t seed, int as_envelope, int device) {
+    if (cudaSetDevice(device) != cudaSuccess) {
+        nfc::set_error("cudaSetDevice(%d) failed", device);
+        return -1;
+    }
+    return nfc::synth_render(dev_out, n, first_index, codes, lens, n_runs, carrier, pause, tag_high, noise, fade, fade_period, seed,
+                             as_envelope, nullptr);
+}
+
+const char *nfc_last_error(void) { return nfc::g_err; }
+int nfc_abi_version(void) { return NFC_ABI_VERSION; }
+int nfc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+}  // extern "C"
