@@ -205,6 +205,19 @@ void nfc_ts_get_scalars(const nfc_ts *t, double *ss, int *cur_state, int *dur, i
 
 const double *nfc_ts_ring(const nfc_ts *t) { return t->ar; }
 
+void nfc_ts_set_state(nfc_ts *t, const double *ring, double ss, int cur_state, int dur, int last_bit, int index,
+                      int64_t pos) {
+    for (int i = 0; i < t->L; i++) t->ar[i] = ring[i];
+    t->ss = ss;
+    t->cur_state = cur_state;
+    t->dur = dur;
+    t->last_bit = last_bit;
+    t->index = index;
+    t->filled = t->L;
+    t->stable = 1;
+    t->pos = pos;
+}
+
 /* --------------------------------------------------------- decoders + framing */
 typedef struct { /* packets.py:57-79 */
     int type, start, started;
@@ -511,6 +524,34 @@ const nfc_frame *nfc_dec_frames(const nfc_dec *d, int64_t *count) {
 const uint8_t *nfc_dec_bits(const nfc_dec *d, int64_t *count) {
     *count = d->bits.n;
     return d->bits.p;
+}
+
+void nfc_dec_get_state(const nfc_dec *d, int *miller_s, int *manch_s, int *started, int *npending,
+                       uint8_t *pending_bits, int pending_cap) {
+    *miller_s = ml_get_stage(&d->ml) | (d->ml.has_started << 2) | ((d->ml.prev != 0) << 3);
+    *manch_s = d->mc.prev_set | (((int)d->mc.prev + 1) << 1);
+    int o = 0;
+    for (int t = 0; t < 2; t++) {
+        started[t] = d->pp[t].started;
+        npending[t] = (int)d->pp[t].cur.n;
+        for (int64_t i = 0; i < d->pp[t].cur.n && o < pending_cap; i++) pending_bits[o++] = d->pp[t].cur.p[i];
+    }
+}
+
+void nfc_dec_set_state(nfc_dec *d, int miller_s, int manch_s, const int *started, const int *npending,
+                       const uint8_t *pending_bits) {
+    ml_set_stage(&d->ml, ST_BEGINNING);
+    ml_set_stage(&d->ml, miller_s & 3);
+    d->ml.has_started = (miller_s >> 2) & 1;
+    d->ml.prev = (miller_s >> 3) & 1;
+    d->mc.prev_set = manch_s & 1;
+    d->mc.prev = ((manch_s >> 1) & 3) - 1;
+    int o = 0;
+    for (int t = 0; t < 2; t++) {
+        d->pp[t].started = started[t];
+        d->pp[t].cur.n = 0;
+        for (int i = 0; i < npending[t]; i++) bytevec_push(&d->pp[t].cur, pending_bits[o++]);
+    }
 }
 
 /* ------------------------------------------------------------- fsm.py tail */

@@ -65,6 +65,9 @@ const nfc_event *nfc_ts_events(const nfc_ts *, int64_t *count);
 /* state inspection (transition_sink.py:20-34,102-106) */
 void nfc_ts_get_scalars(const nfc_ts *, double *ss, int *cur_state, int *dur, int *last_bit, int *index, int *filled, int *stable);
 const double *nfc_ts_ring(const nfc_ts *);
+/* restore the attributes saved at transition_sink.py:102-106 (checkpoint / time-shard stitching tests) */
+void nfc_ts_set_state(nfc_ts *, const double *ring, double ss, int cur_state, int dur, int last_bit, int index,
+                      int64_t pos);
 
 /* ---- background grouping + decoders + framing
  *      (background.py:30-52, manchester.py:13-61, miller.py:13-197, packets.py:57-98) ---- */
@@ -77,6 +80,13 @@ void nfc_dec_feed(nfc_dec *, const nfc_event *ev, int64_t n, double factor);
 const nfc_symbol *nfc_dec_symbols(const nfc_dec *, int64_t *count);
 const nfc_frame *nfc_dec_frames(const nfc_dec *, int64_t *count);
 const uint8_t *nfc_dec_bits(const nfc_dec *, int64_t *count);
+/* decoder / PacketProcessor attributes as small integers:
+ * miller = stage | _has_started << 2 | _prev << 3 (miller.py:14-29), manch = _prev_set | (_prev + 1) << 1
+ * (manchester.py:23-25), started[t] / pending bits per PacketProcessor (packets.py:63-65). */
+void nfc_dec_get_state(const nfc_dec *, int *miller, int *manch, int *started, int *npending, uint8_t *pending_bits,
+                       int pending_cap);
+void nfc_dec_set_state(nfc_dec *, int miller, int manch, const int *started, const int *npending,
+                       const uint8_t *pending_bits);
 
 /* ---- host tail of the path (fsm.py:28-66,114-131) ---- */
 /* _fix_ending: writes the repaired frame to out (capacity n+1), returns its length.

@@ -50,6 +50,10 @@ def lib():
         L.nfc_ts_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)] + [C.POINTER(C.c_int)] * 6
         L.nfc_ts_ring.restype = C.c_void_p
         L.nfc_ts_ring.argtypes = [C.c_void_p]
+        L.nfc_ts_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        L.nfc_dec_get_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int]
+        L.nfc_dec_set_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.nfc_dec_new.restype = C.c_void_p
         L.nfc_dec_new.argtypes = [C.c_int, C.c_int]
         L.nfc_dec_free.argtypes = [C.c_void_p]
@@ -118,8 +122,30 @@ class TransitionSink:
         return out
 
 
+    def set_state(self, ring, ss, cur_state, dur, last_bit, index, pos):
+        r = np.ascontiguousarray(ring, dtype=np.float64)
+        self._L.nfc_ts_set_state(self._h, r.ctypes.data, ss, cur_state, dur, last_bit, index, pos)
+
+
 class Decoders:
     """background.py + manchester.py + miller.py + packets.py on the event stream."""
+
+    def get_state(self):
+        mi, ma = C.c_int(), C.c_int()
+        started = np.zeros(2, np.int32)
+        npend = np.zeros(2, np.int32)
+        bits = np.zeros(1 << 16, np.uint8)
+        self._L.nfc_dec_get_state(self._h, C.byref(mi), C.byref(ma), started.ctypes.data, npend.ctypes.data,
+                                  bits.ctypes.data, bits.size)
+        return dict(miller=mi.value, manch=ma.value, started=started.tolist(), pending=npend.tolist(),
+                    pending_bits=bits[: int(npend.sum())].copy())
+
+    def set_state(self, st):
+        started = np.asarray(st["started"], np.int32)
+        npend = np.asarray(st["pending"], np.int32)
+        bits = np.ascontiguousarray(st["pending_bits"], np.uint8)
+        self._L.nfc_dec_set_state(self._h, st["miller"], st["manch"], started.ctypes.data, npend.ctypes.data,
+                                  bits.ctypes.data if bits.size else None)
 
     def __init__(self, reader=True, tag=True):
         self._L = lib()
