@@ -114,7 +114,8 @@ typedef struct {
     int32_t started[2];    /* PacketProcessor._started per type */
     int32_t pending[2];    /* len(PacketProcessor._cur) per type */
     int32_t serial_mode;   /* 1 once the stream left the exactly-summable regime */
-    int64_t lastL, lrun_start; /* position of the last LOW sample / start of its run (hysteresis carry) */
+    int64_t lastL, lrun_start; /* position of the last LOW sample / start of its run (hysteresis carry);
+                                * set lastL = INT64_MIN in set_state to have both derived from cur_state/last_bit/dur */
 } nfc_state;
 /* ring: av_window floats (the _ar list), may be NULL.  pending_bits: pending[0]+pending[1] bytes, may be NULL. */
 int nfc_stream_get_state(nfc_stream *s, nfc_state *st, float *ring, uint8_t *pending_bits);

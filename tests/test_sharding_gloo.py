@@ -1,0 +1,152 @@
+"""Time-shard stitching across ranks (world_size 2 and 3, gloo, CPU).  The per-rank engine here is an
+oracle-backed stand-in with the same interface as usrp_nfc_b200._cabi.Stream; what is under test is the
+host logic of usrp_nfc_b200/sharding.py: halo, seam verification, repair, frame ownership, gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class OracleEngine(object):
+    """Stream-like facade over the oracle (test infrastructure)."""
+
+    def __init__(self, rate, hi_val, av_window, max_len):
+        from oracle import oracle
+        self.o, self.args = oracle, (rate, 0.1, hi_val, av_window, max_len)
+        self.L = av_window
+        self.reset()
+
+    def reset(self):
+        self.ts = self.o.TransitionSink(*self.args)
+        self.dec = self.o.Decoders(True, True)
+        self.base_pos = 0
+
+    def push_all(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        off = 0
+        while off < x.size:
+            used, ev = self.ts.work(x[off: off + 8192])
+            if ev is not None:
+                ev = ev.copy()
+                ev["pos"] += self.base_pos
+                self.dec.feed(ev, self.ts.factor)
+            off += used
+        return off
+
+    def drain_frames(self):
+        fr, bits = self.dec.frames()
+        self.dec.clear()
+        return fr, bits
+
+    def state(self):
+        from usrp_nfc_b200 import _cabi
+        s = self.ts.state()
+        d = self.dec.get_state()
+        st = _cabi.State()
+        # the oracle counts positions from the samples it was offered
+        st.pos = self._pos()
+        st.ss = s["ss"]
+        st.cur_state, st.last_bit, st.dur, st.index, st.stable = s["cur_state"], s["last_bit"], s["dur"], s["index"], s["stable"]
+        st.miller_state, st.manch_state = d["miller"], d["manch"]
+        st.started[0], st.started[1] = d["started"]
+        st.pending[0], st.pending[1] = d["pending"]
+        return st, s["ring"].astype(np.float32), d["pending_bits"]
+
+    def _pos(self):
+        # transition_sink keeps no absolute counter; track it through the events' pos field base
+        import ctypes as C
+        return int(C.c_int64.from_address(self._pos_addr()).value) if False else self._count()
+
+    def _count(self):
+        # nfc_ts exposes no counter getter: run an empty work() and read pos from a sentinel event is
+        # overkill -- keep our own count instead
+        return getattr(self, "_n", 0)
+
+    def set_state(self, st, ring, pend):
+        self.ts.set_state(np.asarray(ring, np.float64), st.ss, st.cur_state, st.dur, st.last_bit, st.pos % self.L, st.pos)
+        self.dec.set_state(dict(miller=st.miller_state, manch=st.manch_state, started=[st.started[0], st.started[1]],
+                                pending=[st.pending[0], st.pending[1]], pending_bits=pend))
+        self._n = st.pos
+        self.base_pos = 0
+
+
+# count consumed samples by wrapping push_all
+_orig_push = OracleEngine.push_all
+
+
+def _push_counting(self, x):
+    n = _orig_push(self, x)
+    self._n = getattr(self, "_n", 0) + n
+    return n
+
+
+OracleEngine.push_all = _push_counting
+_orig_reset = OracleEngine.reset
+
+
+def _reset_counting(self):
+    _orig_reset(self)
+    self._n = 0
+
+
+OracleEngine.reset = _reset_counting
+
+
+def _worker(rank, world, port, halo_windows, q):
+    import torch.distributed as dist
+    from oracle import oracle
+    from usrp_nfc_b200 import _cabi, sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = synth.load_sessions()["classic1k"]
+    pcm = synth.capture(frames, 2e6, 31, channel=synth.Channel(pause=0.02, tag_high=1.07), sessions=2)
+    x = synth.envelope(synth.pcm_to_float(pcm))
+    eng = OracleEngine(2e6, 1.09, 2000, 50)
+    res = sharding.decode_time_sharded(eng, lambda a, b: x[a:b], x.size, 2000, _cabi.State, dist=dist,
+                                       halo_windows=halo_windows)
+    merged = sharding.gather_frames(res["frames"], dist)
+    if rank == 0:
+        want = oracle.decode_capture(x, 2e6, hi_val=1.09)
+        ok = len(merged) == len(want["frames"])
+        ok = ok and all(p == int(w["pos"]) and t == int(w["type"]) and np.array_equal(b, wb)
+                        for (p, t, b), w, wb in zip(merged, want["frames"], want["frame_bits"]))
+        q.put((ok, len(merged), len(want["frames"])))
+    q.put(("rank", rank, res["repaired"], res["seam_ok"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo_windows", [(2, 16), (3, 1), (2, 0)])
+def test_time_shards_stitch_exactly(world, halo_windows):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + world * 7 + halo_windows
+    procs = [ctx.Process(target=_worker, args=(r, world, port, halo_windows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world + 1)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    verdict = [g for g in got if g[0] is True or g[0] is False]
+    assert verdict and verdict[0][0], verdict
+    ranks = [g for g in got if g[0] == "rank"]
+    if halo_windows <= 1:
+        # too short a halo cannot converge in dense traffic: at least one shard must have been repaired
+        assert any(r[2] for r in ranks), ranks
+
+
+def test_plan_alignment():
+    from usrp_nfc_b200 import sharding
+    for L in (2000, 13560, 20000, 2001):
+        bounds, halo = sharding.plan(10 ** 7 + 3, 8, L)
+        assert bounds[0][0] == 0 and bounds[-1][1] == 10 ** 7 + 3
+        for a, b in bounds[:-1]:
+            assert a % L == 0 and b % L == 0 and a % 4 == 0
+        assert halo % L == 0 and halo % 4 == 0 and halo >= 16 * L

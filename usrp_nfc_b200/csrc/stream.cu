@@ -893,8 +893,27 @@ int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, 
     nfc::SlicerHdr *hd = reinterpret_cast<nfc::SlicerHdr *>(blk.data());
     hd->ss = st->ss;
     hd->pos = st->pos;
-    hd->lastL = st->lastL;
-    hd->lrun_start = st->lrun_start;
+    if (st->lastL == INT64_MIN) {
+        // hysteresis carry not supplied (a state saved from the reference's attributes): it is a function
+        // of (cur_state, last_bit, dur) -- see vals_from_classes in tests/algomodel.py
+        const int64_t P = st->pos;
+        if (st->cur_state == 2 && st->last_bit == -1) {
+            hd->lastL = P - 1;
+            hd->lrun_start = P - st->dur;
+        } else if (st->cur_state == 2) {
+            hd->lastL = P - st->dur - 1;
+            hd->lrun_start = hd->lastL;
+        } else if (st->last_bit == -1) {  // timeout on the last LOW sample: cur_state back to 0, run continues
+            hd->lastL = P - 1;
+            hd->lrun_start = P - 1 - s.sp.mx;
+        } else {
+            hd->lastL = nfc::NO_POS;
+            hd->lrun_start = nfc::NO_POS;
+        }
+    } else {
+        hd->lastL = st->lastL;
+        hd->lrun_start = st->lrun_start;
+    }
     hd->last_val = st->last_bit;
     memcpy(nfc::state_ring(hd), ring, (size_t)s.sp.L * 4);
     NFC_CUDA_CHECK(cudaMemcpy(s.state.p, blk.data(), blk.size(), cudaMemcpyHostToDevice));

@@ -1,0 +1,185 @@
+"""Time-segment sharding of one long capture across GPUs, one process per GPU.
+
+Rank 0 decodes its shard from the true stream start.  Every other rank starts cold `halo` samples before
+its shard, exactly like the reference's warm-up (transition_sink.py:109-125): the first av_window samples
+fill the ring unconditionally, the halo is decoded and thrown away.  That is speculation, so each seam is
+verified: the state rank r-1 really ended in must equal the state rank r assumed at its first sample
+(ring and ss bit for bit, cur_state / last_bit / dur, decoder and framer state, pending frame bits).  A rank
+whose assumption was wrong decodes its shard again from its predecessor's true state.  The only traffic is
+one all_gather of seam states (about 4*av_window bytes each) and a gather of frame records; there is no
+data-path collective.  Frames belong to the shard in which they close; the merged log is ordered by rank,
+which is the order of the closing positions.
+
+The engine is duck-typed (push_all, state, set_state, reset, drain_frames): the product passes
+usrp_nfc_b200._cabi.Stream; the gloo tests on CPU pass an oracle-backed stand-in.
+"""
+import numpy as np
+
+INT64_MIN = -(2 ** 63)
+PEND_CAP = 8192  # bits of an unfinished frame carried across a seam (a frame holds at most a few hundred)
+
+
+def plan(total, world, av_window, halo_windows=16):
+    """Shard boundaries and halo: multiples of av_window (ring slots line up) and of 4 (vector loads)."""
+    import math
+    q = av_window * 4 // math.gcd(av_window, 4)
+    per = -(-total // world)
+    per = -(-per // q) * q
+    bounds = [(min(r * per, total), min((r + 1) * per, total)) for r in range(world)]
+    halo = halo_windows * av_window
+    halo = -(-halo // q) * q
+    return bounds, halo
+
+
+class SeamState(object):
+    """Engine state in absolute stream coordinates, as one flat float64 vector (for all_gather)."""
+    NH = 16
+
+    def __init__(self, vec, L):
+        self.vec, self.L = vec, L
+
+    @staticmethod
+    def size(L):
+        return SeamState.NH + L + PEND_CAP
+
+    @staticmethod
+    def from_engine(engine, base, L):
+        st, ring, pend = engine.state()
+        v = np.zeros(SeamState.size(L), dtype=np.float64)
+        v[0] = st.pos + base
+        v[1] = np.float64(st.ss)
+        v[2:5] = (st.cur_state, st.last_bit, st.dur)
+        v[5:7] = (st.miller_state, st.manch_state)
+        v[7:9] = (st.started[0], st.started[1])
+        v[9:11] = (st.pending[0], st.pending[1])
+        v[11] = st.serial_mode
+        if len(pend) > PEND_CAP:
+            raise ValueError("unfinished frame longer than PEND_CAP bits at a seam")
+        v[SeamState.NH: SeamState.NH + L] = ring
+        v[SeamState.NH + L: SeamState.NH + L + len(pend)] = pend
+        return SeamState(v, L)
+
+    def npend(self):
+        return int(self.vec[9] + self.vec[10])
+
+    def equal(self, other, strict_dur=False):
+        a, b = self.vec, other.vec
+        if a[0] != b[0] or a[1].tobytes() != b[1].tobytes():
+            return False
+        if not np.array_equal(a[2:4], b[2:4]) or not np.array_equal(a[5:11], b[5:11]):
+            return False
+        idle = a[2] == 0 and a[3] == 0  # dur then only phases the dropped type -1 events
+        if (strict_dur or not idle) and a[4] != b[4]:
+            return False
+        L = self.L
+        ra = a[self.NH: self.NH + L].astype(np.float32).view(np.uint32)
+        rb = b[self.NH: self.NH + L].astype(np.float32).view(np.uint32)
+        if not np.array_equal(ra, rb):
+            return False
+        n = self.npend()
+        return np.array_equal(a[self.NH + L: self.NH + L + n], b[self.NH + L: self.NH + L + n])
+
+    def apply(self, engine, state_cls):
+        """Load into a freshly reset engine, in absolute coordinates (base 0)."""
+        v, L = self.vec, self.L
+        st = state_cls()
+        st.pos = int(v[0])
+        st.ss = float(v[1])
+        st.cur_state, st.last_bit, st.dur = int(v[2]), int(v[3]), int(v[4])
+        st.index = int(v[0]) % L
+        st.stable = 1
+        st.miller_state, st.manch_state = int(v[5]), int(v[6])
+        st.started[0], st.started[1] = int(v[7]), int(v[8])
+        st.pending[0], st.pending[1] = int(v[9]), int(v[10])
+        st.serial_mode = int(v[11])
+        st.lastL = INT64_MIN  # derived from (cur_state, last_bit, dur) by set_state
+        st.lrun_start = INT64_MIN
+        ring = v[self.NH: self.NH + L].astype(np.float32)
+        pend = v[self.NH + L: self.NH + L + self.npend()].astype(np.uint8)
+        engine.set_state(st, ring, pend)
+
+
+def _all_gather(vec, dist, group, device):
+    import torch
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(vec).to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [o.cpu().numpy() for o in out]
+
+
+def _broadcast(vec, src, dist, group, device):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(vec)).to(device)
+    dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy()
+
+
+def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, group=None, device="cpu",
+                        halo_windows=16, strict_dur=False):
+    """Decode this rank's time shard of a `total`-sample capture.
+
+    fetch(a, b) returns samples [a, b) (numpy array, or a CUDA tensor for a device-resident capture).
+    Returns dict(frames=[(abs_pos, type, bits)], repaired=bool, seam_ok=[...], bounds=(begin, end)).
+    """
+    rank = dist.get_rank(group) if dist is not None else 0
+    world = dist.get_world_size(group) if dist is not None else 1
+    L = av_window
+    bounds, halo = plan(total, world, L, halo_windows)
+    begin, end = bounds[rank]
+    base = 0
+    engine.reset()
+    if rank > 0 and begin - halo - L > 0:
+        base = begin - halo - L
+        if begin > base:
+            engine.push_all(fetch(base, begin))
+        engine.drain_frames()  # frames closed inside the halo belong to the previous shard
+    elif rank > 0:
+        engine.push_all(fetch(0, begin))  # shard too close to the stream start: decode from the true start
+        engine.drain_frames()
+    assumed = SeamState.from_engine(engine, base, L) if rank > 0 else None
+    if end > begin:
+        engine.push_all(fetch(begin, end))
+    rec, bits = engine.drain_frames()
+    frames = [(int(r["pos"]) + base, int(r["type"]), b) for r, b in zip(rec, bits)]
+    final = SeamState.from_engine(engine, base, L) if begin < end or rank == 0 else assumed
+    repaired, seam_ok = False, [True] * world
+    if world > 1:
+        finals = [SeamState(v, L) for v in _all_gather(final.vec, dist, group, device)]
+        zero = np.zeros(SeamState.size(L))
+        assumes = [SeamState(v, L) for v in _all_gather(assumed.vec if assumed is not None else zero, dist, group, device)]
+        for k in range(1, world):
+            ok = finals[k - 1].equal(assumes[k], strict_dur)
+            seam_ok[k] = ok
+            if ok:
+                continue
+            # rank k redoes its shard from the true state; everybody learns its new final state
+            if rank == k:
+                engine.reset()
+                finals[k - 1].apply(engine, state_cls)
+                if end > begin:
+                    engine.push_all(fetch(begin, end))
+                rec, bits = engine.drain_frames()
+                frames = [(int(r["pos"]), int(r["type"]), b) for r, b in zip(rec, bits)]
+                final = SeamState.from_engine(engine, 0, L)
+                repaired = True
+                vec = final.vec
+            else:
+                vec = np.zeros(SeamState.size(L))
+            finals[k] = SeamState(_broadcast(vec, k, dist, group, device), L)
+    return dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo)
+
+
+def gather_frames(frames, dist=None, group=None):
+    """Frame records of all ranks on rank 0, in stream order (rank order = closing-position order)."""
+    if dist is None or dist.get_world_size(group) == 1:
+        return frames
+    out = [None] * dist.get_world_size(group) if dist.get_rank(group) == 0 else None
+    payload = [(p, t, np.asarray(b, dtype=np.uint8).tobytes()) for p, t, b in frames]
+    dist.gather_object(payload, out, dst=0, group=group)
+    if out is None:
+        return None
+    merged = []
+    for part in out:
+        merged.extend((p, t, np.frombuffer(b, dtype=np.uint8)) for p, t, b in part)
+    return merged
