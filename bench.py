@@ -193,7 +193,7 @@ def main():
     def step():
         s.reset()
         s.push_all(x)
-        fr, _ = s.drain_frames()
+        fr, _ = s.drain_frames_flat()
         return len(fr)
 
     def barrier():
@@ -250,7 +250,7 @@ def main():
         for _ in range(2):
             se.reset()
             se.push_all(xh_np)
-            se.drain_frames()
+            se.drain_frames_flat()
         se.reset_stats()
         barrier()
         t0 = time.perf_counter()
@@ -258,7 +258,7 @@ def main():
         for _ in range(esteps):
             se.reset()
             se.push_all(xh_np)
-            fr_e, _ = se.drain_frames()
+            fr_e, _ = se.drain_frames_flat()
         barrier()
         e_wall = (time.perf_counter() - t0) / esteps
         est = se.stats()

@@ -98,7 +98,8 @@ int64_t nfc_stream_push(nfc_stream *s, const void *items, int64_t n, int mem, in
  * and removes them from the stream.  Pass cap = 0 to query the number available. */
 int64_t nfc_stream_drain_events(nfc_stream *s, nfc_event *out, int64_t cap);
 int64_t nfc_stream_drain_symbols(nfc_stream *s, nfc_symbol *out, int64_t cap);
-/* Frames whose bits fit: writes records to out (bit_off relative to bits) and one byte per bit. */
+/* All pending frames at once: records to out (bit_off relative to bits) and one byte per bit; returns -2 when
+ * cap or bits_cap is too small (query first with cap = 0 and nfc_stream_pending_frame_bits). */
 int64_t nfc_stream_drain_frames(nfc_stream *s, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap);
 int64_t nfc_stream_pending_frame_bits(nfc_stream *s); /* bytes the next full drain needs */
 
@@ -134,6 +135,7 @@ typedef struct {
     int64_t slicer_launches;
     int64_t samples;         /* items decoded on the device */
     int64_t segments, seam_mismatches, serial_segments, overflow_retries;
+    int64_t linecode_scan_fallbacks; /* slabs where the frame-boundary search gave up and the scan path ran */
     int64_t h2d_bytes, d2h_bytes;
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);

@@ -40,6 +40,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("slicer_ms", C.c_double), ("launches", C.c_int64),
                 ("slicer_launches", C.c_int64), ("samples", C.c_int64), ("segments", C.c_int64),
                 ("seam_mismatches", C.c_int64), ("serial_segments", C.c_int64), ("overflow_retries", C.c_int64),
+                ("linecode_scan_fallbacks", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
@@ -187,6 +188,20 @@ class Stream(object):
             got = L.nfc_stream_drain_frames(self._h, fr.ctypes.data, n, bits.ctypes.data, nb)
             fr = fr[:got]
         return fr, [bits[f["bit_off"]: f["bit_off"] + f["nbits"]].copy() for f in fr]
+
+    def drain_frames_flat(self):
+        """-> (frame records, one uint8 array with all frame bits; record.bit_off indexes into it)."""
+        L = lib()
+        n = L.nfc_stream_drain_frames(self._h, None, 0, None, 0)
+        nb = L.nfc_stream_pending_frame_bits(self._h)
+        fr = np.zeros(n, dtype=FRAME_DTYPE)
+        bits = np.zeros(max(nb, 1), dtype=np.uint8)
+        if n:
+            got = L.nfc_stream_drain_frames(self._h, fr.ctypes.data, n, bits.ctypes.data, nb)
+            if got < 0:
+                raise NfcError(last_error())
+            fr = fr[:got]
+        return fr, bits[:nb]
 
     def state(self):
         st = State()

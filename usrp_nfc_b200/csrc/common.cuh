@@ -130,6 +130,9 @@ struct LineTables {
     // [dclass][v + 1][state]
     const TabEntry *miller;
     const TabEntry *manch;
+    // [dclass][v + 1]: 0xFF or the state every state of the machine is sent to (universal reset)
+    const uint8_t *reset_miller;
+    const uint8_t *reset_manch;
     int n_dclass_miller, n_dclass_manch;
     int decode_reader, decode_tag;
 };

@@ -18,7 +18,8 @@
 
 namespace nfc {
 
-static const int CHUNK = 128;
+static const int CHUNK = 256;
+static const int LOOKBACK_LIMIT = 4096;  // events searched backwards for a reset before giving up
 static const int RSTATES = 32, GSTATES = 16;
 
 struct __align__(16) ChunkMap {
@@ -186,21 +187,72 @@ struct CountSink {
     }
 };
 
-__device__ __forceinline__ void chunk_start_state(const ChunkMap *prefix, uint32_t c, const DecCarry &carry, int &rs, int &gs) {
-    const int rs0 = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
-    const int gs0 = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
-    rs = prefix[c].r[rs0];
-    gs = prefix[c].g[gs0];
-}
-
-__global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
-                                   const ChunkMap *__restrict__ prefix, DecCarry carry,
-                                   ChunkCnt *__restrict__ cnts, uint32_t n_chunks) {
+// ---- frame-boundary search: the state at a chunk start from the nearest reset before it ------------
+// An event whose duration is out of range resets its decoder whatever the state was (tables.cpp,
+// reset_*): scan backwards to the nearest such event of each direction, then replay forward from there.
+// start[c] = R state | G state << 8.  Chunks that find no reset within LOOKBACK_LIMIT events raise *unresolved
+// (the host then takes the transfer-function scan below for the slab).
+__global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt, DecCarry carry,
+                                   uint16_t *__restrict__ start, uint32_t n_chunks, int *__restrict__ unresolved) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
-    int rs, gs;
-    chunk_start_state(prefix, c, carry, rs, gs);
+    int rs = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
+    int gs = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
+    const int64_t i0 = (int64_t)c * CHUNK;
+    bool foundR = !tv.use_reader, foundG = !tv.use_tag;
+    int64_t iR = -1, iG = -1;  // index of the reset event found (-1: replay from event 0 with the carry)
+    int64_t i = i0 - 1;
+    int steps = 0;
+    while (i >= 0 && !(foundR && foundG) && steps < LOOKBACK_LIMIT) {
+        const EventRec e = ev[i];
+        if (!foundR && e.type == 1) {
+            const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
+            if (r != 0xFF) { foundR = true; iR = i; rs = r; }
+        } else if (!foundG && e.type == 0) {
+            const uint8_t r = lt.reset_manch[(int)tv.dcg[e.d] * 4 + (e.v + 1)];
+            if (r != 0xFF) { foundG = true; iG = i; gs = r; }
+        }
+        i--;
+        steps++;
+    }
+    if (i >= 0 && !(foundR && foundG)) {
+        atomicOr(unresolved, 1);
+        start[c] = 0;
+        return;
+    }
+    NullSink sink;
+    // replay from the earliest point a still-unknown machine needs (a disabled direction needs nothing)
+    const int64_t fromR = tv.use_reader ? iR + 1 : i0, fromG = tv.use_tag ? iG + 1 : i0;
+    const int64_t from = fromR < fromG ? fromR : fromG;
+    for (int64_t k = from; k < i0; k++) {
+        const EventRec e = ev[k];
+        int dummy_r = 0, dummy_g = 0;
+        if (e.type == 1) {
+            if (k > iR) step_event(e, tv, rs, dummy_g, sink);
+        } else if (e.type == 0) {
+            if (k > iG) step_event(e, tv, dummy_r, gs, sink);
+        }
+    }
+    start[c] = (uint16_t)(rs | (gs << 8));
+}
+
+// start states from the composed transfer functions (fallback path)
+__global__ void chunk_start_from_maps_kernel(const ChunkMap *__restrict__ prefix, DecCarry carry,
+                                             uint16_t *__restrict__ start, uint32_t n_chunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int rs0 = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
+    const int gs0 = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
+    start[c] = (uint16_t)(prefix[c].r[rs0] | (prefix[c].g[gs0] << 8));
+}
+
+__global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+                                   const uint16_t *__restrict__ start, ChunkCnt *__restrict__ cnts, uint32_t n_chunks) {
+    NFC_TABLE_SMEM
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
     CountSink sink;
     sink.c = ChunkCnt{0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
@@ -257,14 +309,13 @@ struct LineOut {
 };
 
 __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
-                                   const ChunkMap *__restrict__ prefix, DecCarry carry,
+                                   const uint16_t *__restrict__ start,
                                    const ChunkCnt *__restrict__ cnt_prefix, LineOut out, uint32_t n_chunks,
                                    DecCarry *__restrict__ carry_out, uint32_t *__restrict__ pending_out) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
-    int rs, gs;
-    chunk_start_state(prefix, c, carry, rs, gs);
+    int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
     const ChunkCnt pc = cnt_prefix[c];
     WriteSink sink;
     sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.em = out.em;
@@ -293,30 +344,50 @@ size_t linecode_scratch_bytes(uint32_t n_chunks) {
     return scan_scratch_elems(n_chunks) * sizeof(ChunkMap) + scan_scratch_elems(n_chunks) * sizeof(ChunkCnt);
 }
 
-// Passes A + B.  Leaves chunk start maps in d_prefix, count prefixes in d_cnt_prefix and the totals in *d_total.
-int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
-                          void *d_prefix, void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total,
-                          cudaStream_t stream) {
+// Start states by frame-boundary search; *d_unresolved != 0 afterwards means the caller must use the scan path.
+int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_start,
+                          int *d_unresolved, cudaStream_t stream) {
+    const uint32_t nc = linecode_chunks(n_ev);
+    if (nc == 0) return 0;
+    NFC_CUDA_CHECK(cudaMemsetAsync(d_unresolved, 0, sizeof(int), stream));
+    chunk_start_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, carry, d_start, nc, d_unresolved);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Start states by composing chunk transfer functions (always applicable).
+int launch_linecode_start_scan(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
+                               void *d_prefix, void *d_scratch, uint16_t *d_start, cudaStream_t stream) {
     const uint32_t nc = linecode_chunks(n_ev);
     if (nc == 0) return 0;
     ChunkMap *maps = (ChunkMap *)d_maps, *prefix = (ChunkMap *)d_prefix;
-    ChunkCnt *cnts = (ChunkCnt *)d_cnts, *cprefix = (ChunkCnt *)d_cnt_prefix;
     const unsigned nb = (nc + 127) / 128;
     chunk_map_kernel<<<nb, 128, 0, stream>>>(d_ev, n_ev, lt, maps, nc);
     NFC_CUDA_CHECK(cudaGetLastError());
     ChunkMap ident;
     for (int s = 0; s < RSTATES; s++) ident.r[s] = (uint8_t)s;
     for (int s = 0; s < GSTATES; s++) ident.g[s] = (uint8_t)s;
-    ChunkMap *scr_m = (ChunkMap *)d_scratch;
-    if (device_exclusive_scan<ChunkMap, ComposeMap>(maps, prefix, nc, ident, ComposeMap(), scr_m, nullptr, stream)) return -1;
-    chunk_count_kernel<<<nb, 128, 0, stream>>>(d_ev, n_ev, lt, prefix, carry, cnts, nc);
+    if (device_exclusive_scan<ChunkMap, ComposeMap>(maps, prefix, nc, ident, ComposeMap(), (ChunkMap *)d_scratch, nullptr, stream))
+        return -1;
+    chunk_start_from_maps_kernel<<<nb, 128, 0, stream>>>(prefix, carry, d_start, nc);
     NFC_CUDA_CHECK(cudaGetLastError());
-    ChunkCnt zero = {0, 0, 0, 0, 0, 0, 0, 0};
-    ChunkCnt *scr_c = (ChunkCnt *)((char *)d_scratch + scan_scratch_elems(nc) * sizeof(ChunkMap));
-    return device_exclusive_scan<ChunkCnt, CombineCnt>(cnts, cprefix, nc, zero, CombineCnt(), scr_c, (ChunkCnt *)d_total, stream);
+    return 0;
 }
 
-int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, const void *d_prefix,
+// Counts per chunk from the start states, scanned into d_cnt_prefix; totals in *d_total.
+int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start, void *d_cnts,
+                          void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t stream) {
+    const uint32_t nc = linecode_chunks(n_ev);
+    if (nc == 0) return 0;
+    ChunkCnt *cnts = (ChunkCnt *)d_cnts, *cprefix = (ChunkCnt *)d_cnt_prefix;
+    chunk_count_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_start, cnts, nc);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    ChunkCnt zero = {0, 0, 0, 0, 0, 0, 0, 0};
+    return device_exclusive_scan<ChunkCnt, CombineCnt>(cnts, cprefix, nc, zero, CombineCnt(), (ChunkCnt *)d_scratch,
+                                                       (ChunkCnt *)d_total, stream);
+}
+
+int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
                           uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
@@ -326,9 +397,8 @@ int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables 
     out.sym = d_sym; out.bits0 = d_bits0; out.bits1 = d_bits1; out.em = (EmissionRec *)d_em;
     out.cap_sym = cap_sym; out.cap_b0 = cap_b0; out.cap_b1 = cap_b1; out.cap_em = cap_em;
     out.pending0 = pending0; out.pending1 = pending1;
-    chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, (const ChunkMap *)d_prefix, carry,
-                                                             (const ChunkCnt *)d_cnt_prefix, out, nc, d_carry_out,
-                                                             d_pending_out);
+    chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_start, (const ChunkCnt *)d_cnt_prefix, out,
+                                                             nc, d_carry_out, d_pending_out);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

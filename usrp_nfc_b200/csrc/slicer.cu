@@ -131,7 +131,22 @@ __device__ __forceinline__ bool st2_forced(int64_t i, int64_t b, int64_t a, int 
 }
 
 // ---------------------------------------------------------------- block-wide primitives
-template <int NT>
+struct RowRec {      // one warp x one row of a tile (128 samples), positions relative to the tile start
+    int first;       // (first_pos << 2) | (val + 1) of the first active sample, INT_MAX when the row part is empty
+    int last;        // (last_pos << 2) | (val + 1) of the last active sample, -1 when empty
+    int inner;       // emitted transitions strictly inside (not at the first active sample)
+    int lastL;       // last LOW sample, -1 if none
+    int firstH;      // first HIGH-class sample, INT_MAX if none
+    int lastS;       // last LOW-run start strictly inside, -1 if none
+    int pad0, pad1;
+};
+struct WarpRec {
+    double dsum;     // sum of admitted (x - prev), exact
+    float absd;      // sum of admitted |x - prev| (bounds how far ss can move inside the tile)
+    unsigned flags;  // 1 = some sample was not robustly classifiable
+};
+
+template <int NT, int R>
 struct BlockShared {
     static const int NW = NT / 32;
     double wsum[2][NW];
@@ -140,9 +155,20 @@ struct BlockShared {
     int wmaxL[NW];      // tile-relative index of the last LOW sample per warp
     int wmaxS[NW];      // tile-relative index of the last LOW-run start per warp
     unsigned flags[3];
-    int last_val;
     int emin, emax;
     double red[NW];
+    RowRec rows[2][R * NW];
+    WarpRec warps[2][NW];
+};
+
+// everything a segment carries from tile to tile (identical in all threads of the CTA)
+struct SegCarry {
+    double ss0;
+    int64_t lastL, lrun_start;
+    int last_val;
+    uint32_t seg_count;
+    unsigned round_no;
+    int scan_buf, cnt_buf;
 };
 
 template <int NT>
@@ -198,24 +224,300 @@ __device__ __forceinline__ void exp_track(float x, int &emin, int &emax) {
     }
 }
 
-// ---------------------------------------------------------------- the segment kernel
-template <int NT, int K>
-__global__ void __launch_bounds__(NT) slicer_kernel(const SegWork *__restrict__ works,
-                                                    const SlicerParams *__restrict__ params) {
-    constexpr int T = NT * K;
+// ---------------------------------------------------------------- exact tile (fix-point over prefix sums)
+// One tile of NT*K samples starting at stream index P0, classes decided with every sample's own exact ss.
+// Always correct (inside the exactly-summable regime); several block barriers per tile.
+template <int NT, int K, int R>
+__device__ __noinline__ void exact_tile(const SegWork &w, const SlicerParams &p, float *ring, BlockShared<NT, R> &sh,
+                                        const int64_t P0, const int slot0, SegCarry &c, int &emin, int &emax) {
     constexpr int NW = NT / 32;
-    extern __shared__ __align__(16) float ring[];
-    __shared__ BlockShared<NT> sh;
+    const int L = p.L, mx = p.mx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p0 = P0 + (int64_t)tid * K;
+    const double ss0 = c.ss0;
+    const int64_t lastL = c.lastL, lrun_start = c.lrun_start;
+    const int last_val = c.last_val;
 
-    const SegWork w = works[blockIdx.x];
-    const SlicerParams p = params[w.param_idx];
+    float x[K], prev[K];
+    bool act[K];
+    load_samples<K>(w, p, p0, x);
+#pragma unroll
+    for (int j = 0; j < K; j++) act[j] = (p0 + j >= w.warm_begin) && (p0 + j < w.end);
+
+    int slot[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        int s = slot0 + j;
+        slot[j] = s >= L ? s - L : s;
+    }
+    if (K == 4 && (L & 3) == 0) {
+        float4 v = *reinterpret_cast<const float4 *>(ring + slot0);
+        prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) prev[j] = ring[slot[j]];
+    }
+
+    int cls[K];
+    bool forced[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        cls[j] = act[j] ? classify(x[j], ss0, p) : CLS_MID;  // guess: ss frozen at the tile start
+        forced[j] = false;
+    }
+    const bool carry_recent = lastL != NO_POS && (P0 - lastL) <= (int64_t)mx + 1;
+
+    double total = 0.0;
+    bool had_slow = false, anyL = false;
+    for (;;) {
+        const unsigned fb = c.round_no % 3u;
+        if (tid == 0) sh.flags[(c.round_no + 1u) % 3u] = 0u;
+        double pre[K];
+        double run = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            pre[j] = run;
+            const bool admit = act[j] && (cls[j] == CLS_MID || (cls[j] == CLS_HIGH && forced[j]));
+            if (admit) run += (double)x[j] - (double)prev[j];  // cur - prev (transition_sink.py:82)
+        }
+        const double base = block_excl_scan<NT>(run, total, sh.wsum, c.scan_buf);
+        c.scan_buf ^= 1;
+
+        unsigned f = 0u;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (act[j]) {
+                const int cc = classify(x[j], ss0 + (base + pre[j]), p);
+                if (cc != cls[j]) { f |= 1u; cls[j] = cc; }
+                if (cc == CLS_HIGH) f |= 2u;
+                if (cc == CLS_LOW) f |= 4u;
+            }
+        }
+        f = __reduce_or_sync(FULL, f);
+        if (lane == 0 && f) atomicOr(&sh.flags[fb], f);
+        if (lane == 31) sh.wlastcls[warp] = act[K - 1] ? cls[K - 1] : 2;  // 2 = "no sample"
+        __syncthreads();
+        unsigned flags = sh.flags[fb];
+        c.round_no++;
+
+        if ((flags & 2u) && ((flags & 4u) || carry_recent)) {
+            // ---- hysteresis: distance from each HIGH sample to the last LOW sample / its run start
+            int pc = __shfl_up_sync(FULL, cls[K - 1], 1);
+            const bool pact = __shfl_up_sync(FULL, (int)act[K - 1], 1) != 0;
+            if (lane == 0) {
+                pc = CLS_MID;
+                bool found = false;
+                for (int ww = warp - 1; ww >= 0 && !found; ww--) {
+                    int cc = sh.wlastcls[ww];
+                    if (cc != 2) { pc = cc; found = true; }
+                }
+                if (!found) pc = (last_val == -1) ? CLS_LOW : CLS_MID;
+            } else if (!pact) {
+                pc = (last_val == -1) ? CLS_LOW : CLS_MID;  // inactive prefix of the first tile
+            }
+            int myL = -1, myS = -1;
+            int preL[K], preS[K];
+            {
+                int c_prev = pc;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    preL[j] = myL;
+                    preS[j] = myS;
+                    if (act[j]) {
+                        if (cls[j] == CLS_LOW) {
+                            if (c_prev != CLS_LOW) myS = tid * K + j;
+                            myL = tid * K + j;
+                        }
+                        c_prev = cls[j];
+                    }
+                }
+            }
+            int incL = myL, incS = myS;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int a = __shfl_up_sync(FULL, incL, o), b = __shfl_up_sync(FULL, incS, o);
+                if (lane >= o) { incL = max(incL, a); incS = max(incS, b); }
+            }
+            int exL = __shfl_up_sync(FULL, incL, 1), exS = __shfl_up_sync(FULL, incS, 1);
+            if (lane == 0) { exL = -1; exS = -1; }
+            if (lane == 31) { sh.wmaxL[warp] = incL; sh.wmaxS[warp] = incS; }
+            __syncthreads();
+            for (int ww = 0; ww < warp; ww++) {
+                exL = max(exL, sh.wmaxL[ww]);
+                exS = max(exS, sh.wmaxS[ww]);
+            }
+            unsigned f2 = 0u;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                bool fo = false;
+                if (act[j] && cls[j] == CLS_HIGH) {
+                    const int bl = max(exL, preL[j]);
+                    const int sl = max(exS, preS[j]);
+                    const int64_t b = bl >= 0 ? P0 + bl : lastL;
+                    const int64_t a = sl >= 0 ? P0 + sl : lrun_start;
+                    fo = st2_forced(p0 + j, b, a, mx);
+                }
+                if (fo != forced[j]) { f2 = 1u; forced[j] = fo; }
+            }
+            const unsigned fb2 = c.round_no % 3u;
+            if (tid == 0) sh.flags[(c.round_no + 1u) % 3u] = 0u;
+            f2 = __reduce_or_sync(FULL, f2);
+            if (lane == 0 && f2) atomicOr(&sh.flags[fb2], f2);
+            __syncthreads();
+            flags |= sh.flags[fb2] & 1u;
+            c.round_no++;
+            had_slow = true;
+        } else if (had_slow) {
+            // `forced` flags are only ever set in the (block-uniform) branch above; once the tile no longer
+            // needs it they are cleared, which changes `admit`, so vote for another round.
+            unsigned f2 = 0u;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                if (forced[j]) { f2 = 1u; forced[j] = false; }
+            }
+            if (__syncthreads_or((int)f2)) flags |= 1u;
+            had_slow = false;
+        }
+        if (!(flags & 1u)) {  // converged: `total` belongs to the final classes
+            anyL = (flags & 4u) != 0u;
+            break;
+        }
+    }
+
+    // ---- ring update (transition_sink.py:75-81) and exponent tracking
+    float nv[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const bool admit = act[j] && (cls[j] == CLS_MID || (cls[j] == CLS_HIGH && forced[j]));
+        nv[j] = admit ? x[j] : prev[j];
+        if (admit) exp_track(x[j], emin, emax);
+    }
+    if (K == 4 && (L & 3) == 0 && act[0] && act[K - 1]) {
+        *reinterpret_cast<float4 *>(ring + slot0) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            if (act[j]) ring[slot[j]] = nv[j];
+    }
+
+    // ---- vals and transitions
+    int val[K];
+#pragma unroll
+    for (int j = 0; j < K; j++)
+        val[j] = act[j] ? (cls[j] == CLS_LOW ? -1 : ((cls[j] == CLS_HIGH && !forced[j]) ? 1 : 0)) : 3;  // 3 = none
+    int mylast = 3;
+#pragma unroll
+    for (int j = 0; j < K; j++)
+        if (val[j] != 3) mylast = val[j];
+    int pv;
+    {
+        const unsigned has = __ballot_sync(FULL, mylast != 3);
+        const unsigned lower = has & ((1u << lane) - 1u);
+        const int src = lower ? 31 - __clz(lower) : 0;
+        const int got = __shfl_sync(FULL, mylast, src);
+        pv = lower ? got : 3;
+        int wl = __shfl_sync(FULL, mylast, has ? 31 - __clz(has) : 0);
+        if (!has) wl = 3;
+        if (lane == 0) sh.wlastcls[warp] = wl;  // reuse: last defined val of the warp (3 = none)
+    }
+    __syncthreads();
+    if (pv == 3) {
+        pv = last_val;
+        for (int ww = warp - 1; ww >= 0; ww--) {
+            const int cc = sh.wlastcls[ww];
+            if (cc != 3) { pv = cc; break; }
+        }
+    }
+    int ntr = 0;
+    unsigned trmask = 0u;
+    int maxS = -1, maxL = -1;
+    {
+        int c_prev = pv;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (val[j] != 3) {
+                if (val[j] != c_prev) {
+                    if (p0 + j >= w.begin) { trmask |= 1u << j; ntr++; }
+                    if (val[j] == -1) maxS = tid * K + j;
+                }
+                if (val[j] == -1) maxL = tid * K + j;
+                c_prev = val[j];
+            }
+        }
+    }
+    if (anyL) {
+        int mL = __reduce_max_sync(FULL, maxL), mS = __reduce_max_sync(FULL, maxS);
+        if (lane == 0) { sh.wmaxL[warp] = mL; sh.wmaxS[warp] = mS; }
+    }
+    int tot_tr = 0;
+    const int tr_base = block_excl_scan_int<NT>(ntr, tot_tr, sh.wcnt, c.cnt_buf);
+    c.cnt_buf ^= 1;
+    if (tot_tr) {
+        uint32_t idx = c.seg_count + (uint32_t)tr_base;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (trmask & (1u << j)) {
+                if (idx < w.trans_cap) w.trans[idx] = pack_trans((uint32_t)(p0 + j - w.slab_pos0), val[j]);
+                idx++;
+            }
+        }
+        c.seg_count += (uint32_t)tot_tr;
+    }
+    // ---- carries into the next tile
+    c.ss0 = ss0 + total;
+    if (anyL) {
+        int mL = -1, mS = -1;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) {
+            mL = max(mL, sh.wmaxL[ww]);
+            mS = max(mS, sh.wmaxS[ww]);
+        }
+        if (mL >= 0) {
+            c.lastL = P0 + mL;
+            if (mS >= 0) c.lrun_start = P0 + mS;
+        }
+    }
+    {
+        int lv = 3;
+        for (int ww = NW - 1; ww >= 0; ww--) {
+            const int cc = sh.wlastcls[ww];
+            if (cc != 3) { lv = cc; break; }
+        }
+        if (lv != 3) c.last_val = lv;
+    }
+    __syncthreads();  // ring writes and shared scratch settle before the next tile reads them
+}
+
+// ---------------------------------------------------------------- the segment kernel
+// A tile is R rows of NT*4 samples.  Fast path (one block barrier per tile): every sample is classified in
+// float against thresholds widened by a guard band that covers any ss the tile can reach; the band is
+// justified afterwards by the block sum of admitted |x - prev|.  Tiles where a sample falls inside the band,
+// the sum exceeds the band, or a HIGH sample follows a LOW sample closely (hysteresis) are redone exactly.
+template <int NT, int K, int R>
+__global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegWork *__restrict__ works,
+                                                                      const SlicerParams *__restrict__ params) {
+    constexpr int SUB = NT * K;      // samples per row
+    constexpr int T = SUB * R;       // samples per tile
+    constexpr int NW = NT / 32;
+    static_assert(R * NW <= 32, "one lane per row record");
+    extern __shared__ __align__(16) float ring[];
+    __shared__ BlockShared<NT, R> sh;
+
+    // the work item and the parameters live in shared memory: one copy per CTA, no registers held
+    __shared__ SegWork w_s;
+    __shared__ SlicerParams p_s;
+    if (threadIdx.x == 0) {
+        w_s = works[blockIdx.x];
+        p_s = params[w_s.param_idx];
+    }
+    __syncthreads();
+    const SegWork &w = w_s;
+    const SlicerParams &p = p_s;
     const int L = p.L, mx = p.mx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- entry state
-    double ss0;
-    int64_t lastL, lrun_start;
-    int last_val;
+    SegCarry c;
     int status = SEG_OK;
     int emin = 1 << 30, emax = 0;
 
@@ -226,10 +528,10 @@ __global__ void __launch_bounds__(NT) slicer_kernel(const SegWork *__restrict__ 
             ring[i] = v;
             exp_track(v, emin, emax);
         }
-        ss0 = w.state_in->ss;
-        lastL = w.state_in->lastL;
-        lrun_start = w.state_in->lrun_start;
-        last_val = w.state_in->last_val;
+        c.ss0 = w.state_in->ss;
+        c.lastL = w.state_in->lastL;
+        c.lrun_start = w.state_in->lrun_start;
+        c.last_val = w.state_in->last_val;
     } else {
         // cold start: the previous L samples, unconditionally (transition_sink.py:118)
         double part = 0.0;
@@ -244,29 +546,33 @@ __global__ void __launch_bounds__(NT) slicer_kernel(const SegWork *__restrict__ 
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
         if (lane == 0) sh.red[warp] = part;
         __syncthreads();
-        ss0 = 0.0;
-        for (int i = 0; i < NW; i++) ss0 += sh.red[i];
-        lastL = NO_POS;
-        lrun_start = NO_POS;
-        last_val = 0;
+        double s0 = 0.0;
+        for (int i = 0; i < NW; i++) s0 += sh.red[i];
+        c.ss0 = s0;
+        c.lastL = NO_POS;
+        c.lrun_start = NO_POS;
+        c.last_val = 0;
     }
-    if (tid == 0) {
-        sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
-        sh.last_val = last_val;
-    }
+    if (tid == 0) sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
     __syncthreads();
+    c.seg_count = 0;
+    c.scan_buf = 0;
+    c.cnt_buf = 0;
+    c.round_no = 0;
 
-    uint32_t seg_count = 0;
-    int scan_buf = 0, cnt_buf = 0;
-    unsigned round_no = 0;
+    const bool fast_ok = (K == 4) && ((L & 3) == 0) && p.lo > 0.0 && p.hi > p.lo;
+    const bool end_barrier = 2 * T > L;  // a tile would read ring slots the previous tile wrote
+    const double loL = p.lo / p.Ld, hiL = p.hi / p.Ld;
+    float absd_prev = 0.0f;              // admitted |x - prev| of the previous tile: sizes the next guard band
+    float xmin = 3.0e38f, xmax = 0.0f;   // admitted samples of the fast path (all > 0 and finite)
+    unsigned tile_no = 0;
 
     const int64_t tile_first = w.warm_begin / T;
     const int64_t tile_last = (w.end > w.warm_begin) ? (w.end - 1) / T : tile_first - 1;
     int slot0 = (int)((tile_first * T + (int64_t)tid * K) % L);
 
-    for (int64_t tile = tile_first; tile <= tile_last; tile++) {
+    for (int64_t tile = tile_first; tile <= tile_last; tile++, tile_no++) {
         const int64_t P0 = tile * T;
-        const int64_t p0 = P0 + (int64_t)tid * K;
 
         if (w.seam_in && P0 == w.begin && w.begin > w.warm_begin) {
             // snapshot of the speculative state at the first emitted sample
@@ -274,282 +580,277 @@ __global__ void __launch_bounds__(NT) slicer_kernel(const SegWork *__restrict__ 
             for (int i = tid; i < L; i += NT) dst[i] = ring[i];
             if (tid == 0) {
                 SlicerHdr h;
-                h.ss = ss0; h.pos = w.begin; h.lastL = lastL; h.lrun_start = lrun_start;
-                h.last_val = last_val; h.emin = 0; h.emax = 0; h.status = 0;
+                h.ss = c.ss0; h.pos = w.begin; h.lastL = c.lastL; h.lrun_start = c.lrun_start;
+                h.last_val = c.last_val; h.emin = 0; h.emax = 0; h.status = 0;
                 *w.seam_in = h;
             }
         }
 
-        float x[K], prev[K];
-        bool act[K];
-        load_samples<K>(w, p, p0, x);
-#pragma unroll
-        for (int j = 0; j < K; j++) act[j] = (p0 + j >= w.warm_begin) && (p0 + j < w.end);
+        bool done = false;
+        if (fast_ok && c.ss0 > 0.0) {
+            // ---------------------------------------------------------------- fast path
+            const int buf = tile_no & 1;
+            // guard band: ss stays within ss0 +- Dg inside the tile (verified below)
+            const float Dg = fmaxf(2.0f * absd_prev, (float)(c.ss0 * 0x1p-16));
+            const double g = (double)Dg / c.ss0 + 0x1p-20;
+            const double tl = c.ss0 * loL, th = c.ss0 * hiL;
+            const float A1 = __double2float_rd(tl * (1.0 - g)), A2 = __double2float_ru(tl * (1.0 + g));
+            const float B1 = __double2float_rd(th * (1.0 - g)), B2 = __double2float_ru(th * (1.0 + g));
 
-        // ring slots of this thread's samples: (p0 + j) mod L
-        int slot[K];
+            float x[R * 4];
+            unsigned clsbits = 0u;  // 2 bits per sample: 0 LOW, 1 MID, 2 HIGH, 3 none
+            double dsum = 0.0;
+            float absd = 0.0f;
+            unsigned uncertain = 0u;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            int s = slot0 + j;
-            slot[j] = s >= L ? s - L : s;
-        }
-        if (K == 4 && (L & 3) == 0) {
-            float4 v = *reinterpret_cast<const float4 *>(ring + slot0);
-            prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
-        } else {
+            for (int r = 0; r < R; r++) {
+                const int64_t p0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4;
+                float xr[4];
+                load_samples<4>(w, p, p0, xr);
+                int s0 = slot0 + r * SUB;
+                if (s0 >= L) s0 -= L;
+                const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                int mylast = 3, myfirst = INT_MAX, ntr = 0, myL = -1, myH = INT_MAX, myS = -1, mylastpacked = -1;
+                int vals[4];
 #pragma unroll
-            for (int j = 0; j < K; j++) prev[j] = ring[slot[j]];
-        }
-
-        double dl[K];
-        int cls[K];
-        bool forced[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            dl[j] = act[j] ? (double)x[j] - (double)prev[j] : 0.0;  // cur - prev (transition_sink.py:82)
-            cls[j] = act[j] ? classify(x[j], ss0, p) : CLS_MID;      // guess: ss frozen at the tile start
-            forced[j] = false;
-        }
-        const bool carry_recent = lastL != NO_POS && (P0 - lastL) <= (int64_t)mx + 1;
-
-        double total = 0.0;
-        bool had_slow = false, anyL = false;
-        // ---- fix-point: classes <-> prefix sums of the gated deltas
-        for (;;) {
-            const unsigned fb = round_no % 3u;
-            if (tid == 0) sh.flags[(round_no + 1u) % 3u] = 0u;
-            double pre[K];
-            double run = 0.0;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                pre[j] = run;
-                const bool admit = act[j] && (cls[j] == CLS_MID || (cls[j] == CLS_HIGH && forced[j]));
-                if (admit) run += dl[j];
-            }
-            const double base = block_excl_scan<NT>(run, total, sh.wsum, scan_buf);
-            scan_buf ^= 1;
-
-            unsigned f = 0u;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (act[j]) {
-                    const int c = classify(x[j], ss0 + (base + pre[j]), p);
-                    if (c != cls[j]) { f |= 1u; cls[j] = c; }
-                    if (c == CLS_HIGH) f |= 2u;
-                    if (c == CLS_LOW) f |= 4u;
-                }
-            }
-            f = __reduce_or_sync(FULL, f);
-            if (lane == 0 && f) atomicOr(&sh.flags[fb], f);
-            if (lane == 31) sh.wlastcls[warp] = act[K - 1] ? cls[K - 1] : 2;  // 2 = "no sample"
-            __syncthreads();
-            unsigned flags = sh.flags[fb];
-            round_no++;
-
-            if ((flags & 2u) && ((flags & 4u) || carry_recent)) {
-                // ---- hysteresis: distance from each HIGH sample to the last LOW sample / its run start
-                // previous sample's class for this thread's first sample
-                int pc = __shfl_up_sync(FULL, cls[K - 1], 1);
-                const bool pact = __shfl_up_sync(FULL, (int)act[K - 1], 1) != 0;
-                if (lane == 0) {
-                    pc = CLS_MID;
-                    bool found = false;
-                    for (int ww = warp - 1; ww >= 0 && !found; ww--) {
-                        int c = sh.wlastcls[ww];
-                        if (c != 2) { pc = c; found = true; }
+                for (int j = 0; j < 4; j++) {
+                    x[r * 4 + j] = xr[j];
+                    const bool act = (p0 + j >= w.warm_begin) && (p0 + j < w.end);
+                    const float xv = xr[j];
+                    const bool isL = xv < A1, notL = xv > A2, isH = xv > B2, notH = xv < B1;
+                    const bool robust = isL || (notL && (isH || notH));
+                    int code = isL ? 0 : ((notL && isH) ? 2 : 1);
+                    if (!act) code = 3;
+                    else if (!robust) uncertain = 1u;
+                    clsbits |= (unsigned)code << (2 * (r * 4 + j));
+                    if (act && notL && notH) {  // robust MID: admitted
+                        dsum += (double)xv - (double)prev[j];
+                        absd += fabsf(xv - prev[j]);
+                        xmin = fminf(xmin, xv > 0.0f ? xv : xmin);
+                        xmax = fmaxf(xmax, xv);
                     }
-                    if (!found) pc = (last_val == -1) ? CLS_LOW : CLS_MID;
-                } else if (!pact) {
-                    pc = (last_val == -1) ? CLS_LOW : CLS_MID;  // inactive prefix of the first tile
+                    vals[j] = act ? code - 1 : 3;  // val = class here (no forced HIGH in the fast path)
                 }
-                // thread-local last LOW index / last LOW-run start index (tile relative), inclusive of own samples
-                int myL = -1, myS = -1;
-                int preL[K], preS[K];
-                {
-                    int c_prev = pc;
+                // row records (per warp): transitions strictly inside, first / last active sample, LOW / HIGH positions
 #pragma unroll
-                    for (int j = 0; j < K; j++) {
-                        preL[j] = myL;
-                        preS[j] = myS;
-                        if (act[j]) {
-                            if (cls[j] == CLS_LOW) {
-                                if (c_prev != CLS_LOW) myS = tid * K + j;
-                                myL = tid * K + j;
+                for (int j = 0; j < 4; j++)
+                    if (vals[j] != 3) mylast = vals[j];
+                int prevv;
+                {   // val of the nearest earlier lane with an active sample (inactive lanes only occur at segment ends)
+                    const unsigned has = __ballot_sync(FULL, mylast != 3);
+                    const unsigned lower = has & ((1u << lane) - 1u);
+                    const int got = __shfl_sync(FULL, mylast, lower ? 31 - __clz(lower) : 0);
+                    prevv = lower ? got : 3;
+                }
+                const int rel0 = r * SUB + tid * 4;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (vals[j] != 3) {
+                        if (prevv == 3) {
+                            myfirst = ((rel0 + j) << 2) | (vals[j] + 1);
+                        } else if (vals[j] != prevv) {
+                            if (p0 + j >= w.begin) ntr++;
+                            if (vals[j] == -1) myS = rel0 + j;
+                        }
+                        if (vals[j] == -1) myL = rel0 + j;
+                        if (vals[j] == 1 && myH == INT_MAX) myH = rel0 + j;
+                        mylastpacked = ((rel0 + j) << 2) | (vals[j] + 1);
+                        prevv = vals[j];
+                    }
+                }
+                RowRec rec;
+                rec.first = __reduce_min_sync(FULL, myfirst);
+                rec.last = __reduce_max_sync(FULL, mylastpacked);
+                rec.inner = __reduce_add_sync(FULL, ntr);
+                rec.lastL = __reduce_max_sync(FULL, myL);
+                rec.firstH = __reduce_min_sync(FULL, myH);
+                rec.lastS = __reduce_max_sync(FULL, myS);
+                rec.pad0 = rec.pad1 = 0;
+                if (lane == 0) sh.rows[buf][r * NW + warp] = rec;
+            }
+            // per-warp sums
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                dsum += __shfl_xor_sync(FULL, dsum, o);
+                absd += __shfl_xor_sync(FULL, absd, o);
+            }
+            uncertain = __reduce_or_sync(FULL, uncertain);
+            if (lane == 0) {
+                WarpRec wr;
+                wr.dsum = dsum; wr.absd = absd; wr.flags = uncertain;
+                sh.warps[buf][warp] = wr;
+            }
+            __syncthreads();  // the tile's only barrier on this path
+
+            // ---- every warp scans the records redundantly: lane l <-> record l (row-major = stream order)
+            double tot = 0.0;
+            float absD = 0.0f;
+            unsigned unc = 0u;
+            if (lane < NW) {
+                const WarpRec wr = sh.warps[buf][lane];
+                tot = wr.dsum; absD = wr.absd; unc = wr.flags;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                tot += __shfl_xor_sync(FULL, tot, o);
+                absD += __shfl_xor_sync(FULL, absD, o);
+            }
+            unc = __reduce_or_sync(FULL, unc);
+            RowRec rec;
+            rec.first = INT_MAX; rec.last = -1; rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1;
+            if (lane < R * NW) rec = sh.rows[buf][lane];
+            const bool has = rec.last >= 0;
+            // last defined val before each record (exclusive), seeded with the carry
+            int ld = has ? (rec.last & 3) - 1 : 3;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(FULL, ld, o);
+                if (lane >= o && ld == 3) ld = n;
+            }
+            int prevlast = __shfl_up_sync(FULL, ld, 1);
+            if (lane == 0 || prevlast == 3) prevlast = c.last_val;
+            const int tile_last_val = __shfl_sync(FULL, ld, 31);
+            // running maximum of the last LOW position before each record (exclusive), seeded with the carry
+            const int64_t cl = c.lastL == NO_POS ? (int64_t)INT_MIN / 2 : c.lastL - P0;
+            const int carryL = (int)max(cl, (int64_t)INT_MIN / 2);
+            int mxL = rec.lastL >= 0 ? rec.lastL : INT_MIN / 2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(FULL, mxL, o);
+                if (lane >= o) mxL = max(mxL, n);
+            }
+            int exL = __shfl_up_sync(FULL, mxL, 1);
+            if (lane == 0) exL = INT_MIN / 2;
+            exL = max(exL, carryL);
+            const bool hasH = rec.firstH != INT_MAX;
+            // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+            const bool st2_risk = hasH && ((rec.lastL >= 0) || ((int64_t)rec.firstH - (int64_t)exL <= (int64_t)mx + 1));
+            const int first_val = has ? (rec.first & 3) - 1 : 3;
+            const int first_pos = has ? (rec.first >> 2) : 0;
+            const bool btrans = has && first_val != prevlast;
+            const int bcount = (btrans && (P0 + first_pos >= w.begin)) ? 1 : 0;
+            const int cnt = rec.inner + bcount;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += n;
+            }
+            const int tot_tr = __shfl_sync(FULL, inc, 31);
+            const int basecnt = inc - cnt;
+            const bool slow = __any_sync(FULL, st2_risk) || unc != 0u || !(absD * 1.001f <= Dg);
+            if (!slow) {
+                done = true;
+                // ---- ring update and transitions, row by row
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int64_t p0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4;
+                    int s0 = slot0 + r * SUB;
+                    if (s0 >= L) s0 -= L;
+                    float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    float nv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    int vals[4];
+                    bool any_act = false, all_act = true;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int code = (clsbits >> (2 * (r * 4 + j))) & 3;
+                        vals[j] = code == 3 ? 3 : code - 1;
+                        if (code == 1) nv[j] = x[r * 4 + j];
+                        any_act = any_act || code != 3;
+                        all_act = all_act && code != 3;
+                    }
+                    if (all_act) {
+                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+                    } else if (any_act) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (vals[j] == 0) ring[s0 + j] = nv[j];
+                    }
+                    const int q = r * NW + warp;
+                    const int rcnt = __shfl_sync(FULL, cnt, q);
+                    if (rcnt > 0) {  // warp-uniform
+                        const int rbase = __shfl_sync(FULL, basecnt, q);
+                        const int rprev = __shfl_sync(FULL, prevlast, q);
+                        int mylast = 3;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (vals[j] != 3) mylast = vals[j];
+                        int prevv;
+                        {
+                            const unsigned hasm = __ballot_sync(FULL, mylast != 3);
+                            const unsigned lower = hasm & ((1u << lane) - 1u);
+                            const int got = __shfl_sync(FULL, mylast, lower ? 31 - __clz(lower) : 0);
+                            prevv = lower ? got : rprev;
+                        }
+                        unsigned trm = 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (vals[j] != 3) {
+                                if (vals[j] != prevv && p0 + j >= w.begin) trm |= 1u << j;
+                                prevv = vals[j];
                             }
-                            c_prev = cls[j];
+                        }
+                        const int mine = __popc(trm);
+                        int pre = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int n = __shfl_up_sync(FULL, pre, o);
+                            if (lane >= o) pre += n;
+                        }
+                        uint32_t idx = c.seg_count + (uint32_t)rbase + (uint32_t)(pre - mine);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (trm & (1u << j)) {
+                                if (idx < w.trans_cap) w.trans[idx] = pack_trans((uint32_t)(p0 + j - w.slab_pos0), vals[j]);
+                                idx++;
+                            }
                         }
                     }
                 }
-                int incL = myL, incS = myS;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int a = __shfl_up_sync(FULL, incL, o), b = __shfl_up_sync(FULL, incS, o);
-                    if (lane >= o) { incL = max(incL, a); incS = max(incS, b); }
+                // ---- carries
+                c.seg_count += (uint32_t)tot_tr;
+                c.ss0 += tot;
+                if (tile_last_val != 3) c.last_val = tile_last_val;
+                const int newL = __reduce_max_sync(FULL, rec.lastL);
+                if (newL >= 0) {
+                    int sc = rec.lastS;
+                    if (btrans && first_val == -1) sc = max(sc, first_pos);
+                    const int newS = __reduce_max_sync(FULL, sc);
+                    c.lastL = P0 + newL;
+                    if (newS >= 0) c.lrun_start = P0 + newS;
                 }
-                int exL = __shfl_up_sync(FULL, incL, 1), exS = __shfl_up_sync(FULL, incS, 1);
-                if (lane == 0) { exL = -1; exS = -1; }
-                if (lane == 31) { sh.wmaxL[warp] = incL; sh.wmaxS[warp] = incS; }
-                __syncthreads();
-                for (int ww = 0; ww < warp; ww++) {
-                    exL = max(exL, sh.wmaxL[ww]);
-                    exS = max(exS, sh.wmaxS[ww]);
-                }
-                unsigned f2 = 0u;
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    bool fo = false;
-                    if (act[j] && cls[j] == CLS_HIGH) {
-                        const int bl = max(exL, preL[j]);
-                        const int sl = max(exS, preS[j]);
-                        const int64_t b = bl >= 0 ? P0 + bl : lastL;
-                        const int64_t a = sl >= 0 ? P0 + sl : lrun_start;
-                        fo = st2_forced(p0 + j, b, a, mx);
-                    }
-                    if (fo != forced[j]) { f2 = 1u; forced[j] = fo; }
-                }
-                // a second vote: did any `forced` flag change?
-                const unsigned fb2 = round_no % 3u;
-                if (tid == 0) sh.flags[(round_no + 1u) % 3u] = 0u;
-                f2 = __reduce_or_sync(FULL, f2);
-                if (lane == 0 && f2) atomicOr(&sh.flags[fb2], f2);
-                __syncthreads();
-                flags |= sh.flags[fb2] & 1u;
-                round_no++;
-                had_slow = true;
-            } else if (had_slow) {
-                // `forced` flags are only ever set in the (block-uniform) branch above; once the tile no
-                // longer needs it they are cleared, which changes `admit`, so vote for another round.
-                unsigned f2 = 0u;
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    if (forced[j]) { f2 = 1u; forced[j] = false; }
-                }
-                if (__syncthreads_or((int)f2)) flags |= 1u;
-                had_slow = false;
-            }
-            if (!(flags & 1u)) {  // converged: `total` belongs to the final classes
-                anyL = (flags & 4u) != 0u;
-                break;
+                absd_prev = absD;
+                if (end_barrier) __syncthreads();
             }
         }
-
-        // ---- ring update (transition_sink.py:75-81) and exponent tracking
-        float nv[K];
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const bool admit = act[j] && (cls[j] == CLS_MID || (cls[j] == CLS_HIGH && forced[j]));
-            nv[j] = admit ? x[j] : prev[j];
-            if (admit) exp_track(x[j], emin, emax);
-        }
-        if (K == 4 && (L & 3) == 0 && act[0] && act[K - 1]) {
-            *reinterpret_cast<float4 *>(ring + slot0) = make_float4(nv[0], nv[1], nv[2], nv[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < K; j++)
-                if (act[j]) ring[slot[j]] = nv[j];
-        }
-
-        // ---- vals and transitions
-        int val[K];
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            val[j] = act[j] ? (cls[j] == CLS_LOW ? -1 : ((cls[j] == CLS_HIGH && !forced[j]) ? 1 : 0)) : 3;  // 3 = none
-        // last defined val of this thread, and of the threads before it
-        int mylast = 3;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            if (val[j] != 3) mylast = val[j];
-        // previous val for the first sample: nearest earlier thread with a defined val, else the carry
-        int pv;
-        {
-            // warp-level: find nearest lower lane with mylast != 3
-            const unsigned has = __ballot_sync(FULL, mylast != 3);
-            const unsigned lower = has & ((1u << lane) - 1u);
-            const int src = lower ? 31 - __clz(lower) : 0;
-            const int got = __shfl_sync(FULL, mylast, src);
-            pv = lower ? got : 3;
-            int wl = __shfl_sync(FULL, mylast, has ? 31 - __clz(has) : 0);
-            if (!has) wl = 3;
-            if (lane == 0) sh.wlastcls[warp] = wl;  // reuse: last defined val of the warp (3 = none)
-        }
-        __syncthreads();
-        if (pv == 3) {
-            pv = last_val;
-            for (int ww = warp - 1; ww >= 0; ww--) {
-                const int c = sh.wlastcls[ww];
-                if (c != 3) { pv = c; break; }
+        if (!done) {
+            // ---------------------------------------------------------------- exact path, row by row
+#pragma unroll 1
+            for (int r = 0; r < R; r++) {
+                const int64_t Pr = P0 + (int64_t)r * SUB;
+                if (Pr >= w.end || Pr + SUB <= w.warm_begin) continue;  // block-uniform
+                int s0 = slot0 + r * SUB;
+                if (s0 >= L) s0 -= L;
+                exact_tile<NT, K, R>(w, p, ring, sh, Pr, s0, c, emin, emax);
             }
+            absd_prev = (float)(c.ss0 * 0x1p-12);
         }
-        int ntr = 0;
-        unsigned trmask = 0u;
-        int maxS = -1, maxL = -1;
-        {
-            int c_prev = pv;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (val[j] != 3) {
-                    if (val[j] != c_prev) {
-                        if (p0 + j >= w.begin) { trmask |= 1u << j; ntr++; }
-                        if (val[j] == -1) maxS = tid * K + j;
-                    }
-                    if (val[j] == -1) maxL = tid * K + j;
-                    c_prev = val[j];
-                }
-            }
-        }
-        if (anyL) {
-            // carry of (lastL, lrun_start): block maxima
-            int mL = __reduce_max_sync(FULL, maxL), mS = __reduce_max_sync(FULL, maxS);
-            if (lane == 0) { sh.wmaxL[warp] = mL; sh.wmaxS[warp] = mS; }
-        }
-        int tot_tr = 0;
-        const int tr_base = block_excl_scan_int<NT>(ntr, tot_tr, sh.wcnt, cnt_buf);
-        cnt_buf ^= 1;
-        if (tot_tr) {
-            uint32_t idx = seg_count + (uint32_t)tr_base;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (trmask & (1u << j)) {
-                    if (idx < w.trans_cap) w.trans[idx] = pack_trans((uint32_t)(p0 + j - w.slab_pos0), val[j]);
-                    idx++;
-                }
-            }
-            seg_count += (uint32_t)tot_tr;
-        }
-        // ---- carries into the next tile
-        ss0 += total;
-        if (anyL) {
-            int mL = -1, mS = -1;
-#pragma unroll
-            for (int ww = 0; ww < NW; ww++) {
-                mL = max(mL, sh.wmaxL[ww]);
-                mS = max(mS, sh.wmaxS[ww]);
-            }
-            if (mL >= 0) {
-                lastL = P0 + mL;
-                if (mS >= 0) lrun_start = P0 + mS;
-            }
-        }
-        {
-            // last defined val of the tile
-            int lv = 3;
-            for (int ww = NW - 1; ww >= 0; ww--) {
-                const int c = sh.wlastcls[ww];
-                if (c != 3) { lv = c; break; }
-            }
-            if (lv != 3) last_val = lv;
-        }
-        slot0 += T;
+        slot0 += T % L;
         if (slot0 >= L) slot0 -= L;
-        __syncthreads();  // ring writes and shared scratch settle before the next tile reads them
     }
 
     // ---- exit: exactness audit and final state
+    if (xmax > 0.0f) {
+        exp_track(xmin, emin, emax);
+        exp_track(xmax, emin, emax);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         emin = min(emin, __shfl_xor_sync(FULL, emin, o));
         emax = max(emax, __shfl_xor_sync(FULL, emax, o));
     }
+    __syncthreads();
     if (tid == 0) { sh.emin = 1 << 30; sh.emax = 0; }
     __syncthreads();
     if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
@@ -557,19 +858,19 @@ __global__ void __launch_bounds__(NT) slicer_kernel(const SegWork *__restrict__ 
     emin = sh.emin; emax = sh.emax;
     if (emax >= 255) status |= SEG_NOT_SANE;
     if (emax > 0 && emax - emin > p.span_limit) status |= SEG_INEXACT;
-    if (seg_count > w.trans_cap) status |= SEG_OVERFLOW;
+    if (c.seg_count > w.trans_cap) status |= SEG_OVERFLOW;
 
     if (w.state_out) {
         float *dst = state_ring(w.state_out);
         for (int i = tid; i < L; i += NT) dst[i] = ring[i];
         if (tid == 0) {
             SlicerHdr h;
-            h.ss = ss0; h.pos = w.end; h.lastL = lastL; h.lrun_start = lrun_start;
-            h.last_val = last_val; h.emin = emin; h.emax = emax; h.status = status;
+            h.ss = c.ss0; h.pos = w.end; h.lastL = c.lastL; h.lrun_start = c.lrun_start;
+            h.last_val = c.last_val; h.emin = emin; h.emax = emax; h.status = status;
             *w.state_out = h;
         }
     }
-    if (tid == 0 && w.trans_count) *w.trans_count = seg_count;
+    if (tid == 0 && w.trans_count) *w.trans_count = c.seg_count;
     if (tid == 0 && w.status) *w.status = status;
 }
 
@@ -696,21 +997,60 @@ __global__ void seam_compare_kernel(const SlicerHdr *const *__restrict__ truth, 
 }
 
 // ---------------------------------------------------------------- host launchers
+// rows per tile of the vector kernel for a given window: a tile must fit twice into the ring
+int slicer_rows(int L) { return L >= 8192 ? 4 : (L >= 4096 ? 2 : 1); }
+int slicer_tile(int L, bool vec_ok) { return (vec_ok && L >= 1024) ? 1024 * slicer_rows(L) : 256; }
+
+template <int NT, int K, int R>
+static int launch_one(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
+    auto k = slicer_kernel<NT, K, R>;
+    NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_works, NT, smem, stream>>>(d_works, d_params);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok,
                   cudaStream_t stream) {
     if (n_works <= 0) return 0;
     const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
     if (vec_ok && L >= 1024) {
-        auto k = slicer_kernel<256, 4>;
-        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
-    } else {
-        auto k = slicer_kernel<256, 1>;
-        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+        switch (slicer_rows(L)) {
+            case 4: return launch_one<256, 4, 4>(d_works, n_works, d_params, smem, stream);
+            case 2: return launch_one<256, 4, 2>(d_works, n_works, d_params, smem, stream);
+            default: return launch_one<256, 4, 1>(d_works, n_works, d_params, smem, stream);
+        }
     }
-    NFC_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    return launch_one<256, 1, 1>(d_works, n_works, d_params, smem, stream);
+}
+
+// CTAs of the slicer kernel that fit on the device at once (for sizing the number of segments)
+int slicer_resident_ctas(int L, bool vec_ok) {
+    int dev = 0, sms = 0, per = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
+    cudaError_t e;
+    if (vec_ok && L >= 1024) {
+        switch (slicer_rows(L)) {
+            case 4:
+                cudaFuncSetAttribute(slicer_kernel<256, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 4>, 256, smem);
+                break;
+            case 2:
+                cudaFuncSetAttribute(slicer_kernel<256, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 2>, 256, smem);
+                break;
+            default:
+                cudaFuncSetAttribute(slicer_kernel<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 1>, 256, smem);
+        }
+    } else {
+        cudaFuncSetAttribute(slicer_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 1, 1>, 256, smem);
+    }
+    if (e != cudaSuccess || per < 1) per = 1;
+    return sms * per;
 }
 
 int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,

@@ -35,12 +35,18 @@ size_t linecode_map_bytes();
 size_t linecode_cnt_bytes();
 size_t linecode_emission_bytes();
 size_t linecode_scratch_bytes(uint32_t n_chunks);
-int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
-                          void *d_prefix, void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t);
-int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, const void *d_prefix,
+int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_start,
+                          int *d_unresolved, cudaStream_t);
+int launch_linecode_start_scan(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
+                               void *d_prefix, void *d_scratch, uint16_t *d_start, cudaStream_t);
+int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start, void *d_cnts,
+                          void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t);
+int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
                           uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t);
+int slicer_tile(int L, bool vec_ok);
+int slicer_resident_ctas(int L, bool vec_ok);
 int synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens, int64_t n_runs,
                  float carrier, float pause, float tag_high, float noise, float fade, double fade_period, uint64_t seed,
                  int as_envelope, cudaStream_t);
@@ -130,20 +136,21 @@ struct Stream {
     // device scratch
     DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
         seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
-        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring;
+        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 
     // results
     std::vector<nfc_event> out_events;
     std::vector<nfc_symbol> out_symbols;
-    std::vector<nfc_frame> out_frames;
-    std::vector<uint8_t> out_bits;
+    std::vector<nfc_frame> out_frames;   // bit_off is relative to out_fbits[type]
+    std::vector<uint8_t> out_fbits[2];   // forwarded frame bits per type, frames back to back
+    int resident_ctas = 0;
     size_t ev_head = 0, sym_head = 0, fr_head = 0;
 
     nfc_stats stats;
 
-    int tile() const { return (vec_ok() && sp.L >= 1024) ? 1024 : 256; }
+    int tile() const { return slicer_tile(sp.L, vec_ok()); }
     bool vec_ok() const { return (sp.L % 4) == 0; }
     bool parallel_ok() const { return sp.L >= 256 && sp.L <= 56000 && !force_serial && !serial_mode; }
 
@@ -203,17 +210,22 @@ int Stream::init(const nfc_params *p) {
     }
     const size_t dcm = ht.dclass_miller.size(), dcg = ht.dclass_manch.size();
     const size_t tm = ht.miller.size() * sizeof(TabEntry), tg = ht.manch.size() * sizeof(TabEntry);
-    const size_t o1 = (dcm + 255) / 256 * 256, o2 = o1 + (dcg + 255) / 256 * 256, o3 = o2 + (tm + 255) / 256 * 256;
-    if (tab_d.ensure(o3 + tg)) return -1;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o1 = up(dcm), o2 = o1 + up(dcg), o3 = o2 + up(tm), o4 = o3 + up(tg), o5 = o4 + up(ht.reset_miller.size());
+    if (tab_d.ensure(o5 + up(ht.reset_manch.size()))) return -1;
     char *base = tab_d.as<char>();
     NFC_CUDA_CHECK(cudaMemcpy(base, ht.dclass_miller.data(), dcm, cudaMemcpyHostToDevice));
     NFC_CUDA_CHECK(cudaMemcpy(base + o1, ht.dclass_manch.data(), dcg, cudaMemcpyHostToDevice));
     NFC_CUDA_CHECK(cudaMemcpy(base + o2, ht.miller.data(), tm, cudaMemcpyHostToDevice));
     NFC_CUDA_CHECK(cudaMemcpy(base + o3, ht.manch.data(), tg, cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpy(base + o4, ht.reset_miller.data(), ht.reset_miller.size(), cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpy(base + o5, ht.reset_manch.data(), ht.reset_manch.size(), cudaMemcpyHostToDevice));
     lt.dclass_miller = (const uint8_t *)base;
     lt.dclass_manch = (const uint8_t *)(base + o1);
     lt.miller = (const TabEntry *)(base + o2);
     lt.manch = (const TabEntry *)(base + o3);
+    lt.reset_miller = (const uint8_t *)(base + o4);
+    lt.reset_manch = (const uint8_t *)(base + o5);
     lt.n_dclass_miller = ht.n_dclass_miller;
     lt.n_dclass_manch = ht.n_dclass_manch;
     lt.decode_reader = p->decode_reader;
@@ -223,6 +235,7 @@ int Stream::init(const nfc_params *p) {
     if (state.ensure(state_block_bytes(sp.L))) return -1;
     if (carry_d.ensure(256)) return -1;
     if (totals_d.ensure(256)) return -1;
+    resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok()) : 1;
     return 0;
 }
 
@@ -230,7 +243,7 @@ void Stream::destroy() {
     DevBuf *all[] = {&params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
-                     &serial_ring, &state};
+                     &serial_ring, &start_d, &state};
     for (DevBuf *b : all) b->release();
     if (pinned) cudaFreeHost(pinned);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -352,10 +365,15 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
         H = (Hs + T - 1) / T * T;
         int64_t S = seg_len;
         if (S <= 0) {
-            S = (b - a) / 600;
-            S = std::max<int64_t>(S, 4 * H);
-            S = std::min<int64_t>(S, (int64_t)256 * L);
-            S = std::max<int64_t>(S, 4 * H);
+            // as many segments as CTAs fit on the device at once (times k), each at least 6 halos long so that
+            // the speculative halo costs little, at most 256 windows so that a redo stays cheap
+            const int64_t n = b - a, res = std::max(1, resident_ctas);
+            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)256 * L, s_min);
+            int64_t k = 1;
+            while (n / (res * (k + 1)) >= s_min) k++;
+            S = n / (res * k);
+            if (S < s_min) S = s_min;
+            if (S > s_max) S = s_max;
         }
         S = (S + T - 1) / T * T;
         int64_t b1 = a + std::max<int64_t>(S, (int64_t)L + H);
@@ -564,21 +582,38 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
     uint32_t *d_pend = reinterpret_cast<uint32_t *>(carry_d.as<char>() + 128);
     const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
     if (nc > 0 && want_line) {
-        if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes()) ||
-            cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) || cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
-            line_scr.ensure(linecode_scratch_bytes(nc) + 256))
+        if (start_d.ensure((size_t)nc * 2 + 64) || cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
+            cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) || line_scr.ensure(linecode_scratch_bytes(nc) + 256))
             return -1;
-        if (launch_linecode_count(events_d.as<EventRec>(), M, lt, dec_carry, maps_d.p, prefix_d.p, cnts_d.p, cprefix_d.p,
-                                  line_scr.p, totals_d.as<char>() + 64, cs))
+        int *d_unres = reinterpret_cast<int *>(totals_d.as<char>() + 128);
+        if (launch_linecode_start(events_d.as<EventRec>(), M, lt, dec_carry, start_d.as<uint16_t>(), d_unres, cs)) return -1;
+        if (launch_linecode_count(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p,
+                                  totals_d.as<char>() + 64, cs))
             return -1;
-        stats.launches += 8;
+        stats.launches += 5;
+        int unres = 0;
         NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&unres, d_unres, sizeof(int), cudaMemcpyDeviceToHost, cs));
         NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        if (unres) {
+            // some chunk saw no decoder reset within the search limit: compose chunk transfer functions instead
+            stats.linecode_scan_fallbacks++;
+            if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes())) return -1;
+            if (launch_linecode_start_scan(events_d.as<EventRec>(), M, lt, dec_carry, maps_d.p, prefix_d.p, line_scr.p,
+                                           start_d.as<uint16_t>(), cs))
+                return -1;
+            if (launch_linecode_count(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p,
+                                      line_scr.p, totals_d.as<char>() + 64, cs))
+                return -1;
+            stats.launches += 9;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
+            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        }
         const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
         if ((want_sym && sym_d.ensure(((size_t)tot.nsym + 16) * sizeof(SymbolRec))) || bits0_d.ensure((size_t)tot.nbit0 + 16) ||
             bits1_d.ensure((size_t)tot.nbit1 + 16) || em_d.ensure(((size_t)tot.nemit + 16) * linecode_emission_bytes()))
             return -1;
-        if (launch_linecode_write(events_d.as<EventRec>(), M, lt, dec_carry, prefix_d.p, cprefix_d.p,
+        if (launch_linecode_write(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cprefix_d.p,
                                   want_sym ? sym_d.as<SymbolRec>() : nullptr, want_sym ? tot.nsym : 0, bits0_d.as<uint8_t>(),
                                   tot.nbit0, bits1_d.as<uint8_t>(), tot.nbit1, em_d.p, tot.nemit, pending[0], pending[1], d_dc,
                                   d_pend, cs))
@@ -666,6 +701,8 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         for (int t = 0; t < 2; t++) hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
         size_t last_end[2] = {0, 0};
         bool any[2] = {false, false};
+        const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
+        out_frames.reserve(out_frames.size() + tot.nemit);
         for (uint32_t i = 0; i < tot.nemit; i++) {
             const int t = em[i].type;
             const size_t end = old[t] + em[i].bit_end;  // index into hbits[t]
@@ -678,14 +715,16 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
             }
             nfc_frame f;
             f.pos = a + (int64_t)em[i].rel_pos;
-            f.bit_off = (int64_t)out_bits.size();
+            f.bit_off = (int64_t)(fbase[t] + end - em[i].nbits);  // frames of one type are back to back
             f.nbits = (int32_t)em[i].nbits;
             f.type = t;
-            out_bits.insert(out_bits.end(), hbits[t].begin() + (long)(end - em[i].nbits), hbits[t].begin() + (long)end);
             out_frames.push_back(f);
         }
         for (int t = 0; t < 2; t++)
-            if (any[t]) hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+            if (any[t]) {
+                out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+                hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+            }
     }
     return 0;
 }
@@ -776,7 +815,8 @@ int nfc_stream_reset(nfc_stream *h) {
     s.out_events.clear();
     s.out_symbols.clear();
     s.out_frames.clear();
-    s.out_bits.clear();
+    s.out_fbits[0].clear();
+    s.out_fbits[1].clear();
     s.ev_head = s.sym_head = s.fr_head = 0;
     return 0;
 }
@@ -801,33 +841,32 @@ int64_t nfc_stream_drain_symbols(nfc_stream *h, nfc_symbol *out, int64_t cap) {
 
 int64_t nfc_stream_pending_frame_bits(nfc_stream *h) {
     if (!h) return -1;
-    int64_t n = 0;
-    for (size_t i = h->s.fr_head; i < h->s.out_frames.size(); i++) n += h->s.out_frames[i].nbits;
-    return n;
+    return (int64_t)(h->s.out_fbits[0].size() + h->s.out_fbits[1].size());
 }
 
 int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap) {
     if (!h) return -1;
     Stream &s = h->s;
-    const int64_t avail = (int64_t)(s.out_frames.size() - s.fr_head);
+    const int64_t avail = (int64_t)s.out_frames.size();
     if (cap <= 0 || !out) return avail;
-    int64_t n = 0, used = 0;
-    while (n < cap && s.fr_head < s.out_frames.size()) {
-        const nfc_frame &f = s.out_frames[s.fr_head];
-        if (used + f.nbits > bits_cap) break;
-        out[n] = f;
-        out[n].bit_off = used;
-        if (f.nbits) memcpy(bits + used, s.out_bits.data() + f.bit_off, (size_t)f.nbits);
-        used += f.nbits;
-        n++;
-        s.fr_head++;
+    const int64_t nb0 = (int64_t)s.out_fbits[0].size(), nb1 = (int64_t)s.out_fbits[1].size();
+    if (cap < avail || bits_cap < nb0 + nb1 || (!bits && nb0 + nb1 > 0)) {
+        nfc::set_error("drain_frames: buffers too small (%lld frames, %lld bits pending)", (long long)avail,
+                       (long long)(nb0 + nb1));
+        return -2;
     }
-    if (s.fr_head == s.out_frames.size()) {
-        s.out_frames.clear();
-        s.out_bits.clear();
-        s.fr_head = 0;
+    // all pending frames at once: tag->reader bits first, then reader->tag bits
+    if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0);
+    if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1);
+    for (int64_t i = 0; i < avail; i++) {
+        out[i] = s.out_frames[(size_t)i];
+        if (out[i].type == 1) out[i].bit_off += nb0;
     }
-    return n;
+    s.out_frames.clear();
+    s.out_fbits[0].clear();
+    s.out_fbits[1].clear();
+    s.fr_head = 0;
+    return avail;
 }
 
 int nfc_stream_get_state(nfc_stream *h, nfc_state *st, float *ring, uint8_t *pending_bits) {

@@ -47,10 +47,14 @@ Step miller_step(int state, int cur, double dur) {
     } else if (dur > hi) {
         err = TOO_LONG;
     }
-    if (err) {  // miller.py:173-176: _reset(), _prev untouched
+    if (err) {  // miller.py:173-176: _reset(); the reference leaves _prev untouched here
         s.out[s.nout++] = err;
         stage = 0;
         started = 0;
+        // _prev is dead after a reset: it is read only in handle_beginning with _has_started set, which is
+        // reached only through ZERO_STAGE_0, and every exit of that stage writes _prev or resets again.
+        // Canonical 0 makes out-of-range events send every state to one state (frame-boundary search).
+        prev = 0;
         s.next = pack();
         return s;
     }
@@ -105,7 +109,8 @@ Step manch_step(int state, int cur, double dur) {
     const double lo = HALF - 1, mid = HALF + 1, hi = 2 * HALF + 1;  // manchester.py:17-20
     int prev_set = state & 1, prev = ((state >> 1) & 3) - 1;
     Step s = {0, 0, {0, 0}};
-    auto pack = [&]() { return prev_set | ((prev + 1) << 1); };
+    // _prev is read only while _prev_set: canonical 0 otherwise
+    auto pack = [&]() { return prev_set | (((prev_set ? prev : 0) + 1) << 1); };
     int err = 0;
     if (dur < lo) err = TOO_SHORT;
     else if (dur > hi) err = TOO_LONG;
@@ -144,7 +149,7 @@ TabEntry entry_of(const Step &s) {
 
 template <class StepFn>
 bool build_one(StepFn step, int nstates, int max_len, double factor, std::vector<uint8_t> &dclass,
-               std::vector<TabEntry> &table, int &nclass) {
+               std::vector<TabEntry> &table, int &nclass, std::vector<uint8_t> &reset) {
     std::map<std::vector<TabEntry>, int> seen;
     std::vector<std::vector<TabEntry>> cols;
     dclass.assign((size_t)max_len + 1, 0);
@@ -168,14 +173,27 @@ bool build_one(StepFn step, int nstates, int max_len, double factor, std::vector
     nclass = (int)cols.size();
     table.assign((size_t)nclass * 4 * nstates, 0);
     for (int c = 0; c < nclass; c++) std::memcpy(&table[(size_t)c * 4 * nstates], cols[c].data(), sizeof(TabEntry) * 4 * nstates);
+    // universal resets: every state goes to the same state and the last symbol emitted is an error code
+    reset.assign((size_t)nclass * 4, 0xFF);
+    for (int c = 0; c < nclass; c++)
+        for (int v = 0; v < 4; v++) {
+            const TabEntry *row = &table[((size_t)c * 4 + v) * nstates];
+            bool uni = true;
+            for (int st = 0; st < nstates && uni; st++) {
+                const int n = tab_nout(row[st]);
+                const int last = n == 0 ? 0 : (n == 1 ? tab_out0(row[st]) : tab_out1(row[st]));
+                uni = tab_next(row[st]) == tab_next(row[0]) && n > 0 && last >= 2;
+            }
+            if (uni) reset[(size_t)c * 4 + v] = (uint8_t)tab_next(row[0]);  // _started = 0 after an error symbol
+        }
     return true;
 }
 }  // namespace
 
 bool build_tables(int max_len, double factor, HostTables &t) {
     t.max_len = max_len;
-    if (!build_one(miller_step, MILLER_STATES, max_len, factor, t.dclass_miller, t.miller, t.n_dclass_miller)) return false;
-    if (!build_one(manch_step, MANCH_STATES, max_len, factor, t.dclass_manch, t.manch, t.n_dclass_manch)) return false;
+    if (!build_one(miller_step, MILLER_STATES, max_len, factor, t.dclass_miller, t.miller, t.n_dclass_miller, t.reset_miller)) return false;
+    if (!build_one(manch_step, MANCH_STATES, max_len, factor, t.dclass_manch, t.manch, t.n_dclass_manch, t.reset_manch)) return false;
     return true;
 }
 
