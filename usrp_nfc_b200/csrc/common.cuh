@@ -49,6 +49,7 @@ enum InputKind { IN_ENVELOPE_F32 = 0, IN_REAL_F32 = 1, IN_IQ_F32 = 2, IN_PCM_S16
 struct SlicerParams {
     double lo, hi;   // lo_val, hi_val (transition_sink.py:32-33)
     double Ld;       // (double)av_window
+    double loL, hiL; // lo / L and hi / L: sample-domain thresholds are ss * loL and ss * hiL
     int L;           // av_window (transition_sink.py:27)
     int mx;          // max_len   (transition_sink.py:20)
     int cls_ss0_x0;  // class when ss == 0 and bit == 0 (ratio = 1)        transition_sink.py:59-61

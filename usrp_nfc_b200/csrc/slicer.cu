@@ -27,6 +27,7 @@
 namespace nfc {
 
 static const unsigned FULL = 0xffffffffu;
+__device__ unsigned long long g_tile_stats[8];  // tiles by fast / exact path, exact rounds, -, cycles in fast attempts / exact path (thread 0)
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
 
 // ---------------------------------------------------------------- sample loading / envelope
@@ -159,6 +160,8 @@ struct BlockShared {
     double red[NW];
     RowRec rows[2][R * NW];
     WarpRec warps[2][NW];
+    double rsum[R * NW];  // per-record sums for the band refinement
+    float rabs[R * NW];
 };
 
 // everything a segment carries from tile to tile (identical in all threads of the CTA)
@@ -228,12 +231,17 @@ __device__ __forceinline__ void exp_track(float x, int &emin, int &emax) {
 // One tile of NT*K samples starting at stream index P0, classes decided with every sample's own exact ss.
 // Always correct (inside the exactly-summable regime); several block barriers per tile.
 template <int NT, int K, int R>
-__device__ __noinline__ void exact_tile(const SegWork &w, const SlicerParams &p, float *ring, BlockShared<NT, R> &sh,
-                                        const int64_t P0, const int slot0, SegCarry &c, int &emin, int &emax) {
+__device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *pp, float *ring, BlockShared<NT, R> *shp,
+                                        const int64_t P0, const int slot0, SegCarry *cs) {
     constexpr int NW = NT / 32;
+    const SegWork &w = *wp;
+    const SlicerParams &p = *pp;
+    BlockShared<NT, R> &sh = *shp;
     const int L = p.L, mx = p.mx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p0 = P0 + (int64_t)tid * K;
+    SegCarry c = *cs;  // shared -> registers (identical in all threads)
+    int emin = 1 << 30, emax = 0;
     const double ss0 = c.ss0;
     const int64_t lastL = c.lastL, lrun_start = c.lrun_start;
     const int last_val = c.last_val;
@@ -485,7 +493,14 @@ __device__ __noinline__ void exact_tile(const SegWork &w, const SlicerParams &p,
         }
         if (lv != 3) c.last_val = lv;
     }
-    __syncthreads();  // ring writes and shared scratch settle before the next tile reads them
+    emin = __reduce_min_sync(FULL, emin);
+    emax = __reduce_max_sync(FULL, emax);
+    if (lane == 0) {
+        atomicMin(&sh.emin, emin);
+        atomicMax(&sh.emax, emax);
+    }
+    if (tid == 0) *cs = c;
+    __syncthreads();  // carry, ring writes and shared scratch settle before the next tile reads them
 }
 
 // ---------------------------------------------------------------- the segment kernel
@@ -506,6 +521,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
     // the work item and the parameters live in shared memory: one copy per CTA, no registers held
     __shared__ SegWork w_s;
     __shared__ SlicerParams p_s;
+    __shared__ SegCarry c_s;
     if (threadIdx.x == 0) {
         w_s = works[blockIdx.x];
         p_s = params[w_s.param_idx];
@@ -553,7 +569,11 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
         c.lrun_start = NO_POS;
         c.last_val = 0;
     }
-    if (tid == 0) sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
+    if (tid == 0) {
+        sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
+        sh.emin = 1 << 30;
+        sh.emax = 0;
+    }
     __syncthreads();
     c.seg_count = 0;
     c.scan_buf = 0;
@@ -562,10 +582,9 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
 
     const bool fast_ok = (K == 4) && ((L & 3) == 0) && p.lo > 0.0 && p.hi > p.lo;
     const bool end_barrier = 2 * T > L;  // a tile would read ring slots the previous tile wrote
-    const double loL = p.lo / p.Ld, hiL = p.hi / p.Ld;
     float absd_prev = 0.0f;              // admitted |x - prev| of the previous tile: sizes the next guard band
-    float xmin = 3.0e38f, xmax = 0.0f;   // admitted samples of the fast path (all > 0 and finite)
-    unsigned tile_no = 0;
+    unsigned tile_no = 0, n_fast = 0, n_slow = 0, n_refined = 0;
+    long long cyc_fast = 0, cyc_slow = 0;
 
     const int64_t tile_first = w.warm_begin / T;
     const int64_t tile_last = (w.end > w.warm_begin) ? (w.end - 1) / T : tile_first - 1;
@@ -587,86 +606,106 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
         }
 
         bool done = false;
-        if (fast_ok && c.ss0 > 0.0) {
+        const long long t_a = clock64();
+        // interior tile: every sample is inside the segment and the input buffer, and either all or none of
+        // its transitions are written (anything else goes to the exact path, which masks per sample)
+        const bool interior = P0 >= w.warm_begin && P0 + T <= w.end && P0 >= w.in_begin && P0 + T <= w.in_end &&
+                              (P0 >= w.begin || P0 + T <= w.begin);
+        if (fast_ok && interior && c.ss0 > 0.0) {
             // ---------------------------------------------------------------- fast path
             const int buf = tile_no & 1;
-            // guard band: ss stays within ss0 +- Dg inside the tile (verified below)
-            const float Dg = fmaxf(2.0f * absd_prev, (float)(c.ss0 * 0x1p-16));
+            const bool emit = P0 >= w.begin;
+            // guard band: ss stays within ss0 +- Dg inside the tile (verified after the barrier)
+            const float Dg = fmaxf(1.25f * absd_prev, (float)(c.ss0 * 0x1p-14));
             const double g = (double)Dg / c.ss0 + 0x1p-20;
-            const double tl = c.ss0 * loL, th = c.ss0 * hiL;
-            const float A1 = __double2float_rd(tl * (1.0 - g)), A2 = __double2float_ru(tl * (1.0 + g));
-            const float B1 = __double2float_rd(th * (1.0 - g)), B2 = __double2float_ru(th * (1.0 + g));
+            const double tl = c.ss0 * p.loL, th = c.ss0 * p.hiL;
+            float A1 = __double2float_rd(tl * (1.0 - g)), A2 = __double2float_ru(tl * (1.0 + g));
+            float B1 = __double2float_rd(th * (1.0 - g)), B2 = __double2float_ru(th * (1.0 + g));
+            const float TL = __double2float_rn(tl), TH = __double2float_rn(th);  // the guess for samples inside a band
 
             float x[R * 4];
-            unsigned clsbits = 0u;  // 2 bits per sample: 0 LOW, 1 MID, 2 HIGH, 3 none
+            unsigned clsbits = 0u;  // 2 bits per sample: 0 LOW, 1 MID, 2 HIGH
+            unsigned uncbits = 0u;  // 1 bit per sample: inside a guard band
             double dsum = 0.0;
             float absd = 0.0f;
-            unsigned uncertain = 0u;
+            const char *inb = reinterpret_cast<const char *>(w.in);
+            const int kind = p.input_kind;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int64_t p0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4;
+                const int64_t i0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4 - w.in_pos0;
                 float xr[4];
-                load_samples<4>(w, p, p0, xr);
+                if (kind == IN_ENVELOPE_F32 || kind == IN_REAL_F32) {
+                    const float4 v = ldg_stream4(reinterpret_cast<const float4 *>(inb + i0 * 4));
+                    xr[0] = v.x; xr[1] = v.y; xr[2] = v.z; xr[3] = v.w;
+                    if (kind == IN_REAL_F32) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) xr[j] = env_real(xr[j]);
+                    }
+                } else if (kind == IN_IQ_F32) {
+                    const float4 *q = reinterpret_cast<const float4 *>(inb + i0 * 8);
+                    const float4 a = ldg_stream4(q), b = ldg_stream4(q + 1);
+                    xr[0] = env_iq(a.x, a.y); xr[1] = env_iq(a.z, a.w); xr[2] = env_iq(b.x, b.y); xr[3] = env_iq(b.z, b.w);
+                } else {
+                    const short4 sv = __ldg(reinterpret_cast<const short4 *>(inb + i0 * 2));
+                    xr[0] = env_real(__fdiv_rn((float)sv.x, p.pcm_scale));
+                    xr[1] = env_real(__fdiv_rn((float)sv.y, p.pcm_scale));
+                    xr[2] = env_real(__fdiv_rn((float)sv.z, p.pcm_scale));
+                    xr[3] = env_real(__fdiv_rn((float)sv.w, p.pcm_scale));
+                }
                 int s0 = slot0 + r * SUB;
                 if (s0 >= L) s0 -= L;
                 const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
                 const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                int mylast = 3, myfirst = INT_MAX, ntr = 0, myL = -1, myH = INT_MAX, myS = -1, mylastpacked = -1;
-                int vals[4];
+                unsigned codes = 0u, uncs = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    x[r * 4 + j] = xr[j];
-                    const bool act = (p0 + j >= w.warm_begin) && (p0 + j < w.end);
                     const float xv = xr[j];
-                    const bool isL = xv < A1, notL = xv > A2, isH = xv > B2, notH = xv < B1;
-                    const bool robust = isL || (notL && (isH || notH));
-                    int code = isL ? 0 : ((notL && isH) ? 2 : 1);
-                    if (!act) code = 3;
-                    else if (!robust) uncertain = 1u;
-                    clsbits |= (unsigned)code << (2 * (r * 4 + j));
-                    if (act && notL && notH) {  // robust MID: admitted
+                    x[r * 4 + j] = xv;
+                    const bool lowg = xv < TL, highg = xv > TH;  // guess (exact for samples outside the bands)
+                    const bool robust = (xv < A1) || ((xv > A2) && ((xv > B2) || (xv < B1)));
+                    const unsigned code = lowg ? 0u : (highg ? 2u : 1u);
+                    codes |= code << (2 * j);
+                    uncs |= (robust ? 0u : 1u) << j;
+                    if (code == 1u) {  // MID: admitted
                         dsum += (double)xv - (double)prev[j];
                         absd += fabsf(xv - prev[j]);
-                        xmin = fminf(xmin, xv > 0.0f ? xv : xmin);
-                        xmax = fmaxf(xmax, xv);
-                    }
-                    vals[j] = act ? code - 1 : 3;  // val = class here (no forced HIGH in the fast path)
-                }
-                // row records (per warp): transitions strictly inside, first / last active sample, LOW / HIGH positions
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (vals[j] != 3) mylast = vals[j];
-                int prevv;
-                {   // val of the nearest earlier lane with an active sample (inactive lanes only occur at segment ends)
-                    const unsigned has = __ballot_sync(FULL, mylast != 3);
-                    const unsigned lower = has & ((1u << lane) - 1u);
-                    const int got = __shfl_sync(FULL, mylast, lower ? 31 - __clz(lower) : 0);
-                    prevv = lower ? got : 3;
-                }
-                const int rel0 = r * SUB + tid * 4;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (vals[j] != 3) {
-                        if (prevv == 3) {
-                            myfirst = ((rel0 + j) << 2) | (vals[j] + 1);
-                        } else if (vals[j] != prevv) {
-                            if (p0 + j >= w.begin) ntr++;
-                            if (vals[j] == -1) myS = rel0 + j;
-                        }
-                        if (vals[j] == -1) myL = rel0 + j;
-                        if (vals[j] == 1 && myH == INT_MAX) myH = rel0 + j;
-                        mylastpacked = ((rel0 + j) << 2) | (vals[j] + 1);
-                        prevv = vals[j];
                     }
                 }
+                clsbits |= codes << (8 * r);
+                uncbits |= uncs << (4 * r);
+                // ---- row record of this warp (128 samples), computed from ballots: all lanes get the same values
                 RowRec rec;
-                rec.first = __reduce_min_sync(FULL, myfirst);
-                rec.last = __reduce_max_sync(FULL, mylastpacked);
-                rec.inner = __reduce_add_sync(FULL, ntr);
-                rec.lastL = __reduce_max_sync(FULL, myL);
-                rec.firstH = __reduce_min_sync(FULL, myH);
-                rec.lastS = __reduce_max_sync(FULL, myS);
-                rec.pad0 = rec.pad1 = 0;
+                rec.first = (r * SUB + warp * 128) << 2 | 1; rec.last = (r * SUB + warp * 128 + 127) << 2 | 1;
+                rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1; rec.pad0 = rec.pad1 = 0;
+                if (__any_sync(FULL, codes != 0x55u)) {  // something other than MID in these 128 samples
+                    unsigned Lm[4], Hm[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        Lm[j] = __ballot_sync(FULL, ((codes >> (2 * j)) & 3u) == 0u);
+                        Hm[j] = __ballot_sync(FULL, ((codes >> (2 * j)) & 3u) == 2u);
+                    }
+                    const int base = r * SUB + warp * 128;  // sample (lane, j) sits at base + 4*lane + j
+                    // transitions between consecutive samples: (lane,j)->(lane,j+1), and (lane,3)->(lane+1,0)
+                    int inner = 0;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) inner += __popc((Lm[j] ^ Lm[j + 1]) | (Hm[j] ^ Hm[j + 1]));
+                    inner += __popc(((Lm[3] ^ (Lm[0] >> 1)) | (Hm[3] ^ (Hm[0] >> 1))) & 0x7fffffffu);
+                    int lastL = -1, firstH = INT_MAX, lastS = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (Lm[j]) lastL = max(lastL, base + 4 * (31 - __clz(Lm[j])) + j);
+                        if (Hm[j]) firstH = min(firstH, base + 4 * (__ffs(Hm[j]) - 1) + j);
+                        // LOW-run starts strictly inside: LOW here, previous sample not LOW
+                        const unsigned st = j == 0 ? (Lm[0] & ~(Lm[3] << 1) & ~1u) : (Lm[j] & ~Lm[j - 1]);
+                        if (st) lastS = max(lastS, base + 4 * (31 - __clz(st)) + j);
+                    }
+                    const int fv = (Lm[0] & 1u) ? -1 : ((Hm[0] & 1u) ? 1 : 0);
+                    const int lv = (Lm[3] >> 31) ? -1 : ((Hm[3] >> 31) ? 1 : 0);
+                    rec.first = (base << 2) | (fv + 1);
+                    rec.last = ((base + 127) << 2) | (lv + 1);
+                    rec.inner = emit ? inner : 0;
+                    rec.lastL = lastL; rec.firstH = firstH; rec.lastS = lastS;
+                }
                 if (lane == 0) sh.rows[buf][r * NW + warp] = rec;
             }
             // per-warp sums
@@ -675,7 +714,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                 dsum += __shfl_xor_sync(FULL, dsum, o);
                 absd += __shfl_xor_sync(FULL, absd, o);
             }
-            uncertain = __reduce_or_sync(FULL, uncertain);
+            const unsigned uncertain = __any_sync(FULL, uncbits != 0u) ? 1u : 0u;
             if (lane == 0) {
                 WarpRec wr;
                 wr.dsum = dsum; wr.absd = absd; wr.flags = uncertain;
@@ -696,7 +735,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                 tot += __shfl_xor_sync(FULL, tot, o);
                 absD += __shfl_xor_sync(FULL, absD, o);
             }
-            unc = __reduce_or_sync(FULL, unc);
+            unc = __any_sync(FULL, unc != 0u) ? 1u : 0u;
             RowRec rec;
             rec.first = INT_MAX; rec.last = -1; rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1;
             if (lane < R * NW) rec = sh.rows[buf][lane];
@@ -729,8 +768,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
             const int first_val = has ? (rec.first & 3) - 1 : 3;
             const int first_pos = has ? (rec.first >> 2) : 0;
             const bool btrans = has && first_val != prevlast;
-            const int bcount = (btrans && (P0 + first_pos >= w.begin)) ? 1 : 0;
-            const int cnt = rec.inner + bcount;
+            const int cnt = rec.inner + ((btrans && emit) ? 1 : 0);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -739,57 +777,121 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
             }
             const int tot_tr = __shfl_sync(FULL, inc, 31);
             const int basecnt = inc - cnt;
-            const bool slow = __any_sync(FULL, st2_risk) || unc != 0u || !(absD * 1.001f <= Dg);
+            bool slow = __any_sync(FULL, st2_risk);
+            absd_prev = absD;  // sizes the next tile's band
+            if (!slow && !(absD * 1.001f <= Dg)) {
+                // the window sum moved further than the band assumed: widen the band to what was measured (the
+                // guessed classes, hence the sums, do not depend on the band) and re-mark the samples inside it
+                const double gw = (double)(absD * 1.001f) / c.ss0 + 0x1p-20;
+                A1 = __double2float_rd(tl * (1.0 - gw)); A2 = __double2float_ru(tl * (1.0 + gw));
+                B1 = __double2float_rd(th * (1.0 - gw)); B2 = __double2float_ru(th * (1.0 + gw));
+                uncbits = 0u;
+#pragma unroll
+                for (int k = 0; k < R * 4; k++) {
+                    const float xv = x[k];
+                    const bool robust = (xv < A1) || ((xv > A2) && ((xv > B2) || (xv < B1)));
+                    uncbits |= (robust ? 0u : 1u) << k;
+                }
+                unc = 1u;  // block-uniform: take the refinement path, which votes
+            }
+            if (!slow && unc) {
+                // ---- some samples sit inside the tile-wide band: re-test them against the band of their own
+                // 128-sample record, whose start ss is exact given the guessed classes (self-consistency)
+                double rsum[R];
+                float rabs[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    int s0 = slot0 + r * SUB;
+                    if (s0 >= L) s0 -= L;
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    double ds = 0.0;
+                    float da = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (((clsbits >> (2 * (r * 4 + j))) & 3u) == 1u) {
+                            ds += (double)x[r * 4 + j] - (double)prev[j];
+                            da += fabsf(x[r * 4 + j] - prev[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        ds += __shfl_xor_sync(FULL, ds, o);
+                        da += __shfl_xor_sync(FULL, da, o);
+                    }
+                    rsum[r] = ds; rabs[r] = da;
+                    if (lane == 0) { sh.rsum[r * NW + warp] = ds; sh.rabs[r * NW + warp] = da; }
+                }
+                __syncthreads();
+                double pre = (lane < R * NW) ? sh.rsum[lane] : 0.0;
+                const double own = pre;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double n = __shfl_up_sync(FULL, pre, o);
+                    if (lane >= o) pre += n;
+                }
+                pre -= own;  // exclusive: sum of the records before record `lane`
+                unsigned bad = 0u;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int q = r * NW + warp;
+                    const double ssq = c.ss0 + __shfl_sync(FULL, pre, q);
+                    if (((uncbits >> (4 * r)) & 15u) != 0u) {
+                        if (!(ssq > 0.0)) { bad = 1u; continue; }
+                        const double g2 = (double)(rabs[r] * 1.001f) / ssq + 0x1p-20;
+                        const double tl2 = ssq * p.loL, th2 = ssq * p.hiL;
+                        const float a1 = __double2float_rd(tl2 * (1.0 - g2)), a2 = __double2float_ru(tl2 * (1.0 + g2));
+                        const float b1 = __double2float_rd(th2 * (1.0 - g2)), b2 = __double2float_ru(th2 * (1.0 + g2));
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if ((uncbits >> (4 * r + j)) & 1u) {
+                                const float xv = x[r * 4 + j];
+                                const unsigned code = (clsbits >> (2 * (r * 4 + j))) & 3u;
+                                // the guessed class must hold for every ss the record can reach
+                                const bool ok = code == 0u ? (xv < a1) : (code == 2u ? (xv > a2 && xv > b2) : (xv > a2 && xv < b1));
+                                if (!ok) bad = 1u;
+                            }
+                        }
+                    }
+                }
+                slow = __syncthreads_or((int)bad) != 0;
+                if (!slow) n_refined++;
+            }
             if (!slow) {
                 done = true;
+                // admitted samples lie strictly between the LOW and HIGH bands: exponent range from the thresholds
+                exp_track(A1, emin, emax);
+                exp_track(B2, emin, emax);
                 // ---- ring update and transitions, row by row
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const int64_t p0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4;
                     int s0 = slot0 + r * SUB;
                     if (s0 >= L) s0 -= L;
-                    float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                    float nv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                    int vals[4];
-                    bool any_act = false, all_act = true;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int code = (clsbits >> (2 * (r * 4 + j))) & 3;
-                        vals[j] = code == 3 ? 3 : code - 1;
-                        if (code == 1) nv[j] = x[r * 4 + j];
-                        any_act = any_act || code != 3;
-                        all_act = all_act && code != 3;
-                    }
-                    if (all_act) {
-                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(nv[0], nv[1], nv[2], nv[3]);
-                    } else if (any_act) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (vals[j] == 0) ring[s0 + j] = nv[j];
+                    const unsigned codes = (clsbits >> (8 * r)) & 0xffu;
+                    if (codes == 0x55u) {
+                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(x[r * 4], x[r * 4 + 1], x[r * 4 + 2], x[r * 4 + 3]);
+                    } else {
+                        float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                        if (((codes >> 0) & 3u) == 1u) pv4.x = x[r * 4 + 0];
+                        if (((codes >> 2) & 3u) == 1u) pv4.y = x[r * 4 + 1];
+                        if (((codes >> 4) & 3u) == 1u) pv4.z = x[r * 4 + 2];
+                        if (((codes >> 6) & 3u) == 1u) pv4.w = x[r * 4 + 3];
+                        *reinterpret_cast<float4 *>(ring + s0) = pv4;
                     }
                     const int q = r * NW + warp;
                     const int rcnt = __shfl_sync(FULL, cnt, q);
                     if (rcnt > 0) {  // warp-uniform
                         const int rbase = __shfl_sync(FULL, basecnt, q);
                         const int rprev = __shfl_sync(FULL, prevlast, q);
-                        int mylast = 3;
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (vals[j] != 3) mylast = vals[j];
-                        int prevv;
-                        {
-                            const unsigned hasm = __ballot_sync(FULL, mylast != 3);
-                            const unsigned lower = hasm & ((1u << lane) - 1u);
-                            const int got = __shfl_sync(FULL, mylast, lower ? 31 - __clz(lower) : 0);
-                            prevv = lower ? got : rprev;
-                        }
+                        const int v3 = (int)((codes >> 6) & 3u) - 1;
+                        int prevv = __shfl_up_sync(FULL, v3, 1);
+                        if (lane == 0) prevv = rprev;
                         unsigned trm = 0u;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            if (vals[j] != 3) {
-                                if (vals[j] != prevv && p0 + j >= w.begin) trm |= 1u << j;
-                                prevv = vals[j];
-                            }
+                            const int v = (int)((codes >> (2 * j)) & 3u) - 1;
+                            if (v != prevv) trm |= 1u << j;
+                            prevv = v;
                         }
                         const int mine = __popc(trm);
                         int pre = mine;
@@ -799,10 +901,11 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                             if (lane >= o) pre += n;
                         }
                         uint32_t idx = c.seg_count + (uint32_t)rbase + (uint32_t)(pre - mine);
+                        const uint32_t rel = (uint32_t)(P0 + (int64_t)r * SUB + (int64_t)tid * 4 - w.slab_pos0);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             if (trm & (1u << j)) {
-                                if (idx < w.trans_cap) w.trans[idx] = pack_trans((uint32_t)(p0 + j - w.slab_pos0), vals[j]);
+                                if (idx < w.trans_cap) w.trans[idx] = pack_trans(rel + j, (int)((codes >> (2 * j)) & 3u) - 1);
                                 idx++;
                             }
                         }
@@ -820,38 +923,38 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                     c.lastL = P0 + newL;
                     if (newS >= 0) c.lrun_start = P0 + newS;
                 }
-                absd_prev = absD;
+                n_fast++;
                 if (end_barrier) __syncthreads();
             }
         }
+        const long long t_b = clock64();
+        cyc_fast += t_b - t_a;
         if (!done) {
             // ---------------------------------------------------------------- exact path, row by row
+            if (tid == 0) c_s = c;
+            __syncthreads();
 #pragma unroll 1
             for (int r = 0; r < R; r++) {
                 const int64_t Pr = P0 + (int64_t)r * SUB;
                 if (Pr >= w.end || Pr + SUB <= w.warm_begin) continue;  // block-uniform
                 int s0 = slot0 + r * SUB;
                 if (s0 >= L) s0 -= L;
-                exact_tile<NT, K, R>(w, p, ring, sh, Pr, s0, c, emin, emax);
+                exact_tile<NT, K, R>(&w_s, &p_s, ring, &sh, Pr, s0, &c_s);
             }
-            absd_prev = (float)(c.ss0 * 0x1p-12);
+            c = c_s;
+            n_slow++;
+            cyc_slow += clock64() - t_b;
         }
         slot0 += T % L;
         if (slot0 >= L) slot0 -= L;
     }
 
     // ---- exit: exactness audit and final state
-    if (xmax > 0.0f) {
-        exp_track(xmin, emin, emax);
-        exp_track(xmax, emin, emax);
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         emin = min(emin, __shfl_xor_sync(FULL, emin, o));
         emax = max(emax, __shfl_xor_sync(FULL, emax, o));
     }
-    __syncthreads();
-    if (tid == 0) { sh.emin = 1 << 30; sh.emax = 0; }
     __syncthreads();
     if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
     __syncthreads();
@@ -872,6 +975,14 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
     }
     if (tid == 0 && w.trans_count) *w.trans_count = c.seg_count;
     if (tid == 0 && w.status) *w.status = status;
+    if (tid == 0) {
+        atomicAdd(&g_tile_stats[0], (unsigned long long)n_fast);
+        atomicAdd(&g_tile_stats[1], (unsigned long long)n_slow);
+        atomicAdd(&g_tile_stats[2], (unsigned long long)c.round_no);
+        atomicAdd(&g_tile_stats[3], (unsigned long long)n_refined);
+        atomicAdd(&g_tile_stats[4], (unsigned long long)cyc_fast);
+        atomicAdd(&g_tile_stats[5], (unsigned long long)cyc_slow);
+    }
 }
 
 // ---------------------------------------------------------------- strictly sequential path
@@ -1022,6 +1133,15 @@ int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_par
         }
     }
     return launch_one<256, 1, 1>(d_works, n_works, d_params, smem, stream);
+}
+
+int slicer_tile_stats(unsigned long long *out4, bool reset) {
+    NFC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z)));
+    }
+    return 0;
 }
 
 // CTAs of the slicer kernel that fit on the device at once (for sizing the number of segments)

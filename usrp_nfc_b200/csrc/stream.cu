@@ -47,6 +47,7 @@ int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables 
                           uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t);
 int slicer_tile(int L, bool vec_ok);
 int slicer_resident_ctas(int L, bool vec_ok);
+int slicer_tile_stats(unsigned long long *out4, bool reset);
 int synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens, int64_t n_runs,
                  float carrier, float pause, float tag_high, float noise, float fade, double fade_period, uint64_t seed,
                  int as_envelope, cudaStream_t);
@@ -196,6 +197,8 @@ int Stream::init(const nfc_params *p) {
     sp.L = p->av_window;
     sp.Ld = (double)p->av_window;
     sp.mx = p->max_len;
+    sp.loL = sp.lo / sp.Ld;
+    sp.hiL = sp.hi / sp.Ld;
     sp.cls_ss0_x0 = classify_ratio_host(1.0, sp.lo, sp.hi);            // transition_sink.py:60-61
     sp.cls_ss0_xn = classify_ratio_host(sp.hi + 0.1, sp.lo, sp.hi);    // transition_sink.py:62-63
     sp.span_limit = std::max(0, 28 - ceil_log2(sp.L) - 1);
@@ -987,6 +990,16 @@ int nfc_stream_set_tuning(nfc_stream *h, int64_t seg_len, int64_t halo, int64_t 
 
 int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
     if (!h || !st) return -1;
+    cudaSetDevice(h->s.prm.device);
+    unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (nfc::slicer_tile_stats(ts, false) == 0) {
+        h->s.stats.fast_cycles = (int64_t)ts[4];
+        h->s.stats.exact_cycles = (int64_t)ts[5];  // device-wide counters (all streams of this process)
+        h->s.stats.fast_tiles = (int64_t)ts[0];
+        h->s.stats.exact_tiles = (int64_t)ts[1];
+        h->s.stats.exact_rounds = (int64_t)ts[2];
+        h->s.stats.refined_tiles = (int64_t)ts[3];
+    }
     *st = h->s.stats;
     return 0;
 }
@@ -994,6 +1007,9 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
 int nfc_stream_reset_stats(nfc_stream *h) {
     if (!h) return -1;
     memset(&h->s.stats, 0, sizeof(h->s.stats));
+    unsigned long long ts[8];
+    cudaSetDevice(h->s.prm.device);
+    nfc::slicer_tile_stats(ts, true);
     return 0;
 }
 
