@@ -139,6 +139,7 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
     int64_t fast_tiles, exact_tiles, exact_rounds; /* slicer tiles by path (device-wide counters) */
     int64_t refined_tiles;                         /* fast tiles that needed the per-record band refinement */
+    int64_t st2_tiles, refine_failed_tiles;        /* why tiles went to the exact path: hysteresis risk / band refinement failed */
     int64_t fast_cycles, exact_cycles;             /* SM cycles one thread per segment spent on each path, summed */
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);

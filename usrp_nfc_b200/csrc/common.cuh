@@ -69,6 +69,8 @@ struct SlicerHdr {
     int32_t last_val;    // val of the last processed sample (== _last_bit)
     int32_t emin, emax;  // biased exponent range of the ring contents / admitted samples
     int32_t status;      // SEG_* flags accumulated while producing this state
+    uint32_t count;      // transitions the segment had written when this snapshot was taken
+    uint32_t pad;
 };
 static const int64_t NO_POS = INT64_MIN / 4;
 
@@ -97,6 +99,9 @@ struct SegWork {
                                 // ring <- samples [warm_begin - L, warm_begin) unconditionally,
                                 // like the reference's warm-up (transition_sink.py:109-125)
     SlicerHdr *seam_in;   // snapshot at `begin` (cold starts only; may be nullptr)
+    // checkpoints of a speculative segment: a redo from the true state stops at the first one it reproduces
+    int64_t ckpt_pos[3];  // tile-aligned stream positions (unused entries: INT64_MAX)
+    SlicerHdr *ckpt_state[3];
     SlicerHdr *state_out; // state at `end`
     TransRec *trans;      // output, in order
     uint32_t trans_cap;

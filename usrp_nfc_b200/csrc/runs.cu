@@ -43,6 +43,14 @@ __global__ void gather_trans_kernel(const SegWork *__restrict__ works, const uin
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dense[off + i] = w.trans[i];
 }
 
+// pieces of segment transition lists -> dense array (offsets computed on the host: there are few pieces)
+__global__ void gather_pieces_kernel(const TransRec *const *__restrict__ src, const uint32_t *__restrict__ n,
+                                     const uint32_t *__restrict__ offsets, TransRec *__restrict__ dense) {
+    const TransRec *s = src[blockIdx.x];
+    const uint32_t cnt = n[blockIdx.x], off = offsets[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) dense[off + i] = s[i];
+}
+
 // ---- per-run event derivation ---------------------------------------------------------------
 struct RunView {
     const TransRec *tr;  // dense transitions of the window, ascending
@@ -161,6 +169,14 @@ int launch_gather_transitions(const SegWork *d_works, const uint32_t *d_counts, 
     seg_offsets_kernel<<<1, 1024, 0, stream>>>(d_counts, d_offsets, n_segs);
     NFC_CUDA_CHECK(cudaGetLastError());
     gather_trans_kernel<<<n_segs, 256, 0, stream>>>(d_works, d_counts, d_offsets, d_dense);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gather_pieces(const TransRec *const *d_src, const uint32_t *d_n, const uint32_t *d_off, int n_pieces,
+                         TransRec *d_dense, cudaStream_t stream) {
+    if (n_pieces <= 0) return 0;
+    gather_pieces_kernel<<<n_pieces, 256, 0, stream>>>(d_src, d_n, d_off, d_dense);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -49,6 +49,8 @@ __device__ __forceinline__ float load_one(const void *in, int64_t idx, const Sli
     }
 }
 
+__device__ __forceinline__ int item_size(int kind) { return kind == IN_IQ_F32 ? 8 : (kind == IN_PCM_S16 ? 2 : 4); }
+
 // streaming 128-bit load: the sample stream is read exactly once
 __device__ __forceinline__ float4 ldg_stream4(const float4 *ptr) {
     float4 r;
@@ -161,7 +163,6 @@ struct BlockShared {
     RowRec rows[2][R * NW];
     WarpRec warps[2][NW];
     double rsum[R * NW];  // per-record sums for the band refinement
-    float rabs[R * NW];
 };
 
 // everything a segment carries from tile to tile (identical in all threads of the CTA)
@@ -582,15 +583,15 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
 
     const bool fast_ok = (K == 4) && ((L & 3) == 0) && p.lo > 0.0 && p.hi > p.lo;
     const bool end_barrier = 2 * T > L;  // a tile would read ring slots the previous tile wrote
-    float absd_prev = 0.0f;              // admitted |x - prev| of the previous tile: sizes the next guard band
-    unsigned tile_no = 0, n_fast = 0, n_slow = 0, n_refined = 0;
-    long long cyc_fast = 0, cyc_slow = 0;
+    float absd_prev = 0.0f, absd_prev2 = 0.0f;  // admitted |x - prev| of the last two tiles: size the next guard band
+    double tot_prev = 0.0;               // window-sum change over the previous tile: predicts the drift inside this one
+    unsigned tile_no = 0, n_fast = 0, n_slow = 0, n_refined = 0, n_st2 = 0, n_refbad = 0;
 
     const int64_t tile_first = w.warm_begin / T;
     const int64_t tile_last = (w.end > w.warm_begin) ? (w.end - 1) / T : tile_first - 1;
     int slot0 = (int)((tile_first * T + (int64_t)tid * K) % L);
 
-    for (int64_t tile = tile_first; tile <= tile_last; tile++, tile_no++) {
+    for (int64_t tile = tile_first; tile <= tile_last; tile++) {
         const int64_t P0 = tile * T;
 
         if (w.seam_in && P0 == w.begin && w.begin > w.warm_begin) {
@@ -600,204 +601,263 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
             if (tid == 0) {
                 SlicerHdr h;
                 h.ss = c.ss0; h.pos = w.begin; h.lastL = c.lastL; h.lrun_start = c.lrun_start;
-                h.last_val = c.last_val; h.emin = 0; h.emax = 0; h.status = 0;
+                h.last_val = c.last_val; h.emin = 0; h.emax = 0; h.status = 0; h.count = 0; h.pad = 0;
                 *w.seam_in = h;
             }
         }
 
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (w.ckpt_state[j] && P0 == w.ckpt_pos[j]) {  // block-uniform
+                float *dst = state_ring(w.ckpt_state[j]);
+                for (int i = tid; i < L; i += NT) dst[i] = ring[i];
+                if (tid == 0) {
+                    SlicerHdr h;
+                    h.ss = c.ss0; h.pos = P0; h.lastL = c.lastL; h.lrun_start = c.lrun_start;
+                    h.last_val = c.last_val; h.emin = 0; h.emax = 0; h.status = 0; h.count = c.seg_count; h.pad = 0;
+                    *w.ckpt_state[j] = h;
+                }
+            }
+        }
+
         bool done = false;
-        const long long t_a = clock64();
         // interior tile: every sample is inside the segment and the input buffer, and either all or none of
         // its transitions are written (anything else goes to the exact path, which masks per sample)
         const bool interior = P0 >= w.warm_begin && P0 + T <= w.end && P0 >= w.in_begin && P0 + T <= w.in_end &&
                               (P0 >= w.begin || P0 + T <= w.begin);
         if (fast_ok && interior && c.ss0 > 0.0) {
             // ---------------------------------------------------------------- fast path
-            const int buf = tile_no & 1;
             const bool emit = P0 >= w.begin;
             // guard band: ss stays within ss0 +- Dg inside the tile (verified after the barrier)
-            const float Dg = fmaxf(1.25f * absd_prev, (float)(c.ss0 * 0x1p-14));
-            const double g = (double)Dg / c.ss0 + 0x1p-20;
+            const float Dg = fmaxf(2.0f * fmaxf(absd_prev, absd_prev2), (float)(c.ss0 * 0x1p-14));
             const double tl = c.ss0 * p.loL, th = c.ss0 * p.hiL;
-            float A1 = __double2float_rd(tl * (1.0 - g)), A2 = __double2float_ru(tl * (1.0 + g));
-            float B1 = __double2float_rd(th * (1.0 - g)), B2 = __double2float_ru(th * (1.0 + g));
-            const float TL = __double2float_rn(tl), TH = __double2float_rn(th);  // the guess for samples inside a band
+            float A1, A2, B1, B2;
+            {
+                const double g = (double)Dg / c.ss0 + 0x1p-20;
+                A1 = __double2float_rd(tl * (1.0 - g)); A2 = __double2float_ru(tl * (1.0 + g));
+                B1 = __double2float_rd(th * (1.0 - g)); B2 = __double2float_ru(th * (1.0 + g));
+            }
+            // the guess for samples inside a band uses the ss predicted for each row from the previous tile's drift
+            const double drift_row = tot_prev * (1.0 / R);
 
             float x[R * 4];
             unsigned clsbits = 0u;  // 2 bits per sample: 0 LOW, 1 MID, 2 HIGH
-            unsigned uncbits = 0u;  // 1 bit per sample: inside a guard band
-            double dsum = 0.0;
-            float absd = 0.0f;
-            const char *inb = reinterpret_cast<const char *>(w.in);
+            unsigned uncbits = 0u;  // 1 bit per sample: inside a guard band (class not proven yet); filled on demand
+            bool any_unc = false;   // some sample of this thread is inside a band
             const int kind = p.input_kind;
+            const bool f32in = kind == IN_ENVELOPE_F32 || kind == IN_REAL_F32;
+            // ---- phase 0: loads (all rows in flight at once; next tile requested into L2), guessed classes
+            {
+                const char *rowp = reinterpret_cast<const char *>(w.in) + (P0 - w.in_pos0 + (int64_t)tid * 4) * (int64_t)item_size(kind);
+                if (f32in) {
+                    float4 xin[R];
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int64_t i0 = P0 + (int64_t)r * SUB + (int64_t)tid * 4 - w.in_pos0;
-                float xr[4];
-                if (kind == IN_ENVELOPE_F32 || kind == IN_REAL_F32) {
-                    const float4 v = ldg_stream4(reinterpret_cast<const float4 *>(inb + i0 * 4));
-                    xr[0] = v.x; xr[1] = v.y; xr[2] = v.z; xr[3] = v.w;
+                    for (int r = 0; r < R; r++) xin[r] = ldg_stream4(reinterpret_cast<const float4 *>(rowp + (size_t)r * SUB * 4));
+                    if (tid < T / 32 && P0 + 2 * T <= w.in_end)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (size_t)T * 4 + (size_t)tid * 112));
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        x[r * 4 + 0] = xin[r].x; x[r * 4 + 1] = xin[r].y; x[r * 4 + 2] = xin[r].z; x[r * 4 + 3] = xin[r].w;
+                    }
                     if (kind == IN_REAL_F32) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) xr[j] = env_real(xr[j]);
+                        for (int k = 0; k < R * 4; k++) x[k] = env_real(x[k]);
                     }
                 } else if (kind == IN_IQ_F32) {
-                    const float4 *q = reinterpret_cast<const float4 *>(inb + i0 * 8);
-                    const float4 a = ldg_stream4(q), b = ldg_stream4(q + 1);
-                    xr[0] = env_iq(a.x, a.y); xr[1] = env_iq(a.z, a.w); xr[2] = env_iq(b.x, b.y); xr[3] = env_iq(b.z, b.w);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float4 *q = reinterpret_cast<const float4 *>(rowp + (size_t)r * SUB * 8);
+                        const float4 a = ldg_stream4(q), b = ldg_stream4(q + 1);
+                        x[r * 4 + 0] = env_iq(a.x, a.y); x[r * 4 + 1] = env_iq(a.z, a.w);
+                        x[r * 4 + 2] = env_iq(b.x, b.y); x[r * 4 + 3] = env_iq(b.z, b.w);
+                    }
                 } else {
-                    const short4 sv = __ldg(reinterpret_cast<const short4 *>(inb + i0 * 2));
-                    xr[0] = env_real(__fdiv_rn((float)sv.x, p.pcm_scale));
-                    xr[1] = env_real(__fdiv_rn((float)sv.y, p.pcm_scale));
-                    xr[2] = env_real(__fdiv_rn((float)sv.z, p.pcm_scale));
-                    xr[3] = env_real(__fdiv_rn((float)sv.w, p.pcm_scale));
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const short4 sv = __ldg(reinterpret_cast<const short4 *>(rowp + (size_t)r * SUB * 2));
+                        x[r * 4 + 0] = env_real(__fdiv_rn((float)sv.x, p.pcm_scale));
+                        x[r * 4 + 1] = env_real(__fdiv_rn((float)sv.y, p.pcm_scale));
+                        x[r * 4 + 2] = env_real(__fdiv_rn((float)sv.z, p.pcm_scale));
+                        x[r * 4 + 3] = env_real(__fdiv_rn((float)sv.w, p.pcm_scale));
+                    }
                 }
-                int s0 = slot0 + r * SUB;
-                if (s0 >= L) s0 -= L;
-                const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                unsigned codes = 0u, uncs = 0u;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const double ssp = c.ss0 + ((double)r + 0.5) * drift_row;
+                // a robust sample must get its proven class: clamp the guess thresholds into the bands
+                const float TL = fminf(fmaxf(__double2float_rn(ssp * p.loL), A1), A2);
+                const float TH = fminf(fmaxf(__double2float_rn(ssp * p.hiL), B1), B2);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float xv = xr[j];
-                    x[r * 4 + j] = xv;
-                    const bool lowg = xv < TL, highg = xv > TH;  // guess (exact for samples outside the bands)
-                    const bool robust = (xv < A1) || ((xv > A2) && ((xv > B2) || (xv < B1)));
-                    const unsigned code = lowg ? 0u : (highg ? 2u : 1u);
-                    codes |= code << (2 * j);
-                    uncs |= (robust ? 0u : 1u) << j;
-                    if (code == 1u) {  // MID: admitted
-                        dsum += (double)xv - (double)prev[j];
-                        absd += fabsf(xv - prev[j]);
-                    }
+                    const float xv = x[r * 4 + j];
+                    const unsigned code = 1u + (xv > TH ? 1u : 0u) - (xv < TL ? 1u : 0u);
+                    clsbits |= code << (2 * (r * 4 + j));
+                    any_unc = any_unc || ((xv >= A1) && (xv <= A2)) || ((xv >= B1) && (xv <= B2));
                 }
-                clsbits |= codes << (8 * r);
-                uncbits |= uncs << (4 * r);
-                // ---- row record of this warp (128 samples), computed from ballots: all lanes get the same values
-                RowRec rec;
-                rec.first = (r * SUB + warp * 128) << 2 | 1; rec.last = (r * SUB + warp * 128 + 127) << 2 | 1;
-                rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1; rec.pad0 = rec.pad1 = 0;
-                if (__any_sync(FULL, codes != 0x55u)) {  // something other than MID in these 128 samples
-                    unsigned Lm[4], Hm[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        Lm[j] = __ballot_sync(FULL, ((codes >> (2 * j)) & 3u) == 0u);
-                        Hm[j] = __ballot_sync(FULL, ((codes >> (2 * j)) & 3u) == 2u);
-                    }
-                    const int base = r * SUB + warp * 128;  // sample (lane, j) sits at base + 4*lane + j
-                    // transitions between consecutive samples: (lane,j)->(lane,j+1), and (lane,3)->(lane+1,0)
-                    int inner = 0;
-#pragma unroll
-                    for (int j = 0; j < 3; j++) inner += __popc((Lm[j] ^ Lm[j + 1]) | (Hm[j] ^ Hm[j + 1]));
-                    inner += __popc(((Lm[3] ^ (Lm[0] >> 1)) | (Hm[3] ^ (Hm[0] >> 1))) & 0x7fffffffu);
-                    int lastL = -1, firstH = INT_MAX, lastS = -1;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (Lm[j]) lastL = max(lastL, base + 4 * (31 - __clz(Lm[j])) + j);
-                        if (Hm[j]) firstH = min(firstH, base + 4 * (__ffs(Hm[j]) - 1) + j);
-                        // LOW-run starts strictly inside: LOW here, previous sample not LOW
-                        const unsigned st = j == 0 ? (Lm[0] & ~(Lm[3] << 1) & ~1u) : (Lm[j] & ~Lm[j - 1]);
-                        if (st) lastS = max(lastS, base + 4 * (31 - __clz(st)) + j);
-                    }
-                    const int fv = (Lm[0] & 1u) ? -1 : ((Hm[0] & 1u) ? 1 : 0);
-                    const int lv = (Lm[3] >> 31) ? -1 : ((Hm[3] >> 31) ? 1 : 0);
-                    rec.first = (base << 2) | (fv + 1);
-                    rec.last = ((base + 127) << 2) | (lv + 1);
-                    rec.inner = emit ? inner : 0;
-                    rec.lastL = lastL; rec.firstH = firstH; rec.lastS = lastS;
-                }
-                if (lane == 0) sh.rows[buf][r * NW + warp] = rec;
             }
-            // per-warp sums
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                dsum += __shfl_xor_sync(FULL, dsum, o);
-                absd += __shfl_xor_sync(FULL, absd, o);
-            }
-            const unsigned uncertain = __any_sync(FULL, uncbits != 0u) ? 1u : 0u;
-            if (lane == 0) {
-                WarpRec wr;
-                wr.dsum = dsum; wr.absd = absd; wr.flags = uncertain;
-                sh.warps[buf][warp] = wr;
-            }
-            __syncthreads();  // the tile's only barrier on this path
-
-            // ---- every warp scans the records redundantly: lane l <-> record l (row-major = stream order)
-            double tot = 0.0;
-            float absD = 0.0f;
-            unsigned unc = 0u;
-            if (lane < NW) {
-                const WarpRec wr = sh.warps[buf][lane];
-                tot = wr.dsum; absD = wr.absd; unc = wr.flags;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                tot += __shfl_xor_sync(FULL, tot, o);
-                absD += __shfl_xor_sync(FULL, absD, o);
-            }
-            unc = __any_sync(FULL, unc != 0u) ? 1u : 0u;
-            RowRec rec;
-            rec.first = INT_MAX; rec.last = -1; rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1;
-            if (lane < R * NW) rec = sh.rows[buf][lane];
-            const bool has = rec.last >= 0;
-            // last defined val before each record (exclusive), seeded with the carry
-            int ld = has ? (rec.last & 3) - 1 : 3;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(FULL, ld, o);
-                if (lane >= o && ld == 3) ld = n;
-            }
-            int prevlast = __shfl_up_sync(FULL, ld, 1);
-            if (lane == 0 || prevlast == 3) prevlast = c.last_val;
-            const int tile_last_val = __shfl_sync(FULL, ld, 31);
-            // running maximum of the last LOW position before each record (exclusive), seeded with the carry
-            const int64_t cl = c.lastL == NO_POS ? (int64_t)INT_MIN / 2 : c.lastL - P0;
-            const int carryL = (int)max(cl, (int64_t)INT_MIN / 2);
-            int mxL = rec.lastL >= 0 ? rec.lastL : INT_MIN / 2;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(FULL, mxL, o);
-                if (lane >= o) mxL = max(mxL, n);
-            }
-            int exL = __shfl_up_sync(FULL, mxL, 1);
-            if (lane == 0) exL = INT_MIN / 2;
-            exL = max(exL, carryL);
-            const bool hasH = rec.firstH != INT_MAX;
-            // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
-            const bool st2_risk = hasH && ((rec.lastL >= 0) || ((int64_t)rec.firstH - (int64_t)exL <= (int64_t)mx + 1));
-            const int first_val = has ? (rec.first & 3) - 1 : 3;
-            const int first_pos = has ? (rec.first >> 2) : 0;
-            const bool btrans = has && first_val != prevlast;
-            const int cnt = rec.inner + ((btrans && emit) ? 1 : 0);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(FULL, inc, o);
-                if (lane >= o) inc += n;
-            }
-            const int tot_tr = __shfl_sync(FULL, inc, 31);
-            const int basecnt = inc - cnt;
-            bool slow = __any_sync(FULL, st2_risk);
-            absd_prev = absD;  // sizes the next tile's band
-            if (!slow && !(absD * 1.001f <= Dg)) {
-                // the window sum moved further than the band assumed: widen the band to what was measured (the
-                // guessed classes, hence the sums, do not depend on the band) and re-mark the samples inside it
-                const double gw = (double)(absD * 1.001f) / c.ss0 + 0x1p-20;
-                A1 = __double2float_rd(tl * (1.0 - gw)); A2 = __double2float_ru(tl * (1.0 + gw));
-                B1 = __double2float_rd(th * (1.0 - gw)); B2 = __double2float_ru(th * (1.0 + gw));
-                uncbits = 0u;
+            if (__any_sync(FULL, any_unc)) {  // rare: remember which samples
 #pragma unroll
                 for (int k = 0; k < R * 4; k++) {
                     const float xv = x[k];
-                    const bool robust = (xv < A1) || ((xv > A2) && ((xv > B2) || (xv < B1)));
-                    uncbits |= (robust ? 0u : 1u) << k;
+                    const bool inband = ((xv >= A1) && (xv <= A2)) || ((xv >= B1) && (xv <= B2));
+                    uncbits |= (inband ? 1u : 0u) << k;
                 }
-                unc = 1u;  // block-uniform: take the refinement path, which votes
             }
-            if (!slow && unc) {
-                // ---- some samples sit inside the tile-wide band: re-test them against the band of their own
-                // 128-sample record, whose start ss is exact given the guessed classes (self-consistency)
-                double rsum[R];
+
+            bool slow = false;
+            double tot = 0.0;
+            float absD = 0.0f;
+            int tot_tr = 0, cnt = 0, basecnt = 0, prevlast = 0, tile_last_val = 3, first_val = 3, first_pos = 0;
+            bool btrans = false;
+            RowRec rec;
+            for (int iter = 0;; iter++, tile_no++) {
+                const int buf = tile_no & 1;
+                // ---- phase 1: sums of the admitted deltas and the row records, from the current classes
+                double dsum = 0.0;
+                float absd = 0.0f;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    int s0 = slot0 + r * SUB;
+                    if (s0 >= L) s0 -= L;
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    const unsigned codes = (clsbits >> (8 * r)) & 0xffu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (((codes >> (2 * j)) & 3u) == 1u) {  // MID: admitted
+                            dsum += (double)x[r * 4 + j] - (double)prev[j];
+                            absd += fabsf(x[r * 4 + j] - prev[j]);
+                        }
+                    }
+                    // row record of this warp (128 samples): per-thread edges, warp reductions
+                    RowRec rr;
+                    const int base = r * SUB + warp * 128;  // sample (lane, j) sits at base + 4*lane + j
+                    rr.first = (base << 2) | 1; rr.last = ((base + 127) << 2) | 1;
+                    rr.inner = 0; rr.lastL = -1; rr.firstH = INT_MAX; rr.lastS = -1; rr.pad0 = rr.pad1 = 0;
+                    if (__any_sync(FULL, codes != 0x55u)) {  // something other than MID in these 128 samples
+                        const unsigned c3 = (codes >> 6) & 3u;
+                        unsigned pc = __shfl_up_sync(FULL, c3, 1);      // previous sample's class for j = 0
+                        const unsigned lastc = __shfl_sync(FULL, c3, 31);
+                        const unsigned firstc = __shfl_sync(FULL, codes & 3u, 0);
+                        if (lane == 0) pc = codes & 3u;                  // the record's first sample is not "inside"
+                        // class of the previous sample for each j, packed like `codes`
+                        const unsigned prevs = ((codes << 2) | pc) & 0xffu;
+                        const unsigned diff = codes ^ prevs;             // non-zero 2-bit field = transition
+                        const unsigned tr = (diff | (diff >> 1)) & 0x55u;
+                        const unsigned isL = ~(codes | (codes >> 1)) & 0x55u;   // field == 0
+                        const unsigned isH = (codes >> 1) & 0x55u;              // field == 2
+                        const unsigned pL = ~(prevs | (prevs >> 1)) & 0x55u;
+                        if (emit) rr.inner = __reduce_add_sync(FULL, __popc(tr));
+                        const int pos0 = base + 4 * lane;
+                        // highest j with LOW / lowest j with HIGH / highest j where a LOW run starts (bit 2j -> j)
+                        const int myL = isL ? pos0 + ((31 - __clz(isL)) >> 1) : -1;
+                        const int myH = isH ? pos0 + ((__ffs(isH) - 1) >> 1) : INT_MAX;
+                        const unsigned st = isL & ~pL & (lane == 0 ? ~1u : ~0u);
+                        const int myS = st ? pos0 + ((31 - __clz(st)) >> 1) : -1;
+                        rr.lastL = __reduce_max_sync(FULL, myL);
+                        rr.firstH = __reduce_min_sync(FULL, myH);
+                        rr.lastS = __reduce_max_sync(FULL, myS);
+                        rr.first = (base << 2) | (int)firstc;
+                        rr.last = ((base + 127) << 2) | (int)lastc;
+                    }
+                    if (lane == 0) sh.rows[buf][r * NW + warp] = rr;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dsum += __shfl_xor_sync(FULL, dsum, o);
+                    absd += __shfl_xor_sync(FULL, absd, o);
+                }
+                const unsigned uncertain = __any_sync(FULL, uncbits != 0u) ? 1u : 0u;
+                if (lane == 0) {
+                    WarpRec wr;
+                    wr.dsum = dsum; wr.absd = absd; wr.flags = uncertain;
+                    sh.warps[buf][warp] = wr;
+                }
+                __syncthreads();  // the only barrier of a tile whose samples are all outside the bands
+
+                // ---- phase 2: every warp scans the records redundantly: lane l <-> record l (row-major = stream order)
+                tot = 0.0;
+                absD = 0.0f;
+                unsigned unc = 0u;
+                if (lane < NW) {
+                    const WarpRec wr = sh.warps[buf][lane];
+                    tot = wr.dsum; absD = wr.absd; unc = wr.flags;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    tot += __shfl_xor_sync(FULL, tot, o);
+                    absD += __shfl_xor_sync(FULL, absD, o);
+                }
+                unc = __any_sync(FULL, unc != 0u) ? 1u : 0u;
+                rec.first = INT_MAX; rec.last = -1; rec.inner = 0; rec.lastL = -1; rec.firstH = INT_MAX; rec.lastS = -1;
+                if (lane < R * NW) rec = sh.rows[buf][lane];
+                const bool has = rec.last >= 0;
+                // last defined val before each record (exclusive), seeded with the carry
+                int ld = has ? (rec.last & 3) - 1 : 3;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(FULL, ld, o);
+                    if (lane >= o && ld == 3) ld = n;
+                }
+                prevlast = __shfl_up_sync(FULL, ld, 1);
+                if (lane == 0 || prevlast == 3) prevlast = c.last_val;
+                tile_last_val = __shfl_sync(FULL, ld, 31);
+                // running maximum of the last LOW position before each record (exclusive), seeded with the carry
+                const int64_t cl = c.lastL == NO_POS ? (int64_t)INT_MIN / 2 : c.lastL - P0;
+                const int carryL = (int)max(cl, (int64_t)INT_MIN / 2);
+                int mxL = rec.lastL >= 0 ? rec.lastL : INT_MIN / 2;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(FULL, mxL, o);
+                    if (lane >= o) mxL = max(mxL, n);
+                }
+                int exL = __shfl_up_sync(FULL, mxL, 1);
+                if (lane == 0) exL = INT_MIN / 2;
+                exL = max(exL, carryL);
+                const bool hasH = rec.firstH != INT_MAX;
+                // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+                const bool st2_risk = hasH && ((rec.lastL >= 0) || ((int64_t)rec.firstH - (int64_t)exL <= (int64_t)mx + 1));
+                first_val = has ? (rec.first & 3) - 1 : 3;
+                first_pos = has ? (rec.first >> 2) : 0;
+                btrans = has && first_val != prevlast;
+                cnt = rec.inner + ((btrans && emit) ? 1 : 0);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += n;
+                }
+                tot_tr = __shfl_sync(FULL, inc, 31);
+                basecnt = inc - cnt;
+                if (__any_sync(FULL, st2_risk)) {
+                    n_st2++;
+                    slow = true;
+                    break;
+                }
+                if (!(absD * 1.001f <= Dg) || iter > 0) {
+                    // the window sum moved further than the band assumed (or classes were just corrected): size the
+                    // band from what was measured and re-mark the samples inside it
+                    const double gw = (double)(fmaxf(absD, Dg) * 1.001f) / c.ss0 + 0x1p-20;
+                    A1 = __double2float_rd(tl * (1.0 - gw)); A2 = __double2float_ru(tl * (1.0 + gw));
+                    B1 = __double2float_rd(th * (1.0 - gw)); B2 = __double2float_ru(th * (1.0 + gw));
+                    if (iter == 0) {
+                        uncbits = 0u;
+#pragma unroll
+                        for (int k = 0; k < R * 4; k++) {
+                            const float xv = x[k];
+                            const bool inband = ((xv >= A1) && (xv <= A2)) || ((xv >= B1) && (xv <= B2));
+                            uncbits |= (inband ? 1u : 0u) << k;
+                        }
+                        unc = 1u;  // block-uniform: take the refinement path, which votes
+                    }
+                }
+                if (!unc) break;  // every class is proven
+
+                // ---- refinement: samples inside the tile-wide band.  First against the band of their own 128-sample
+                // record, whose start ss is exact given the current classes; what even that cannot decide gets its
+                // own exact ss (prefix inside the record) and the exact ratio test.  A sample whose exact class
+                // differs from the current one is corrected and the tile goes round again (self-consistency).
                 float rabs[R];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -819,8 +879,8 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                         ds += __shfl_xor_sync(FULL, ds, o);
                         da += __shfl_xor_sync(FULL, da, o);
                     }
-                    rsum[r] = ds; rabs[r] = da;
-                    if (lane == 0) { sh.rsum[r * NW + warp] = ds; sh.rabs[r * NW + warp] = da; }
+                    rabs[r] = da;
+                    if (lane == 0) sh.rsum[r * NW + warp] = ds;
                 }
                 __syncthreads();
                 double pre = (lane < R * NW) ? sh.rsum[lane] : 0.0;
@@ -831,13 +891,14 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                     if (lane >= o) pre += n;
                 }
                 pre -= own;  // exclusive: sum of the records before record `lane`
-                unsigned bad = 0u;
+                unsigned flipped = 0u, bad = 0u;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int q = r * NW + warp;
                     const double ssq = c.ss0 + __shfl_sync(FULL, pre, q);
+                    unsigned resid = 0u;
                     if (((uncbits >> (4 * r)) & 15u) != 0u) {
-                        if (!(ssq > 0.0)) { bad = 1u; continue; }
+                        if (!(ssq > 0.0)) bad = 1u;
                         const double g2 = (double)(rabs[r] * 1.001f) / ssq + 0x1p-20;
                         const double tl2 = ssq * p.loL, th2 = ssq * p.hiL;
                         const float a1 = __double2float_rd(tl2 * (1.0 - g2)), a2 = __double2float_ru(tl2 * (1.0 + g2));
@@ -847,16 +908,58 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                             if ((uncbits >> (4 * r + j)) & 1u) {
                                 const float xv = x[r * 4 + j];
                                 const unsigned code = (clsbits >> (2 * (r * 4 + j))) & 3u;
-                                // the guessed class must hold for every ss the record can reach
+                                // does the current class hold for every ss the record can reach?
                                 const bool ok = code == 0u ? (xv < a1) : (code == 2u ? (xv > a2 && xv > b2) : (xv > a2 && xv < b1));
-                                if (!ok) bad = 1u;
+                                if (!ok) resid |= 1u << j;
+                            }
+                        }
+                    }
+                    if (__any_sync(FULL, resid != 0u)) {  // warp-uniform
+                        int s0 = slot0 + r * SUB;
+                        if (s0 >= L) s0 -= L;
+                        const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                        const float prev[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                        double pre4[4];
+                        double run = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            pre4[j] = run;
+                            if (((clsbits >> (2 * (r * 4 + j))) & 3u) == 1u) run += (double)x[r * 4 + j] - (double)prev[j];
+                        }
+                        double incl = run;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double n = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += n;
+                        }
+                        const double lane_base = ssq + (incl - run);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (resid & (1u << j)) {
+                                const unsigned cc = (unsigned)(classify(x[r * 4 + j], lane_base + pre4[j], p) + 1);
+                                const int sh2 = 2 * (r * 4 + j);
+                                if (cc != ((clsbits >> sh2) & 3u)) {
+                                    clsbits = (clsbits & ~(3u << sh2)) | (cc << sh2);  // corrected; verified again next round
+                                    flipped = 1u;
+                                }
                             }
                         }
                     }
                 }
-                slow = __syncthreads_or((int)bad) != 0;
-                if (!slow) n_refined++;
+                const int vote = __syncthreads_or((int)(flipped | (bad << 1)));
+                if (vote == 0) {  // every sample inside the bands has been verified against its exact ss
+                    n_refined++;
+                    break;
+                }
+                if (__syncthreads_or((int)bad) || iter >= 3) {
+                    n_refbad++;
+                    slow = true;
+                    break;
+                }
             }
+            tile_no++;
+            absd_prev2 = absd_prev;
+            absd_prev = absD;  // sizes the next tiles' band
             if (!slow) {
                 done = true;
                 // admitted samples lie strictly between the LOW and HIGH bands: exponent range from the thresholds
@@ -914,6 +1017,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                 // ---- carries
                 c.seg_count += (uint32_t)tot_tr;
                 c.ss0 += tot;
+                tot_prev = tot;
                 if (tile_last_val != 3) c.last_val = tile_last_val;
                 const int newL = __reduce_max_sync(FULL, rec.lastL);
                 if (newL >= 0) {
@@ -927,8 +1031,6 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                 if (end_barrier) __syncthreads();
             }
         }
-        const long long t_b = clock64();
-        cyc_fast += t_b - t_a;
         if (!done) {
             // ---------------------------------------------------------------- exact path, row by row
             if (tid == 0) c_s = c;
@@ -941,9 +1043,9 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
                 if (s0 >= L) s0 -= L;
                 exact_tile<NT, K, R>(&w_s, &p_s, ring, &sh, Pr, s0, &c_s);
             }
+            tot_prev = c_s.ss0 - c.ss0;
             c = c_s;
             n_slow++;
-            cyc_slow += clock64() - t_b;
         }
         slot0 += T % L;
         if (slot0 >= L) slot0 -= L;
@@ -969,7 +1071,7 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
         if (tid == 0) {
             SlicerHdr h;
             h.ss = c.ss0; h.pos = w.end; h.lastL = c.lastL; h.lrun_start = c.lrun_start;
-            h.last_val = c.last_val; h.emin = emin; h.emax = emax; h.status = status;
+            h.last_val = c.last_val; h.emin = emin; h.emax = emax; h.status = status; h.count = c.seg_count; h.pad = 0;
             *w.state_out = h;
         }
     }
@@ -980,8 +1082,8 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
         atomicAdd(&g_tile_stats[1], (unsigned long long)n_slow);
         atomicAdd(&g_tile_stats[2], (unsigned long long)c.round_no);
         atomicAdd(&g_tile_stats[3], (unsigned long long)n_refined);
-        atomicAdd(&g_tile_stats[4], (unsigned long long)cyc_fast);
-        atomicAdd(&g_tile_stats[5], (unsigned long long)cyc_slow);
+        atomicAdd(&g_tile_stats[6], (unsigned long long)n_st2);
+        atomicAdd(&g_tile_stats[7], (unsigned long long)n_refbad);
     }
 }
 
@@ -1029,7 +1131,7 @@ __global__ void slicer_serial_kernel(const SegWork *__restrict__ works, const Sl
             for (int i = 0; i < L; i++) dst[i] = ring[i];
             SlicerHdr h;
             h.ss = ss; h.pos = q; h.lastL = lastL; h.lrun_start = lrun_start;
-            h.last_val = last_val; h.emin = 0; h.emax = 0; h.status = 0;
+            h.last_val = last_val; h.emin = 0; h.emax = 0; h.status = 0; h.count = 0; h.pad = 0;
             *w.seam_in = h;
         }
         const float x = load_one(w.in, q - w.in_pos0, p);
@@ -1066,6 +1168,7 @@ __global__ void slicer_serial_kernel(const SegWork *__restrict__ works, const Sl
         h.ss = ss; h.pos = w.end; h.lastL = lastL; h.lrun_start = lrun_start;
         h.last_val = last_val; h.emin = 0; h.emax = 0;
         h.status = count > w.trans_cap ? SEG_OVERFLOW : SEG_OK;
+        h.count = count; h.pad = 0;
         *w.state_out = h;
     }
     if (w.trans_count) *w.trans_count = count;

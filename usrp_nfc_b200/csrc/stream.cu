@@ -26,6 +26,8 @@ int launch_seam_compare(const SlicerHdr *const *d_truth, const SlicerHdr *const 
                         const SlicerParams *d_params, int *d_mismatch, int n, cudaStream_t);
 int launch_gather_transitions(const SegWork *d_works, const uint32_t *d_counts, uint32_t *d_offsets, int n_segs,
                               TransRec *d_dense, cudaStream_t);
+int launch_gather_pieces(const TransRec *const *d_src, const uint32_t *d_n, const uint32_t *d_off, int n_pieces,
+                         TransRec *d_dense, cudaStream_t);
 int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
                      uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total, cudaStream_t);
 int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
@@ -137,7 +139,9 @@ struct Stream {
     // device scratch
     DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
         seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
-        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d;
+        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
+        redo_counts, pieces_d;
+    std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 
@@ -246,7 +250,7 @@ void Stream::destroy() {
     DevBuf *all[] = {&params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
-                     &serial_ring, &start_d, &state};
+                     &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state};
     for (DevBuf *b : all) b->release();
     if (pinned) cudaFreeHost(pinned);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -388,11 +392,14 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
     }
     const int nseg = (int)begins.size();
     const size_t sblk = state_block_bytes(L);
+    const int NCK = 3;
+    // checkpoints of every speculative segment, at 1, 3 and 7 halos after its first emitted sample
+    const int64_t ck_off[NCK] = {H, 3 * H, 7 * H};
     // state blocks: [seam_in k][state_out k] per segment
-    if (states_d.ensure(sblk * 2 * (size_t)nseg)) return -1;
-    if (seg_counts.ensure(sizeof(uint32_t) * (size_t)nseg) || seg_offsets.ensure(sizeof(uint32_t) * ((size_t)nseg + 1)) ||
-        seg_status.ensure(sizeof(int32_t) * (size_t)nseg) || works_d.ensure(sizeof(SegWork) * (size_t)nseg) ||
-        mismatch_d.ensure(sizeof(int) * (size_t)nseg) || seam_ptrs.ensure((sizeof(void *) * 2 + sizeof(int)) * (size_t)nseg))
+    if (states_d.ensure(sblk * 2 * (size_t)nseg) || (nseg > 1 && ckpt_d.ensure(sblk * NCK * (size_t)nseg))) return -1;
+    if (seg_counts.ensure(sizeof(uint32_t) * (size_t)nseg) || seg_status.ensure(sizeof(int32_t) * (size_t)nseg) ||
+        works_d.ensure(sizeof(SegWork) * (size_t)nseg) || mismatch_d.ensure(sizeof(int) * (size_t)nseg) ||
+        seam_ptrs.ensure((sizeof(void *) * 2 + sizeof(int)) * (size_t)nseg))
         return -1;
     if (serial && serial_ring.ensure((size_t)L * 4 + 64)) return -1;
 
@@ -404,6 +411,10 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
     std::vector<SegWork> works((size_t)nseg);
     std::vector<uint32_t> counts((size_t)nseg);
     std::vector<int32_t> status((size_t)nseg);
+    struct Piece {
+        const TransRec *src;
+        uint32_t n;
+    };
 
     for (int attempt = 0; attempt < 4; attempt++) {
         size_t total_cap = 0;
@@ -415,6 +426,7 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
         if (trans_seg.ensure(total_cap * sizeof(TransRec) + 16)) return -1;
         auto seam_in = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k)); };
         auto st_out = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k + 1)); };
+        auto ckpt = [&](int k, int j) { return reinterpret_cast<SlicerHdr *>(ckpt_d.as<char>() + sblk * ((size_t)k * NCK + (size_t)j)); };
         for (int k = 0; k < nseg; k++) {
             SegWork &w = works[(size_t)k];
             w.in = d_in;
@@ -427,6 +439,11 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
             w.slab_pos0 = a;
             w.state_in = k == 0 ? state.as<SlicerHdr>() : nullptr;
             w.seam_in = k == 0 ? nullptr : seam_in(k);
+            for (int j = 0; j < NCK; j++) {
+                const bool use = k > 0 && w.begin + ck_off[j] < w.end;
+                w.ckpt_pos[j] = use ? w.begin + ck_off[j] : INT64_MAX;
+                w.ckpt_state[j] = use ? ckpt(k, j) : nullptr;
+            }
             w.state_out = st_out(k);
             w.trans = trans_seg.as<TransRec>() + toff[(size_t)k];
             w.trans_cap = caps[(size_t)k];
@@ -448,66 +465,33 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
         stats.slicer_launches++;
         stats.segments += nseg;
 
-        // ---- seams: verify and repair
+        // ---- seams: compare what each speculative segment assumed with what its predecessor reached
+        std::vector<int> mism((size_t)nseg, 0);
+        std::vector<const SlicerHdr *> truth((size_t)nseg, nullptr), assumed((size_t)nseg, nullptr);
+        std::vector<int> pidx((size_t)nseg, 0);
+        char *sp_base = seam_ptrs.as<char>();
+        auto compare = [&](int n) -> int {
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base, truth.data(), sizeof(void *) * (size_t)n, cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(), sizeof(void *) * (size_t)n,
+                                           cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + 2 * sizeof(void *) * (size_t)nseg, pidx.data(), sizeof(int) * (size_t)n,
+                                           cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaMemsetAsync(mismatch_d.p, 0, sizeof(int) * (size_t)n, cs));
+            if (launch_seam_compare((const SlicerHdr *const *)sp_base,
+                                    (const SlicerHdr *const *)(sp_base + sizeof(void *) * (size_t)nseg),
+                                    (const int *)(sp_base + 2 * sizeof(void *) * (size_t)nseg), params_d.as<SlicerParams>(),
+                                    mismatch_d.as<int>(), n, cs))
+                return -1;
+            stats.launches++;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(mism.data(), mismatch_d.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, cs));
+            return 0;
+        };
         if (nseg > 1) {
-            std::vector<const SlicerHdr *> truth((size_t)nseg), assumed((size_t)nseg);
-            std::vector<int> pidx((size_t)nseg, 0);
-            for (int k = 0; k < nseg; k++) {
-                truth[(size_t)k] = k == 0 ? nullptr : st_out(k - 1);
-                assumed[(size_t)k] = k == 0 ? nullptr : seam_in(k);
+            for (int k = 1; k < nseg; k++) {
+                truth[(size_t)k] = st_out(k - 1);
+                assumed[(size_t)k] = seam_in(k);
             }
-            char *sp_base = seam_ptrs.as<char>();
-            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base, truth.data(), sizeof(void *) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
-            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(), sizeof(void *) * (size_t)nseg,
-                                           cudaMemcpyHostToDevice, cs));
-            NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + 2 * sizeof(void *) * (size_t)nseg, pidx.data(), sizeof(int) * (size_t)nseg,
-                                           cudaMemcpyHostToDevice, cs));
-            std::vector<int> mism((size_t)nseg, 0);
-            std::vector<char> fixed((size_t)nseg, 0);  // segment was redone from a true state: its seam is settled
-            for (int round = 0; round < nseg + 1; round++) {
-                NFC_CUDA_CHECK(cudaMemsetAsync(mismatch_d.p, 0, sizeof(int) * (size_t)nseg, cs));
-                if (launch_seam_compare((const SlicerHdr *const *)sp_base,
-                                        (const SlicerHdr *const *)(sp_base + sizeof(void *) * (size_t)nseg),
-                                        (const int *)(sp_base + 2 * sizeof(void *) * (size_t)nseg),
-                                        params_d.as<SlicerParams>(), mismatch_d.as<int>(), nseg, cs))
-                    return -1;
-                stats.launches++;
-                NFC_CUDA_CHECK(cudaMemcpyAsync(mism.data(), mismatch_d.p, sizeof(int) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
-                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
-                // redo, from their predecessor's final state, the flagged segments whose predecessor is settled
-                std::vector<SegWork> redo;
-                std::vector<int> redo_k;
-                bool prev_pending = false;
-                for (int k = 1; k < nseg; k++) {
-                    const bool bad = mism[(size_t)k] && !fixed[(size_t)k];
-                    if (bad && !prev_pending) {
-                        SegWork w = works[(size_t)k];
-                        w.warm_begin = w.begin;
-                        w.state_in = st_out(k - 1);
-                        w.seam_in = nullptr;
-                        redo.push_back(w);
-                        redo_k.push_back(k);
-                    }
-                    prev_pending = bad;
-                }
-                if (redo.empty()) break;
-                stats.seam_mismatches += (int64_t)redo.size();
-                if (works_d.ensure(sizeof(SegWork) * ((size_t)nseg + redo.size()))) return -1;
-                // works_d may have been reallocated: re-upload everything
-                NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
-                SegWork *d_redo = works_d.as<SegWork>() + nseg;
-                NFC_CUDA_CHECK(cudaMemcpyAsync(d_redo, redo.data(), sizeof(SegWork) * redo.size(), cudaMemcpyHostToDevice, cs));
-                if (launch_slicer(d_redo, (int)redo.size(), params_d.as<SlicerParams>(), L, vec_ok(), cs)) return -1;
-                stats.launches++;
-                stats.slicer_launches++;
-                for (int k : redo_k) {
-                    fixed[(size_t)k] = 1;
-                    // the redone segment now starts from the truth: make its seam compare equal to itself
-                    assumed[(size_t)k] = truth[(size_t)k];
-                }
-                NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(),
-                                               sizeof(void *) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
-            }
+            if (compare(nseg)) return -1;
         }
         NFC_CUDA_CHECK(cudaMemcpyAsync(counts.data(), seg_counts.p, sizeof(uint32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
@@ -529,16 +513,175 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
             stats.overflow_retries++;
             continue;
         }
-        // ---- dense ordered transitions
-        size_t R = 0;
-        for (int k = 0; k < nseg; k++) R += counts[(size_t)k];
-        if (trans_dense.ensure((R + 16) * sizeof(TransRec))) return -1;
-        if (launch_gather_transitions(works_d.as<SegWork>(), seg_counts.as<uint32_t>(), seg_offsets.as<uint32_t>(), nseg,
-                                      trans_dense.as<TransRec>(), cs))
+
+        // ---- repair: a segment whose assumption was wrong is redone from its predecessor's true final state,
+        // checkpoint by checkpoint, and stops as soon as it reproduces a checkpoint of the speculative run: from
+        // there on the speculative output is the true output.  Only a redo that reaches the segment end changes
+        // the segment's final state, and then the next seam is checked again.
+        std::vector<std::vector<Piece>> pieces((size_t)nseg);
+        for (int k = 0; k < nseg; k++) pieces[(size_t)k].push_back(Piece{works[(size_t)k].trans, counts[(size_t)k]});
+        std::vector<char> bad((size_t)nseg, 0);
+        int nbad = 0;
+        for (int k = 1; k < nseg; k++) {
+            bad[(size_t)k] = mism[(size_t)k] ? 1 : 0;
+            nbad += bad[(size_t)k];
+        }
+        for (int guard = 0; nbad > 0 && guard < nseg + 2; guard++) {
+            // this round: the flagged segments whose predecessor is settled
+            std::vector<int> ks;
+            for (int k = 1; k < nseg; k++)
+                if (bad[(size_t)k] && !bad[(size_t)k - 1]) ks.push_back(k);
+            const int nr = (int)ks.size();
+            stats.seam_mismatches += nr;
+            size_t rcap_total = 0;
+            std::vector<size_t> roff((size_t)nr);
+            for (int i = 0; i < nr; i++) {
+                roff[(size_t)i] = rcap_total;
+                rcap_total += caps[(size_t)ks[(size_t)i]];
+            }
+            if (redo_states.ensure(sblk * (size_t)nr) || redo_trans.ensure(rcap_total * sizeof(TransRec) + 16) ||
+                redo_counts.ensure(sizeof(uint32_t) * 2 * (size_t)nr) || works_d.ensure(sizeof(SegWork) * ((size_t)nseg + (size_t)nr)))
+                return -1;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+            auto tmp_state = [&](int i) { return reinterpret_cast<SlicerHdr *>(redo_states.as<char>() + sblk * (size_t)i); };
+            std::vector<uint32_t> used((size_t)nr, 0);
+            std::vector<int64_t> at((size_t)nr);
+            std::vector<char> active((size_t)nr, 1);
+            for (int i = 0; i < nr; i++) at[(size_t)i] = works[(size_t)ks[(size_t)i]].begin;
+            for (int stage = 0; stage <= NCK; stage++) {
+                std::vector<SegWork> redo;
+                std::vector<int> who;
+                for (int i = 0; i < nr; i++) {
+                    if (!active[(size_t)i]) continue;
+                    const int k = ks[(size_t)i];
+                    const SegWork &ws = works[(size_t)k];
+                    const int64_t target = (stage < NCK && ws.ckpt_state[stage]) ? ws.ckpt_pos[stage] : ws.end;
+                    if (stage < NCK && !ws.ckpt_state[stage]) continue;  // no such checkpoint: a later stage runs on
+                    SegWork w = ws;
+                    w.warm_begin = w.begin = at[(size_t)i];
+                    w.end = target;
+                    w.state_in = at[(size_t)i] == ws.begin ? st_out(k - 1) : tmp_state(i);
+                    w.seam_in = nullptr;
+                    for (int j = 0; j < NCK; j++) { w.ckpt_pos[j] = INT64_MAX; w.ckpt_state[j] = nullptr; }
+                    w.state_out = tmp_state(i);
+                    w.trans = redo_trans.as<TransRec>() + roff[(size_t)i] + used[(size_t)i];
+                    w.trans_cap = caps[(size_t)k] - std::min(caps[(size_t)k], used[(size_t)i]);
+                    w.trans_count = redo_counts.as<uint32_t>() + i;
+                    w.status = reinterpret_cast<int32_t *>(redo_counts.as<uint32_t>() + nr + i);
+                    redo.push_back(w);
+                    who.push_back(i);
+                }
+                if (redo.empty()) continue;
+                SegWork *d_redo = works_d.as<SegWork>() + nseg;
+                NFC_CUDA_CHECK(cudaMemcpyAsync(d_redo, redo.data(), sizeof(SegWork) * redo.size(), cudaMemcpyHostToDevice, cs));
+                if (launch_slicer(d_redo, (int)redo.size(), params_d.as<SlicerParams>(), L, vec_ok(), cs)) return -1;
+                stats.launches++;
+                stats.slicer_launches++;
+                // did each redo reproduce the checkpoint it stopped at?
+                const int nw = (int)who.size();
+                std::vector<SlicerHdr> ck_hdr((size_t)nw);
+                for (int q = 0; q < nw; q++) {
+                    const int i = who[(size_t)q], k = ks[(size_t)i];
+                    truth[(size_t)q] = tmp_state(i);
+                    assumed[(size_t)q] = stage < NCK ? works[(size_t)k].ckpt_state[stage] : tmp_state(i);
+                    pidx[(size_t)q] = 0;
+                    if (stage < NCK)
+                        NFC_CUDA_CHECK(cudaMemcpyAsync(&ck_hdr[(size_t)q], works[(size_t)k].ckpt_state[stage], sizeof(SlicerHdr),
+                                                       cudaMemcpyDeviceToHost, cs));
+                }
+                if (compare(nw)) return -1;
+                std::vector<uint32_t> rc((size_t)nr * 2);
+                NFC_CUDA_CHECK(cudaMemcpyAsync(rc.data(), redo_counts.p, sizeof(uint32_t) * 2 * (size_t)nr, cudaMemcpyDeviceToHost, cs));
+                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+                for (int q = 0; q < nw; q++) {
+                    const int i = who[(size_t)q], k = ks[(size_t)i];
+                    const uint32_t got = rc[(size_t)i];
+                    if (got > redo[(size_t)q].trans_cap) {
+                        over = true;
+                        caps[(size_t)k] = caps[(size_t)k] * 2 + got;
+                    }
+                    used[(size_t)i] += std::min(got, redo[(size_t)q].trans_cap);
+                    at[(size_t)i] = redo[(size_t)q].end;
+                    const TransRec *rbase = redo_trans.as<TransRec>() + roff[(size_t)i];
+                    if (stage < NCK && !mism[(size_t)q]) {
+                        // converged with the speculative run: keep its output from this checkpoint on
+                        const uint32_t cc = ck_hdr[(size_t)q].count;
+                        pieces[(size_t)k].clear();
+                        pieces[(size_t)k].push_back(Piece{rbase, used[(size_t)i]});
+                        pieces[(size_t)k].push_back(Piece{works[(size_t)k].trans + cc, counts[(size_t)k] - std::min(counts[(size_t)k], cc)});
+                        active[(size_t)i] = 0;
+                        bad[(size_t)k] = 0;
+                    } else if (stage == NCK || at[(size_t)i] >= works[(size_t)k].end) {
+                        // redone to its end: new final state, next seam must be looked at again
+                        pieces[(size_t)k].clear();
+                        pieces[(size_t)k].push_back(Piece{rbase, used[(size_t)i]});
+                        NFC_CUDA_CHECK(cudaMemcpyAsync(st_out(k), tmp_state(i), sblk, cudaMemcpyDeviceToDevice, cs));
+                        active[(size_t)i] = 0;
+                        bad[(size_t)k] = 0;
+                        if (k + 1 < nseg) bad[(size_t)k + 1] = 2;  // unknown: re-compare below
+                    }
+                }
+                if (over) break;
+            }
+            if (over) break;
+            // re-compare the seams behind segments that were redone to their end
+            std::vector<int> unk;
+            for (int k = 1; k < nseg; k++)
+                if (bad[(size_t)k] == 2) unk.push_back(k);
+            if (!unk.empty()) {
+                for (size_t q = 0; q < unk.size(); q++) {
+                    truth[q] = st_out(unk[q] - 1);
+                    assumed[q] = seam_in(unk[q]);
+                    pidx[q] = 0;
+                }
+                if (compare((int)unk.size())) return -1;
+                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+                for (size_t q = 0; q < unk.size(); q++) bad[(size_t)unk[q]] = mism[q] ? 1 : 0;
+            }
+            nbad = 0;
+            for (int k = 1; k < nseg; k++) nbad += bad[(size_t)k] ? 1 : 0;
+            if (nbad > 0) {
+                // another round will overwrite redo_trans / redo_states: detach the buffers this round's pieces use
+                kept_bufs.push_back(redo_trans);
+                redo_trans = DevBuf();
+            }
+        }
+        if (over) {
+            stats.overflow_retries++;
+            for (DevBuf &kb : kept_bufs) kb.release();
+            kept_bufs.clear();
+            continue;
+        }
+        if (nbad > 0) {
+            set_error("seam repair did not settle");
             return -1;
-        stats.launches += 2;
+        }
+        // ---- dense ordered transitions
+        std::vector<const TransRec *> psrc;
+        std::vector<uint32_t> pn, poff;
+        size_t R = 0;
+        for (int k = 0; k < nseg; k++)
+            for (const Piece &pc : pieces[(size_t)k]) {
+                psrc.push_back(pc.src);
+                pn.push_back(pc.n);
+                poff.push_back((uint32_t)R);
+                R += pc.n;
+            }
+        const size_t np = psrc.size();
+        if (trans_dense.ensure((R + 16) * sizeof(TransRec)) || pieces_d.ensure(np * (sizeof(void *) + 8) + 64)) return -1;
+        char *pb = pieces_d.as<char>();
+        NFC_CUDA_CHECK(cudaMemcpyAsync(pb, psrc.data(), np * sizeof(void *), cudaMemcpyHostToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(pb + np * sizeof(void *), pn.data(), np * 4, cudaMemcpyHostToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(pb + np * (sizeof(void *) + 4), poff.data(), np * 4, cudaMemcpyHostToDevice, cs));
+        if (launch_gather_pieces((const TransRec *const *)pb, (const uint32_t *)(pb + np * sizeof(void *)),
+                                 (const uint32_t *)(pb + np * (sizeof(void *) + 4)), (int)np, trans_dense.as<TransRec>(), cs))
+            return -1;
+        stats.launches++;
         // the slab's final state becomes the stream's state
         NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));  // pieces may live in buffers released below
+        for (DevBuf &kb : kept_bufs) kb.release();
+        kept_bufs.clear();
         *R_out = (uint32_t)R;
         return 0;
     }
@@ -999,6 +1142,8 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
         h->s.stats.exact_tiles = (int64_t)ts[1];
         h->s.stats.exact_rounds = (int64_t)ts[2];
         h->s.stats.refined_tiles = (int64_t)ts[3];
+        h->s.stats.st2_tiles = (int64_t)ts[6];
+        h->s.stats.refine_failed_tiles = (int64_t)ts[7];
     }
     *st = h->s.stats;
     return 0;
