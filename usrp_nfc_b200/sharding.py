@@ -115,12 +115,21 @@ def _broadcast(vec, src, dist, group, device):
     return t.cpu().numpy()
 
 
+def _drain(engine, flat):
+    if flat and hasattr(engine, "drain_frames_flat"):
+        rec, bits = engine.drain_frames_flat()
+        return rec, bits, True
+    rec, bits = engine.drain_frames()
+    return rec, bits, False
+
+
 def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, group=None, device="cpu",
-                        halo_windows=16, strict_dur=False):
+                        halo_windows=16, strict_dur=False, flat=False):
     """Decode this rank's time shard of a `total`-sample capture.
 
     fetch(a, b) returns samples [a, b) (numpy array, or a CUDA tensor for a device-resident capture).
     Returns dict(frames=[(abs_pos, type, bits)], repaired=bool, seam_ok=[...], bounds=(begin, end)).
+    With flat=True the frames stay in the engine's bulk form: dict(records, bits, pos_offset, n_frames).
     """
     rank = dist.get_rank(group) if dist is not None else 0
     world = dist.get_world_size(group) if dist is not None else 1
@@ -140,8 +149,9 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
     assumed = SeamState.from_engine(engine, base, L) if rank > 0 else None
     if end > begin:
         engine.push_all(fetch(begin, end))
-    rec, bits = engine.drain_frames()
-    frames = [(int(r["pos"]) + base, int(r["type"]), b) for r, b in zip(rec, bits)]
+    rec, bits, is_flat = _drain(engine, flat)
+    pos_offset = base
+    frames = None if is_flat else [(int(r["pos"]) + base, int(r["type"]), b) for r, b in zip(rec, bits)]
     final = SeamState.from_engine(engine, base, L) if begin < end or rank == 0 else assumed
     repaired, seam_ok = False, [True] * world
     if world > 1:
@@ -159,15 +169,19 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
                 finals[k - 1].apply(engine, state_cls)
                 if end > begin:
                     engine.push_all(fetch(begin, end))
-                rec, bits = engine.drain_frames()
-                frames = [(int(r["pos"]), int(r["type"]), b) for r, b in zip(rec, bits)]
+                rec, bits, is_flat = _drain(engine, flat)
+                pos_offset = 0
+                frames = None if is_flat else [(int(r["pos"]), int(r["type"]), b) for r, b in zip(rec, bits)]
                 final = SeamState.from_engine(engine, 0, L)
                 repaired = True
                 vec = final.vec
             else:
                 vec = np.zeros(SeamState.size(L))
             finals[k] = SeamState(_broadcast(vec, k, dist, group, device), L)
-    return dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo)
+    out = dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo, n_frames=len(rec))
+    if frames is None:
+        out.update(records=rec, bits=bits, pos_offset=pos_offset)
+    return out
 
 
 def gather_frames(frames, dist=None, group=None):
