@@ -240,7 +240,12 @@ def main():
     wall_ms = wall * 1e3 / args.steps
     t = torch.tensor([wall_ms, dev_ms, float(frames), float(st["launches"]), float(st["seam_mismatches"]),
                       st["slicer_ms"] / args.steps], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [{"wall_ms": float(a[0]), "device_ms": float(a[1]), "slicer_ms": float(a[5]), "frames": int(a[2]),
+                     "seam_mismatches": int(a[4])} for a in allt]
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
@@ -326,6 +331,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "sharding": {"kind": "time shards of one capture, halo %d av_windows, seam states all_gathered and verified" % args.halo_windows,
                          "ranks_redone_last_step": repaired_ranks} if world > 1 else None,
+            "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
             "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "exact_rounds", "refined_tiles", "st2_tiles", "refine_failed_tiles", "segments", "fast_cycles", "exact_cycles")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
