@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rate", type=float, default=RATE, help="13.56e6 (configs[2]) or 20e6 (configs[4])")
     ap.add_argument("--halo-windows", type=int, default=16, help="speculative halo of a time shard, in av_windows")
+    ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
+    ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()
     globals()["RATE"] = args.rate
 
@@ -138,7 +140,7 @@ def main():
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     codes, lens, params = build_schedule(RATE, 2024)
     period = int(lens.sum())
-    chan = dict(carrier=0.5, pause=0.015, tag_high=1.07, noise=0.003, fade=0.05, fade_period=round(RATE * 0.02))
+    chan = dict(carrier=0.5, pause=0.015, tag_high=args.tag_high, noise=0.003, fade=args.fade, fade_period=round(RATE * 0.02))
     workload = "synthetic ISO 14443A reader+tag traffic, %.3g samples at %.2f MS/s per GPU" % (args.samples, RATE / 1e6)
     config = {"workload": workload, "samp_rate": RATE, "hi_val": HI_VAL, "input": "float32 envelope resident in HBM",
               "l2": "input (%.1f GB per step) is far larger than L2; no flush needed" % (args.samples * 4 / 1e9),

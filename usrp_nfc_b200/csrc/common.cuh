@@ -109,6 +109,10 @@ struct SegWork {
     int32_t *status;      // SegStatus flags of this run of the segment
     int32_t param_idx;    // into the SlicerParams array (batches of captures differ in hi_val, rates)
     int32_t pad;
+    // bitmap output (streaming kernel): 8 words per chunk of 128 samples, chunk k covers stream positions
+    // [bm_pos0 + 128k, bm_pos0 + 128k + 128); words 0-3: val != -1 of sample 4l+j at bit l of word j, words 4-7: val == 1
+    uint32_t *bitmap;     // nullptr: transitions are written to `trans` instead
+    int64_t bm_pos0;      // multiple of 128
 };
 
 // ---- run -> event carry (the reference's cur_state / last_bit / dur at a window start) ----

@@ -23,6 +23,7 @@
 //    sample is compared bit for bit with the predecessor's final state (seam_compare_kernel)
 //    and the segment is redone from the true state when it differs.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nfc {
 
@@ -231,7 +232,7 @@ __device__ __forceinline__ void exp_track(float x, int &emin, int &emax) {
 // ---------------------------------------------------------------- exact tile (fix-point over prefix sums)
 // One tile of NT*K samples starting at stream index P0, classes decided with every sample's own exact ss.
 // Always correct (inside the exactly-summable regime); several block barriers per tile.
-template <int NT, int K, int R>
+template <int NT, int K, int R, bool BM = false>
 __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *pp, float *ring, BlockShared<NT, R> *shp,
                                         const int64_t P0, const int slot0, SegCarry *cs) {
     constexpr int NW = NT / 32;
@@ -461,7 +462,21 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
     int tot_tr = 0;
     const int tr_base = block_excl_scan_int<NT>(ntr, tot_tr, sh.wcnt, c.cnt_buf);
     c.cnt_buf ^= 1;
-    if (tot_tr) {
+    if (BM) {
+        // bitmap output: this warp's 128 samples are one chunk (sample 4*lane + j <-> bit lane of word j)
+        if (K == 4 && w.bitmap) {
+            unsigned wv = 0u;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const bool on = val[j] != 3 && (p0 + j >= w.begin);
+                const unsigned bn = __ballot_sync(FULL, on && val[j] != -1), bh = __ballot_sync(FULL, on && val[j] == 1);
+                if (lane == j) wv = bn;
+                if (lane == 4 + j) wv = bh;
+            }
+            const int64_t cfirst = P0 + (int64_t)warp * 128;
+            if (lane < 8 && cfirst + 127 >= w.begin && cfirst < w.end) w.bitmap[((cfirst - w.bm_pos0) >> 7) * 8 + lane] = wv;
+        }
+    } else if (tot_tr) {
         uint32_t idx = c.seg_count + (uint32_t)tr_base;
 #pragma unroll
         for (int j = 0; j < K; j++) {
@@ -1087,6 +1102,10 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
     }
 }
 
+}  // namespace nfc
+#include "slicer_fast.cuh"
+namespace nfc {
+
 // ---------------------------------------------------------------- strictly sequential path
 // The reference recurrence, literally, one thread per segment: used when av_window is smaller
 // than a tile, when the exponent audit fails (inexact sums, negative or non-finite samples) and
@@ -1224,6 +1243,32 @@ static int launch_one(const SegWork *d_works, int n_works, const SlicerParams *d
     return 0;
 }
 
+// the streaming kernel needs two tiles of 4096 samples to fit into the window; NFC_SLICER_OLD=1 keeps the first kernel
+bool slicer_streaming_ok(int L, bool vec_ok) {
+    static const bool old = getenv("NFC_SLICER_OLD") && getenv("NFC_SLICER_OLD")[0] == '1';
+    return vec_ok && L >= 8192 && !old;
+}
+
+template <int KIND>
+static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
+    auto k = slicer_fast_kernel<256, 4, 3, KIND>;
+    NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t stream) {
+    if (n_works <= 0) return 0;
+    const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
+    switch (kind) {
+        case IN_ENVELOPE_F32: return launch_fast<IN_ENVELOPE_F32>(d_works, n_works, d_params, smem, stream);
+        case IN_REAL_F32: return launch_fast<IN_REAL_F32>(d_works, n_works, d_params, smem, stream);
+        case IN_IQ_F32: return launch_fast<IN_IQ_F32>(d_works, n_works, d_params, smem, stream);
+        default: return launch_fast<IN_PCM_S16>(d_works, n_works, d_params, smem, stream);
+    }
+}
+
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok,
                   cudaStream_t stream) {
     if (n_works <= 0) return 0;
@@ -1254,7 +1299,10 @@ int slicer_resident_ctas(int L, bool vec_ok) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
     cudaError_t e;
-    if (vec_ok && L >= 1024) {
+    if (slicer_streaming_ok(L, vec_ok)) {
+        cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, smem);
+    } else if (vec_ok && L >= 1024) {
         switch (slicer_rows(L)) {
             case 4:
                 cudaFuncSetAttribute(slicer_kernel<256, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,623 @@
+// slicer_fast.cuh -- the streaming slicer kernel (included by slicer.cu after exact_tile).
+//
+// Same contract as slicer_kernel (transition_sink.py:55-82 over one time segment per CTA, ring in shared
+// memory), built for instruction count: per sample everything is float32 (eleven instructions, inline PTX with
+// packed f32x2 adds and three-input min), the window sum is carried as a rigorous interval, and exact
+// arithmetic is only done where a decision needs it.  Output is fixed-rate: two bits per sample (val != -1,
+// val == 1) into a bitmap; extract.cu turns the bitmap into the ordered transition list in a data-parallel pass.
+//
+//  * A tile is NW*R chunks of 128 samples; warp w owns chunks [w*R, (w+1)*R) = R*128 contiguous samples, lane l
+//    the samples 4l..4l+3 of each chunk (one 128-bit load, one 128-bit ring read, one 128-bit ring write).
+//  * Per chunk the thresholds ss*lo/L and ss*hi/L are *guessed* (from the carried window sum and the previous
+//    tile's drift) and every sample is classified by the guess.  The warp reduces (REDUX) per chunk: the
+//    fixed-point sums of the admitted x - prev and |x - prev|, and the margins min |x - guess| to both guesses.
+//  * After the first block barrier warp 0 scans the 32 chunk records (lane = chunk): the prefix of the sums gives
+//    the window sum each chunk really saw (as an interval), hence the band the true thresholds lie in; the guess
+//    is *proven* for a chunk when that band lies strictly inside (guess - margin, guess + margin): no sample is
+//    between a guess and any value the true threshold can take.  Otherwise the tile is repeated once with the
+//    measured thresholds as the guess; if a sample really sits inside the band, or a HIGH sample follows a LOW
+//    sample closely enough for the hysteresis to matter, the tile is handed to exact_tile.  Warp 0 also prepares
+//    the next tile's guesses; a second barrier publishes verdict and guesses.
+//  * The window sum is carried as [ss_lo, ss_hi]: float rounding and fixed-point conversion errors are bounded
+//    and added to the interval.  Where the exact value is needed (exact_tile, state snapshots, segment end) it
+//    is recomputed as the sum of the ring in double (exact inside the audited exponent span, see slicer.cu).
+#pragma once
+
+namespace nfc {
+
+struct __align__(32) FastRec {  // one chunk of 128 samples
+    int S;          // round(sum of admitted (x - prev) / q)
+    int A;          // >= sum of admitted |x - prev| / q
+    float mL, mH;   // min |x - guessed LOW threshold|, min |x - guessed HIGH threshold| (NaN if a sample is NaN)
+    unsigned meta;  // bits 0-1 first class code, 2-3 last class code, then FM_* flags
+    unsigned lpos;  // bits 0-7 last LOW sample + 1 (0 = none / not computed), 8-15 last LOW-run start strictly inside + 1
+    unsigned pad0, pad1;
+};
+enum { FM_HASL = 16u, FM_HASH = 32u, FM_BAD = 128u };
+enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2 };
+enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_N };
+
+static const int FAST_CH = 128;  // samples per chunk
+
+__device__ __forceinline__ float redux_min_nan(float v) {
+    float r;
+    asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float redux_min(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+
+// Two samples of transition_sink.py:59-82 against guessed thresholds TL < TH (nTL2 / nTH2: {-TL,-TL}, {-TH,-TH}).
+// NL / H: ballots of "not LOW" / "HIGH"; n: what the ring slot holds afterwards; s2: two running sums of n - prev
+// (0 when not admitted), a: running sum of |n - prev|; mL / mH: running min of |x - TL| / |x - TH|, NaN-propagating.
+__device__ __forceinline__ void classify_pair(float x0, float x1, float p0, float p1, float TL, float TH, unsigned long long nTL2,
+                                              unsigned long long nTH2, float &mL, float &mH, unsigned long long &s2, float &a,
+                                              unsigned &NL0, unsigned &NL1, unsigned &H0, unsigned &H1, float &n0, float &n1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pnl0, ph0, pa0, pnl1, ph1, pa1;\n\t"
+        ".reg .b64 xx, uu, vv, dd;\n\t"
+        ".reg .f32 u0, u1, v0, v1, d0, d1;\n\t"
+        "mov.b64 xx, {%10, %11};\n\t"
+        "add.rn.f32x2 uu, xx, %16;\n\t"
+        "add.rn.f32x2 vv, xx, %17;\n\t"
+        "mov.b64 {u0, u1}, uu;\n\t"
+        "mov.b64 {v0, v1}, vv;\n\t"
+        "abs.f32 u0, u0;\n\t abs.f32 u1, u1;\n\t abs.f32 v0, v0;\n\t abs.f32 v1, v1;\n\t"
+        "min.NaN.f32 %0, %0, u0, u1;\n\t"
+        "min.NaN.f32 %1, %1, v0, v1;\n\t"
+        "setp.gt.f32 pnl0, %10, %14;\n\t"
+        "setp.gt.and.f32 ph0|pa0, %10, %15, pnl0;\n\t"  // ph: HIGH; pa: not LOW and not HIGH = admitted
+        "vote.sync.ballot.b32 %4, pnl0, 0xffffffff;\n\t"
+        "vote.sync.ballot.b32 %6, ph0, 0xffffffff;\n\t"
+        "selp.f32 %8, %10, %12, pa0;\n\t"
+        "setp.gt.f32 pnl1, %11, %14;\n\t"
+        "setp.gt.and.f32 ph1|pa1, %11, %15, pnl1;\n\t"
+        "vote.sync.ballot.b32 %5, pnl1, 0xffffffff;\n\t"
+        "vote.sync.ballot.b32 %7, ph1, 0xffffffff;\n\t"
+        "selp.f32 %9, %11, %13, pa1;\n\t"
+        "sub.f32 d0, %8, %12;\n\t"
+        "sub.f32 d1, %9, %13;\n\t"
+        "mov.b64 dd, {d0, d1};\n\t"
+        "add.rn.f32x2 %2, %2, dd;\n\t"
+        "abs.f32 d0, d0;\n\t abs.f32 d1, d1;\n\t"
+        "add.f32 %3, %3, d0;\n\t"
+        "add.f32 %3, %3, d1;\n\t"
+        "}"
+        : "+f"(mL), "+f"(mH), "+l"(s2), "+f"(a), "=r"(NL0), "=r"(NL1), "=r"(H0), "=r"(H1), "=f"(n0), "=f"(n1)
+        : "f"(x0), "f"(x1), "f"(p0), "f"(p1), "f"(TL), "f"(TH), "l"(nTL2), "l"(nTH2));
+}
+
+// block-uniform state of the streaming path, written by warp 0 (and thread 0), read by everyone after a barrier
+struct __align__(16) FastUni {
+    float q, invq, invqA, hwf;        // fixed-point step of the coming tile, half width of its ss interval (float, rounded up)
+    float TLb, THb, tot_prev, a_est;  // thresholds at the interval's midpoint; last tile's drift; expected sum |x - prev| per tile
+    double ss_lo, ss_hi;              // the window sum at the start of the coming tile lies in [ss_lo, ss_hi]
+    float thr_min, thr_max;           // admitted samples of streamed tiles lie strictly between these
+    int ok;                           // the coming tile may be streamed (ss > 0, step representable)
+    int verdict;
+    float gTL[32], gTH[32];           // guessed thresholds per chunk of the coming tile (or of the repeat)
+    unsigned stats[FS_N];
+};
+
+template <int NT, int R>
+struct FastShared {
+    static const int NW = NT / 32;
+    static const int NC = NW * R;
+    FastRec recs[32];
+    uint32_t bm[NC * 8];  // the tile's bitmap words, chunk-major
+    FastUni uni;
+    double red[NW];
+};
+
+// exact window sum = sum of the ring (any order: exact inside the audited exponent span)
+template <int NT>
+__device__ __noinline__ double ring_sum_exact(const float *ring, int L, double *red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();  // all ring writes of earlier tiles have landed
+    double part = 0.0;
+    for (int i = tid * 4; i < L; i += NT * 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(ring + i);
+        part += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; i++) s += red[i];
+    __syncthreads();  // red may be reused
+    return s;
+}
+
+// warp 0: constants and guessed thresholds of the coming tile from (ss_lo, ss_hi, tot_prev, a_est)
+template <int NC>
+__device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss_hi, float tot_prev, float a_est, double loL, double hiL,
+                                             int lane) {
+    const double ssm = 0.5 * (ss_lo + ss_hi);
+    const float hwf = __double2float_ru(__dsub_ru(ss_hi, ssm)) + __double2float_ru(__dsub_ru(ssm, ss_lo));
+    const float ssf = __double2float_rd(ssm);
+    bool ok = ss_lo > 0.0 && ssf < 1.0e30f && ssf > 1.0e-30f;
+    if (!(a_est > 0.0f)) a_est = ssf * 0x1p-7f;
+    const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;  // fixed-point step: a power of two near a_est * 2^-26
+    ok = ok && ae > 40u && ae < 250u;
+    const float TLb = __double2float_rn(ssm * loL), THb = __double2float_rn(ssm * hiL);
+    const float srel = ok ? tot_prev * (1.0f / NC) / ssf : 0.0f;  // predicted relative change of ss per chunk
+    const float f = fmaf(srel, (float)lane + 0.5f, 1.0f);
+    u.gTL[lane] = TLb * f;
+    u.gTH[lane] = THb * f;
+    if (lane == 0) {
+        const unsigned qe = ok ? ae - 25u : 127u;
+        u.q = __uint_as_float(qe << 23);
+        u.invq = __uint_as_float((254u - qe) << 23);
+        u.invqA = u.invq * (1.0f + 0x1p-20f);
+        u.hwf = hwf;
+        u.TLb = TLb;
+        u.THb = THb;
+        u.tot_prev = tot_prev;
+        u.a_est = a_est;
+        u.ss_lo = ss_lo;
+        u.ss_hi = ss_hi;
+        u.ok = ok ? 1 : 0;
+    }
+}
+
+// KIND: InputKind of the segment's samples (compile-time: the load path has no branches)
+template <int NT, int R, int MINB, int KIND>
+__global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__restrict__ works,
+                                                               const SlicerParams *__restrict__ params) {
+    constexpr int NW = NT / 32;
+    constexpr int NC = NW * R;            // chunks per tile
+    constexpr int WS = R * FAST_CH;       // samples per warp per tile
+    constexpr int T = NW * WS;            // samples per tile
+    constexpr int SUB = NT * 4;           // exact_tile row
+    constexpr int XR = T / SUB;           // exact_tile rows per tile
+    static_assert(NC == 32, "one lane per chunk record");
+    static_assert(T % SUB == 0, "tile is a whole number of exact rows");
+    static_assert(R == 4, "one bitmap word per lane and tile; four guesses per 128-bit read");
+    extern __shared__ __align__(16) float ring[];
+    __shared__ BlockShared<NT, 4> sh;
+    __shared__ FastShared<NT, R> fs;
+    __shared__ SegWork w_s;
+    __shared__ SlicerParams p_s;
+    __shared__ SegCarry c_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        w_s = works[blockIdx.x];
+        p_s = params[w_s.param_idx];
+    }
+    if (tid < FS_N) fs.uni.stats[tid] = 0u;
+    __syncthreads();
+    const SegWork &w = w_s;
+    const SlicerParams &p = p_s;
+    FastUni &uni = fs.uni;
+    const int L = p.L;
+
+    // ---- entry state (as slicer_kernel); the carry lives in shared memory (c_s), thread 0 / warp 0 maintain it
+    int emin = 1 << 30, emax = 0;
+    {
+        double ss0;
+        if (w.state_in) {
+            const float *src = state_ring(w.state_in);
+            for (int i = tid; i < L; i += NT) {
+                float v = src[i];
+                ring[i] = v;
+                exp_track(v, emin, emax);
+            }
+            ss0 = w.state_in->ss;
+        } else {
+            double part = 0.0;
+            for (int i = tid; i < L; i += NT) {
+                const int64_t q = w.warm_begin - L + i;
+                float v = load_one(w.in, q - w.in_pos0, p);
+                ring[(int)(q % L)] = v;
+                part += (double)v;
+                exp_track(v, emin, emax);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+            if (lane == 0) sh.red[warp] = part;
+            __syncthreads();
+            ss0 = 0.0;
+            for (int i = 0; i < NW; i++) ss0 += sh.red[i];
+        }
+        if (tid == 0) {
+            SegCarry c;
+            c.ss0 = ss0;
+            c.lastL = w.state_in ? w.state_in->lastL : NO_POS;
+            c.lrun_start = w.state_in ? w.state_in->lrun_start : NO_POS;
+            c.last_val = w.state_in ? w.state_in->last_val : 0;
+            c.seg_count = 0; c.scan_buf = 0; c.cnt_buf = 0; c.round_no = 0;
+            c_s = c;
+            sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
+            sh.emin = 1 << 30;
+            sh.emax = 0;
+            uni.thr_min = 3.0e38f;
+            uni.thr_max = 0.0f;
+        }
+        if (warp == 0) fast_prepare<NC>(uni, ss0, ss0, 0.0f, -1.0f, p.loL, p.hiL, lane);
+    }
+    __syncthreads();
+
+    const bool fast_ok = ((L & 3) == 0) && L >= 2 * T && p.lo > 0.0 && p.hi > p.lo && w.bitmap != nullptr;
+
+    // ---- the segment in tiles (indices relative to the first one)
+    const int64_t tile_first = w.warm_begin / T;
+    const int ntiles = (w.end > w.warm_begin) ? (int)((w.end - 1) / T - tile_first) + 1 : 0;
+    int t_int_lo, t_int_hi, t_strad, t_emit;
+    {
+        const int64_t lo_pos = max(w.warm_begin, w.in_begin), hi_pos = min(w.end, w.in_end);
+        t_int_lo = (int)((lo_pos + T - 1) / T - tile_first);                // first tile that is all inside
+        t_int_hi = hi_pos >= 0 ? (int)(hi_pos / T - tile_first) : 0;        // one past the last such tile
+        t_strad = (w.begin % T) ? (int)(w.begin / T - tile_first) : -1;     // tile cut by `begin`
+        t_emit = (int)((w.begin + T - 1) / T - tile_first);                 // tiles from here on are written
+        if (!fast_ok) t_int_hi = t_int_lo;
+    }
+    // tiles before which a state snapshot is due (seam, checkpoints): the next one in t_snap
+    auto snap_tile = [&](int j) -> int {  // j = 0: seam, 1..3: checkpoints
+        if (j == 0) return (w.seam_in && w.begin > w.warm_begin && (w.begin % T) == 0) ? (int)(w.begin / T - tile_first) : -1;
+        return (w.ckpt_state[j - 1] && w.ckpt_pos[j - 1] != INT64_MAX && (w.ckpt_pos[j - 1] % T) == 0)
+                   ? (int)(w.ckpt_pos[j - 1] / T - tile_first) : -1;
+    };
+    auto next_snap = [&](int after) -> int {
+        int best = INT_MAX;
+        for (int j = 0; j < 4; j++) {
+            const int ts = snap_tile(j);
+            if (ts > after && ts < best) best = ts;
+        }
+        return best;
+    };
+    int t_snap = next_snap(-1);
+
+    // exact_tile's slot of this thread's first sample of a row, and this kernel's (warp-contiguous layout)
+    int slot_x = (int)((tile_first * T + (int64_t)tid * 4) % L);
+    int slot_w = (int)((tile_first * T + (int64_t)warp * WS + (int64_t)lane * 4) % L);
+    const int slot_step = T % L;
+    // this thread's first sample of the first tile in the input buffer
+    constexpr int ITEM = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
+    const char *xptr = reinterpret_cast<const char *>(w.in) + (tile_first * T - w.in_pos0 + (int64_t)warp * WS + (int64_t)lane * 4) * ITEM;
+    constexpr int tile_bytes = T * ITEM;
+    uint32_t *bm_out = w.bitmap ? w.bitmap + ((tile_first * T - w.bm_pos0) >> 7) * 8 + warp * (R * 8) + lane : nullptr;
+
+    float4 xin[R];
+    bool have_x = false;
+
+    auto load_tile = [&](const char *src) {
+        if (KIND == IN_ENVELOPE_F32 || KIND == IN_REAL_F32) {
+#pragma unroll
+            for (int r = 0; r < R; r++) xin[r] = ldg_stream4(reinterpret_cast<const float4 *>(src + r * FAST_CH * 4));
+            if (KIND == IN_REAL_F32) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    xin[r].x = env_real(xin[r].x); xin[r].y = env_real(xin[r].y);
+                    xin[r].z = env_real(xin[r].z); xin[r].w = env_real(xin[r].w);
+                }
+            }
+        } else if (KIND == IN_IQ_F32) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float4 *q = reinterpret_cast<const float4 *>(src + r * FAST_CH * 8);
+                const float4 a = ldg_stream4(q), b = ldg_stream4(q + 1);
+                xin[r] = make_float4(env_iq(a.x, a.y), env_iq(a.z, a.w), env_iq(b.x, b.y), env_iq(b.z, b.w));
+            }
+        } else {
+            const float pcm_scale = p.pcm_scale;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const short4 sv = __ldg(reinterpret_cast<const short4 *>(src + r * FAST_CH * 2));
+                xin[r] = make_float4(env_real(__fdiv_rn((float)sv.x, pcm_scale)), env_real(__fdiv_rn((float)sv.y, pcm_scale)),
+                                     env_real(__fdiv_rn((float)sv.z, pcm_scale)), env_real(__fdiv_rn((float)sv.w, pcm_scale)));
+            }
+        }
+    };
+    // the exact window sum into c_s.ss0 (and the interval collapsed onto it); ends with a barrier
+    auto make_exact = [&]() {
+        const double lo = uni.ss_lo, hi = uni.ss_hi;
+        double s = lo;
+        if (lo != hi) s = ring_sum_exact<NT>(ring, L, fs.red);
+        else __syncthreads();
+        if (tid == 0) {
+            if (lo != hi) uni.stats[FS_RESUM]++;
+            uni.ss_lo = uni.ss_hi = s;
+            c_s.ss0 = s;
+        }
+        __syncthreads();
+    };
+    auto snapshot = [&](SlicerHdr *dsth, int64_t pos) {
+        make_exact();
+        float *dst = state_ring(dsth);
+        for (int i = tid; i < L; i += NT) dst[i] = ring[i];
+        if (tid == 0) {
+            SlicerHdr h;
+            h.ss = c_s.ss0; h.pos = pos; h.lastL = c_s.lastL; h.lrun_start = c_s.lrun_start;
+            h.last_val = c_s.last_val; h.emin = 0; h.emax = 0; h.status = 0; h.count = 0; h.pad = 0;
+            *dsth = h;
+        }
+    };
+
+    int64_t P0 = tile_first * T;
+    for (int t = 0; t < ntiles; t++, P0 += T, xptr += tile_bytes, bm_out += NC * 8) {
+        if (t == t_snap) {
+            if (t == snap_tile(0)) snapshot(w.seam_in, w.begin);
+            for (int j = 1; j < 4; j++)
+                if (t == snap_tile(j)) snapshot(w.ckpt_state[j - 1], P0);
+            t_snap = next_snap(t);
+            // the interval collapsed: the coming tile's constants follow it
+            if (warp == 0) {
+                const double lo = uni.ss_lo, hi = uni.ss_hi;
+                const float tp = uni.tot_prev, ae = uni.a_est;
+                __syncwarp();
+                fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
+            }
+            __syncthreads();
+        }
+
+        bool done = false;
+        bool x_ready = have_x;  // this tile's samples were requested during the previous tile
+        have_x = false;
+        if (t >= t_int_lo && t < t_int_hi && t != t_strad && uni.ok) {
+            for (int iter = 0;; iter++) {
+                if (!x_ready) load_tile(xptr);
+                x_ready = false;
+                const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
+                const float4 tl4 = *reinterpret_cast<const float4 *>(&uni.gTL[warp * R]);
+                const float4 th4 = *reinterpret_cast<const float4 *>(&uni.gTH[warp * R]);
+                const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
+
+                float n[R * 4];
+                // ------------------------------------------------------------ phase 1: classify, sums, margins, maps
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int ch = warp * R + r;
+                    int s0 = slot_w + r * FAST_CH;
+                    if (s0 >= L) s0 -= L;
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    unsigned NLm[4], Hm[4];
+                    unsigned long long s2 = 0ull;
+                    float a = 0.0f, mL = INFINITY, mH = INFINITY;
+                    const unsigned long long nTL2 = pack2(-thL[r], -thL[r]), nTH2 = pack2(-thH[r], -thH[r]);
+                    classify_pair(xin[r].x, xin[r].y, pv4.x, pv4.y, thL[r], thH[r], nTL2, nTH2, mL, mH, s2, a, NLm[0], NLm[1], Hm[0],
+                                  Hm[1], n[r * 4 + 0], n[r * 4 + 1]);
+                    classify_pair(xin[r].z, xin[r].w, pv4.z, pv4.w, thL[r], thH[r], nTL2, nTH2, mL, mH, s2, a, NLm[2], NLm[3], Hm[2],
+                                  Hm[3], n[r * 4 + 2], n[r * 4 + 3]);
+                    float sa, sb;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s2));
+                    const float af = a * kq.z;
+                    const int si = __float2int_rn((sa + sb) * kq.y);
+                    const int ai = __float2int_ru(fminf(af, 1048576.0f));
+                    const int S = __reduce_add_sync(FULL, si), A = __reduce_add_sync(FULL, ai);
+                    mL = redux_min_nan(mL);
+                    mH = redux_min_nan(mH);
+                    const unsigned allNL = NLm[0] & NLm[1] & NLm[2] & NLm[3];
+                    const unsigned anyH = Hm[0] | Hm[1] | Hm[2] | Hm[3];
+                    const unsigned fc = (NLm[0] & 1u) + (Hm[0] & 1u), lc = (NLm[3] >> 31) + (Hm[3] >> 31);
+                    unsigned meta = fc | (lc << 2);
+                    if (__any_sync(FULL, !(af < 1048576.0f))) meta |= FM_BAD;  // a lane's sum does not fit (or is NaN)
+                    if (anyH != 0u) meta |= FM_HASH;
+                    unsigned lpos = 0u;
+                    if (allNL != FULL) {
+                        meta |= FM_HASL;
+                        const int nbk = (p.mx + FAST_CH) / FAST_CH;  // chunks at the tile end whose LOW samples can still matter later
+                        if (lc == 0u || ch >= NC - nbk) {
+                            // last LOW sample, last LOW-run start strictly inside (chunk positions 4l+j)
+                            int bestL = -1, bestS = -1;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const unsigned lw = ~NLm[j];
+                                const unsigned pw = j == 0 ? ((NLm[3] << 1) & ~1u) : NLm[j - 1];  // predecessor not LOW
+                                const unsigned sw = lw & pw;
+                                if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
+                                if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
+                            }
+                            lpos = (unsigned)(bestL + 1) | ((unsigned)(bestS + 1) << 8);
+                        }
+                    }
+                    if (lane == 0) {
+                        uint4 *rw = reinterpret_cast<uint4 *>(&fs.recs[ch]);
+                        rw[0] = make_uint4((unsigned)S, (unsigned)A, __float_as_uint(mL), __float_as_uint(mH));
+                        *reinterpret_cast<uint2 *>(rw + 1) = make_uint2(meta, lpos);
+                        uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[ch * 8]);
+                        bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
+                        bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
+                    }
+                }
+                // next tile's samples on their way while this one is settled
+                if (t + 1 >= t_int_lo && t + 1 < t_int_hi && t + 1 != t_strad) {
+                    load_tile(xptr + tile_bytes);
+                    have_x = true;
+                }
+                __syncthreads();
+
+                // ------------------------------------------------------------ phase 2 (warp 0): lane = chunk
+                if (warp == 0) {
+                    const uint4 r0 = *reinterpret_cast<const uint4 *>(&fs.recs[lane]);
+                    const uint2 r1 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint4 *>(&fs.recs[lane]) + 1);
+                    const int S = (int)r0.x, A = (int)r0.y;
+                    const float mL = __uint_as_float(r0.z), mH = __uint_as_float(r0.w);
+                    const unsigned meta = r1.x, lpos = r1.y;
+                    const float q = kq.x, hwf = kq.w;
+                    const float loLf = (float)p.loL, hiLf = (float)p.hiL;
+                    int incS = S;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incS, o);
+                        if (lane >= o) incS += v;
+                    }
+                    const int totS = __shfl_sync(FULL, incS, 31);
+                    const int totA = __reduce_add_sync(FULL, A);
+                    const unsigned metaor = __reduce_or_sync(FULL, meta);
+                    // error of the fixed-point sums (conversion: half a step per lane and chunk; float rounding: 2^-21 of |d|)
+                    const float Ef = ((float)(16 * NC) + (float)totA * 0x1p-21f) * q * 1.01f;
+                    // measured: inside chunk c the window sum stays within (midpoint of the tile's start interval) + mid +- rr
+                    const float mid = ((float)(incS - S) + 0.5f * (float)S) * q;
+                    const float rr = (hwf + Ef + 0.5f * (float)A * q) * 1.001f;
+                    const float tlm = fmaf(mid, loLf, uni.TLb), thm = fmaf(mid, hiLf, uni.THb);
+                    const float rl = fmaf(rr, loLf, tlm * 0x1p-19f), rh = fmaf(rr, hiLf, thm * 0x1p-19f);
+                    // the guess is proven when no sample lies between it and any value the true threshold can take
+                    const float gl = uni.gTL[lane], gh = uni.gTH[lane];
+                    const bool fine = (mL > fabsf(tlm - gl) + rl) && (mH > fabsf(thm - gh) + rh) && (tlm - rl > 0.0f);
+                    const bool all_fine = __all_sync(FULL, fine);
+                    // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+                    bool st2 = false;
+                    if (metaor & FM_HASH) {
+                        const int mx = p.mx;
+                        const int nb = (mx + FAST_CH) / FAST_CH;  // chunks a LOW sample can reach forward through the hysteresis
+                        const unsigned Lmask = __ballot_sync(FULL, (meta & FM_HASL) != 0u);
+                        const int lo_c = max(lane - nb, 0);
+                        const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
+                        bool risk = (meta & FM_HASH) && win != 0u;
+                        const int64_t cl = c_s.lastL;
+                        if ((meta & FM_HASH) && cl != NO_POS) {
+                            const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
+                            if (dist <= (int64_t)mx + 1) risk = true;
+                        }
+                        st2 = __any_sync(FULL, risk);
+                    }
+                    if (!all_fine || st2 || (metaor & FM_BAD)) {
+                        const bool redo = !st2 && !(metaor & FM_BAD) && iter == 0;
+                        if (redo) {  // go round again with the measured thresholds as the guess
+                            uni.gTL[lane] = tlm;
+                            uni.gTH[lane] = thm;
+                        }
+                        if (lane == 0) {
+                            uni.verdict = redo ? FV_REDO : FV_SLOW;
+                            if (metaor & FM_BAD) uni.a_est *= 16.0f;
+                            uni.stats[redo ? FS_REDO : ((metaor & FM_BAD) ? FS_BAD : (st2 ? FS_ST2 : FS_UNC))]++;
+                        }
+                    } else {
+                        // ---- carries and the coming tile's constants
+                        const float Ed_f = Ef;
+                        const double delta = (double)totS * (double)q;  // exact
+                        const double ss_lo = __dadd_rd(uni.ss_lo, __dadd_rd(delta, -(double)Ed_f));
+                        const double ss_hi = __dadd_ru(uni.ss_hi, __dadd_ru(delta, (double)Ed_f));
+                        const float a_new = fmaxf((float)totA * q, uni.TLb * 0x1p-16f);
+                        // admitted samples lie strictly between the LOW and HIGH bands: exponent range from the thresholds
+                        const float tmin = redux_min(tlm - rl), tmax = -redux_min(-(thm + rh));
+                        const int lastc = (int)((meta >> 2) & 3u), firstc = (int)(meta & 3u);
+                        const int lv_prev = c_s.last_val + 1;  // class code of the sample before the tile
+                        int prevlast = __shfl_up_sync(FULL, lastc, 1);
+                        if (lane == 0) prevlast = lv_prev;
+                        const int lv_new = __shfl_sync(FULL, lastc, NC - 1) - 1;
+                        int newL = -1, newS = -1;
+                        if (metaor & FM_HASL) {
+                            const int lp = (int)(lpos & 0xffu), sp = (int)((lpos >> 8) & 0xffu);
+                            const int candL = lp ? lane * FAST_CH + lp - 1 : -1;
+                            int candS = sp ? lane * FAST_CH + sp - 1 : -1;
+                            if (lp && firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
+                            newL = __reduce_max_sync(FULL, candL);
+                            newS = __reduce_max_sync(FULL, candS);
+                        }
+                        if (lane == 0) {
+                            uni.verdict = FV_ACCEPT;
+                            uni.stats[FS_FAST]++;
+                            uni.thr_min = fminf(uni.thr_min, tmin);
+                            uni.thr_max = fmaxf(uni.thr_max, tmax);
+                            c_s.last_val = lv_new;
+                            if (newL >= 0) {
+                                c_s.lastL = P0 + newL;
+                                if (newS >= 0) c_s.lrun_start = P0 + newS;
+                            }
+                        }
+                        fast_prepare<NC>(uni, ss_lo, ss_hi, (float)delta, a_new, p.loL, p.hiL, lane);
+                    }
+                }
+                __syncthreads();
+                const int verdict = uni.verdict;
+                if (verdict == FV_ACCEPT) {
+                    // ---- ring update, bitmap out
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        int s0 = slot_w + r * FAST_CH;
+                        if (s0 >= L) s0 -= L;
+                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(n[r * 4], n[r * 4 + 1], n[r * 4 + 2], n[r * 4 + 3]);
+                    }
+                    if (t >= t_emit) *bm_out = fs.bm[warp * (R * 8) + lane];
+                    done = true;
+                    break;
+                }
+                have_x = false;  // xin is needed for this tile again, or the exact path reloads
+                if (verdict == FV_SLOW) break;
+            }
+        }
+        if (!done) {
+            // ---------------------------------------------------------------- exact path, row by row
+            make_exact();
+            const double ss_before = c_s.ss0;
+            __syncthreads();
+#pragma unroll 1
+            for (int r = 0; r < XR; r++) {
+                const int64_t Pr = P0 + (int64_t)r * SUB;
+                if (Pr >= w.end || Pr + SUB <= w.warm_begin) continue;  // block-uniform
+                int s0 = slot_x + r * SUB;
+                while (s0 >= L) s0 -= L;
+                exact_tile<NT, 4, 4, true>(&w_s, &p_s, ring, &sh, Pr, s0, &c_s);
+            }
+            if (warp == 0) {
+                const double ss1 = c_s.ss0;
+                const float ae = uni.a_est;
+                __syncwarp();
+                if (lane == 0) uni.stats[FS_SLOW]++;
+                fast_prepare<NC>(uni, ss1, ss1, (float)(ss1 - ss_before), ae, p.loL, p.hiL, lane);
+            }
+            have_x = false;
+            __syncthreads();
+        }
+        slot_x += slot_step;
+        if (slot_x >= L) slot_x -= L;
+        slot_w += slot_step;
+        if (slot_w >= L) slot_w -= L;
+    }
+
+    // ---- exit: exactness audit and final state
+    make_exact();
+    if (uni.stats[FS_FAST]) {
+        exp_track(uni.thr_min, emin, emax);
+        exp_track(uni.thr_max, emin, emax);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        emin = min(emin, __shfl_xor_sync(FULL, emin, o));
+        emax = max(emax, __shfl_xor_sync(FULL, emax, o));
+    }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
+    __syncthreads();
+    emin = sh.emin; emax = sh.emax;
+    int status = SEG_OK;
+    if (emax >= 255) status |= SEG_NOT_SANE;
+    if (emax > 0 && emax - emin > p.span_limit) status |= SEG_INEXACT;
+
+    if (w.state_out) {
+        float *dst = state_ring(w.state_out);
+        for (int i = tid; i < L; i += NT) dst[i] = ring[i];
+        if (tid == 0) {
+            SlicerHdr h;
+            h.ss = c_s.ss0; h.pos = w.end; h.lastL = c_s.lastL; h.lrun_start = c_s.lrun_start;
+            h.last_val = c_s.last_val; h.emin = emin; h.emax = emax; h.status = status; h.count = 0; h.pad = 0;
+            *w.state_out = h;
+        }
+    }
+    if (tid == 0 && w.trans_count) *w.trans_count = 0;
+    if (tid == 0 && w.status) *w.status = status;
+    if (tid == 0) {
+        atomicAdd(&g_tile_stats[0], (unsigned long long)uni.stats[FS_FAST]);
+        atomicAdd(&g_tile_stats[1], (unsigned long long)uni.stats[FS_SLOW]);
+        atomicAdd(&g_tile_stats[2], (unsigned long long)uni.stats[FS_BAD]);
+        atomicAdd(&g_tile_stats[3], (unsigned long long)uni.stats[FS_UNC]);
+        atomicAdd(&g_tile_stats[4], (unsigned long long)uni.stats[FS_RESUM]);
+        atomicAdd(&g_tile_stats[5], (unsigned long long)uni.stats[FS_REDO]);
+        atomicAdd(&g_tile_stats[6], (unsigned long long)uni.stats[FS_ST2]);
+        atomicAdd(&g_tile_stats[7], (unsigned long long)uni.stats[FS_VER]);
+    }
+}
+
+}  // namespace nfc

@@ -20,6 +20,13 @@ namespace nfc {
 
 // ---- launchers implemented in the kernel files
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok, cudaStream_t);
+bool slicer_streaming_ok(int L, bool vec_ok);
+int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t);
+int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, int carry_val, uint32_t *d_block_counts,
+                         uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total, cudaStream_t);
+int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, int carry_val,
+                         const uint32_t *d_block_offsets, TransRec *d_out, uint32_t out_cap, cudaStream_t);
+size_t extract_blocks(int64_t bm_pos0, int64_t a, int64_t b);
 int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,
                          size_t ring_stride, cudaStream_t);
 int launch_seam_compare(const SlicerHdr *const *d_truth, const SlicerHdr *const *d_assumed, const int *d_param_idx,
@@ -140,7 +147,7 @@ struct Stream {
     DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
         seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
         line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
-        redo_counts, pieces_d;
+        redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr;
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -167,6 +174,9 @@ struct Stream {
     int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b);
     int run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial, uint32_t *R_out,
                    bool *fell_back);
+    int run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, uint32_t *R_out,
+                      bool *fell_back);
+    bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
 int Stream::ensure_pinned(size_t bytes) {
@@ -250,7 +260,8 @@ void Stream::destroy() {
     DevBuf *all[] = {&params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
-                     &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state};
+                     &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
+                     &ex_counts, &ex_offsets, &ex_scr};
     for (DevBuf *b : all) b->release();
     if (pinned) cudaFreeHost(pinned);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -689,12 +700,249 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
     return -1;
 }
 
+// The streaming kernel over [a, b): class bitmap of the slab (fixed-rate output, no per-segment lists), seams
+// verified and repaired like run_slicer, then the dense ordered transitions extracted from the bitmap.
+int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, uint32_t *R_out,
+                          bool *fell_back) {
+    const int L = sp.L;
+    const int T = tile();
+    *fell_back = false;
+    // ---- plan segments (as run_slicer)
+    std::vector<int64_t> begins;
+    begins.push_back(a);
+    const int64_t Hs = halo > 0 ? halo : (int64_t)16 * L;
+    const int64_t H = (Hs + T - 1) / T * T;
+    {
+        int64_t S = seg_len;
+        if (S <= 0) {
+            const int64_t n = b - a, res = std::max(1, resident_ctas);
+            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)256 * L, s_min);
+            int64_t k = 1;
+            while (n / (res * (k + 1)) >= s_min) k++;
+            S = n / (res * k);
+            if (S < s_min) S = s_min;
+            if (S > s_max) S = s_max;
+        }
+        S = (S + T - 1) / T * T;
+        int64_t b1 = a + std::max<int64_t>(S, (int64_t)L + H);
+        b1 = (b1 + T - 1) / T * T;
+        while (b1 + S / 2 <= b && b1 < b) {
+            begins.push_back(b1);
+            b1 += S;
+        }
+    }
+    const int nseg = (int)begins.size();
+    const size_t sblk = state_block_bytes(L);
+    const int NCK = 3;
+    const int64_t ck_off[NCK] = {H, 3 * H, 7 * H};
+    if (states_d.ensure(sblk * 2 * (size_t)nseg) || (nseg > 1 && ckpt_d.ensure(sblk * NCK * (size_t)nseg))) return -1;
+    if (seg_status.ensure(sizeof(int32_t) * (size_t)nseg) || works_d.ensure(sizeof(SegWork) * (size_t)nseg * 2) ||
+        mismatch_d.ensure(sizeof(int) * (size_t)nseg) || seam_ptrs.ensure((sizeof(void *) * 2 + sizeof(int)) * (size_t)nseg))
+        return -1;
+    // bitmap of the slab, chunk 0 at the tile boundary at or before a
+    const int64_t bm_pos0 = a / T * T;
+    const size_t n_chunks = (size_t)((b - bm_pos0 + 127) / 128);
+    if (bitmap_d.ensure((n_chunks + 64) * 32)) return -1;
+
+    std::vector<SegWork> works((size_t)nseg);
+    std::vector<int32_t> status((size_t)nseg);
+    auto seam_in = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k)); };
+    auto st_out = [&](int k) { return reinterpret_cast<SlicerHdr *>(states_d.as<char>() + sblk * (2 * (size_t)k + 1)); };
+    auto ckpt = [&](int k, int j) { return reinterpret_cast<SlicerHdr *>(ckpt_d.as<char>() + sblk * ((size_t)k * NCK + (size_t)j)); };
+    for (int k = 0; k < nseg; k++) {
+        SegWork &w = works[(size_t)k];
+        memset(&w, 0, sizeof(w));
+        w.in = d_in;
+        w.in_pos0 = in_pos0;
+        w.in_begin = in_begin;
+        w.in_end = in_end;
+        w.begin = begins[(size_t)k];
+        w.end = k + 1 < nseg ? begins[(size_t)k + 1] : b;
+        w.warm_begin = k == 0 ? a : w.begin - H;
+        w.slab_pos0 = a;
+        w.state_in = k == 0 ? state.as<SlicerHdr>() : nullptr;
+        w.seam_in = k == 0 ? nullptr : seam_in(k);
+        for (int j = 0; j < NCK; j++) {
+            const bool use = k > 0 && w.begin + ck_off[j] < w.end;
+            w.ckpt_pos[j] = use ? w.begin + ck_off[j] : INT64_MAX;
+            w.ckpt_state[j] = use ? ckpt(k, j) : nullptr;
+        }
+        w.state_out = st_out(k);
+        w.trans = nullptr;
+        w.trans_cap = 0;
+        w.trans_count = nullptr;
+        w.status = seg_status.as<int32_t>() + k;
+        w.param_idx = 0;
+        w.bitmap = bitmap_d.as<uint32_t>();
+        w.bm_pos0 = bm_pos0;
+    }
+    NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+    if (launch_slicer_streaming(works_d.as<SegWork>(), nseg, params_d.as<SlicerParams>(), L, sp.input_kind, cs)) return -1;
+    stats.launches++;
+    stats.slicer_launches++;
+    stats.segments += nseg;
+
+    // ---- seams
+    std::vector<int> mism((size_t)nseg, 0);
+    std::vector<const SlicerHdr *> truth((size_t)nseg, nullptr), assumed((size_t)nseg, nullptr);
+    std::vector<int> pidx((size_t)nseg, 0);
+    char *sp_base = seam_ptrs.as<char>();
+    auto compare = [&](int n) -> int {
+        NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base, truth.data(), sizeof(void *) * (size_t)n, cudaMemcpyHostToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + sizeof(void *) * (size_t)nseg, assumed.data(), sizeof(void *) * (size_t)n,
+                                       cudaMemcpyHostToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(sp_base + 2 * sizeof(void *) * (size_t)nseg, pidx.data(), sizeof(int) * (size_t)n,
+                                       cudaMemcpyHostToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemsetAsync(mismatch_d.p, 0, sizeof(int) * (size_t)n, cs));
+        if (launch_seam_compare((const SlicerHdr *const *)sp_base, (const SlicerHdr *const *)(sp_base + sizeof(void *) * (size_t)nseg),
+                                (const int *)(sp_base + 2 * sizeof(void *) * (size_t)nseg), params_d.as<SlicerParams>(),
+                                mismatch_d.as<int>(), n, cs))
+            return -1;
+        stats.launches++;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(mism.data(), mismatch_d.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, cs));
+        return 0;
+    };
+    if (nseg > 1) {
+        for (int k = 1; k < nseg; k++) {
+            truth[(size_t)k] = st_out(k - 1);
+            assumed[(size_t)k] = seam_in(k);
+        }
+        if (compare(nseg)) return -1;
+    }
+    NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    int st_all = 0;
+    for (int k = 0; k < nseg; k++) st_all |= status[(size_t)k];
+    if (st_all & (SEG_INEXACT | SEG_NOT_SANE)) {
+        *fell_back = true;  // caller redoes the slab with the sequential kernel
+        return 0;
+    }
+
+    // ---- repair: redo a wrong segment from its predecessor's true final state, checkpoint by checkpoint; the
+    // redo overwrites the bitmap in place and stops at the first checkpoint of the speculative run it reproduces
+    std::vector<char> bad((size_t)nseg, 0);
+    int nbad = 0;
+    for (int k = 1; k < nseg; k++) {
+        bad[(size_t)k] = mism[(size_t)k] ? 1 : 0;
+        nbad += bad[(size_t)k];
+    }
+    for (int guard = 0; nbad > 0 && guard < nseg + 2; guard++) {
+        std::vector<int> ks;
+        for (int k = 1; k < nseg; k++)
+            if (bad[(size_t)k] && !bad[(size_t)k - 1]) ks.push_back(k);
+        const int nr = (int)ks.size();
+        stats.seam_mismatches += nr;
+        if (redo_states.ensure(sblk * (size_t)nr) || redo_counts.ensure(sizeof(int32_t) * (size_t)nr)) return -1;
+        auto tmp_state = [&](int i) { return reinterpret_cast<SlicerHdr *>(redo_states.as<char>() + sblk * (size_t)i); };
+        std::vector<int64_t> at((size_t)nr);
+        std::vector<char> active((size_t)nr, 1);
+        for (int i = 0; i < nr; i++) at[(size_t)i] = works[(size_t)ks[(size_t)i]].begin;
+        for (int stage = 0; stage <= NCK; stage++) {
+            std::vector<SegWork> redo;
+            std::vector<int> who;
+            for (int i = 0; i < nr; i++) {
+                if (!active[(size_t)i]) continue;
+                const int k = ks[(size_t)i];
+                const SegWork &ws = works[(size_t)k];
+                if (stage < NCK && !ws.ckpt_state[stage]) continue;  // no such checkpoint: a later stage runs on
+                const int64_t target = stage < NCK ? ws.ckpt_pos[stage] : ws.end;
+                SegWork w = ws;
+                w.warm_begin = w.begin = at[(size_t)i];
+                w.end = target;
+                w.state_in = at[(size_t)i] == ws.begin ? st_out(k - 1) : tmp_state(i);
+                w.seam_in = nullptr;
+                for (int j = 0; j < NCK; j++) { w.ckpt_pos[j] = INT64_MAX; w.ckpt_state[j] = nullptr; }
+                w.state_out = tmp_state(i);
+                w.status = redo_counts.as<int32_t>() + i;
+                redo.push_back(w);
+                who.push_back(i);
+            }
+            if (redo.empty()) continue;
+            SegWork *d_redo = works_d.as<SegWork>() + nseg;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(d_redo, redo.data(), sizeof(SegWork) * redo.size(), cudaMemcpyHostToDevice, cs));
+            if (launch_slicer_streaming(d_redo, (int)redo.size(), params_d.as<SlicerParams>(), L, sp.input_kind, cs)) return -1;
+            stats.launches++;
+            stats.slicer_launches++;
+            const int nw = (int)who.size();
+            for (int q = 0; q < nw; q++) {
+                const int i = who[(size_t)q], k = ks[(size_t)i];
+                truth[(size_t)q] = tmp_state(i);
+                assumed[(size_t)q] = stage < NCK ? works[(size_t)k].ckpt_state[stage] : tmp_state(i);
+                pidx[(size_t)q] = 0;
+            }
+            if (compare(nw)) return -1;
+            std::vector<int32_t> rst((size_t)nr, 0);
+            NFC_CUDA_CHECK(cudaMemcpyAsync(rst.data(), redo_counts.p, sizeof(int32_t) * (size_t)nr, cudaMemcpyDeviceToHost, cs));
+            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            for (int q = 0; q < nw; q++) {
+                const int i = who[(size_t)q], k = ks[(size_t)i];
+                if (rst[(size_t)i] & (SEG_INEXACT | SEG_NOT_SANE)) {
+                    *fell_back = true;
+                    return 0;
+                }
+                at[(size_t)i] = redo[(size_t)q].end;
+                if (stage < NCK && !mism[(size_t)q]) {
+                    active[(size_t)i] = 0;  // converged with the speculative run: its bitmap from here on is the true one
+                    bad[(size_t)k] = 0;
+                } else if (stage == NCK || at[(size_t)i] >= works[(size_t)k].end) {
+                    NFC_CUDA_CHECK(cudaMemcpyAsync(st_out(k), tmp_state(i), sblk, cudaMemcpyDeviceToDevice, cs));
+                    active[(size_t)i] = 0;
+                    bad[(size_t)k] = 0;
+                    if (k + 1 < nseg) bad[(size_t)k + 1] = 2;  // unknown: re-compare below
+                }
+            }
+        }
+        std::vector<int> unk;
+        for (int k = 1; k < nseg; k++)
+            if (bad[(size_t)k] == 2) unk.push_back(k);
+        if (!unk.empty()) {
+            for (size_t q = 0; q < unk.size(); q++) {
+                truth[q] = st_out(unk[q] - 1);
+                assumed[q] = seam_in(unk[q]);
+                pidx[q] = 0;
+            }
+            if (compare((int)unk.size())) return -1;
+            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            for (size_t q = 0; q < unk.size(); q++) bad[(size_t)unk[q]] = mism[q] ? 1 : 0;
+        }
+        nbad = 0;
+        for (int k = 1; k < nseg; k++) nbad += bad[(size_t)k] ? 1 : 0;
+    }
+    if (nbad > 0) {
+        set_error("seam repair did not settle");
+        return -1;
+    }
+
+    // ---- bitmap -> dense ordered transitions
+    const size_t nblk = extract_blocks(bm_pos0, a, b);
+    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
+    if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
+                             ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
+        return -1;
+    stats.launches += 4;
+    uint32_t R = 0;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
+    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
+                             trans_dense.as<TransRec>(), R, cs))
+        return -1;
+    stats.launches++;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
+    *R_out = R;
+    return 0;
+}
+
 int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b) {
     NFC_CUDA_CHECK(cudaEventRecord(ev_a, cs));
     uint32_t R = 0;
     bool fell_back = false;
     const bool par = parallel_ok();
-    if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) return -1;
+    if (streaming_ok()) {
+        if (run_slicer_bm(d_in, in_pos0, in_begin, in_end, a, b, &R, &fell_back)) return -1;
+    } else if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) {
+        return -1;
+    }
     if (fell_back) {
         serial_mode = true;  // sums are no longer exactly representable: stay on the sequential kernel
         if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, true, &R, &fell_back)) return -1;
