@@ -31,10 +31,10 @@ struct __align__(32) FastRec {  // one chunk of 128 samples
     float mL, mH;   // min |x - guessed LOW threshold|, min |x - guessed HIGH threshold| (NaN if a sample is NaN)
     unsigned meta;  // bits 0-1 first class code, 2-3 last class code, then FM_* flags
     unsigned lpos;  // bits 0-7 last LOW sample + 1 (0 = none / not computed), 8-15 last LOW-run start strictly inside + 1
-    unsigned pad0, pad1;
+    float W, pad;   // precise pass: smallest slack of any lane, in ss units: margin / (lo/L) - |guessed ss error| - |steps inside the lane|
 };
 enum { FM_HASL = 16u, FM_HASH = 32u, FM_BAD = 128u };
-enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2 };
+enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3 };
 enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_N };
 
 static const int FAST_CH = 128;  // samples per chunk
@@ -42,6 +42,11 @@ static const int FAST_CH = 128;  // samples per chunk
 __device__ __forceinline__ float redux_min_nan(float v) {
     float r;
     asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
 __device__ __forceinline__ float redux_min(float v) {
@@ -104,7 +109,9 @@ struct __align__(16) FastUni {
     float thr_min, thr_max;           // admitted samples of streamed tiles lie strictly between these
     int ok;                           // the coming tile may be streamed (ss > 0, step representable)
     int verdict;
-    float gTL[32], gTH[32];           // guessed thresholds per chunk of the coming tile (or of the repeat)
+    float gTL[32], gTH[32];           // guessed thresholds per chunk of the coming tile (or of the repeat), at the chunk's middle
+    float gMid[32];                   // the guessed ss behind them (relative to the interval's midpoint)
+    float gC0[32];                    // repeat: the measured ss at the chunk's first sample (relative to the midpoint) the guess assumes
     unsigned stats[FS_N];
 };
 
@@ -148,15 +155,16 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     const float ssf = __double2float_rd(ssm);
     bool ok = ss_lo > 0.0 && ssf < 1.0e30f && ssf > 1.0e-30f;
     if (!(a_est > 0.0f)) a_est = ssf * 0x1p-7f;
-    const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;  // fixed-point step: a power of two near a_est * 2^-26
-    ok = ok && ae > 40u && ae < 250u;
+    const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;  // fixed-point step: a power of two near a_est * 2^-31
+    ok = ok && ae > 45u && ae < 250u;
     const float TLb = __double2float_rn(ssm * loL), THb = __double2float_rn(ssm * hiL);
     const float srel = ok ? tot_prev * (1.0f / NC) / ssf : 0.0f;  // predicted relative change of ss per chunk
     const float f = fmaf(srel, (float)lane + 0.5f, 1.0f);
     u.gTL[lane] = TLb * f;
     u.gTH[lane] = THb * f;
+    u.gMid[lane] = ssf * (f - 1.0f);
     if (lane == 0) {
-        const unsigned qe = ok ? ae - 25u : 127u;
+        const unsigned qe = ok ? ae - 30u : 127u;
         u.q = __uint_as_float(qe << 23);
         u.invq = __uint_as_float((254u - qe) << 23);
         u.invqA = u.invq * (1.0f + 0x1p-20f);
@@ -365,13 +373,27 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         bool x_ready = have_x;  // this tile's samples were requested during the previous tile
         have_x = false;
         if (t >= t_int_lo && t < t_int_hi && t != t_strad && uni.ok) {
-            for (int iter = 0;; iter++) {
+            int n_meas = 0, n_coarse = 0;  // repeats of this tile: with measured guesses, with a coarser fixed-point step
+            for (;;) {
                 if (!x_ready) load_tile(xptr);
                 x_ready = false;
                 const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
                 const float4 tl4 = *reinterpret_cast<const float4 *>(&uni.gTL[warp * R]);
                 const float4 th4 = *reinterpret_cast<const float4 *>(&uni.gTH[warp * R]);
-                const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
+                float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
+                // a repeated tile is classified sample by sample against the measured window sums (precise pass)
+                const bool precise = n_meas > 0;
+                const float loLf = (float)p.loL, hiLf = (float)p.hiL;
+                float c0g[R] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float invLo = 0.0f, invHi = 0.0f, TLb = 0.0f, THb = 0.0f;
+                if (precise) {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(&uni.gC0[warp * R]);
+                    c0g[0] = c4.x; c0g[1] = c4.y; c0g[2] = c4.z; c0g[3] = c4.w;
+                    invLo = (1.0f - 0x1p-20f) / loLf;
+                    invHi = (1.0f - 0x1p-20f) / hiLf;
+                    TLb = uni.TLb;
+                    THb = uni.THb;
+                }
 
                 float n[R * 4];
                 // ------------------------------------------------------------ phase 1: classify, sums, margins, maps
@@ -391,9 +413,51 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                                   Hm[3], n[r * 4 + 2], n[r * 4 + 3]);
                     float sa, sb;
                     asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s2));
+                    float ssum = sa + sb;
+                    float W = 0.0f;
+                    if (precise) {
+                        // steps before each lane under the classes just guessed ...
+                        float incA = ssum;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float v = __shfl_up_sync(FULL, incA, o);
+                            if (lane >= o) incA += v;
+                        }
+                        const float PA = incA - ssum;
+                        // ... give every sample its own guessed ss: (chunk start the repeat assumes) + (steps before it).
+                        // Classify again, in order inside the lane; the margins are now against per-sample thresholds.
+                        const float base = c0g[r] + PA;
+                        const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
+                        const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                        const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                        float run = 0.0f, wmin = INFINITY;
+                        a = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
+                            const bool pnl = xs[j] > tl, ph = xs[j] > th;
+                            NLm[j] = __ballot_sync(FULL, pnl);
+                            Hm[j] = __ballot_sync(FULL, ph);
+                            const float nn = (pnl && !ph) ? xs[j] : ps[j];
+                            const float d = nn - ps[j];
+                            n[r * 4 + j] = nn;
+                            run += d;
+                            a += fabsf(d);
+                            wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
+                        }
+                        ssum = run;
+                        float incB = ssum;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float v = __shfl_up_sync(FULL, incB, o);
+                            if (lane >= o) incB += v;
+                        }
+                        // slack of the lane, in ss units: margin less what the second classification moved the steps before it by
+                        W = redux_min_nan(wmin - fabsf((incB - ssum) - PA) * 1.001f);
+                    }
                     const float af = a * kq.z;
-                    const int si = __float2int_rn((sa + sb) * kq.y);
-                    const int ai = __float2int_ru(fminf(af, 1048576.0f));
+                    const int si = __float2int_rn(ssum * kq.y);
+                    const int ai = __float2int_ru(fminf(af, 33554432.0f));
                     const int S = __reduce_add_sync(FULL, si), A = __reduce_add_sync(FULL, ai);
                     mL = redux_min_nan(mL);
                     mH = redux_min_nan(mH);
@@ -401,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     const unsigned anyH = Hm[0] | Hm[1] | Hm[2] | Hm[3];
                     const unsigned fc = (NLm[0] & 1u) + (Hm[0] & 1u), lc = (NLm[3] >> 31) + (Hm[3] >> 31);
                     unsigned meta = fc | (lc << 2);
-                    if (__any_sync(FULL, !(af < 1048576.0f))) meta |= FM_BAD;  // a lane's sum does not fit (or is NaN)
+                    if (__any_sync(FULL, !(af < 33554432.0f))) meta |= FM_BAD;  // a lane's sum does not fit 2^25 (or is NaN)
                     if (anyH != 0u) meta |= FM_HASH;
                     unsigned lpos = 0u;
                     if (allNL != FULL) {
@@ -424,7 +488,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     if (lane == 0) {
                         uint4 *rw = reinterpret_cast<uint4 *>(&fs.recs[ch]);
                         rw[0] = make_uint4((unsigned)S, (unsigned)A, __float_as_uint(mL), __float_as_uint(mH));
-                        *reinterpret_cast<uint2 *>(rw + 1) = make_uint2(meta, lpos);
+                        rw[1] = make_uint4(meta, lpos, __float_as_uint(W), 0u);
                         uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[ch * 8]);
                         bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
                         bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
@@ -440,32 +504,48 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 // ------------------------------------------------------------ phase 2 (warp 0): lane = chunk
                 if (warp == 0) {
                     const uint4 r0 = *reinterpret_cast<const uint4 *>(&fs.recs[lane]);
-                    const uint2 r1 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint4 *>(&fs.recs[lane]) + 1);
+                    const uint4 r1 = *(reinterpret_cast<const uint4 *>(&fs.recs[lane]) + 1);
                     const int S = (int)r0.x, A = (int)r0.y;
                     const float mL = __uint_as_float(r0.z), mH = __uint_as_float(r0.w);
                     const unsigned meta = r1.x, lpos = r1.y;
                     const float q = kq.x, hwf = kq.w;
-                    const float loLf = (float)p.loL, hiLf = (float)p.hiL;
-                    int incS = S;
+                    long long incS = S;  // chunk sums stay below 2^30 in magnitude, their prefix needs more
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(FULL, incS, o);
+                        const long long v = __shfl_up_sync(FULL, incS, o);
                         if (lane >= o) incS += v;
                     }
-                    const int totS = __shfl_sync(FULL, incS, 31);
-                    const int totA = __reduce_add_sync(FULL, A);
+                    const long long totS = __shfl_sync(FULL, incS, 31);
+                    float totA = (float)A;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) totA += __shfl_xor_sync(FULL, totA, o);
+                    totA *= 1.0f + 0x1p-20f;
                     const unsigned metaor = __reduce_or_sync(FULL, meta);
-                    // error of the fixed-point sums (conversion: half a step per lane and chunk; float rounding: 2^-21 of |d|)
-                    const float Ef = ((float)(16 * NC) + (float)totA * 0x1p-21f) * q * 1.01f;
-                    // measured: inside chunk c the window sum stays within (midpoint of the tile's start interval) + mid +- rr
-                    const float mid = ((float)(incS - S) + 0.5f * (float)S) * q;
-                    const float rr = (hwf + Ef + 0.5f * (float)A * q) * 1.001f;
-                    const float tlm = fmaf(mid, loLf, uni.TLb), thm = fmaf(mid, hiLf, uni.THb);
-                    const float rl = fmaf(rr, loLf, tlm * 0x1p-19f), rh = fmaf(rr, hiLf, thm * 0x1p-19f);
-                    // the guess is proven when no sample lies between it and any value the true threshold can take
+                    // error of the fixed-point sums (conversion: half a step per lane and chunk; float rounding: 2^-20 of |d|)
+                    const float Ef = ((float)(16 * NC) + totA * 0x1p-20f) * q * 1.01f;
+                    // measured: the window sum at the chunk's first sample (relative to the midpoint of the tile's start
+                    // interval) is c0 +- (hwf + Ef); inside the chunk it moves within [V, U] around the guessed line
+                    const float c0 = (float)(incS - S) * q;
+                    const float slack = (hwf + Ef) * 1.001f;
                     const float gl = uni.gTL[lane], gh = uni.gTH[lane];
-                    const bool fine = (mL > fabsf(tlm - gl) + rl) && (mH > fabsf(thm - gh) + rh) && (tlm - rl > 0.0f);
+                    bool fine;
+                    if (precise) {
+                        // the lanes' slack must cover what the chunk's start is off the assumed one by, and the interval
+                        const float W = __uint_as_float(r1.z);
+                        const float need = (fabsf(c0 - uni.gC0[lane]) + slack) * (1.0f + 0x1p-18f) + uni.TLb * (0x1p-21f / loLf);
+                        fine = (W > need) && (gl > 0.0f);
+                    } else {
+                        // inside the chunk ss moves within [V, U] of its start: the sums of the negative / positive steps
+                        const float U = 0.5f * (float)(A + S) * q, V = -0.5f * (float)(A - S) * q;
+                        const float off = c0 - uni.gMid[lane];
+                        const float dev = fmaxf(fabsf(off + U + slack), fabsf(off + V - slack));  // |ss - guessed ss| at any sample
+                        const float rl = fmaf(dev, loLf, gl * 0x1p-19f), rh = fmaf(dev, hiLf, gh * 0x1p-19f);
+                        // the guess is proven when no sample lies between it and any value the true threshold can take
+                        fine = (mL > rl) && (mH > rh) && (gl - rl > 0.0f);
+                    }
                     const bool all_fine = __all_sync(FULL, fine);
+                    const float mid = c0 + 0.5f * (float)S * q;  // measured window sum at the chunk's middle
+                    const float tlm = fmaf(mid, loLf, uni.TLb), thm = fmaf(mid, hiLf, uni.THb);
                     // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
                     bool st2 = false;
                     if (metaor & FM_HASH) {
@@ -483,15 +563,29 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         st2 = __any_sync(FULL, risk);
                     }
                     if (!all_fine || st2 || (metaor & FM_BAD)) {
-                        const bool redo = !st2 && !(metaor & FM_BAD) && iter == 0;
-                        if (redo) {  // go round again with the measured thresholds as the guess
+                        const bool bad = (metaor & FM_BAD) != 0u;
+                        const bool redo = !st2 && (bad ? n_coarse < 3 : n_meas < 1);
+                        if (redo && !bad) {  // go round again with a line through the measured window sums as the guess
                             uni.gTL[lane] = tlm;
                             uni.gTH[lane] = thm;
+                            uni.gMid[lane] = mid;
+                            uni.gC0[lane] = c0;
                         }
                         if (lane == 0) {
-                            uni.verdict = redo ? FV_REDO : FV_SLOW;
-                            if (metaor & FM_BAD) uni.a_est *= 16.0f;
-                            uni.stats[redo ? FS_REDO : ((metaor & FM_BAD) ? FS_BAD : (st2 ? FS_ST2 : FS_UNC))]++;
+                            uni.verdict = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : FV_SLOW;
+                            if (bad) {  // a lane's sum did not fit: coarser fixed-point step
+                                const float ae = uni.a_est * 16.0f;
+                                const unsigned e = (__float_as_uint(ae) >> 23) & 0xffu;
+                                if (e > 45u && e < 250u) {
+                                    uni.a_est = ae;
+                                    uni.q = __uint_as_float((e - 30u) << 23);
+                                    uni.invq = __uint_as_float((254u - (e - 30u)) << 23);
+                                    uni.invqA = uni.invq * (1.0f + 0x1p-20f);
+                                } else {
+                                    uni.verdict = FV_SLOW;
+                                }
+                            }
+                            uni.stats[redo ? FS_REDO : (bad ? FS_BAD : (st2 ? FS_ST2 : FS_UNC))]++;
                         }
                     } else {
                         // ---- carries and the coming tile's constants
@@ -499,9 +593,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         const double delta = (double)totS * (double)q;  // exact
                         const double ss_lo = __dadd_rd(uni.ss_lo, __dadd_rd(delta, -(double)Ed_f));
                         const double ss_hi = __dadd_ru(uni.ss_hi, __dadd_ru(delta, (double)Ed_f));
-                        const float a_new = fmaxf((float)totA * q, uni.TLb * 0x1p-16f);
+                        const float a_new = fmaxf(fmaxf(totA * q, 0.25f * uni.a_est), uni.TLb * 0x1p-16f);  // follows the traffic, decays slowly
                         // admitted samples lie strictly between the LOW and HIGH bands: exponent range from the thresholds
-                        const float tmin = redux_min(tlm - rl), tmax = -redux_min(-(thm + rh));
+                        const float tmin = redux_min(gl * 0.5f), tmax = -redux_min(-(gh * 2.0f));  // one binade of slack either way
                         const int lastc = (int)((meta >> 2) & 3u), firstc = (int)(meta & 3u);
                         const int lv_prev = c_s.last_val + 1;  // class code of the sample before the tile
                         int prevlast = __shfl_up_sync(FULL, lastc, 1);
@@ -546,6 +640,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 }
                 have_x = false;  // xin is needed for this tile again, or the exact path reloads
                 if (verdict == FV_SLOW) break;
+                if (verdict == FV_REDO) n_meas++;
+                else n_coarse++;
             }
         }
         if (!done) {
