@@ -25,15 +25,12 @@
 
 namespace nfc {
 
-struct __align__(32) FastRec {  // one chunk of 128 samples
+struct __align__(16) FastRec {  // one chunk of 128 samples
     int S;          // round(sum of admitted (x - prev) / q)
     int A;          // >= sum of admitted |x - prev| / q
-    float mL, mH;   // min |x - guessed LOW threshold|, min |x - guessed HIGH threshold| (NaN if a sample is NaN)
-    unsigned meta;  // bits 0-1 first class code, 2-3 last class code, then FM_* flags
-    unsigned lpos;  // bits 0-7 last LOW sample + 1 (0 = none / not computed), 8-15 last LOW-run start strictly inside + 1
-    float W, pad;   // precise pass: smallest slack of any lane, in ss units: margin / (lo/L) - |guessed ss error| - |steps inside the lane|
+    float mL, mH;   // cheap pass: min |x - guessed LOW threshold|, min |x - guessed HIGH threshold| (NaN: a sample is NaN, or
+                    // a lane's sum does not fit the fixed point); precise pass: mL = smallest slack of any lane, in ss units
 };
-enum { FM_HASL = 16u, FM_HASH = 32u, FM_BAD = 128u };
 enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3 };
 enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_N };
 
@@ -101,18 +98,30 @@ __device__ __forceinline__ void classify_pair(float x0, float x1, float p0, floa
         : "f"(x0), "f"(x1), "f"(p0), "f"(p1), "f"(TL), "f"(TH), "l"(nTL2), "l"(nTH2));
 }
 
-// block-uniform state of the streaming path, written by warp 0 (and thread 0), read by everyone after a barrier
+// block-uniform state of the streaming path, written by warps 0 and 1 (and thread 0), read by everyone after a barrier
 struct __align__(16) FastUni {
     float q, invq, invqA, hwf;        // fixed-point step of the coming tile, half width of its ss interval (float, rounded up)
     float TLb, THb, tot_prev, a_est;  // thresholds at the interval's midpoint; last tile's drift; expected sum |x - prev| per tile
     double ss_lo, ss_hi;              // the window sum at the start of the coming tile lies in [ss_lo, ss_hi]
     float thr_min, thr_max;           // admitted samples of streamed tiles lie strictly between these
     int ok;                           // the coming tile may be streamed (ss > 0, step representable)
-    int verdict;
+    int verdict;                      // warp 0: what the sums say
+    int st2, cand_last_val, cand_newL, cand_newS;  // warp 1: hysteresis risk; the carries the tile would leave
     float gTL[32], gTH[32];           // guessed thresholds per chunk of the coming tile (or of the repeat), at the chunk's middle
     float gMid[32];                   // the guessed ss behind them (relative to the interval's midpoint)
     float gC0[32];                    // repeat: the measured ss at the chunk's first sample (relative to the midpoint) the guess assumes
     unsigned stats[FS_N];
+};
+
+// per-segment constants
+struct __align__(16) FastPlan {
+    int64_t tile0_pos;                // stream position of the first tile
+    const char *xbase;                // input item of that position
+    uint32_t *bm_base;                // bitmap word of that position's chunk
+    int ntiles, t_int_lo, t_int_hi, t_strad, t_emit;  // tile indices relative to the first: see below
+    int t_snap[4];                    // tiles before which a state snapshot is due (seam, three checkpoints), or -1
+    int nb;                           // chunks a LOW sample can reach forward through the hysteresis
+    float loLf, hiLf;
 };
 
 template <int NT, int R>
@@ -122,6 +131,7 @@ struct FastShared {
     FastRec recs[32];
     uint32_t bm[NC * 8];  // the tile's bitmap words, chunk-major
     FastUni uni;
+    FastPlan plan;
     double red[NW];
 };
 
@@ -179,6 +189,76 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     }
 }
 
+// One chunk (row r of this warp) of phase 1.  PRECISE: the repeat pass, every sample against its own guessed ss.
+template <bool PRECISE>
+__device__ __forceinline__ void fast_row(const float4 x4, const float4 pv4, float thL, float thH, float invq, float invqA, float c0g,
+                                         float TLb, float THb, float loLf, float hiLf, int lane, float (&n)[4], FastRec *rec, uint32_t *bmw) {
+    unsigned NLm[4], Hm[4];
+    unsigned long long s2 = 0ull;
+    float a = 0.0f, mL = INFINITY, mH = INFINITY;
+    const unsigned long long nTL2 = pack2(-thL, -thL), nTH2 = pack2(-thH, -thH);
+    classify_pair(x4.x, x4.y, pv4.x, pv4.y, thL, thH, nTL2, nTH2, mL, mH, s2, a, NLm[0], NLm[1], Hm[0], Hm[1], n[0], n[1]);
+    classify_pair(x4.z, x4.w, pv4.z, pv4.w, thL, thH, nTL2, nTH2, mL, mH, s2, a, NLm[2], NLm[3], Hm[2], Hm[3], n[2], n[3]);
+    float sa, sb;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s2));
+    float ssum = sa + sb;
+    if (PRECISE) {
+        // steps before each lane under the classes just guessed ...
+        float incA = ssum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(FULL, incA, o);
+            if (lane >= o) incA += v;
+        }
+        const float PA = incA - ssum;
+        // ... give every sample its own guessed ss: (chunk start the repeat assumes) + (steps before it).  Classify again,
+        // in order inside the lane; the margins are now against per-sample thresholds, in ss units.
+        const float base = c0g + PA;
+        const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
+        const float invLo = (1.0f - 0x1p-20f) / loLf, invHi = (1.0f - 0x1p-20f) / hiLf;
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+        float run = 0.0f, wmin = INFINITY;
+        a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
+            const bool pnl = xs[j] > tl, ph = xs[j] > th;
+            NLm[j] = __ballot_sync(FULL, pnl);
+            Hm[j] = __ballot_sync(FULL, ph);
+            const float nn = (pnl && !ph) ? xs[j] : ps[j];
+            const float d = nn - ps[j];
+            n[j] = nn;
+            run += d;
+            a += fabsf(d);
+            wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
+        }
+        ssum = run;
+        float incB = ssum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(FULL, incB, o);
+            if (lane >= o) incB += v;
+        }
+        // slack of the lane, in ss units: margin less what the second classification moved the steps before it by
+        mL = wmin - fabsf((incB - ssum) - PA) * 1.001f;
+        mH = INFINITY;
+    }
+    const float af = a * invqA;
+    if (!(af < 33554432.0f)) mL = __int_as_float(0x7fc00000);  // a lane's sum does not fit 2^25 (or is NaN)
+    const int si = __float2int_rn(ssum * invq);
+    const int ai = __float2int_ru(fminf(af, 33554432.0f));
+    const int S = __reduce_add_sync(FULL, si), A = __reduce_add_sync(FULL, ai);
+    mL = redux_min_nan(mL);
+    if (!PRECISE) mH = redux_min_nan(mH);
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(rec) = make_uint4((unsigned)S, (unsigned)A, __float_as_uint(mL), __float_as_uint(mH));
+        uint4 *bw = reinterpret_cast<uint4 *>(bmw);
+        bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
+        bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
+    }
+}
+
 // KIND: InputKind of the segment's samples (compile-time: the load path has no branches)
 template <int NT, int R, int MINB, int KIND>
 __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__restrict__ works,
@@ -189,42 +269,52 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     constexpr int T = NW * WS;            // samples per tile
     constexpr int SUB = NT * 4;           // exact_tile row
     constexpr int XR = T / SUB;           // exact_tile rows per tile
+    constexpr int ITEM = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
+    constexpr int tile_bytes = T * ITEM;
     static_assert(NC == 32, "one lane per chunk record");
     static_assert(T % SUB == 0, "tile is a whole number of exact rows");
     static_assert(R == 4, "one bitmap word per lane and tile; four guesses per 128-bit read");
+    static_assert(NW >= 2, "warps 0 and 1 share the verification");
     extern __shared__ __align__(16) float ring[];
     __shared__ BlockShared<NT, 4> sh;
     __shared__ FastShared<NT, R> fs;
     __shared__ SegWork w_s;
     __shared__ SlicerParams p_s;
     __shared__ SegCarry c_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
         w_s = works[blockIdx.x];
         p_s = params[w_s.param_idx];
     }
-    if (tid < FS_N) fs.uni.stats[tid] = 0u;
+    if (threadIdx.x < FS_N) fs.uni.stats[threadIdx.x] = 0u;
     __syncthreads();
     const SegWork &w = w_s;
     const SlicerParams &p = p_s;
     FastUni &uni = fs.uni;
+    const FastPlan &plan = fs.plan;
     const int L = p.L;
 
-    // ---- entry state (as slicer_kernel); the carry lives in shared memory (c_s), thread 0 / warp 0 maintain it
-    int emin = 1 << 30, emax = 0;
+    // ---- entry state (as slicer_kernel); the carry lives in shared memory (c_s), thread 0 / warps 0 and 1 maintain it
     {
+        int emin = 1 << 30, emax = 0;
+        if (threadIdx.x == 0) {
+            sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
+            sh.emin = 1 << 30;
+            sh.emax = 0;
+        }
         double ss0;
         if (w.state_in) {
             const float *src = state_ring(w.state_in);
-            for (int i = tid; i < L; i += NT) {
+            for (int i = threadIdx.x; i < L; i += NT) {
                 float v = src[i];
                 ring[i] = v;
                 exp_track(v, emin, emax);
             }
             ss0 = w.state_in->ss;
+            __syncthreads();
         } else {
             double part = 0.0;
-            for (int i = tid; i < L; i += NT) {
+            for (int i = threadIdx.x; i < L; i += NT) {
                 const int64_t q = w.warm_begin - L + i;
                 float v = load_one(w.in, q - w.in_pos0, p);
                 ring[(int)(q % L)] = v;
@@ -238,7 +328,10 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             ss0 = 0.0;
             for (int i = 0; i < NW; i++) ss0 += sh.red[i];
         }
-        if (tid == 0) {
+        emin = __reduce_min_sync(FULL, emin);
+        emax = __reduce_max_sync(FULL, emax);
+        if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
+        if (threadIdx.x == 0) {
             SegCarry c;
             c.ss0 = ss0;
             c.lastL = w.state_in ? w.state_in->lastL : NO_POS;
@@ -246,60 +339,59 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             c.last_val = w.state_in ? w.state_in->last_val : 0;
             c.seg_count = 0; c.scan_buf = 0; c.cnt_buf = 0; c.round_no = 0;
             c_s = c;
-            sh.flags[0] = sh.flags[1] = sh.flags[2] = 0u;
-            sh.emin = 1 << 30;
-            sh.emax = 0;
             uni.thr_min = 3.0e38f;
             uni.thr_max = 0.0f;
+            // ---- the segment in tiles (indices relative to the first one)
+            const bool fast_ok = ((L & 3) == 0) && L >= 2 * T && p.lo > 0.0 && p.hi > p.lo && w.bitmap != nullptr;
+            FastPlan pl;
+            const int64_t tile_first = w.warm_begin / T;
+            pl.tile0_pos = tile_first * T;
+            pl.xbase = reinterpret_cast<const char *>(w.in) + (pl.tile0_pos - w.in_pos0) * ITEM;
+            pl.bm_base = w.bitmap ? w.bitmap + ((pl.tile0_pos - w.bm_pos0) >> 7) * 8 : nullptr;
+            pl.ntiles = (w.end > w.warm_begin) ? (int)((w.end - 1) / T - tile_first) + 1 : 0;
+            const int64_t lo_pos = max(w.warm_begin, w.in_begin), hi_pos = min(w.end, w.in_end);
+            pl.t_int_lo = (int)((lo_pos + T - 1) / T - tile_first);             // first tile that is all inside
+            pl.t_int_hi = hi_pos >= 0 ? (int)(hi_pos / T - tile_first) : 0;     // one past the last such tile
+            if (!fast_ok) pl.t_int_hi = pl.t_int_lo;
+            pl.t_strad = (w.begin % T) ? (int)(w.begin / T - tile_first) : -1;  // tile cut by `begin`
+            pl.t_emit = (int)((w.begin + T - 1) / T - tile_first);              // tiles from here on are written
+            pl.t_snap[0] = (w.seam_in && w.begin > w.warm_begin && (w.begin % T) == 0) ? (int)(w.begin / T - tile_first) : -1;
+            for (int j = 0; j < 3; j++)
+                pl.t_snap[j + 1] = (w.ckpt_state[j] && w.ckpt_pos[j] != INT64_MAX && (w.ckpt_pos[j] % T) == 0)
+                                       ? (int)(w.ckpt_pos[j] / T - tile_first) : -1;
+            pl.nb = (p.mx + FAST_CH) / FAST_CH;
+            pl.loLf = (float)p.loL;
+            pl.hiLf = (float)p.hiL;
+            fs.plan = pl;
         }
         if (warp == 0) fast_prepare<NC>(uni, ss0, ss0, 0.0f, -1.0f, p.loL, p.hiL, lane);
     }
     __syncthreads();
 
-    const bool fast_ok = ((L & 3) == 0) && L >= 2 * T && p.lo > 0.0 && p.hi > p.lo && w.bitmap != nullptr;
-
-    // ---- the segment in tiles (indices relative to the first one)
-    const int64_t tile_first = w.warm_begin / T;
-    const int ntiles = (w.end > w.warm_begin) ? (int)((w.end - 1) / T - tile_first) + 1 : 0;
-    int t_int_lo, t_int_hi, t_strad, t_emit;
-    {
-        const int64_t lo_pos = max(w.warm_begin, w.in_begin), hi_pos = min(w.end, w.in_end);
-        t_int_lo = (int)((lo_pos + T - 1) / T - tile_first);                // first tile that is all inside
-        t_int_hi = hi_pos >= 0 ? (int)(hi_pos / T - tile_first) : 0;        // one past the last such tile
-        t_strad = (w.begin % T) ? (int)(w.begin / T - tile_first) : -1;     // tile cut by `begin`
-        t_emit = (int)((w.begin + T - 1) / T - tile_first);                 // tiles from here on are written
-        if (!fast_ok) t_int_hi = t_int_lo;
-    }
-    // tiles before which a state snapshot is due (seam, checkpoints): the next one in t_snap
-    auto snap_tile = [&](int j) -> int {  // j = 0: seam, 1..3: checkpoints
-        if (j == 0) return (w.seam_in && w.begin > w.warm_begin && (w.begin % T) == 0) ? (int)(w.begin / T - tile_first) : -1;
-        return (w.ckpt_state[j - 1] && w.ckpt_pos[j - 1] != INT64_MAX && (w.ckpt_pos[j - 1] % T) == 0)
-                   ? (int)(w.ckpt_pos[j - 1] / T - tile_first) : -1;
-    };
     auto next_snap = [&](int after) -> int {
         int best = INT_MAX;
+#pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int ts = snap_tile(j);
+            const int ts = plan.t_snap[j];
             if (ts > after && ts < best) best = ts;
         }
         return best;
     };
     int t_snap = next_snap(-1);
+    const int ntiles = plan.ntiles;
+    const int64_t tile0_pos = plan.tile0_pos;
 
     // exact_tile's slot of this thread's first sample of a row, and this kernel's (warp-contiguous layout)
-    int slot_x = (int)((tile_first * T + (int64_t)tid * 4) % L);
-    int slot_w = (int)((tile_first * T + (int64_t)warp * WS + (int64_t)lane * 4) % L);
+    int slot_x = (int)((tile0_pos + (int64_t)threadIdx.x * 4) % L);
+    int slot_w = (int)((tile0_pos + (int64_t)warp * WS + (int64_t)lane * 4) % L);
     const int slot_step = T % L;
-    // this thread's first sample of the first tile in the input buffer
-    constexpr int ITEM = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
-    const char *xptr = reinterpret_cast<const char *>(w.in) + (tile_first * T - w.in_pos0 + (int64_t)warp * WS + (int64_t)lane * 4) * ITEM;
-    constexpr int tile_bytes = T * ITEM;
-    uint32_t *bm_out = w.bitmap ? w.bitmap + ((tile_first * T - w.bm_pos0) >> 7) * 8 + warp * (R * 8) + lane : nullptr;
+    const int xoff = (warp * WS + lane * 4) * ITEM;  // this thread's first sample inside a tile of the input
 
     float4 xin[R];
     bool have_x = false;
 
-    auto load_tile = [&](const char *src) {
+    auto load_tile = [&](int t) {
+        const char *src = plan.xbase + (int64_t)t * tile_bytes + xoff;
         if (KIND == IN_ENVELOPE_F32 || KIND == IN_REAL_F32) {
 #pragma unroll
             for (int r = 0; r < R; r++) xin[r] = ldg_stream4(reinterpret_cast<const float4 *>(src + r * FAST_CH * 4));
@@ -327,13 +419,14 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             }
         }
     };
+    auto streamable = [&](int t) { return t >= plan.t_int_lo && t < plan.t_int_hi && t != plan.t_strad; };
     // the exact window sum into c_s.ss0 (and the interval collapsed onto it); ends with a barrier
     auto make_exact = [&]() {
         const double lo = uni.ss_lo, hi = uni.ss_hi;
         double s = lo;
         if (lo != hi) s = ring_sum_exact<NT>(ring, L, fs.red);
         else __syncthreads();
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             if (lo != hi) uni.stats[FS_RESUM]++;
             uni.ss_lo = uni.ss_hi = s;
             c_s.ss0 = s;
@@ -343,8 +436,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     auto snapshot = [&](SlicerHdr *dsth, int64_t pos) {
         make_exact();
         float *dst = state_ring(dsth);
-        for (int i = tid; i < L; i += NT) dst[i] = ring[i];
-        if (tid == 0) {
+        for (int i = threadIdx.x; i < L; i += NT) dst[i] = ring[i];
+        if (threadIdx.x == 0) {
             SlicerHdr h;
             h.ss = c_s.ss0; h.pos = pos; h.lastL = c_s.lastL; h.lrun_start = c_s.lrun_start;
             h.last_val = c_s.last_val; h.emin = 0; h.emax = 0; h.status = 0; h.count = 0; h.pad = 0;
@@ -352,12 +445,11 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         }
     };
 
-    int64_t P0 = tile_first * T;
-    for (int t = 0; t < ntiles; t++, P0 += T, xptr += tile_bytes, bm_out += NC * 8) {
+    for (int t = 0; t < ntiles; t++) {
         if (t == t_snap) {
-            if (t == snap_tile(0)) snapshot(w.seam_in, w.begin);
+            if (t == plan.t_snap[0]) snapshot(w.seam_in, w.begin);
             for (int j = 1; j < 4; j++)
-                if (t == snap_tile(j)) snapshot(w.ckpt_state[j - 1], P0);
+                if (t == plan.t_snap[j]) snapshot(w.ckpt_state[j - 1], tile0_pos + (int64_t)t * T);
             t_snap = next_snap(t);
             // the interval collapsed: the coming tile's constants follow it
             if (warp == 0) {
@@ -372,168 +464,85 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         bool done = false;
         bool x_ready = have_x;  // this tile's samples were requested during the previous tile
         have_x = false;
-        if (t >= t_int_lo && t < t_int_hi && t != t_strad && uni.ok) {
+        if (streamable(t) && uni.ok) {
             int n_meas = 0, n_coarse = 0;  // repeats of this tile: with measured guesses, with a coarser fixed-point step
             for (;;) {
-                if (!x_ready) load_tile(xptr);
+                if (!x_ready) load_tile(t);
                 x_ready = false;
                 const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
                 const float4 tl4 = *reinterpret_cast<const float4 *>(&uni.gTL[warp * R]);
                 const float4 th4 = *reinterpret_cast<const float4 *>(&uni.gTH[warp * R]);
-                float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
-                // a repeated tile is classified sample by sample against the measured window sums (precise pass)
-                const bool precise = n_meas > 0;
-                const float loLf = (float)p.loL, hiLf = (float)p.hiL;
-                float c0g[R] = {0.0f, 0.0f, 0.0f, 0.0f};
-                float invLo = 0.0f, invHi = 0.0f, TLb = 0.0f, THb = 0.0f;
-                if (precise) {
-                    const float4 c4 = *reinterpret_cast<const float4 *>(&uni.gC0[warp * R]);
-                    c0g[0] = c4.x; c0g[1] = c4.y; c0g[2] = c4.z; c0g[3] = c4.w;
-                    invLo = (1.0f - 0x1p-20f) / loLf;
-                    invHi = (1.0f - 0x1p-20f) / hiLf;
-                    TLb = uni.TLb;
-                    THb = uni.THb;
-                }
+                const bool precise = n_meas > 0;  // a repeated tile is classified sample by sample against the measured sums
 
-                float n[R * 4];
+                float n[R][4];
                 // ------------------------------------------------------------ phase 1: classify, sums, margins, maps
+                {
+                    int s0 = slot_w;
+                    FastRec *rec = &fs.recs[warp * R];
+                    uint32_t *bmw = &fs.bm[warp * R * 8];
+                    if (!precise) {
+                        const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int ch = warp * R + r;
-                    int s0 = slot_w + r * FAST_CH;
-                    if (s0 >= L) s0 -= L;
-                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                    unsigned NLm[4], Hm[4];
-                    unsigned long long s2 = 0ull;
-                    float a = 0.0f, mL = INFINITY, mH = INFINITY;
-                    const unsigned long long nTL2 = pack2(-thL[r], -thL[r]), nTH2 = pack2(-thH[r], -thH[r]);
-                    classify_pair(xin[r].x, xin[r].y, pv4.x, pv4.y, thL[r], thH[r], nTL2, nTH2, mL, mH, s2, a, NLm[0], NLm[1], Hm[0],
-                                  Hm[1], n[r * 4 + 0], n[r * 4 + 1]);
-                    classify_pair(xin[r].z, xin[r].w, pv4.z, pv4.w, thL[r], thH[r], nTL2, nTH2, mL, mH, s2, a, NLm[2], NLm[3], Hm[2],
-                                  Hm[3], n[r * 4 + 2], n[r * 4 + 3]);
-                    float sa, sb;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s2));
-                    float ssum = sa + sb;
-                    float W = 0.0f;
-                    if (precise) {
-                        // steps before each lane under the classes just guessed ...
-                        float incA = ssum;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const float v = __shfl_up_sync(FULL, incA, o);
-                            if (lane >= o) incA += v;
+                        for (int r = 0; r < R; r++) {
+                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                            fast_row<false>(xin[r], pv4, thL[r], thH[r], kq.y, kq.z, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, lane, n[r], rec + r,
+                                            bmw + r * 8);
+                            s0 += FAST_CH;
+                            if (s0 >= L) s0 -= L;
                         }
-                        const float PA = incA - ssum;
-                        // ... give every sample its own guessed ss: (chunk start the repeat assumes) + (steps before it).
-                        // Classify again, in order inside the lane; the margins are now against per-sample thresholds.
-                        const float base = c0g[r] + PA;
-                        const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
-                        const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
-                        const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                        float run = 0.0f, wmin = INFINITY;
-                        a = 0.0f;
+                    } else {
+                        const float4 c4 = *reinterpret_cast<const float4 *>(&uni.gC0[warp * R]);
+                        const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
+                        const float c0g[R] = {c4.x, c4.y, c4.z, c4.w};
+                        const float TLb = uni.TLb, THb = uni.THb;
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
-                            const bool pnl = xs[j] > tl, ph = xs[j] > th;
-                            NLm[j] = __ballot_sync(FULL, pnl);
-                            Hm[j] = __ballot_sync(FULL, ph);
-                            const float nn = (pnl && !ph) ? xs[j] : ps[j];
-                            const float d = nn - ps[j];
-                            n[r * 4 + j] = nn;
-                            run += d;
-                            a += fabsf(d);
-                            wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
+                        for (int r = 0; r < R; r++) {
+                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                            fast_row<true>(xin[r], pv4, thL[r], thH[r], kq.y, kq.z, c0g[r], TLb, THb, plan.loLf, plan.hiLf, lane, n[r],
+                                           rec + r, bmw + r * 8);
+                            s0 += FAST_CH;
+                            if (s0 >= L) s0 -= L;
                         }
-                        ssum = run;
-                        float incB = ssum;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const float v = __shfl_up_sync(FULL, incB, o);
-                            if (lane >= o) incB += v;
-                        }
-                        // slack of the lane, in ss units: margin less what the second classification moved the steps before it by
-                        W = redux_min_nan(wmin - fabsf((incB - ssum) - PA) * 1.001f);
-                    }
-                    const float af = a * kq.z;
-                    const int si = __float2int_rn(ssum * kq.y);
-                    const int ai = __float2int_ru(fminf(af, 33554432.0f));
-                    const int S = __reduce_add_sync(FULL, si), A = __reduce_add_sync(FULL, ai);
-                    mL = redux_min_nan(mL);
-                    mH = redux_min_nan(mH);
-                    const unsigned allNL = NLm[0] & NLm[1] & NLm[2] & NLm[3];
-                    const unsigned anyH = Hm[0] | Hm[1] | Hm[2] | Hm[3];
-                    const unsigned fc = (NLm[0] & 1u) + (Hm[0] & 1u), lc = (NLm[3] >> 31) + (Hm[3] >> 31);
-                    unsigned meta = fc | (lc << 2);
-                    if (__any_sync(FULL, !(af < 33554432.0f))) meta |= FM_BAD;  // a lane's sum does not fit 2^25 (or is NaN)
-                    if (anyH != 0u) meta |= FM_HASH;
-                    unsigned lpos = 0u;
-                    if (allNL != FULL) {
-                        meta |= FM_HASL;
-                        const int nbk = (p.mx + FAST_CH) / FAST_CH;  // chunks at the tile end whose LOW samples can still matter later
-                        if (lc == 0u || ch >= NC - nbk) {
-                            // last LOW sample, last LOW-run start strictly inside (chunk positions 4l+j)
-                            int bestL = -1, bestS = -1;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const unsigned lw = ~NLm[j];
-                                const unsigned pw = j == 0 ? ((NLm[3] << 1) & ~1u) : NLm[j - 1];  // predecessor not LOW
-                                const unsigned sw = lw & pw;
-                                if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
-                                if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
-                            }
-                            lpos = (unsigned)(bestL + 1) | ((unsigned)(bestS + 1) << 8);
-                        }
-                    }
-                    if (lane == 0) {
-                        uint4 *rw = reinterpret_cast<uint4 *>(&fs.recs[ch]);
-                        rw[0] = make_uint4((unsigned)S, (unsigned)A, __float_as_uint(mL), __float_as_uint(mH));
-                        rw[1] = make_uint4(meta, lpos, __float_as_uint(W), 0u);
-                        uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[ch * 8]);
-                        bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
-                        bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
                     }
                 }
                 // next tile's samples on their way while this one is settled
-                if (t + 1 >= t_int_lo && t + 1 < t_int_hi && t + 1 != t_strad) {
-                    load_tile(xptr + tile_bytes);
+                if (t + 1 < ntiles && streamable(t + 1)) {
+                    load_tile(t + 1);
                     have_x = true;
                 }
                 __syncthreads();
 
-                // ------------------------------------------------------------ phase 2 (warp 0): lane = chunk
                 if (warp == 0) {
+                    // -------------------------------------------------------- phase 2a (warp 0): the sums, lane = chunk
                     const uint4 r0 = *reinterpret_cast<const uint4 *>(&fs.recs[lane]);
-                    const uint4 r1 = *(reinterpret_cast<const uint4 *>(&fs.recs[lane]) + 1);
                     const int S = (int)r0.x, A = (int)r0.y;
                     const float mL = __uint_as_float(r0.z), mH = __uint_as_float(r0.w);
-                    const unsigned meta = r1.x, lpos = r1.y;
                     const float q = kq.x, hwf = kq.w;
-                    long long incS = S;  // chunk sums stay below 2^30 in magnitude, their prefix needs more
+                    const float loLf = plan.loLf, hiLf = plan.hiLf;
+                    // window sum at each chunk's first sample, relative to the midpoint of the tile's start interval
+                    const float Sf = (float)S * q;
+                    float inc = Sf;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const long long v = __shfl_up_sync(FULL, incS, o);
-                        if (lane >= o) incS += v;
+                        const float v = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += v;
                     }
-                    const long long totS = __shfl_sync(FULL, incS, 31);
-                    float totA = (float)A;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) totA += __shfl_xor_sync(FULL, totA, o);
-                    totA *= 1.0f + 0x1p-20f;
-                    const unsigned metaor = __reduce_or_sync(FULL, meta);
-                    // error of the fixed-point sums (conversion: half a step per lane and chunk; float rounding: 2^-20 of |d|)
+                    const float c0 = inc - Sf;
+                    // the tile's totals: exact sum of the chunk sums (they stay below 2^30), upper bound of the |step| sums
+                    const long long totS = ((long long)__reduce_add_sync(FULL, S >> 8) << 8) + (long long)__reduce_add_sync(FULL, S & 0xff);
+                    const float totA = (float)((unsigned)__reduce_add_sync(FULL, (A >> 6) + 1)) * 64.0f;
+                    const bool nanm = !(mL == mL) || !(mH == mH);
+                    const bool bad = __any_sync(FULL, nanm);
+                    // error of the sums: conversion (half a step per lane and chunk), float rounding (2^-20 of |d|, also covers
+                    // the float prefix above)
                     const float Ef = ((float)(16 * NC) + totA * 0x1p-20f) * q * 1.01f;
-                    // measured: the window sum at the chunk's first sample (relative to the midpoint of the tile's start
-                    // interval) is c0 +- (hwf + Ef); inside the chunk it moves within [V, U] around the guessed line
-                    const float c0 = (float)(incS - S) * q;
                     const float slack = (hwf + Ef) * 1.001f;
                     const float gl = uni.gTL[lane], gh = uni.gTH[lane];
                     bool fine;
                     if (precise) {
                         // the lanes' slack must cover what the chunk's start is off the assumed one by, and the interval
-                        const float W = __uint_as_float(r1.z);
                         const float need = (fabsf(c0 - uni.gC0[lane]) + slack) * (1.0f + 0x1p-18f) + uni.TLb * (0x1p-21f / loLf);
-                        fine = (W > need) && (gl > 0.0f);
+                        fine = (mL > need) && (gl > 0.0f);
                     } else {
                         // inside the chunk ss moves within [V, U] of its start: the sums of the negative / positive steps
                         const float U = 0.5f * (float)(A + S) * q, V = -0.5f * (float)(A - S) * q;
@@ -544,36 +553,18 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         fine = (mL > rl) && (mH > rh) && (gl - rl > 0.0f);
                     }
                     const bool all_fine = __all_sync(FULL, fine);
-                    const float mid = c0 + 0.5f * (float)S * q;  // measured window sum at the chunk's middle
-                    const float tlm = fmaf(mid, loLf, uni.TLb), thm = fmaf(mid, hiLf, uni.THb);
-                    // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
-                    bool st2 = false;
-                    if (metaor & FM_HASH) {
-                        const int mx = p.mx;
-                        const int nb = (mx + FAST_CH) / FAST_CH;  // chunks a LOW sample can reach forward through the hysteresis
-                        const unsigned Lmask = __ballot_sync(FULL, (meta & FM_HASL) != 0u);
-                        const int lo_c = max(lane - nb, 0);
-                        const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
-                        bool risk = (meta & FM_HASH) && win != 0u;
-                        const int64_t cl = c_s.lastL;
-                        if ((meta & FM_HASH) && cl != NO_POS) {
-                            const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
-                            if (dist <= (int64_t)mx + 1) risk = true;
-                        }
-                        st2 = __any_sync(FULL, risk);
-                    }
-                    if (!all_fine || st2 || (metaor & FM_BAD)) {
-                        const bool bad = (metaor & FM_BAD) != 0u;
-                        const bool redo = !st2 && (bad ? n_coarse < 3 : n_meas < 1);
-                        if (redo && !bad) {  // go round again with a line through the measured window sums as the guess
-                            uni.gTL[lane] = tlm;
-                            uni.gTH[lane] = thm;
+                    if (!all_fine || bad) {
+                        const bool redo = bad ? n_coarse < 3 : n_meas < 1;
+                        if (redo && !bad) {  // go round again with the measured window sums as the guess
+                            const float mid = c0 + 0.5f * Sf;  // measured window sum at the chunk's middle
+                            uni.gTL[lane] = fmaf(mid, loLf, uni.TLb);
+                            uni.gTH[lane] = fmaf(mid, hiLf, uni.THb);
                             uni.gMid[lane] = mid;
                             uni.gC0[lane] = c0;
                         }
                         if (lane == 0) {
-                            uni.verdict = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : FV_SLOW;
-                            if (bad) {  // a lane's sum did not fit: coarser fixed-point step
+                            int v = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : FV_SLOW;
+                            if (bad && redo) {  // a lane's sum did not fit: coarser fixed-point step
                                 const float ae = uni.a_est * 16.0f;
                                 const unsigned e = (__float_as_uint(ae) >> 23) & 0xffu;
                                 if (e > 45u && e < 250u) {
@@ -582,59 +573,108 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                                     uni.invq = __uint_as_float((254u - (e - 30u)) << 23);
                                     uni.invqA = uni.invq * (1.0f + 0x1p-20f);
                                 } else {
-                                    uni.verdict = FV_SLOW;
+                                    v = FV_SLOW;
                                 }
                             }
-                            uni.stats[redo ? FS_REDO : (bad ? FS_BAD : (st2 ? FS_ST2 : FS_UNC))]++;
+                            uni.verdict = v;
+                            uni.stats[v == FV_SLOW ? (bad ? FS_BAD : FS_UNC) : FS_REDO]++;
                         }
                     } else {
-                        // ---- carries and the coming tile's constants
-                        const float Ed_f = Ef;
+                        // ---- the window sum after the tile and the coming tile's constants
                         const double delta = (double)totS * (double)q;  // exact
-                        const double ss_lo = __dadd_rd(uni.ss_lo, __dadd_rd(delta, -(double)Ed_f));
-                        const double ss_hi = __dadd_ru(uni.ss_hi, __dadd_ru(delta, (double)Ed_f));
+                        const double ss_lo = __dadd_rd(uni.ss_lo, __dadd_rd(delta, -(double)Ef));
+                        const double ss_hi = __dadd_ru(uni.ss_hi, __dadd_ru(delta, (double)Ef));
                         const float a_new = fmaxf(fmaxf(totA * q, 0.25f * uni.a_est), uni.TLb * 0x1p-16f);  // follows the traffic, decays slowly
-                        // admitted samples lie strictly between the LOW and HIGH bands: exponent range from the thresholds
-                        const float tmin = redux_min(gl * 0.5f), tmax = -redux_min(-(gh * 2.0f));  // one binade of slack either way
-                        const int lastc = (int)((meta >> 2) & 3u), firstc = (int)(meta & 3u);
-                        const int lv_prev = c_s.last_val + 1;  // class code of the sample before the tile
-                        int prevlast = __shfl_up_sync(FULL, lastc, 1);
-                        if (lane == 0) prevlast = lv_prev;
-                        const int lv_new = __shfl_sync(FULL, lastc, NC - 1) - 1;
-                        int newL = -1, newS = -1;
-                        if (metaor & FM_HASL) {
-                            const int lp = (int)(lpos & 0xffu), sp = (int)((lpos >> 8) & 0xffu);
-                            const int candL = lp ? lane * FAST_CH + lp - 1 : -1;
-                            int candS = sp ? lane * FAST_CH + sp - 1 : -1;
-                            if (lp && firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
-                            newL = __reduce_max_sync(FULL, candL);
-                            newS = __reduce_max_sync(FULL, candS);
-                        }
+                        // admitted samples lie strictly between the guessed thresholds' surroundings: one binade of slack either way
+                        const float tmin = redux_min(gl * 0.5f), tmax = -redux_min(-(gh * 2.0f));
                         if (lane == 0) {
                             uni.verdict = FV_ACCEPT;
-                            uni.stats[FS_FAST]++;
                             uni.thr_min = fminf(uni.thr_min, tmin);
                             uni.thr_max = fmaxf(uni.thr_max, tmax);
-                            c_s.last_val = lv_new;
-                            if (newL >= 0) {
-                                c_s.lastL = P0 + newL;
-                                if (newS >= 0) c_s.lrun_start = P0 + newS;
-                            }
                         }
                         fast_prepare<NC>(uni, ss_lo, ss_hi, (float)delta, a_new, p.loL, p.hiL, lane);
                     }
+                } else if (warp == 1) {
+                    // -------------------------------------------------------- phase 2b (warp 1): the class maps, lane = chunk
+                    const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8]);
+                    const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8 + 4]);
+                    const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
+                    const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
+                    const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
+                    const int64_t P0 = tile0_pos + (int64_t)t * T;
+                    // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+                    bool st2 = false;
+                    if (Hmask) {
+                        const int nb = plan.nb;
+                        const int lo_c = max(lane - nb, 0);
+                        const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
+                        bool risk = hasH && win != 0u;
+                        const int64_t cl = c_s.lastL;
+                        if (hasH && cl != NO_POS) {
+                            const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
+                            if (dist <= (int64_t)p.mx + 1) risk = true;
+                        }
+                        st2 = __any_sync(FULL, risk);
+                    }
+                    // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
+                    int newL = -1, newS = -1;
+                    if (Lmask) {
+                        int prevlast = __shfl_up_sync(FULL, lastc, 1);
+                        if (lane == 0) prevlast = c_s.last_val + 1;  // class code of the sample before the tile
+                        int candL = -1, candS = -1;
+                        // only chunks whose LOW samples can still matter later: the run continues, or the tile ends soon
+                        if (hasL && (lastc == 0 || lane >= NC - plan.nb)) {
+                            const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w};
+                            int bestL = -1, bestS = -1;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const unsigned lw = ~NLw[j];
+                                const unsigned pw = j == 0 ? ((NLw[3] << 1) & ~1u) : NLw[j - 1];  // predecessor not LOW
+                                const unsigned sw = lw & pw;
+                                if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
+                                if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
+                            }
+                            candL = lane * FAST_CH + bestL;
+                            if (bestS >= 0) candS = lane * FAST_CH + bestS;
+                            if (firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
+                        }
+                        newL = __reduce_max_sync(FULL, candL);
+                        newS = __reduce_max_sync(FULL, candS);
+                    }
+                    const int lv_new = __shfl_sync(FULL, lastc, NC - 1) - 1;
+                    if (lane == 0) {
+                        uni.st2 = st2 ? 1 : 0;
+                        uni.cand_last_val = lv_new;
+                        uni.cand_newL = newL;
+                        uni.cand_newS = newS;
+                    }
                 }
                 __syncthreads();
-                const int verdict = uni.verdict;
+                int verdict = uni.verdict;
+                if (uni.st2 && verdict != FV_SLOW) {
+                    verdict = FV_SLOW;
+                    if (threadIdx.x == 0) uni.stats[FS_ST2]++;
+                }
                 if (verdict == FV_ACCEPT) {
-                    // ---- ring update, bitmap out
+                    // ---- ring update, bitmap out, carries
+                    int s0 = slot_w;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        int s0 = slot_w + r * FAST_CH;
+                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(n[r][0], n[r][1], n[r][2], n[r][3]);
+                        s0 += FAST_CH;
                         if (s0 >= L) s0 -= L;
-                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(n[r * 4], n[r * 4 + 1], n[r * 4 + 2], n[r * 4 + 3]);
                     }
-                    if (t >= t_emit) *bm_out = fs.bm[warp * (R * 8) + lane];
+                    if (t >= plan.t_emit) plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
+                    if (threadIdx.x == 0) {
+                        uni.stats[FS_FAST]++;
+                        c_s.last_val = uni.cand_last_val;
+                        const int newL = uni.cand_newL, newS = uni.cand_newS;
+                        if (newL >= 0) {
+                            const int64_t P0 = tile0_pos + (int64_t)t * T;
+                            c_s.lastL = P0 + newL;
+                            if (newS >= 0) c_s.lrun_start = P0 + newS;
+                        }
+                    }
                     done = true;
                     break;
                 }
@@ -648,6 +688,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             // ---------------------------------------------------------------- exact path, row by row
             make_exact();
             const double ss_before = c_s.ss0;
+            const int64_t P0 = tile0_pos + (int64_t)t * T;
             __syncthreads();
 #pragma unroll 1
             for (int r = 0; r < XR; r++) {
@@ -675,36 +716,32 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
 
     // ---- exit: exactness audit and final state
     make_exact();
-    if (uni.stats[FS_FAST]) {
+    if (threadIdx.x == 0 && uni.stats[FS_FAST]) {
+        int emin = 1 << 30, emax = 0;
         exp_track(uni.thr_min, emin, emax);
         exp_track(uni.thr_max, emin, emax);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        emin = min(emin, __shfl_xor_sync(FULL, emin, o));
-        emax = max(emax, __shfl_xor_sync(FULL, emax, o));
+        atomicMin(&sh.emin, emin);
+        atomicMax(&sh.emax, emax);
     }
     __syncthreads();
-    if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
-    __syncthreads();
-    emin = sh.emin; emax = sh.emax;
+    const int emin = sh.emin, emax = sh.emax;
     int status = SEG_OK;
     if (emax >= 255) status |= SEG_NOT_SANE;
     if (emax > 0 && emax - emin > p.span_limit) status |= SEG_INEXACT;
 
     if (w.state_out) {
         float *dst = state_ring(w.state_out);
-        for (int i = tid; i < L; i += NT) dst[i] = ring[i];
-        if (tid == 0) {
+        for (int i = threadIdx.x; i < L; i += NT) dst[i] = ring[i];
+        if (threadIdx.x == 0) {
             SlicerHdr h;
             h.ss = c_s.ss0; h.pos = w.end; h.lastL = c_s.lastL; h.lrun_start = c_s.lrun_start;
             h.last_val = c_s.last_val; h.emin = emin; h.emax = emax; h.status = status; h.count = 0; h.pad = 0;
             *w.state_out = h;
         }
     }
-    if (tid == 0 && w.trans_count) *w.trans_count = 0;
-    if (tid == 0 && w.status) *w.status = status;
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
+        if (w.trans_count) *w.trans_count = 0;
+        if (w.status) *w.status = status;
         atomicAdd(&g_tile_stats[0], (unsigned long long)uni.stats[FS_FAST]);
         atomicAdd(&g_tile_stats[1], (unsigned long long)uni.stats[FS_SLOW]);
         atomicAdd(&g_tile_stats[2], (unsigned long long)uni.stats[FS_BAD]);
