@@ -206,7 +206,7 @@ def main():
         if world == 1:
             s.reset()
             s.push_all(x)
-            fr, _ = s.drain_frames_flat()
+            fr, _ = s.drain_frames_flat(reuse=True)
             return len(fr)
         res = sharding.decode_time_sharded(s, lambda a, b: x[a - base: b - base], total, L, _cabi.State, dist=dist,
                                            device="cuda", halo_windows=args.halo_windows, flat=True)
@@ -277,7 +277,7 @@ def main():
         for _ in range(2):
             se.reset()
             se.push_all(xh_np)
-            se.drain_frames_flat()
+            se.drain_frames_flat(reuse=True)
         se.reset_stats()
         barrier()
         t0 = time.perf_counter()
@@ -285,7 +285,7 @@ def main():
         for _ in range(esteps):
             se.reset()
             se.push_all(xh_np)
-            fr_e, _ = se.drain_frames_flat()
+            fr_e, _ = se.drain_frames_flat(reuse=True)
         barrier()
         e_wall = (time.perf_counter() - t0) / esteps
         est = se.stats()

@@ -134,7 +134,7 @@ class Stream(object):
             raise NfcError("nfc_stream_create: " + last_error())
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().nfc_stream_destroy(self._h)
             self._h = None
 
@@ -192,13 +192,21 @@ class Stream(object):
             fr = fr[:got]
         return fr, [bits[f["bit_off"]: f["bit_off"] + f["nbits"]].copy() for f in fr]
 
-    def drain_frames_flat(self):
-        """-> (frame records, one uint8 array with all frame bits; record.bit_off indexes into it)."""
+    def drain_frames_flat(self, reuse=False):
+        """-> (frame records, one uint8 array with all frame bits; record.bit_off indexes into it).
+        reuse=True returns views of buffers owned by this object, valid until the next drain (no allocation per call)."""
         L = lib()
         n = L.nfc_stream_drain_frames(self._h, None, 0, None, 0)
         nb = L.nfc_stream_pending_frame_bits(self._h)
-        fr = np.zeros(n, dtype=FRAME_DTYPE)
-        bits = np.zeros(max(nb, 1), dtype=np.uint8)
+        if reuse:
+            if getattr(self, "_fr_buf", None) is None or self._fr_buf.size < n:
+                self._fr_buf = np.zeros(int(n * 1.25) + 16, dtype=FRAME_DTYPE)
+            if getattr(self, "_bit_buf", None) is None or self._bit_buf.size < max(nb, 1):
+                self._bit_buf = np.zeros(int(nb * 1.25) + 16, dtype=np.uint8)
+            fr, bits = self._fr_buf[:n], self._bit_buf[:max(nb, 1)]
+        else:
+            fr = np.zeros(n, dtype=FRAME_DTYPE)
+            bits = np.zeros(max(nb, 1), dtype=np.uint8)
         if n:
             got = L.nfc_stream_drain_frames(self._h, fr.ctypes.data, n, bits.ctypes.data, nb)
             if got < 0:

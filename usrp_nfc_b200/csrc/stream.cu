@@ -6,10 +6,13 @@
 // The ordered transitions of the slab go through runs.cu (events) and linecode.cu (symbols, frames);
 // only records leave the device.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/usrp_nfc_b200.h"
@@ -126,7 +129,9 @@ struct Stream {
     LineTables lt;
     double factor;
     cudaStream_t cs = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaStream_t cs2 = nullptr;  // device -> host copies of a slab's records, beside the next slab's slicer
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+    int ev_idx = 0;
 
     // stream state
     int64_t pos = 0;
@@ -149,8 +154,26 @@ struct Stream {
         line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
         redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr;
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
-    void *pinned = nullptr;
-    size_t pinned_cap = 0;
+    // results come back into one of two pinned buffers; a worker thread turns the previous slab's records into the
+    // output vectors while the device works on the next slab
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap[2] = {0, 0};
+    int pin_idx = 0;
+    std::thread marshal_thr;
+    int marshal_err = 0;
+    // a slab whose records are on their way to the host: completed (carries taken over, marshalling started) right
+    // before the next slab needs its carries, or when the caller looks at results
+    struct Pending {
+        bool active = false;
+        char *hp = nullptr;
+        size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, off_c = 0, total = 0;
+        uint32_t M = 0, nsym = 0, nbit0 = 0, nbit1 = 0, nemit = 0;
+        int64_t a = 0, b = 0;
+        bool want_ev = false, want_sym = false, want_fr = false, have_line = false;
+        double t0 = 0, t1 = 0, t2 = 0;
+        int ei = 0;
+    } pend;
+    cudaEvent_t ev_d = nullptr;
 
     // results
     std::vector<nfc_event> out_events;
@@ -168,7 +191,10 @@ struct Stream {
 
     int init(const nfc_params *p);
     void destroy();
-    int ensure_pinned(size_t bytes);
+    int ensure_pinned(int idx, size_t bytes);
+    int join_marshal();
+    int finish_pending();
+    int settle() { return finish_pending() || join_marshal() ? -1 : 0; }
     int64_t push(const void *items, int64_t n, int mem, int *called_back);
     int finish_warmup();
     int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b);
@@ -179,13 +205,24 @@ struct Stream {
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
-int Stream::ensure_pinned(size_t bytes) {
-    if (bytes <= pinned_cap) return 0;
-    if (pinned) cudaFreeHost(pinned);
-    pinned = nullptr;
-    pinned_cap = 0;
-    NFC_CUDA_CHECK(cudaMallocHost(&pinned, bytes + bytes / 4 + 4096));
-    pinned_cap = bytes + bytes / 4 + 4096;
+int Stream::ensure_pinned(int idx, size_t bytes) {
+    if (bytes <= pinned_cap[idx]) return 0;
+    if (pinned[idx]) cudaFreeHost(pinned[idx]);
+    pinned[idx] = nullptr;
+    pinned_cap[idx] = 0;
+    NFC_CUDA_CHECK(cudaMallocHost(&pinned[idx], bytes + bytes / 4 + 4096));
+    pinned_cap[idx] = bytes + bytes / 4 + 4096;
+    return 0;
+}
+
+// waits for the records of the previous slab to be in the output vectors
+int Stream::join_marshal() {
+    if (marshal_thr.joinable()) marshal_thr.join();
+    if (marshal_err) {
+        marshal_err = 0;
+        set_error("internal: frame longer than the retained bits");
+        return -1;
+    }
     return 0;
 }
 
@@ -202,9 +239,13 @@ int Stream::init(const nfc_params *p) {
     }
     NFC_CUDA_CHECK(cudaSetDevice(p->device));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    NFC_CUDA_CHECK(cudaEventCreate(&ev_a));
-    NFC_CUDA_CHECK(cudaEventCreate(&ev_b));
-    NFC_CUDA_CHECK(cudaEventCreate(&ev_c));
+    NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        NFC_CUDA_CHECK(cudaEventCreate(&ev_a[i]));
+        NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
+        NFC_CUDA_CHECK(cudaEventCreate(&ev_c[i]));
+    }
+    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
     factor = 1e6 / p->samp_rate;  // transition_sink.py:21
     sp.lo = p->lo_val;
     sp.hi = p->hi_val;
@@ -263,10 +304,17 @@ void Stream::destroy() {
                      &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
                      &ex_counts, &ex_offsets, &ex_scr};
     for (DevBuf *b : all) b->release();
-    if (pinned) cudaFreeHost(pinned);
-    if (ev_a) cudaEventDestroy(ev_a);
-    if (ev_b) cudaEventDestroy(ev_b);
-    if (ev_c) cudaEventDestroy(ev_c);
+    finish_pending();
+    if (marshal_thr.joinable()) marshal_thr.join();
+    for (int i = 0; i < 2; i++)
+        if (pinned[i]) cudaFreeHost(pinned[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ev_a[i]) cudaEventDestroy(ev_a[i]);
+        if (ev_b[i]) cudaEventDestroy(ev_b[i]);
+        if (ev_c[i]) cudaEventDestroy(ev_c[i]);
+    }
+    if (cs2) cudaStreamDestroy(cs2);
+    if (ev_d) cudaEventDestroy(ev_d);
     if (cs) cudaStreamDestroy(cs);
 }
 
@@ -913,7 +961,8 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         return -1;
     }
 
-    // ---- bitmap -> dense ordered transitions
+    // ---- bitmap -> dense ordered transitions (the first sample is compared with the previous slab's last val)
+    if (finish_pending()) return -1;
     const size_t nblk = extract_blocks(bm_pos0, a, b);
     if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
     if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
@@ -933,8 +982,17 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
     return 0;
 }
 
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b) {
-    NFC_CUDA_CHECK(cudaEventRecord(ev_a, cs));
+    static const bool timing = getenv("NFC_TIMING") != nullptr;
+    const double t0 = now_ms();
+    double t1 = t0, t2 = t0;
+    ev_idx ^= 1;
+    const int ei = ev_idx;
+    NFC_CUDA_CHECK(cudaEventRecord(ev_a[ei], cs));
     uint32_t R = 0;
     bool fell_back = false;
     const bool par = parallel_ok();
@@ -947,7 +1005,9 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         serial_mode = true;  // sums are no longer exactly representable: stay on the sequential kernel
         if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, true, &R, &fell_back)) return -1;
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_b, cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_b[ei], cs));
+    t1 = now_ms();
+    if (finish_pending()) return -1;  // the previous slab's carries (its records arrived while the slicer ran)
 
     // ---- runs -> events
     const int keep_dropped = (prm.outputs & NFC_OUT_DROPPED_EVENTS) ? 1 : 0;
@@ -1014,7 +1074,8 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
             return -1;
         stats.launches++;
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_c, cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_c[ei], cs));
+    t2 = now_ms();
 
     // ---- records back to the host
     const bool want_ev = (prm.outputs & NFC_OUT_EVENTS) != 0;
@@ -1034,92 +1095,129 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         off_b0 = place(tot.nbit0);
         off_b1 = place(tot.nbit1);
     }
-    if (ensure_pinned(total)) return -1;
-    char *hp = (char *)pinned;
-    NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_c, carry_d.p, 256, cudaMemcpyDeviceToHost, cs));
-    if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d.p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs));
+    pin_idx ^= 1;  // the worker may still be reading the other buffer
+    if (ensure_pinned(pin_idx, total)) return -1;
+    char *hp = (char *)pinned[pin_idx];
+    NFC_CUDA_CHECK(cudaStreamWaitEvent(cs2, ev_c[ei], 0));
+    NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_c, carry_d.p, 256, cudaMemcpyDeviceToHost, cs2));
+    if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d.p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
     if (want_sym && tot.nsym)
-        NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d.p, (size_t)tot.nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d.p, (size_t)tot.nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
     if (want_fr) {
         if (tot.nemit)
-            NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d.p, (size_t)tot.nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs));
-        if (tot.nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d.p, tot.nbit0, cudaMemcpyDeviceToHost, cs));
-        if (tot.nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d.p, tot.nbit1, cudaMemcpyDeviceToHost, cs));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d.p, (size_t)tot.nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs2));
+        if (tot.nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d.p, tot.nbit0, cudaMemcpyDeviceToHost, cs2));
+        if (tot.nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d.p, tot.nbit1, cudaMemcpyDeviceToHost, cs2));
     }
-    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
-    stats.d2h_bytes += (int64_t)total;
+    NFC_CUDA_CHECK(cudaEventRecord(ev_d, cs2));
+    pend.active = true;
+    pend.hp = hp;
+    pend.off_ev = off_ev; pend.off_sym = off_sym; pend.off_em = off_em; pend.off_b0 = off_b0; pend.off_b1 = off_b1;
+    pend.off_c = off_c; pend.total = total;
+    pend.M = M; pend.nsym = tot.nsym; pend.nbit0 = tot.nbit0; pend.nbit1 = tot.nbit1; pend.nemit = tot.nemit;
+    pend.a = a; pend.b = b;
+    pend.want_ev = want_ev; pend.want_sym = want_sym; pend.want_fr = want_fr; pend.have_line = nc > 0 && want_line;
+    pend.t0 = t0; pend.t1 = t1; pend.t2 = t2;
+    pend.ei = ei;
+    return 0;
+}
+
+// The records of the last slab have arrived: take over its carries and hand the records to the worker thread.
+int Stream::finish_pending() {
+    if (!pend.active) return 0;
+    static const bool timing = getenv("NFC_TIMING") != nullptr;
+    pend.active = false;
+    NFC_CUDA_CHECK(cudaEventSynchronize(ev_d));
+    const double t3 = now_ms();
+    char *hp = pend.hp;
+    const size_t off_ev = pend.off_ev, off_sym = pend.off_sym, off_em = pend.off_em, off_b0 = pend.off_b0, off_b1 = pend.off_b1,
+                 off_c = pend.off_c;
+    const uint32_t M = pend.M;
+    const int64_t a = pend.a;
+    const bool want_ev = pend.want_ev, want_sym = pend.want_sym, want_fr = pend.want_fr;
+    struct Totals {
+        uint32_t nsym, nbit0, nbit1, nemit;
+    } totc = {pend.nsym, pend.nbit0, pend.nbit1, pend.nemit};
+    stats.d2h_bytes += (int64_t)pend.total;
     float ms_ab = 0, ms_ac = 0;
-    cudaEventElapsedTime(&ms_ab, ev_a, ev_b);
-    cudaEventElapsedTime(&ms_ac, ev_a, ev_c);
+    cudaEventElapsedTime(&ms_ab, ev_a[pend.ei], ev_b[pend.ei]);
+    cudaEventElapsedTime(&ms_ac, ev_a[pend.ei], ev_c[pend.ei]);
     stats.slicer_ms += ms_ab;
     stats.kernel_ms += ms_ac;
-
     // ---- carries
     run_carry = *reinterpret_cast<RunCarry *>(hp + off_c);
-    if (nc > 0 && want_line) {
+    if (pend.have_line) {
         dec_carry = *reinterpret_cast<DecCarry *>(hp + off_c + 64);
         pending[0] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[0];
         pending[1] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[1];
     }
-    // ---- marshal records (absolute positions)
-    if (want_ev) {
-        const EventRec *e = reinterpret_cast<const EventRec *>(hp + off_ev);
-        out_events.reserve(out_events.size() + M);
-        for (uint32_t i = 0; i < M; i++) {
-            nfc_event o;
-            o.pos = a + (int64_t)e[i].rel_pos;
-            o.d = e[i].d;
-            o.v = e[i].v;
-            o.type = e[i].type;
-            o.pad = 0;
-            out_events.push_back(o);
-        }
-    }
-    if (want_sym) {
-        const SymbolRec *s = reinterpret_cast<const SymbolRec *>(hp + off_sym);
-        for (uint32_t i = 0; i < tot.nsym; i++) {
-            nfc_symbol o;
-            o.pos = a + (int64_t)s[i].rel_pos;
-            o.type = s[i].type;
-            o.val = s[i].val;
-            o.pad = 0;
-            o.pad2 = 0;
-            out_symbols.push_back(o);
-        }
-    }
-    if (want_fr) {
-        const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
-        const uint8_t *nb[2] = {(const uint8_t *)(hp + off_b0), (const uint8_t *)(hp + off_b1)};
-        const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
-        const size_t old[2] = {hbits[0].size(), hbits[1].size()};
-        for (int t = 0; t < 2; t++) hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
-        size_t last_end[2] = {0, 0};
-        bool any[2] = {false, false};
-        const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
-        out_frames.reserve(out_frames.size() + tot.nemit);
-        for (uint32_t i = 0; i < tot.nemit; i++) {
-            const int t = em[i].type;
-            const size_t end = old[t] + em[i].bit_end;  // index into hbits[t]
-            any[t] = true;
-            last_end[t] = end;
-            if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
-            if (em[i].nbits > end) {
-                set_error("internal: frame longer than the retained bits");
-                return -1;
+    // ---- marshal records (absolute positions) on the worker thread
+    if (join_marshal()) return -1;
+    marshal_thr = std::thread([this, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, totc, a, want_ev, want_sym, want_fr]() {
+        const Totals &tot = totc;
+        // ---- marshal records (absolute positions)
+        if (want_ev) {
+            const EventRec *e = reinterpret_cast<const EventRec *>(hp + off_ev);
+            out_events.reserve(out_events.size() + M);
+            for (uint32_t i = 0; i < M; i++) {
+                nfc_event o;
+                o.pos = a + (int64_t)e[i].rel_pos;
+                o.d = e[i].d;
+                o.v = e[i].v;
+                o.type = e[i].type;
+                o.pad = 0;
+                out_events.push_back(o);
             }
-            nfc_frame f;
-            f.pos = a + (int64_t)em[i].rel_pos;
-            f.bit_off = (int64_t)(fbase[t] + end - em[i].nbits);  // frames of one type are back to back
-            f.nbits = (int32_t)em[i].nbits;
-            f.type = t;
-            out_frames.push_back(f);
         }
-        for (int t = 0; t < 2; t++)
-            if (any[t]) {
-                out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
-                hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+        if (want_sym) {
+            const SymbolRec *s = reinterpret_cast<const SymbolRec *>(hp + off_sym);
+            for (uint32_t i = 0; i < tot.nsym; i++) {
+                nfc_symbol o;
+                o.pos = a + (int64_t)s[i].rel_pos;
+                o.type = s[i].type;
+                o.val = s[i].val;
+                o.pad = 0;
+                o.pad2 = 0;
+                out_symbols.push_back(o);
             }
-    }
+        }
+        if (want_fr) {
+            const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
+            const uint8_t *nb[2] = {(const uint8_t *)(hp + off_b0), (const uint8_t *)(hp + off_b1)};
+            const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
+            const size_t old[2] = {hbits[0].size(), hbits[1].size()};
+            for (int t = 0; t < 2; t++) hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
+            size_t last_end[2] = {0, 0};
+            bool any[2] = {false, false};
+            const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
+            out_frames.reserve(out_frames.size() + tot.nemit);
+            for (uint32_t i = 0; i < tot.nemit; i++) {
+                const int t = em[i].type;
+                const size_t end = old[t] + em[i].bit_end;  // index into hbits[t]
+                any[t] = true;
+                last_end[t] = end;
+                if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
+                if (em[i].nbits > end) {
+                    marshal_err = 1;
+                    return;
+                }
+                nfc_frame f;
+                f.pos = a + (int64_t)em[i].rel_pos;
+                f.bit_off = (int64_t)(fbase[t] + end - em[i].nbits);  // frames of one type are back to back
+                f.nbits = (int32_t)em[i].nbits;
+                f.type = t;
+                out_frames.push_back(f);
+            }
+            for (int t = 0; t < 2; t++)
+                if (any[t]) {
+                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+                    hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+                }
+        }
+    });
+    if (timing)
+        fprintf(stderr, "slab %lld..%lld: slicer %.2f ms (dev %.2f), runs+linecode %.2f (dev %.2f), completed %.2f ms after enqueue\n",
+                (long long)a, (long long)pend.b, pend.t1 - pend.t0, ms_ab, pend.t2 - pend.t1, ms_ac - ms_ab, t3 - pend.t2);
     return 0;
 }
 
@@ -1197,6 +1295,7 @@ int nfc_stream_destroy(nfc_stream *h) {
 int nfc_stream_reset(nfc_stream *h) {
     if (!h) return -1;
     Stream &s = h->s;
+    s.settle();
     s.pos = 0;
     s.stable = false;
     s.serial_mode = false;
@@ -1224,22 +1323,22 @@ int64_t nfc_stream_push(nfc_stream *h, const void *items, int64_t n, int mem, in
 }
 
 int64_t nfc_stream_drain_events(nfc_stream *h, nfc_event *out, int64_t cap) {
-    if (!h) return -1;
+    if (!h || h->s.settle()) return -1;
     return drain_vec(h->s.out_events, h->s.ev_head, out, cap);
 }
 
 int64_t nfc_stream_drain_symbols(nfc_stream *h, nfc_symbol *out, int64_t cap) {
-    if (!h) return -1;
+    if (!h || h->s.settle()) return -1;
     return drain_vec(h->s.out_symbols, h->s.sym_head, out, cap);
 }
 
 int64_t nfc_stream_pending_frame_bits(nfc_stream *h) {
-    if (!h) return -1;
+    if (!h || h->s.settle()) return -1;
     return (int64_t)(h->s.out_fbits[0].size() + h->s.out_fbits[1].size());
 }
 
 int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap) {
-    if (!h) return -1;
+    if (!h || h->s.settle()) return -1;
     Stream &s = h->s;
     const int64_t avail = (int64_t)s.out_frames.size();
     if (cap <= 0 || !out) return avail;
@@ -1268,6 +1367,7 @@ int nfc_stream_get_state(nfc_stream *h, nfc_state *st, float *ring, uint8_t *pen
         nfc::set_error("null argument");
         return -1;
     }
+    if (h->s.settle()) return -1;
     Stream &s = h->s;
     memset(st, 0, sizeof(*st));
     st->pos = s.pos;
@@ -1317,6 +1417,7 @@ int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, 
         return -1;
     }
     Stream &s = h->s;
+    if (s.settle()) return -1;
     if (!st->stable || !ring) {
         nfc::set_error("set_state needs a stable state with its ring");
         return -1;
@@ -1381,6 +1482,7 @@ int nfc_stream_set_tuning(nfc_stream *h, int64_t seg_len, int64_t halo, int64_t 
 
 int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
     if (!h || !st) return -1;
+    h->s.finish_pending();
     cudaSetDevice(h->s.prm.device);
     unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (nfc::slicer_tile_stats(ts, false) == 0) {
