@@ -244,3 +244,28 @@ def test_large_synthetic_stream(rate, n_sessions):
     check_against_oracle(got, want)
     assert len(want["frames"]) >= 200 * n_sessions
     print("samples %d frames %d stats %s" % (x.size, len(want["frames"]), got["stream"].stats()))
+
+
+@pytest.mark.parametrize("n,seg_len", [(48_000_000, 0), (20_000_000, 1_200_000)])
+def test_bench_workload_matches_oracle(n, seg_len):
+    """The bench.py traffic (dense frames, 5 % fade: many samples close to the HIGH threshold, repeated tiles, exact-path
+    tiles, seam repairs) rendered on the device, decoded by the streaming kernel and by the oracle."""
+    import torch
+    import bench
+    rate = 13.56e6
+    codes, lens, p = bench.build_schedule(rate, 2024)
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    _cabi.synth_render(x, codes, lens, carrier=0.5, pause=0.015, tag_high=1.07, noise=0.003, fade=0.05,
+                       fade_period=round(rate * 0.02), seed=7, as_envelope=True, device=0, first_index=123456789)
+    torch.cuda.synchronize()
+    s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_ALL, **p)
+    if seg_len:
+        s.set_tuning(seg_len=seg_len, halo=4 * p["av_window"], slab_len=1 << 23)
+    s.push_all(x)
+    got = dict(events=s.drain_events(), symbols=s.drain_symbols())
+    got["frames"], got["frame_bits"] = s.drain_frames()
+    want = oracle.decode_capture(x.cpu().numpy(), rate, hi_val=1.09, **p)
+    check_against_oracle(got, want)
+    st = s.stats()
+    assert st["fast_tiles"] > 0.9 * (n / 4096) * (0.5 if seg_len else 1)
+    print("stats", st)

@@ -1249,6 +1249,13 @@ bool slicer_streaming_ok(int L, bool vec_ok) {
     return vec_ok && L >= 8192 && !old;
 }
 
+// dynamic shared memory of the streaming kernel: the ring, then the staging buffer of one tile of input
+static size_t fast_smem(int L, int kind) {
+    const size_t ring = ((size_t)L * 4 + 15) / 16 * 16;
+    const size_t item = kind == IN_IQ_F32 ? 0 : (kind == IN_PCM_S16 ? 2 : 4);
+    return ring + 4096 * item;
+}
+
 template <int KIND>
 static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
     auto k = slicer_fast_kernel<256, 4, 3, KIND>;
@@ -1260,7 +1267,7 @@ static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *
 
 int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t stream) {
     if (n_works <= 0) return 0;
-    const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
+    const size_t smem = fast_smem(L, kind);
     switch (kind) {
         case IN_ENVELOPE_F32: return launch_fast<IN_ENVELOPE_F32>(d_works, n_works, d_params, smem, stream);
         case IN_REAL_F32: return launch_fast<IN_REAL_F32>(d_works, n_works, d_params, smem, stream);
@@ -1300,8 +1307,9 @@ int slicer_resident_ctas(int L, bool vec_ok) {
     const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
     cudaError_t e;
     if (slicer_streaming_ok(L, vec_ok)) {
-        cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, smem);
+        const size_t fsm = fast_smem(L, IN_ENVELOPE_F32);
+        cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, fsm);
     } else if (vec_ok && L >= 1024) {
         switch (slicer_rows(L)) {
             case 4:

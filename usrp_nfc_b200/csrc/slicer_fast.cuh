@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     static_assert(R == 4, "one bitmap word per lane and tile; four guesses per 128-bit read");
     static_assert(NW >= 2, "warps 0 and 1 share the verification");
     extern __shared__ __align__(16) float ring[];
-    __shared__ BlockShared<NT, 4> sh;
+    __shared__ BlockShared<NT, 1> sh;  // exact_tile's scratch
     __shared__ FastShared<NT, R> fs;
     __shared__ SegWork w_s;
     __shared__ SlicerParams p_s;
@@ -387,9 +387,57 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     const int slot_step = T % L;
     const int xoff = (warp * WS + lane * 4) * ITEM;  // this thread's first sample inside a tile of the input
 
+    // Samples of the coming tile are copied asynchronously (cp.async) into this thread's four 16-byte slots of a
+    // staging buffer behind the ring while the current tile is settled: no registers held, no scoreboard to wait on.
+    // IQ input (32 KB per tile) does not fit beside the ring: loaded directly, the coming tile only prefetched into L2.
+    constexpr bool STAGED = KIND != IN_IQ_F32;
+    char *xbuf = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16 + (size_t)threadIdx.x * (4 * ITEM);
     float4 xin[R];
     bool have_x = false;
 
+    auto request_tile = [&](int t) {  // start the copy of tile t into the staging buffer
+        const char *src = plan.xbase + (int64_t)t * tile_bytes + xoff;
+        if (STAGED) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // an earlier copy into the same slots must have landed
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(xbuf);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (ITEM == 4)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * (NT * 16)), "l"(src + r * FAST_CH * 4) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + r * (NT * 8)), "l"(src + r * FAST_CH * 2) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * FAST_CH * ITEM));
+#pragma unroll
+            for (int r = 0; r < R; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * FAST_CH * ITEM + 16));
+        }
+    };
+    auto fetch_tile = [&]() {  // the requested tile's samples (as envelope) into xin
+        if (KIND == IN_ENVELOPE_F32 || KIND == IN_REAL_F32) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < R; r++) xin[r] = *reinterpret_cast<const float4 *>(xbuf + r * (NT * 16));
+            if (KIND == IN_REAL_F32) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    xin[r].x = env_real(xin[r].x); xin[r].y = env_real(xin[r].y);
+                    xin[r].z = env_real(xin[r].z); xin[r].w = env_real(xin[r].w);
+                }
+            }
+        } else if (KIND == IN_PCM_S16) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const float pcm_scale = p.pcm_scale;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const short4 sv = *reinterpret_cast<const short4 *>(xbuf + r * (NT * 8));
+                xin[r] = make_float4(env_real(__fdiv_rn((float)sv.x, pcm_scale)), env_real(__fdiv_rn((float)sv.y, pcm_scale)),
+                                     env_real(__fdiv_rn((float)sv.z, pcm_scale)), env_real(__fdiv_rn((float)sv.w, pcm_scale)));
+            }
+        }
+    };
     auto load_tile = [&](int t) {
         const char *src = plan.xbase + (int64_t)t * tile_bytes + xoff;
         if (KIND == IN_ENVELOPE_F32 || KIND == IN_REAL_F32) {
@@ -467,7 +515,12 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         if (streamable(t) && uni.ok) {
             int n_meas = 0, n_coarse = 0;  // repeats of this tile: with measured guesses, with a coarser fixed-point step
             for (;;) {
-                if (!x_ready) load_tile(t);
+                if (STAGED) {
+                    if (!x_ready) request_tile(t);
+                    fetch_tile();
+                } else {
+                    load_tile(t);
+                }
                 x_ready = false;
                 const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
                 const float4 tl4 = *reinterpret_cast<const float4 *>(&uni.gTL[warp * R]);
@@ -507,8 +560,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 }
                 // next tile's samples on their way while this one is settled
                 if (t + 1 < ntiles && streamable(t + 1)) {
-                    load_tile(t + 1);
-                    have_x = true;
+                    request_tile(t + 1);
+                    have_x = STAGED;
                 }
                 __syncthreads();
 
@@ -696,7 +749,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 if (Pr >= w.end || Pr + SUB <= w.warm_begin) continue;  // block-uniform
                 int s0 = slot_x + r * SUB;
                 while (s0 >= L) s0 -= L;
-                exact_tile<NT, 4, 4, true>(&w_s, &p_s, ring, &sh, Pr, s0, &c_s);
+                exact_tile<NT, 4, 1, true>(&w_s, &p_s, ring, &sh, Pr, s0, &c_s);
             }
             if (warp == 0) {
                 const double ss1 = c_s.ss0;
