@@ -168,7 +168,7 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;  // fixed-point step: a power of two near a_est * 2^-31
     ok = ok && ae > 45u && ae < 250u;
     const float TLb = __double2float_rn(ssm * loL), THb = __double2float_rn(ssm * hiL);
-    const float srel = ok ? tot_prev * (1.0f / NC) / ssf : 0.0f;  // predicted relative change of ss per chunk
+    const float srel = ok ? __fdividef(tot_prev * (1.0f / NC), ssf) : 0.0f;  // predicted relative change of ss per chunk (a guess)
     const float f = fmaf(srel, (float)lane + 0.5f, 1.0f);
     u.gTL[lane] = TLb * f;
     u.gTH[lane] = THb * f;

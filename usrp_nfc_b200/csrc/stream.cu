@@ -130,6 +130,9 @@ struct Stream {
     double factor;
     cudaStream_t cs = nullptr;
     cudaStream_t cs2 = nullptr;  // device -> host copies of a slab's records, beside the next slab's slicer
+    cudaStream_t cs3 = nullptr;  // host -> device copies of the next slab's samples, beside this slab's kernels
+    cudaEvent_t ev_h[2] = {nullptr, nullptr};
+    DevBuf staging2[2];
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
     int ev_idx = 0;
 
@@ -240,6 +243,8 @@ int Stream::init(const nfc_params *p) {
     NFC_CUDA_CHECK(cudaSetDevice(p->device));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
+    NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs3, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_h[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         NFC_CUDA_CHECK(cudaEventCreate(&ev_a[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
@@ -314,6 +319,11 @@ void Stream::destroy() {
         if (ev_c[i]) cudaEventDestroy(ev_c[i]);
     }
     if (cs2) cudaStreamDestroy(cs2);
+    if (cs3) cudaStreamDestroy(cs3);
+    for (int i = 0; i < 2; i++) {
+        if (ev_h[i]) cudaEventDestroy(ev_h[i]);
+        staging2[i].release();
+    }
     if (ev_d) cudaEventDestroy(ev_d);
     if (cs) cudaStreamDestroy(cs);
 }
@@ -389,6 +399,23 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
     if (called_back) *called_back = 1;
     int64_t done = 0;
     const int64_t slab = slab_len > 0 ? slab_len : (int64_t)1 << 28;
+    // Host input goes through two staging buffers: the copy of slab k+1 (stream cs3) runs beside the kernels of slab k.
+    const bool host_in = mem == NFC_MEM_HOST;
+    auto stage_host = [&](int64_t off, int64_t m, int64_t a, int buf) -> int {
+        const size_t padb = (size_t)(a - (a - (a & 3))) * ib;
+        if (staging2[buf].ensure(padb + (size_t)m * ib + 64)) return -1;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(staging2[buf].as<char>() + padb, (const char *)items + (size_t)off * ib, (size_t)m * ib,
+                                       cudaMemcpyHostToDevice, cs3));
+        NFC_CUDA_CHECK(cudaEventRecord(ev_h[buf], cs3));
+        stats.h2d_bytes += (int64_t)((size_t)m * ib);
+        return 0;
+    };
+    int hbuf = 0;
+    if (host_in && n > 0) {
+        // the buffers may still be read by kernels of an earlier push: those are complete once the stream is idle
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        if (stage_host(0, std::min(slab, n), pos, hbuf)) return -1;
+    }
     while (done < n) {
         const int64_t m = std::min(slab, n - done);
         const int64_t a = pos, b = pos + m;
@@ -397,14 +424,19 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
         int64_t in_begin = in_pos0;
         const char *src = (const char *)items + (size_t)done * ib;
         const size_t padb = (size_t)(a - in_pos0) * ib;
-        if (mem == NFC_MEM_DEVICE && (((uintptr_t)src - padb) & 15) == 0) {
+        if (host_in) {
+            const int64_t m_next = std::min(slab, n - (done + m));
+            // the other buffer was read by the slicer of the slab before this one, which has completed
+            if (m_next > 0 && stage_host(done + m, m_next, b, hbuf ^ 1)) return -1;
+            NFC_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_h[hbuf], 0));
+            d_in = staging2[hbuf].p;
+            hbuf ^= 1;
+        } else if ((((uintptr_t)src - padb) & 15) == 0) {
             d_in = src - padb;  // usable in place: item with stream index in_pos0 would sit 16-byte aligned
             in_begin = a;       // ... but nothing before the caller's pointer is read
         } else {
             if (staging.ensure(padb + (size_t)m * ib + 64)) return -1;
-            NFC_CUDA_CHECK(cudaMemcpyAsync(staging.as<char>() + padb, src, (size_t)m * ib,
-                                           mem == NFC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
-            if (mem == NFC_MEM_HOST) stats.h2d_bytes += (int64_t)((size_t)m * ib);
+            NFC_CUDA_CHECK(cudaMemcpyAsync(staging.as<char>() + padb, src, (size_t)m * ib, cudaMemcpyDeviceToDevice, cs));
             d_in = staging.p;
         }
         if (process_slab(d_in, in_pos0, in_begin, b, a, b)) return -1;
