@@ -31,7 +31,7 @@ struct __align__(16) FastRec {  // one chunk of 128 samples
     float mL, mH;   // cheap pass: min |x - guessed LOW threshold|, min |x - guessed HIGH threshold| (NaN: a sample is NaN, or
                     // a lane's sum does not fit the fixed point); precise pass: mL = smallest slack of any lane, in ss units
 };
-enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3 };
+enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3, FV_VERIFY = 4 };
 enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_N };
 
 static const int FAST_CH = 128;  // samples per chunk
@@ -133,7 +133,10 @@ struct FastShared {
     FastUni uni;
     FastPlan plan;
     double red[NW];
+    double vtot[32];  // exact verification: sum of the admitted steps of each chunk
 };
+
+__device__ __forceinline__ uint32_t uniform_stats(const FastUni &u, int k) { return u.stats[k] > 0xffffu ? 0xffffu : u.stats[k]; }
 
 // exact window sum = sum of the ring (any order: exact inside the audited exponent span)
 template <int NT>
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     __shared__ SlicerParams p_s;
     __shared__ SegCarry c_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long clk0 = clock64();
     if (threadIdx.x == 0) {
         w_s = works[blockIdx.x];
         p_s = params[w_s.param_idx];
@@ -313,20 +317,49 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             ss0 = w.state_in->ss;
             __syncthreads();
         } else {
-            double part = 0.0;
+            // Speculative start.  Any state will do (the seam check decides whether the segment stands); the closer to the
+            // true one, the sooner it converges.  The true ring holds admitted samples only, so: the previous L samples,
+            // with those a settled slicer would not have admitted (pauses, load modulation) replaced by the level of the rest.
+            auto block_sum2 = [&](double a, double b, double &ra, double &rb) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(FULL, a, o);
+                    b += __shfl_xor_sync(FULL, b, o);
+                }
+                __syncthreads();
+                if (lane == 0) { sh.red[warp] = a; fs.red[warp] = b; }
+                __syncthreads();
+                ra = 0.0; rb = 0.0;
+                for (int i = 0; i < NW; i++) { ra += sh.red[i]; rb += fs.red[i]; }
+            };
+            double part = 0.0, cnt = 0.0;
             for (int i = threadIdx.x; i < L; i += NT) {
                 const int64_t q = w.warm_begin - L + i;
                 float v = load_one(w.in, q - w.in_pos0, p);
                 ring[(int)(q % L)] = v;
                 part += (double)v;
+            }
+            double tot, dummy;
+            block_sum2(part, 0.0, tot, dummy);
+            const float mean0 = (float)(tot / (double)L);
+            part = 0.0;
+            for (int i = threadIdx.x; i < L; i += NT) {
+                const float v = ring[i];
+                if (v > 0.5f * mean0 && v < 1.5f * mean0) { part += (double)v; cnt += 1.0; }
+            }
+            double tsum, tcnt;
+            block_sum2(part, cnt, tsum, tcnt);
+            const float mean1 = tcnt > 0.0 ? (float)(tsum / tcnt) : mean0;
+            const float lo_v = (float)p.lo * mean1, hi_v = (float)p.hi * mean1;
+            part = 0.0;
+            for (int i = threadIdx.x; i < L; i += NT) {
+                float v = ring[i];
+                if (!(v >= lo_v && v <= hi_v) && mean1 > 0.0f) v = mean1;
+                ring[i] = v;
+                part += (double)v;
                 exp_track(v, emin, emax);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-            if (lane == 0) sh.red[warp] = part;
-            __syncthreads();
-            ss0 = 0.0;
-            for (int i = 0; i < NW; i++) ss0 += sh.red[i];
+            block_sum2(part, 0.0, ss0, dummy);
         }
         emin = __reduce_min_sync(FULL, emin);
         emax = __reduce_max_sync(FULL, emax);
@@ -493,6 +526,65 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         }
     };
 
+    // phase 2b (warp 1): the class maps of the tile, lane = chunk: hysteresis risk and the carries the tile would leave
+    auto maps_phase = [&](int t) {
+            const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8]);
+            const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8 + 4]);
+            const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
+            const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
+            const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
+            const int64_t P0 = tile0_pos + (int64_t)t * T;
+            // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+            bool st2 = false;
+            if (Hmask) {
+                const int nb = plan.nb;
+                const int lo_c = max(lane - nb, 0);
+                const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
+                bool risk = hasH && win != 0u;
+                const int64_t cl = c_s.lastL;
+                if (hasH && cl != NO_POS) {
+                    const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
+                    if (dist <= (int64_t)p.mx + 1) risk = true;
+                }
+                st2 = __any_sync(FULL, risk);
+            }
+            // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
+            int newL = -1, newS = -1;
+            if (Lmask) {
+                int prevlast = __shfl_up_sync(FULL, lastc, 1);
+                if (lane == 0) prevlast = c_s.last_val + 1;  // class code of the sample before the tile
+                int candL = -1, candS = -1;
+                // only chunks whose LOW samples can still matter later: the run continues, or the tile ends soon
+                if (hasL && (lastc == 0 || lane >= NC - plan.nb)) {
+                    const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w};
+                    int bestL = -1, bestS = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const unsigned lw = ~NLw[j];
+                        const unsigned pw = j == 0 ? ((NLw[3] << 1) & ~1u) : NLw[j - 1];  // predecessor not LOW
+                        const unsigned sw = lw & pw;
+                        if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
+                        if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
+                    }
+                    candL = lane * FAST_CH + bestL;
+                    if (bestS >= 0) candS = lane * FAST_CH + bestS;
+                    if (firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
+                }
+                newL = __reduce_max_sync(FULL, candL);
+                newS = __reduce_max_sync(FULL, candS);
+            }
+            const int lv_new = __shfl_sync(FULL, lastc, NC - 1) - 1;
+            if (lane == 0) {
+#ifdef NFC_ST2_DEBUG
+                if (st2 && blockIdx.x == 312) printf("st2 seg %d tile %d P0 %lld L %08x H %08x lastL %lld\n", blockIdx.x, t, (long long)P0, Lmask, Hmask, (long long)c_s.lastL);
+#endif
+                uni.st2 = st2 ? 1 : 0;
+                uni.cand_last_val = lv_new;
+                uni.cand_newL = newL;
+                uni.cand_newS = newS;
+            }
+    };
+
     for (int t = 0; t < ntiles; t++) {
         if (t == t_snap) {
             if (t == plan.t_snap[0]) snapshot(w.seam_in, w.begin);
@@ -616,7 +708,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                             uni.gC0[lane] = c0;
                         }
                         if (lane == 0) {
-                            int v = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : FV_SLOW;
+                            // a precise pass that cannot prove itself is checked sample by sample in exact arithmetic
+                            int v = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : ((precise && !bad) ? FV_VERIFY : FV_SLOW);
                             if (bad && redo) {  // a lane's sum did not fit: coarser fixed-point step
                                 const float ae = uni.a_est * 16.0f;
                                 const unsigned e = (__float_as_uint(ae) >> 23) & 0xffu;
@@ -630,7 +723,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                                 }
                             }
                             uni.verdict = v;
-                            uni.stats[v == FV_SLOW ? (bad ? FS_BAD : FS_UNC) : FS_REDO]++;
+                            uni.stats[v == FV_SLOW ? FS_BAD : (v == FV_VERIFY ? FS_UNC : FS_REDO)]++;
                         }
                     } else {
                         // ---- the window sum after the tile and the coming tile's constants
@@ -648,65 +741,124 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         fast_prepare<NC>(uni, ss_lo, ss_hi, (float)delta, a_new, p.loL, p.hiL, lane);
                     }
                 } else if (warp == 1) {
-                    // -------------------------------------------------------- phase 2b (warp 1): the class maps, lane = chunk
-                    const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8]);
-                    const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8 + 4]);
-                    const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
-                    const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
-                    const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
-                    const int64_t P0 = tile0_pos + (int64_t)t * T;
-                    // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
-                    bool st2 = false;
-                    if (Hmask) {
-                        const int nb = plan.nb;
-                        const int lo_c = max(lane - nb, 0);
-                        const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
-                        bool risk = hasH && win != 0u;
-                        const int64_t cl = c_s.lastL;
-                        if (hasH && cl != NO_POS) {
-                            const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
-                            if (dist <= (int64_t)p.mx + 1) risk = true;
-                        }
-                        st2 = __any_sync(FULL, risk);
-                    }
-                    // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
-                    int newL = -1, newS = -1;
-                    if (Lmask) {
-                        int prevlast = __shfl_up_sync(FULL, lastc, 1);
-                        if (lane == 0) prevlast = c_s.last_val + 1;  // class code of the sample before the tile
-                        int candL = -1, candS = -1;
-                        // only chunks whose LOW samples can still matter later: the run continues, or the tile ends soon
-                        if (hasL && (lastc == 0 || lane >= NC - plan.nb)) {
-                            const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w};
-                            int bestL = -1, bestS = -1;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const unsigned lw = ~NLw[j];
-                                const unsigned pw = j == 0 ? ((NLw[3] << 1) & ~1u) : NLw[j - 1];  // predecessor not LOW
-                                const unsigned sw = lw & pw;
-                                if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
-                                if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
-                            }
-                            candL = lane * FAST_CH + bestL;
-                            if (bestS >= 0) candS = lane * FAST_CH + bestS;
-                            if (firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
-                        }
-                        newL = __reduce_max_sync(FULL, candL);
-                        newS = __reduce_max_sync(FULL, candS);
-                    }
-                    const int lv_new = __shfl_sync(FULL, lastc, NC - 1) - 1;
-                    if (lane == 0) {
-                        uni.st2 = st2 ? 1 : 0;
-                        uni.cand_last_val = lv_new;
-                        uni.cand_newL = newL;
-                        uni.cand_newS = newS;
-                    }
+                    maps_phase(t);
                 }
                 __syncthreads();
                 int verdict = uni.verdict;
                 if (uni.st2 && verdict != FV_SLOW) {
                     verdict = FV_SLOW;
                     if (threadIdx.x == 0) uni.stats[FS_ST2]++;
+                }
+                if (verdict == FV_VERIFY) {
+                    // ------------------------------------------------------------ exact fix-point from the precise pass
+                    // Every sample's class is recomputed from its own exact window sum under the current classes, until
+                    // nothing changes: a self-consistent assignment is the sequential answer (the recurrence is causal).
+                    make_exact();  // c_s.ss0: the exact window sum at the tile's first sample
+                    const double ss0 = c_s.ss0;
+                    load_tile(t);  // the staging buffer already holds the coming tile
+                    unsigned cls = 0u;  // two bits per sample: 0 LOW, 1 MID, 2 HIGH
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8]);
+                        const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8 + 4]);
+                        const unsigned nlw[4] = {nl.x, nl.y, nl.z, nl.w}, hw[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) cls |= (((nlw[j] >> lane) & 1u) + ((hw[j] >> lane) & 1u)) << (2 * (r * 4 + j));
+                    }
+                    bool settled = false;
+                    double total = 0.0;
+                    for (int it = 0; it < 8 && !settled; it++) {
+                        double lane_ex[R];
+                        int s0 = slot_w;
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                            double tot = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) tot += (double)xs[j] - (double)ps[j];
+                            double inc = tot;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const double v = __shfl_up_sync(FULL, inc, o);
+                                if (lane >= o) inc += v;
+                            }
+                            lane_ex[r] = inc - tot;
+                            if (lane == 31) fs.vtot[warp * R + r] = inc;
+                            s0 += FAST_CH;
+                            if (s0 >= L) s0 -= L;
+                        }
+                        __syncthreads();
+                        const double ct = fs.vtot[lane];
+                        double cinc = ct;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double v = __shfl_up_sync(FULL, cinc, o);
+                            if (lane >= o) cinc += v;
+                        }
+                        const double chunk_ex = cinc - ct;
+                        total = __shfl_sync(FULL, cinc, 31);
+                        unsigned ncls = 0u;
+                        s0 = slot_w;
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                            double ssj = ss0 + __shfl_sync(FULL, chunk_ex, warp * R + r) + lane_ex[r];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                ncls |= (unsigned)(classify(xs[j], ssj, p) + 1) << (2 * (r * 4 + j));
+                                if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) ssj += (double)xs[j] - (double)ps[j];
+                            }
+                            s0 += FAST_CH;
+                            if (s0 >= L) s0 -= L;
+                        }
+                        const bool changed = ncls != cls;
+                        cls = ncls;
+                        settled = !__syncthreads_or((int)changed);  // also: vtot may be written again
+                    }
+                    if (settled) {
+                        // ---- the tile's outputs from the settled classes
+                        int s0 = slot_w;
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                            unsigned NLm[4], Hm[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const unsigned code = (cls >> (2 * (r * 4 + j))) & 3u;
+                                NLm[j] = __ballot_sync(FULL, code != 0u);
+                                Hm[j] = __ballot_sync(FULL, code == 2u);
+                                n[r][j] = code == 1u ? xs[j] : ps[j];
+                            }
+                            if (lane == 0) {
+                                uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[(warp * R + r) * 8]);
+                                bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
+                                bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
+                            }
+                            s0 += FAST_CH;
+                            if (s0 >= L) s0 -= L;
+                        }
+                        __syncthreads();
+                        if (warp == 0) {
+                            const float ae = uni.a_est;
+                            __syncwarp();
+                            fast_prepare<NC>(uni, ss0 + total, ss0 + total, (float)total, ae, p.loL, p.hiL, lane);
+                        } else if (warp == 1) {
+                            maps_phase(t);
+                        }
+                        __syncthreads();
+                        verdict = uni.st2 ? FV_SLOW : FV_ACCEPT;  // a HIGH sample the hysteresis may hold back: val is not the class
+                        if (verdict == FV_SLOW && threadIdx.x == 0) uni.stats[FS_ST2]++;
+                    } else {
+                        verdict = FV_SLOW;
+                        if (threadIdx.x == 0) uni.stats[FS_VER]++;
+                    }
                 }
                 if (verdict == FV_ACCEPT) {
                     // ---- ring update, bitmap out, carries
@@ -788,7 +940,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         if (threadIdx.x == 0) {
             SlicerHdr h;
             h.ss = c_s.ss0; h.pos = w.end; h.lastL = c_s.lastL; h.lrun_start = c_s.lrun_start;
-            h.last_val = c_s.last_val; h.emin = emin; h.emax = emax; h.status = status; h.count = 0; h.pad = 0;
+            h.last_val = c_s.last_val; h.emin = emin; h.emax = emax; h.status = status;
+            h.count = (uint32_t)((clock64() - clk0) >> 10);                      // diagnostics: kilocycles this segment took,
+            h.pad = (uniform_stats(uni, FS_REDO) << 16) | uniform_stats(uni, FS_SLOW);  // repeated and exact-path tiles
             *w.state_out = h;
         }
     }

@@ -993,6 +993,28 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         return -1;
     }
 
+    if (getenv("NFC_SEGDEBUG")) {
+        std::vector<char> blk(sblk);
+        double sum = 0;
+        uint32_t mn = ~0u, mx = 0;
+        std::vector<uint32_t> kc((size_t)nseg), rs((size_t)nseg);
+        for (int k = 0; k < nseg; k++) {
+            NFC_CUDA_CHECK(cudaMemcpy(blk.data(), st_out(k), sizeof(SlicerHdr), cudaMemcpyDeviceToHost));
+            const SlicerHdr *h = reinterpret_cast<const SlicerHdr *>(blk.data());
+            kc[(size_t)k] = h->count; rs[(size_t)k] = h->pad;
+            sum += h->count; mn = std::min(mn, h->count); mx = std::max(mx, h->count);
+        }
+        fprintf(stderr, "segments %d kcycles min %u avg %.0f max %u\n", nseg, mn, sum / nseg, mx);
+        for (int k = 0; k < nseg; k += std::max(1, nseg / 24))
+            fprintf(stderr, "  seg %d: %u kcyc, redo %u slow %u\n", k, kc[(size_t)k], rs[(size_t)k] >> 16, rs[(size_t)k] & 0xffff);
+        // the slowest
+        for (int q = 0; q < 6; q++) {
+            int best = 0;
+            for (int k = 1; k < nseg; k++) if (kc[(size_t)k] > kc[(size_t)best]) best = k;
+            fprintf(stderr, "  slowest seg %d: %u kcyc, redo %u slow %u\n", best, kc[(size_t)best], rs[(size_t)best] >> 16, rs[(size_t)best] & 0xffff);
+            kc[(size_t)best] = 0;
+        }
+    }
     // ---- bitmap -> dense ordered transitions (the first sample is compared with the previous slab's last val)
     if (finish_pending()) return -1;
     const size_t nblk = extract_blocks(bm_pos0, a, b);

@@ -117,7 +117,10 @@ def _broadcast(vec, src, dist, group, device):
 
 def _drain(engine, flat):
     if flat and hasattr(engine, "drain_frames_flat"):
-        rec, bits = engine.drain_frames_flat()
+        try:
+            rec, bits = engine.drain_frames_flat(reuse=True)  # views of the engine's buffers: no allocation per shard
+        except TypeError:
+            rec, bits = engine.drain_frames_flat()
         return rec, bits, True
     rec, bits = engine.drain_frames()
     return rec, bits, False
