@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 1
+#define NFC_ABI_VERSION 2
 
 /* what a pushed item is */
 enum {
@@ -137,10 +137,15 @@ typedef struct {
     int64_t segments, seam_mismatches, serial_segments, overflow_retries;
     int64_t linecode_scan_fallbacks; /* slabs where the frame-boundary search gave up and the scan path ran */
     int64_t h2d_bytes, d2h_bytes;
-    int64_t fast_tiles, exact_tiles, exact_rounds; /* slicer tiles by path (device-wide counters) */
-    int64_t refined_tiles;                         /* fast tiles that needed the per-record band refinement */
-    int64_t st2_tiles, refine_failed_tiles;        /* why tiles went to the exact path: hysteresis risk / band refinement failed */
-    int64_t fast_cycles, exact_cycles;             /* SM cycles one thread per segment spent on each path, summed */
+    /* slicer tiles by the way they were settled (device-wide counters: all streams of the process) */
+    int64_t fast_tiles;       /* proven by the streaming path (including repeated and fix-point tiles) */
+    int64_t exact_tiles;      /* handed to the exact path (segment edges, hysteresis-relevant HIGH samples, ...) */
+    int64_t repeated_passes;  /* extra streaming passes: measured guesses, or a coarser fixed-point step */
+    int64_t fixpoint_tiles;   /* tiles settled by the exact fix-point pass after the precise pass could not prove itself */
+    int64_t st2_tiles;        /* tiles sent to the exact path because the hysteresis could matter */
+    int64_t unproven_tiles;   /* tiles sent to the exact path because the streaming passes gave up */
+    int64_t ring_resums;      /* exact recomputations of the window sum from the ring */
+    int64_t exact_rounds;     /* fix-point rounds of the exact path (first-generation kernel) */
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
 int nfc_stream_reset_stats(nfc_stream *s);

@@ -42,9 +42,9 @@ class Stats(C.Structure):
                 ("seam_mismatches", C.c_int64), ("serial_segments", C.c_int64), ("overflow_retries", C.c_int64),
                 ("linecode_scan_fallbacks", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("fast_tiles", C.c_int64),
-                ("exact_tiles", C.c_int64), ("exact_rounds", C.c_int64), ("refined_tiles", C.c_int64), ("st2_tiles", C.c_int64), ("refine_failed_tiles", C.c_int64),
-                ("fast_cycles", C.c_int64),
-                ("exact_cycles", C.c_int64)]
+                ("exact_tiles", C.c_int64), ("repeated_passes", C.c_int64), ("fixpoint_tiles", C.c_int64),
+                ("st2_tiles", C.c_int64), ("unproven_tiles", C.c_int64), ("ring_resums", C.c_int64),
+                ("exact_rounds", C.c_int64)]
 
 
 # every symbol include/usrp_nfc_b200.h declares: (restype, argtypes)

@@ -28,7 +28,9 @@
 namespace nfc {
 
 static const unsigned FULL = 0xffffffffu;
-__device__ unsigned long long g_tile_stats[8];  // tiles by fast / exact path, exact rounds, -, cycles in fast attempts / exact path (thread 0)
+// tile counters (device-wide): 0 streamed, 1 exact path, 2 coarse-step retries exhausted, 3 exact fix-point pass, 4 ring resums,
+// 5 repeated passes, 6 hysteresis risk, 7 fix-point pass gave up, 8 exact-path rounds, 9/10 first-generation kernel: refined / refine failed
+__device__ unsigned long long g_tile_stats[16];
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
 
 // ---------------------------------------------------------------- sample loading / envelope
@@ -1095,10 +1097,10 @@ __global__ void __launch_bounds__(NT, (K == 4 ? 4 : 2)) slicer_kernel(const SegW
     if (tid == 0) {
         atomicAdd(&g_tile_stats[0], (unsigned long long)n_fast);
         atomicAdd(&g_tile_stats[1], (unsigned long long)n_slow);
-        atomicAdd(&g_tile_stats[2], (unsigned long long)c.round_no);
-        atomicAdd(&g_tile_stats[3], (unsigned long long)n_refined);
+        atomicAdd(&g_tile_stats[8], (unsigned long long)c.round_no);
+        atomicAdd(&g_tile_stats[9], (unsigned long long)n_refined);
         atomicAdd(&g_tile_stats[6], (unsigned long long)n_st2);
-        atomicAdd(&g_tile_stats[7], (unsigned long long)n_refbad);
+        atomicAdd(&g_tile_stats[10], (unsigned long long)n_refbad);
     }
 }
 
@@ -1291,9 +1293,9 @@ int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_par
 }
 
 int slicer_tile_stats(unsigned long long *out4, bool reset) {
-    NFC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 8));
+    NFC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 16));
     if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long z[16] = {0};
         NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z)));
     }
     return 0;

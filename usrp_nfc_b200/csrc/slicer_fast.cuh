@@ -957,6 +957,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         atomicAdd(&g_tile_stats[5], (unsigned long long)uni.stats[FS_REDO]);
         atomicAdd(&g_tile_stats[6], (unsigned long long)uni.stats[FS_ST2]);
         atomicAdd(&g_tile_stats[7], (unsigned long long)uni.stats[FS_VER]);
+        atomicAdd(&g_tile_stats[8], (unsigned long long)c_s.round_no);
     }
 }
 

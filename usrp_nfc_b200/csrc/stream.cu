@@ -1538,16 +1538,16 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
     if (!h || !st) return -1;
     h->s.finish_pending();
     cudaSetDevice(h->s.prm.device);
-    unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (nfc::slicer_tile_stats(ts, false) == 0) {
-        h->s.stats.fast_cycles = (int64_t)ts[4];
-        h->s.stats.exact_cycles = (int64_t)ts[5];  // device-wide counters (all streams of this process)
+    unsigned long long ts[16] = {0};
+    if (nfc::slicer_tile_stats(ts, false) == 0) {  // device-wide counters (all streams of this process)
         h->s.stats.fast_tiles = (int64_t)ts[0];
         h->s.stats.exact_tiles = (int64_t)ts[1];
-        h->s.stats.exact_rounds = (int64_t)ts[2];
-        h->s.stats.refined_tiles = (int64_t)ts[3];
+        h->s.stats.repeated_passes = (int64_t)ts[5];
+        h->s.stats.fixpoint_tiles = (int64_t)ts[3];
         h->s.stats.st2_tiles = (int64_t)ts[6];
-        h->s.stats.refine_failed_tiles = (int64_t)ts[7];
+        h->s.stats.unproven_tiles = (int64_t)(ts[2] + ts[7]);
+        h->s.stats.ring_resums = (int64_t)ts[4];
+        h->s.stats.exact_rounds = (int64_t)ts[8];
     }
     *st = h->s.stats;
     return 0;
@@ -1556,7 +1556,7 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
 int nfc_stream_reset_stats(nfc_stream *h) {
     if (!h) return -1;
     memset(&h->s.stats, 0, sizeof(h->s.stats));
-    unsigned long long ts[8];
+    unsigned long long ts[16];
     cudaSetDevice(h->s.prm.device);
     nfc::slicer_tile_stats(ts, true);
     return 0;
