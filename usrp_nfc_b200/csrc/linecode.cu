@@ -18,7 +18,10 @@
 
 namespace nfc {
 
-static const int CHUNK = 256;
+#ifndef NFC_LC_CHUNK
+#define NFC_LC_CHUNK 64
+#endif
+static const int CHUNK = NFC_LC_CHUNK;
 static const int LOOKBACK_LIMIT = 4096;  // events searched backwards for a reset before giving up
 static const int RSTATES = 32, GSTATES = 16;
 
@@ -94,6 +97,26 @@ __device__ __forceinline__ void step_event(const EventRec &ev, const TabView &tv
         int started = gs >> 3;
         if (tab_nout(e) > 0) framer_put(started, tab_out0(e), 0, ev.rel_pos, sink);
         gs = (tab_next(e) & 7) | (started << 3);
+    }
+}
+
+// eight events at once (one 64-byte line): the loops below are chains of dependent loads otherwise.
+// `base` is a multiple of 8; the event buffer is padded, so reading a little past n_ev is safe.
+__device__ __forceinline__ void load8(const EventRec *__restrict__ ev, int64_t base, EventRec (&e)[8]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(ev + base);
+    const uint4 q[4] = {__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            EventRec r;
+            r.rel_pos = w[2 * h];
+            r.d = (uint16_t)(w[2 * h + 1] & 0xffffu);
+            r.v = (int8_t)((w[2 * h + 1] >> 16) & 0xffu);
+            r.type = (int8_t)(w[2 * h + 1] >> 24);
+            e[2 * k + h] = r;
+        }
     }
 }
 
@@ -202,19 +225,27 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     const int64_t i0 = (int64_t)c * CHUNK;
     bool foundR = !tv.use_reader, foundG = !tv.use_tag;
     int64_t iR = -1, iG = -1;  // index of the reset event found (-1: replay from event 0 with the carry)
-    int64_t i = i0 - 1;
+    int64_t i = i0 - 1;  // next event to look at, going backwards (i0 is a multiple of 8)
     int steps = 0;
     while (i >= 0 && !(foundR && foundG) && steps < LOOKBACK_LIMIT) {
-        const EventRec e = ev[i];
-        if (!foundR && e.type == 1) {
-            const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
-            if (r != 0xFF) { foundR = true; iR = i; rs = r; }
-        } else if (!foundG && e.type == 0) {
-            const uint8_t r = lt.reset_manch[(int)tv.dcg[e.d] * 4 + (e.v + 1)];
-            if (r != 0xFF) { foundG = true; iG = i; gs = r; }
+        EventRec e8[8];
+        const int64_t base = i & ~(int64_t)7;
+        load8(ev, base, e8);
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            if (base + k <= i && !(foundR && foundG)) {
+                const EventRec e = e8[k];
+                if (!foundR && e.type == 1) {
+                    const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
+                    if (r != 0xFF) { foundR = true; iR = base + k; rs = r; }
+                } else if (!foundG && e.type == 0) {
+                    const uint8_t r = lt.reset_manch[(int)tv.dcg[e.d] * 4 + (e.v + 1)];
+                    if (r != 0xFF) { foundG = true; iG = base + k; gs = r; }
+                }
+            }
         }
-        i--;
-        steps++;
+        steps += (int)(i - base) + 1;
+        i = base - 1;
     }
     if (i >= 0 && !(foundR && foundG)) {
         atomicOr(unresolved, 1);
@@ -225,13 +256,20 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     // replay from the earliest point a still-unknown machine needs (a disabled direction needs nothing)
     const int64_t fromR = tv.use_reader ? iR + 1 : i0, fromG = tv.use_tag ? iG + 1 : i0;
     const int64_t from = fromR < fromG ? fromR : fromG;
-    for (int64_t k = from; k < i0; k++) {
-        const EventRec e = ev[k];
-        int dummy_r = 0, dummy_g = 0;
-        if (e.type == 1) {
-            if (k > iR) step_event(e, tv, rs, dummy_g, sink);
-        } else if (e.type == 0) {
-            if (k > iG) step_event(e, tv, dummy_r, gs, sink);
+    for (int64_t base = from & ~(int64_t)7; base < i0; base += 8) {
+        EventRec e8[8];
+        load8(ev, base, e8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int64_t kk = base + k;
+            if (kk < from || kk >= i0) continue;
+            const EventRec e = e8[k];
+            int dummy_r = 0, dummy_g = 0;
+            if (e.type == 1) {
+                if (kk > iR) step_event(e, tv, rs, dummy_g, sink);
+            } else if (e.type == 0) {
+                if (kk > iG) step_event(e, tv, dummy_r, gs, sink);
+            }
         }
     }
     start[c] = (uint16_t)(rs | (gs << 8));
@@ -256,7 +294,13 @@ __global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     CountSink sink;
     sink.c = ChunkCnt{0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
-    for (uint32_t i = i0; i < i1; i++) step_event(ev[i], tv, rs, gs, sink);
+    for (uint32_t i = i0; i < i1; i += 8) {
+        EventRec e[8];
+        load8(ev, i, e);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (i + k < i1) step_event(e[k], tv, rs, gs, sink);
+    }
     cnts[c] = sink.c;
 }
 
@@ -324,7 +368,13 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     sink.pend0 = pc.has0 ? pc.tail0 : out.pending0 + pc.tail0;
     sink.pend1 = pc.has1 ? pc.tail1 : out.pending1 + pc.tail1;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
-    for (uint32_t i = i0; i < i1; i++) step_event(ev[i], tv, rs, gs, sink);
+    for (uint32_t i = i0; i < i1; i += 8) {
+        EventRec e[8];
+        load8(ev, i, e);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (i + k < i1) step_event(e[k], tv, rs, gs, sink);
+    }
     if (c == n_chunks - 1) {
         DecCarry co;
         co.miller_state = rs & 15; co.started[1] = rs >> 4;
