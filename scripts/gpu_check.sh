@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 free -g > gpurun_out/host.txt 2>&1; nproc >> gpurun_out/host.txt
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider "$@" > gpurun_out/pytest_gpu.log 2>&1
+timeout 420 python -m pytest tests -m gpu -q -x --timeout 150 -p no:cacheprovider "$@" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log

@@ -22,6 +22,7 @@
 //    and added to the interval.  Where the exact value is needed (exact_tile, state snapshots, segment end) it
 //    is recomputed as the sum of the ring in double (exact inside the audited exponent span, see slicer.cu).
 #pragma once
+#include <cstddef>
 
 namespace nfc {
 
@@ -112,6 +113,9 @@ struct __align__(16) FastUni {
     float gC0[32];                    // repeat: the measured ss at the chunk's first sample (relative to the midpoint) the guess assumes
     unsigned stats[FS_N];
 };
+static_assert(offsetof(FastUni, gTL) % 16 == 0 && offsetof(FastUni, gTH) % 16 == 0 && offsetof(FastUni, gMid) % 16 == 0 &&
+                  offsetof(FastUni, gC0) % 16 == 0,
+              "guess arrays are read with 128-bit loads");
 
 // per-segment constants
 struct __align__(16) FastPlan {

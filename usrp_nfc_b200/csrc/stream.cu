@@ -1402,12 +1402,25 @@ int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint
                        (long long)(nb0 + nb1));
         return -2;
     }
-    // all pending frames at once: tag->reader bits first, then reader->tag bits
-    if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0);
-    if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1);
-    for (int64_t i = 0; i < avail; i++) {
-        out[i] = s.out_frames[(size_t)i];
-        if (out[i].type == 1) out[i].bit_off += nb0;
+    // all pending frames at once: tag->reader bits first, then reader->tag bits (large drains: copied by helper threads)
+    auto copy_frames = [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; i++) {
+            out[i] = s.out_frames[(size_t)i];
+            if (out[i].type == 1) out[i].bit_off += nb0;
+        }
+    };
+    if (nb0 + nb1 > (4 << 20)) {
+        std::thread t0([&] { if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0); });
+        std::thread t1([&] { if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1); });
+        std::thread t2([&] { copy_frames(0, avail / 2); });
+        copy_frames(avail / 2, avail);
+        t0.join();
+        t1.join();
+        t2.join();
+    } else {
+        if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0);
+        if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1);
+        copy_frames(0, avail);
     }
     s.out_frames.clear();
     s.out_fbits[0].clear();
