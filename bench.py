@@ -241,7 +241,7 @@ def main():
     dev_ms = st["kernel_ms"] / args.steps
     wall_ms = wall * 1e3 / args.steps
     t = torch.tensor([wall_ms, dev_ms, float(frames), float(st["launches"]), float(st["seam_mismatches"]),
-                      st["slicer_ms"] / args.steps], dtype=torch.float64, device="cuda")
+                      st["slicer_ms"] / args.steps, st["slicer_kernel_ms"] / args.steps], dtype=torch.float64, device="cuda")
     per_rank = None
     if world > 1:
         allt = [torch.empty_like(t) for _ in range(world)]
@@ -252,10 +252,10 @@ def main():
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        wall_ms, dev_ms, slicer_ms = float(mx[0]), float(mx[1]), float(mx[5])
+        wall_ms, dev_ms, slicer_ms, kern_ms = float(mx[0]), float(mx[1]), float(mx[5]), float(mx[6])
         frames_total, launches, mism = int(sm[2]), int(sm[3]), int(sm[4])
     else:
-        slicer_ms = float(t[5])
+        slicer_ms, kern_ms = float(t[5]), float(t[6])
         frames_total, launches, mism = frames, int(st["launches"]), int(st["seam_mismatches"])
     value = world * n / (wall_ms * 1e-3) / 1e6  # whole job, wall clock around the synchronous ABI calls (>= device time)
     repaired_ranks = 0
@@ -314,15 +314,26 @@ def main():
         return 0
 
     peak, peak_src = measured_peak_gbs()
-    slic_launches = max(1, st["slicer_launches"])
-    alg_bytes_per_launch = 4.0 * n * args.steps / slic_launches
-    achieved = 4.0 * n / (slicer_ms * 1e-3) / 1e9 if slicer_ms > 0 else None
+    # the dominant kernel alone: CUDA events around every launch of the streaming slicer kernel, on the library's stream
+    k_launches = max(1, st["slicer_kernel_launches"])
+    alg_bytes_per_launch = 4.0 * n * args.steps / k_launches
+    achieved = 4.0 * n / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    traffic = None
+    try:  # DRAM bytes per sample of the committed ncu --set full capture of this kernel, scaled to this run's launches
+        with open(os.path.join(ROOT, "profiles", "slicer_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = {"bytes_per_launch": tj["dram_bytes_per_sample"] * n * args.steps / k_launches,
+                   "dram_bytes_per_sample": tj["dram_bytes_per_sample"], "source": tj["source"]}
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": None,
+                "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "kernel": "nfc::slicer_fast_kernel<256,4,3,IN_ENVELOPE_F32>", "peak_source": peak_src,
                 "algorithmic_bytes_per_sample": 4, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "avg_launch_ms": slicer_ms * args.steps / slic_launches,
-                "note": "achieved = 4 B x samples / CUDA-event time of the slicer stage per step (streaming kernel, seam checks and repairs, bitmap -> transition extraction)"}
+                "avg_launch_ms": kern_ms * args.steps / k_launches, "launches_per_step": k_launches / args.steps,
+                "slicer_stage_ms_per_step": slicer_ms,
+                "note": "achieved = 4 B x samples / CUDA-event time of the streaming slicer kernel's launches per step; the slicer "
+                        "stage (kernel, seam checks and repairs, bitmap -> transition extraction) is slicer_stage_ms_per_step"}
 
     cpu = None
     if not args.no_cpu_baseline:

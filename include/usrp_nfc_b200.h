@@ -146,6 +146,8 @@ typedef struct {
     int64_t unproven_tiles;   /* tiles sent to the exact path because the streaming passes gave up */
     int64_t ring_resums;      /* exact recomputations of the window sum from the ring */
     int64_t exact_rounds;     /* fix-point rounds of the exact path (first-generation kernel) */
+    double slicer_kernel_ms;  /* CUDA-event time of the streaming slicer kernel's launches alone */
+    int64_t slicer_kernel_launches;
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
 int nfc_stream_reset_stats(nfc_stream *s);

@@ -26,7 +26,7 @@ def launches():
 
 
 def full():
-    out = subprocess.run(["ncu", "-i", "gpurun_out/prof_slicer.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", "gpurun_out/prof_fast.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(out.splitlines()))
     hdr, vals = rd[0], rd[-1]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct",
@@ -35,7 +35,7 @@ def full():
             "sass__inst_executed_local", "sm__throughput.avg.pct", "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit",
             "lts__t_bytes.sum ", "sm__pipe_fp64_cycles_active.avg.pct", "smsp__thread_inst_executed.sum"]
     with open("profiles/%s_slicer_ncu.txt" % tag, "w") as f:
-        f.write("# %s %s\n# ncu --set full --clock-control none --import-source on -k regex:slicer_kernel -s 2 -c 1; "
+        f.write("# %s %s\n# ncu --set full --clock-control none --import-source on -k regex:slicer_fast -s 0 -c 1; "
                 "python bench.py --samples 1e9 --steps 1 --warmup 1 (main slicer launch of the timed step)\n" % (tag, note))
         for h, v in zip(hdr, vals):
             if any(w in h for w in want) and "pcsamp" not in h:

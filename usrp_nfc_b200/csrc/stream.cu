@@ -132,6 +132,7 @@ struct Stream {
     cudaStream_t cs2 = nullptr;  // device -> host copies of a slab's records, beside the next slab's slicer
     cudaStream_t cs3 = nullptr;  // host -> device copies of the next slab's samples, beside this slab's kernels
     cudaEvent_t ev_h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around a launch of the streaming slicer kernel
     DevBuf staging2[2];
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
     int ev_idx = 0;
@@ -245,6 +246,8 @@ int Stream::init(const nfc_params *p) {
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs3, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_h[i], cudaEventDisableTiming));
+    NFC_CUDA_CHECK(cudaEventCreate(&ev_k0));
+    NFC_CUDA_CHECK(cudaEventCreate(&ev_k1));
     for (int i = 0; i < 2; i++) {
         NFC_CUDA_CHECK(cudaEventCreate(&ev_a[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
@@ -320,6 +323,8 @@ void Stream::destroy() {
     }
     if (cs2) cudaStreamDestroy(cs2);
     if (cs3) cudaStreamDestroy(cs3);
+    if (ev_k0) cudaEventDestroy(ev_k0);
+    if (ev_k1) cudaEventDestroy(ev_k1);
     for (int i = 0; i < 2; i++) {
         if (ev_h[i]) cudaEventDestroy(ev_h[i]);
         staging2[i].release();
@@ -857,10 +862,19 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         w.bm_pos0 = bm_pos0;
     }
     NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)nseg, cudaMemcpyHostToDevice, cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_k0, cs));
     if (launch_slicer_streaming(works_d.as<SegWork>(), nseg, params_d.as<SlicerParams>(), L, sp.input_kind, cs)) return -1;
+    NFC_CUDA_CHECK(cudaEventRecord(ev_k1, cs));
     stats.launches++;
     stats.slicer_launches++;
     stats.segments += nseg;
+    auto kernel_time = [&]() {  // after a synchronisation of the stream
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev_k0, ev_k1) == cudaSuccess) {
+            stats.slicer_kernel_ms += ms;
+            stats.slicer_kernel_launches++;
+        }
+    };
 
     // ---- seams
     std::vector<int> mism((size_t)nseg, 0);
@@ -891,6 +905,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
     }
     NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
     NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    kernel_time();
     int st_all = 0;
     for (int k = 0; k < nseg; k++) st_all |= status[(size_t)k];
     if (st_all & (SEG_INEXACT | SEG_NOT_SANE)) {
@@ -940,7 +955,9 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             if (redo.empty()) continue;
             SegWork *d_redo = works_d.as<SegWork>() + nseg;
             NFC_CUDA_CHECK(cudaMemcpyAsync(d_redo, redo.data(), sizeof(SegWork) * redo.size(), cudaMemcpyHostToDevice, cs));
+            NFC_CUDA_CHECK(cudaEventRecord(ev_k0, cs));
             if (launch_slicer_streaming(d_redo, (int)redo.size(), params_d.as<SlicerParams>(), L, sp.input_kind, cs)) return -1;
+            NFC_CUDA_CHECK(cudaEventRecord(ev_k1, cs));
             stats.launches++;
             stats.slicer_launches++;
             const int nw = (int)who.size();
@@ -954,6 +971,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             std::vector<int32_t> rst((size_t)nr, 0);
             NFC_CUDA_CHECK(cudaMemcpyAsync(rst.data(), redo_counts.p, sizeof(int32_t) * (size_t)nr, cudaMemcpyDeviceToHost, cs));
             NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            kernel_time();
             for (int q = 0; q < nw; q++) {
                 const int i = who[(size_t)q], k = ks[(size_t)i];
                 if (rst[(size_t)i] & (SEG_INEXACT | SEG_NOT_SANE)) {
