@@ -86,6 +86,10 @@ int nfc_stream_create(const nfc_params *p, nfc_stream **out);
 int nfc_stream_destroy(nfc_stream *s);
 /* Back to the state right after creation (a fresh transition_sink / background pair); keeps device buffers. */
 int nfc_stream_reset(nfc_stream *s);
+/* New thresholds for the next capture (transition_sink's lo_val / hi_val constructor arguments, transition_sink.py:12):
+ * allowed only on a stream that has consumed nothing since its creation or last reset.  Batches of captures that differ
+ * only in hi_val reuse one stream (and its device buffers) this way. */
+int nfc_stream_set_thresholds(nfc_stream *s, double lo_val, double hi_val);
 
 /* transition_sink.work (transition_sink.py:37-125): offers n items, returns how many were consumed.
  * Like the reference, the call that completes the warm-up consumes only the warm-up part and

@@ -269,3 +269,21 @@ def test_bench_workload_matches_oracle(n, seg_len):
     st = s.stats()
     assert st["fast_tiles"] > 0.9 * (n / 4096) * (0.5 if seg_len else 1)
     print("stats", st)
+
+
+@pytest.mark.parametrize("name,rate,kw", [CAPTURES[1], CAPTURES[2]])
+def test_iq_input_envelope_on_device(name, rate, kw):
+    """Complex baseband input (usrp_src.py:31 complex_to_mag_squared): the envelope RN32(RN32(re^2) + RN32(im^2)) is formed on
+    the device; the oracle gets the same envelope computed in float32 on the host."""
+    case = H.load_case(name)
+    amp = synth.pcm_to_float(case["pcm"])
+    rng = np.random.default_rng(11)
+    phase = rng.uniform(0, 2 * np.pi, amp.size).astype(np.float32)
+    iq = np.empty((amp.size, 2), dtype=np.float32)
+    iq[:, 0] = amp * np.cos(phase)
+    iq[:, 1] = amp * np.sin(phase)
+    env = (iq[:, 0] * iq[:, 0]).astype(np.float32) + (iq[:, 1] * iq[:, 1]).astype(np.float32)
+    want = oracle.decode_capture(env.astype(np.float32), rate, **kw)
+    got = gpu_decode(iq.view(np.complex64).reshape(-1), rate, kind=_cabi.IN_IQ_F32, **kw)
+    check_against_oracle(got, want)
+    assert len(want["frames"]) > 0

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nfc_stream_create": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_void_p)]),
     "nfc_stream_destroy": (C.c_int, [C.c_void_p]),
     "nfc_stream_reset": (C.c_int, [C.c_void_p]),
+    "nfc_stream_set_thresholds": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "nfc_stream_push": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
     "nfc_stream_drain_events": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_symbols": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
@@ -139,6 +140,12 @@ class Stream(object):
             self._h = None
 
     __del__ = close
+
+    def set_thresholds(self, lo_val, hi_val):
+        """lo_val / hi_val for the next capture; only on a freshly created or reset stream."""
+        if lib().nfc_stream_set_thresholds(self._h, float(lo_val), float(hi_val)) != 0:
+            raise NfcError(last_error())
+        self.params.lo_val, self.params.hi_val = float(lo_val), float(hi_val)
 
     def push(self, items):
         """-> (consumed, called_back): transition_sink.work semantics (transition_sink.py:37-125)."""

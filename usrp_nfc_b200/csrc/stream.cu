@@ -1386,6 +1386,28 @@ int nfc_stream_reset(nfc_stream *h) {
     return 0;
 }
 
+int nfc_stream_set_thresholds(nfc_stream *h, double lo_val, double hi_val) {
+    if (!h) return -1;
+    Stream &s = h->s;
+    if (s.settle()) return -1;
+    if (s.pos != 0 || s.stable || !s.warm.empty()) {
+        nfc::set_error("set_thresholds: the stream has consumed samples; reset it first");
+        return -1;
+    }
+    cudaSetDevice(s.prm.device);
+    s.prm.lo_val = lo_val;
+    s.prm.hi_val = hi_val;
+    s.sp.lo = lo_val;
+    s.sp.hi = hi_val;
+    s.sp.loL = s.sp.lo / s.sp.Ld;
+    s.sp.hiL = s.sp.hi / s.sp.Ld;
+    s.sp.cls_ss0_x0 = nfc::classify_ratio_host(1.0, s.sp.lo, s.sp.hi);
+    s.sp.cls_ss0_xn = nfc::classify_ratio_host(s.sp.hi + 0.1, s.sp.lo, s.sp.hi);
+    NFC_CUDA_CHECK(cudaMemcpyAsync(s.params_d.p, &s.sp, sizeof(s.sp), cudaMemcpyHostToDevice, s.cs));
+    NFC_CUDA_CHECK(cudaStreamSynchronize(s.cs));
+    return 0;
+}
+
 int64_t nfc_stream_push(nfc_stream *h, const void *items, int64_t n, int mem, int *called_back) {
     if (!h || (n > 0 && !items)) {
         nfc::set_error("null argument");
