@@ -180,6 +180,7 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     u.gTL[lane] = TLb * f;
     u.gTH[lane] = THb * f;
     u.gMid[lane] = ssf * (f - 1.0f);
+    __syncwarp();  // every lane has read the values of `u` its arguments were computed from
     if (lane == 0) {
         const unsigned qe = ok ? ae - 30u : 127u;
         u.q = __uint_as_float(qe << 23);
@@ -874,6 +875,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         if (s0 >= L) s0 -= L;
                     }
                     if (t >= plan.t_emit) plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
+                    __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
                     if (threadIdx.x == 0) {
                         uni.stats[FS_FAST]++;
                         c_s.last_val = uni.cand_last_val;
