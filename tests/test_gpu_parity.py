@@ -287,3 +287,41 @@ def test_iq_input_envelope_on_device(name, rate, kw):
     got = gpu_decode(iq.view(np.complex64).reshape(-1), rate, kind=_cabi.IN_IQ_F32, **kw)
     check_against_oracle(got, want)
     assert len(want["frames"]) > 0
+
+
+def test_sampled_window_parity_at_scale():
+    """BASELINE-sized streams cannot be decoded by the oracle in test time.  Size-independent check: decode
+    1.5e9 samples on the GPU, then let the oracle decode a few windows cold-started 24 av_windows early (its state converges to
+    the stream's long before the window begins) and compare every frame closing inside the windows."""
+    import torch
+    import bench
+    rate = 13.56e6
+    codes, lens, p = bench.build_schedule(rate, 2024)
+    L = p["av_window"]
+    n = 1_500_000_000
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    _cabi.synth_render(x, codes, lens, carrier=0.5, pause=0.015, tag_high=1.07, noise=0.003, fade=0.05,
+                       fade_period=round(rate * 0.02), seed=99, as_envelope=True, device=0, first_index=0)
+    torch.cuda.synchronize()
+    s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_FRAMES, **p)
+    s.set_tuning(slab_len=1 << 30)
+    s.push_all(x)
+    fr, bits = s.drain_frames_flat()
+    assert len(fr) > 100000
+    rng = np.random.default_rng(1)
+    halo, wlen = 24 * L, 12_000_000
+    for w0 in sorted(rng.integers(halo, n - wlen, 3).tolist()) + [1 << 30]:  # one window across the slab boundary
+        w0 = int(w0)
+        w1 = w0 + wlen
+        want = oracle.decode_capture(x[w0 - halo - L: w1].cpu().numpy(), rate, hi_val=1.09, **p)
+        base = w0 - halo - L
+        wpos = want["frames"]["pos"] + base
+        wsel = np.nonzero((wpos >= w0 + 100000) & (wpos < w1))[0]
+        gsel = np.nonzero((fr["pos"] >= w0 + 100000) & (fr["pos"] < w1))[0]
+        assert len(wsel) == len(gsel) and len(wsel) > 100, (w0, len(wsel), len(gsel))
+        assert np.array_equal(wpos[wsel], fr["pos"][gsel])
+        assert np.array_equal(want["frames"]["type"][wsel], fr["type"][gsel])
+        assert np.array_equal(want["frames"]["nbits"][wsel], fr["nbits"][gsel])
+        for i, j in zip(wsel[:: max(1, len(wsel) // 200)], gsel[:: max(1, len(gsel) // 200)]):
+            g = fr[j]
+            assert np.array_equal(want["frame_bits"][i], bits[g["bit_off"]: g["bit_off"] + g["nbits"]])
