@@ -325,3 +325,82 @@ def test_sampled_window_parity_at_scale():
         for i, j in zip(wsel[:: max(1, len(wsel) // 200)], gsel[:: max(1, len(gsel) // 200)]):
             g = fr[j]
             assert np.array_equal(want["frame_bits"][i], bits[g["bit_off"]: g["bit_off"] + g["nbits"]])
+
+
+def _corner_stream(L, mx, n, seed):
+    """Carrier with long pauses (timeouts inside a LOW run), spikes right after a pause (hysteresis), stretches hovering
+    around the HIGH threshold (samples inside every guard band), strong steps of the level."""
+    rng = np.random.default_rng(seed)
+    x = (0.25 * (1 + 0.01 * rng.standard_normal(n))).astype(np.float32)
+    i = L + 10
+    while i < n - 4 * mx - 10:
+        kind = rng.integers(0, 5)
+        ln = int(rng.choice([1, 2, mx - 1, mx, mx + 1, 2 * mx, 2 * mx + 1, 3 * mx + 1, 6, 700]))
+        ln = min(ln, n - i - 1)
+        if kind == 0:
+            x[i:i + ln] = 1e-4
+            i += ln
+            if rng.random() < 0.7:
+                k = int(rng.integers(0, mx + 4))
+                x[i + k: i + k + int(rng.integers(1, 4))] = 0.4
+        elif kind == 1:
+            x[i:i + ln] = 0.3 * (1 + 0.01 * rng.standard_normal(ln))
+            i += ln
+        elif kind == 2:
+            x[i:i + ln] = 0.2725 * (1 + 0.002 * rng.standard_normal(ln))  # hovering around hi = 1.09
+            i += ln
+        elif kind == 3 and rng.random() < 0.05:
+            x[i:] *= np.float32(rng.choice([0.7, 1.4]))  # the level steps: guesses are off, sums do not fit the fixed point
+        i += int(rng.integers(1, 6 * mx))
+    return x
+
+
+@pytest.mark.parametrize("L,mx,tuning", [(8192, 50, None), (13560, 339, dict(seg_len=131072, halo=4 * 13560)),
+                                         (8196, 7, dict(seg_len=65536, halo=32784)), (20000, 500, None)])
+def test_streaming_kernel_corner_cases(L, mx, tuning):
+    n = 700000
+    x = _corner_stream(L, mx, n, L * 7 + mx)
+    want = oracle.decode_capture(x, 13.56e6, hi_val=1.09, av_window=L, max_len=mx)
+    got = gpu_decode(x, 13.56e6, hi_val=1.09, av_window=L, max_len=mx, tuning=tuning)
+    check_against_oracle(got, want)
+    st = got["stream"].stats()
+    assert not got["stream"].state()[0].serial_mode
+    assert st["fast_tiles"] > 0 and st["exact_tiles"] > 0
+    print("stats", st)
+
+
+def test_streaming_kernel_degenerate_inputs():
+    L, mx = 8192, 50
+    # silence (ss == 0), then a carrier, negative samples, back to silence
+    x = np.zeros(150000, np.float32)
+    x[40000:100000] = 0.25
+    x[60000:60010] = -1.0
+    x[70000:70003] = 0.0
+    want = oracle.decode_capture(x, 13.56e6, av_window=L, max_len=mx)
+    got = gpu_decode(x, 13.56e6, av_window=L, max_len=mx)
+    check_against_oracle(got, want)
+    # thresholds the streaming path does not take (lo_val = 0, hi_val < lo_val): every tile through the exact path
+    rng = np.random.default_rng(3)
+    y = (0.25 * (1 + 0.05 * rng.standard_normal(120000))).astype(np.float32)
+    y[50000:50040] = 1e-5
+    for lo, hi in ((0.0, 1.05), (1.2, 1.1), (0.98, 1.02)):
+        want = oracle.decode_capture(y, 13.56e6, lo_val=lo, hi_val=hi, av_window=L, max_len=mx)
+        got = gpu_decode(y, 13.56e6, lo_val=lo, hi_val=hi, av_window=L, max_len=mx)
+        check_against_oracle(got, want)
+
+
+def test_streaming_kernel_falls_back_on_inexact_or_insane_samples():
+    L, mx = 8192, 50
+    rng = np.random.default_rng(9)
+    n = 100000
+    x = (np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-6, 6, n)).astype(np.float32)  # 40 binades: sums round
+    want = oracle.decode_capture(x, 13.56e6, av_window=L, max_len=mx)
+    got = gpu_decode(x, 13.56e6, av_window=L, max_len=mx)
+    check_against_oracle(got, want)
+    assert got["stream"].state()[0].serial_mode
+    z = (0.25 * (1 + 0.01 * rng.standard_normal(n))).astype(np.float32)
+    z[50000] = np.inf
+    z[60000:60004] = 1e-4
+    want = oracle.decode_capture(z, 13.56e6, av_window=L, max_len=mx)
+    got = gpu_decode(z, 13.56e6, av_window=L, max_len=mx)
+    check_against_oracle(got, want)
