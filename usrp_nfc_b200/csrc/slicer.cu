@@ -1258,11 +1258,23 @@ static size_t fast_smem(int L, int kind) {
     return ring + 4096 * item;
 }
 
+// NFC_SLICER_WIDE=1: 512 threads per segment, two chunks per warp (experiment: more warps per SM, fewer registers per thread)
+static bool fast_wide() {
+    static const bool w = getenv("NFC_SLICER_WIDE") && getenv("NFC_SLICER_WIDE")[0] == '1';
+    return w;
+}
+
 template <int KIND>
 static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
-    auto k = slicer_fast_kernel<256, 4, 3, KIND>;
-    NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+    if (fast_wide()) {
+        auto k = slicer_fast_kernel<512, 2, 2, KIND>;
+        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<n_works, 512, smem, stream>>>(d_works, d_params);
+    } else {
+        auto k = slicer_fast_kernel<256, 4, 3, KIND>;
+        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+    }
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1310,8 +1322,13 @@ int slicer_resident_ctas(int L, bool vec_ok) {
     cudaError_t e;
     if (slicer_streaming_ok(L, vec_ok)) {
         const size_t fsm = fast_smem(L, IN_ENVELOPE_F32);
-        cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, fsm);
+        if (fast_wide()) {
+            cudaFuncSetAttribute(slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, 512, fsm);
+        } else {
+            cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, fsm);
+        }
     } else if (vec_ok && L >= 1024) {
         switch (slicer_rows(L)) {
             case 4:

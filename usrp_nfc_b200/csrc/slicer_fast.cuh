@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     constexpr int tile_bytes = T * ITEM;
     static_assert(NC == 32, "one lane per chunk record");
     static_assert(T % SUB == 0, "tile is a whole number of exact rows");
-    static_assert(R == 4, "one bitmap word per lane and tile; four guesses per 128-bit read");
+    static_assert(R == 4 || R == 2, "bitmap words of a warp are written by its first R * 8 lanes");
     static_assert(NW >= 2, "warps 0 and 1 share the verification");
     extern __shared__ __align__(16) float ring[];
     __shared__ BlockShared<NT, 1> sh;  // exact_tile's scratch
@@ -620,8 +620,12 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 }
                 x_ready = false;
                 const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
-                const float4 tl4 = *reinterpret_cast<const float4 *>(&uni.gTL[warp * R]);
-                const float4 th4 = *reinterpret_cast<const float4 *>(&uni.gTH[warp * R]);
+                float thL[R], thH[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    thL[r] = uni.gTL[warp * R + r];
+                    thH[r] = uni.gTH[warp * R + r];
+                }
                 const bool precise = n_meas > 0;  // a repeated tile is classified sample by sample against the measured sums
 
                 float n[R][4];
@@ -631,7 +635,6 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     FastRec *rec = &fs.recs[warp * R];
                     uint32_t *bmw = &fs.bm[warp * R * 8];
                     if (!precise) {
-                        const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
@@ -641,9 +644,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                             if (s0 >= L) s0 -= L;
                         }
                     } else {
-                        const float4 c4 = *reinterpret_cast<const float4 *>(&uni.gC0[warp * R]);
-                        const float thL[R] = {tl4.x, tl4.y, tl4.z, tl4.w}, thH[R] = {th4.x, th4.y, th4.z, th4.w};
-                        const float c0g[R] = {c4.x, c4.y, c4.z, c4.w};
+                        float c0g[R];
+#pragma unroll
+                        for (int r = 0; r < R; r++) c0g[r] = uni.gC0[warp * R + r];
                         const float TLb = uni.TLb, THb = uni.THb;
 #pragma unroll
                         for (int r = 0; r < R; r++) {
@@ -874,7 +877,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         s0 += FAST_CH;
                         if (s0 >= L) s0 -= L;
                     }
-                    if (t >= plan.t_emit) plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
+                    if (t >= plan.t_emit && lane < R * 8)
+                        plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
                     __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
                     if (threadIdx.x == 0) {
                         uni.stats[FS_FAST]++;
