@@ -267,8 +267,10 @@ def main():
         if world == 1:
             s.reset()
             s.push_all(x)
-            fr, _ = s.drain_frames_flat(reuse=True)
-            return len(fr)
+            fr, _, _ = s.view_frames()  # records and frame bits in host memory (zero-copy view of the library's buffers)
+            nfr = len(fr)
+            s.release_frames()
+            return nfr
         res = sharding.decode_time_sharded(s, lambda a, b: x[a - base: b - base], total, L, _cabi.State, dist=dist,
                                            device="cuda", halo_windows=args.halo_windows, flat=True)
         shard_info.update(repaired=res["repaired"], seam_ok=res["seam_ok"])
@@ -345,7 +347,8 @@ def main():
         for _ in range(2):
             se.reset()
             se.push_all(xh_np)
-            se.drain_frames_flat(reuse=True)
+            se.view_frames()
+            se.release_frames()
         se.reset_stats()
         barrier()
         t0 = time.perf_counter()
@@ -353,7 +356,9 @@ def main():
         for _ in range(esteps):
             se.reset()
             se.push_all(xh_np)
-            fr_e, _ = se.drain_frames_flat(reuse=True)
+            fr_e = se.view_frames()[0]
+            n_fr_e = len(fr_e)
+            se.release_frames()
         barrier()
         e_wall = (time.perf_counter() - t0) / esteps
         est = se.stats()
@@ -362,7 +367,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * ne / float(tt[0]) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(est["h2d_bytes"] / esteps), "d2h_bytes_per_step": int(est["d2h_bytes"] / esteps),
-               "samples_per_step_per_gpu": ne, "ms_per_step": float(tt[0]) * 1e3, "frames_per_step": int(len(fr_e)),
+               "samples_per_step_per_gpu": ne, "ms_per_step": float(tt[0]) * 1e3, "frames_per_step": int(n_fr_e),
                "host_buffer": "int16 PCM (pinned), what wavfile_source reads; normalised and squared on the device"}
         se.close()
         del xh

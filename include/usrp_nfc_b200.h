@@ -106,6 +106,12 @@ int64_t nfc_stream_drain_symbols(nfc_stream *s, nfc_symbol *out, int64_t cap);
  * cap or bits_cap is too small (query first with cap = 0 and nfc_stream_pending_frame_bits). */
 int64_t nfc_stream_drain_frames(nfc_stream *s, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap);
 int64_t nfc_stream_pending_frame_bits(nfc_stream *s); /* bytes the next full drain needs */
+/* Zero-copy variant for bulk consumers: pointers into the stream's own buffers, valid until the next push / drain / reset /
+ * release on this stream.  frames[i].bit_off indexes bits_tag (type 0) or bits_reader (type 1).  Returns the frame count;
+ * nfc_stream_release_frames discards what was viewed (like a drain). */
+int64_t nfc_stream_view_frames(nfc_stream *s, const nfc_frame **frames, const uint8_t **bits_tag, int64_t *n_bits_tag,
+                               const uint8_t **bits_reader, int64_t *n_bits_reader);
+int nfc_stream_release_frames(nfc_stream *s);
 
 /* Implicit streaming state of the reference objects (transition_sink.py:20-34,102-106; decoder and
  * PacketProcessor attributes), for checkpointing and for stitching time-sharded captures. */

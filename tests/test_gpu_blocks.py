@@ -73,3 +73,25 @@ def test_decoder_block_with_fake_fsm_and_emulator():
     d.run(chunk=5000)
     assert emu.enc == d._fsm.process_outgoing and d._fsm.callback == emu.process_packet  # packets.py:88-90
     assert [n for _, n in d._fsm.frames] == case["flen"].tolist()
+
+
+def test_view_frames_is_the_drain_without_the_copy():
+    import numpy as np
+    from tests import helpers as H
+    from usrp_nfc_b200 import _cabi
+    case = H.load_case("rate_1356")
+    x = H.case_input(case)
+    kw = dict(hi_val=1.09, av_window=13560, max_len=339)
+    a = _cabi.Stream(13.56e6, outputs=_cabi.OUT_FRAMES, **kw)
+    b = _cabi.Stream(13.56e6, outputs=_cabi.OUT_FRAMES, **kw)
+    a.push_all(x)
+    b.push_all(x)
+    fr, bits = a.drain_frames_flat()
+    vf, b0, b1 = b.view_frames()
+    assert len(vf) == len(fr) > 0
+    assert np.array_equal(vf["pos"], fr["pos"]) and np.array_equal(vf["nbits"], fr["nbits"]) and np.array_equal(vf["type"], fr["type"])
+    for f, g in zip(fr, vf):
+        src = b0 if g["type"] == 0 else b1
+        assert np.array_equal(bits[f["bit_off"]: f["bit_off"] + f["nbits"]], src[g["bit_off"]: g["bit_off"] + g["nbits"]])
+    b.release_frames()
+    assert len(b.view_frames()[0]) == 0

@@ -59,6 +59,9 @@ SIGNATURES = {
     "nfc_stream_drain_symbols": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_frames": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "nfc_stream_pending_frame_bits": (C.c_int64, [C.c_void_p]),
+    "nfc_stream_view_frames": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "nfc_stream_release_frames": (C.c_int, [C.c_void_p]),
     "nfc_stream_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_tuning": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
@@ -220,6 +223,28 @@ class Stream(object):
                 raise NfcError(last_error())
             fr = fr[:got]
         return fr, bits[:nb]
+
+    def view_frames(self):
+        """Zero-copy bulk access: (frame records, tag->reader bits, reader->tag bits) as numpy views of the stream's own
+        buffers; record.bit_off indexes the bit array of the record's type.  Valid until the next push / drain / reset /
+        release_frames on this stream."""
+        fp, b0, b1 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n0, n1 = C.c_int64(0), C.c_int64(0)
+        n = lib().nfc_stream_view_frames(self._h, C.byref(fp), C.byref(b0), C.byref(n0), C.byref(b1), C.byref(n1))
+        if n < 0:
+            raise NfcError(last_error())
+
+        def arr(ptr, count, dtype):
+            if not count or not ptr.value:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+
+        return arr(fp, n, FRAME_DTYPE), arr(b0, n0.value, np.uint8), arr(b1, n1.value, np.uint8)
+
+    def release_frames(self):
+        if lib().nfc_stream_release_frames(self._h) != 0:
+            raise NfcError(last_error())
 
     def state(self):
         st = State()

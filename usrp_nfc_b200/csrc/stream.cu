@@ -1469,6 +1469,32 @@ int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint
     return avail;
 }
 
+int64_t nfc_stream_view_frames(nfc_stream *h, const nfc_frame **frames, const uint8_t **bits_tag, int64_t *n_bits_tag,
+                               const uint8_t **bits_reader, int64_t *n_bits_reader) {
+    if (!h || !frames || !bits_tag || !n_bits_tag || !bits_reader || !n_bits_reader) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    if (h->s.settle()) return -1;
+    Stream &s = h->s;
+    *frames = s.out_frames.data();
+    *bits_tag = s.out_fbits[0].data();
+    *n_bits_tag = (int64_t)s.out_fbits[0].size();
+    *bits_reader = s.out_fbits[1].data();
+    *n_bits_reader = (int64_t)s.out_fbits[1].size();
+    return (int64_t)s.out_frames.size();
+}
+
+int nfc_stream_release_frames(nfc_stream *h) {
+    if (!h || h->s.settle()) return -1;
+    Stream &s = h->s;
+    s.out_frames.clear();
+    s.out_fbits[0].clear();
+    s.out_fbits[1].clear();
+    s.fr_head = 0;
+    return 0;
+}
+
 int nfc_stream_get_state(nfc_stream *h, nfc_state *st, float *ring, uint8_t *pending_bits) {
     if (!h || !st) {
         nfc::set_error("null argument");
