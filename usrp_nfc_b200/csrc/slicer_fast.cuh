@@ -415,13 +415,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         }
         return best;
     };
-    int t_snap = next_snap(-1);
     const int ntiles = plan.ntiles;
     const int64_t tile0_pos = plan.tile0_pos;
 
-    // exact_tile's slot of this thread's first sample of a row, and this kernel's (warp-contiguous layout)
-    int slot_x = (int)((tile0_pos + (int64_t)threadIdx.x * 4) % L);
-    int slot_w = (int)((tile0_pos + (int64_t)warp * WS + (int64_t)lane * 4) % L);
     const int slot_step = T % L;
     const int xoff = (warp * WS + lane * 4) * ITEM;  // this thread's first sample inside a tile of the input
 
@@ -431,7 +427,6 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     constexpr bool STAGED = KIND != IN_IQ_F32;
     char *xbuf = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16 + (size_t)threadIdx.x * (4 * ITEM);
     float4 xin[R];
-    bool have_x = false;
 
     auto request_tile = [&](int t) {  // start the copy of tile t into the staging buffer
         const char *src = plan.xbase + (int64_t)t * tile_bytes + xoff;
@@ -453,28 +448,16 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             for (int r = 0; r < R; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * FAST_CH * ITEM + 16));
         }
     };
-    auto fetch_tile = [&]() {  // the requested tile's samples (as envelope) into xin
-        if (KIND == IN_ENVELOPE_F32 || KIND == IN_REAL_F32) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-            for (int r = 0; r < R; r++) xin[r] = *reinterpret_cast<const float4 *>(xbuf + r * (NT * 16));
-            if (KIND == IN_REAL_F32) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    xin[r].x = env_real(xin[r].x); xin[r].y = env_real(xin[r].y);
-                    xin[r].z = env_real(xin[r].z); xin[r].w = env_real(xin[r].w);
-                }
-            }
-        } else if (KIND == IN_PCM_S16) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    auto staged_row = [&](int r) -> float4 {  // row r of the requested tile (after cp.async.wait_group 0), as envelope
+        if (KIND == IN_PCM_S16) {
             const float pcm_scale = p.pcm_scale;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const short4 sv = *reinterpret_cast<const short4 *>(xbuf + r * (NT * 8));
-                xin[r] = make_float4(env_real(__fdiv_rn((float)sv.x, pcm_scale)), env_real(__fdiv_rn((float)sv.y, pcm_scale)),
-                                     env_real(__fdiv_rn((float)sv.z, pcm_scale)), env_real(__fdiv_rn((float)sv.w, pcm_scale)));
-            }
+            const short4 sv = *reinterpret_cast<const short4 *>(xbuf + r * (NT * 8));
+            return make_float4(env_real(__fdiv_rn((float)sv.x, pcm_scale)), env_real(__fdiv_rn((float)sv.y, pcm_scale)),
+                               env_real(__fdiv_rn((float)sv.z, pcm_scale)), env_real(__fdiv_rn((float)sv.w, pcm_scale)));
         }
+        float4 v = *reinterpret_cast<const float4 *>(xbuf + r * (NT * 16));
+        if (KIND == IN_REAL_F32) { v.x = env_real(v.x); v.y = env_real(v.y); v.z = env_real(v.z); v.w = env_real(v.w); }
+        return v;
     };
     auto load_tile = [&](int t) {
         const char *src = plan.xbase + (int64_t)t * tile_bytes + xoff;
@@ -590,46 +573,80 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             }
     };
 
-    for (int t = 0; t < ntiles; t++) {
-        if (t == t_snap) {
-            if (t == plan.t_snap[0]) snapshot(w.seam_in, w.begin);
-            for (int j = 1; j < 4; j++)
-                if (t == plan.t_snap[j]) snapshot(w.ckpt_state[j - 1], tile0_pos + (int64_t)t * T);
-            t_snap = next_snap(t);
-            // the interval collapsed: the coming tile's constants follow it
-            if (warp == 0) {
-                const double lo = uni.ss_lo, hi = uni.ss_hi;
-                const float tp = uni.tot_prev, ae = uni.a_est;
-                __syncwarp();
-                fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
-            }
-            __syncthreads();
+    // ring update, bitmap out and carries of an accepted tile
+    auto commit = [&](const float (&n)[R][4], int t, int slot) {
+        int s0 = slot;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            *reinterpret_cast<float4 *>(ring + s0) = make_float4(n[r][0], n[r][1], n[r][2], n[r][3]);
+            s0 += FAST_CH;
+            if (s0 >= L) s0 -= L;
         }
+        if (t >= plan.t_emit && lane < R * 8)
+            plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
+        __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
+        if (threadIdx.x == 0) {
+            uni.stats[FS_FAST]++;
+            c_s.last_val = uni.cand_last_val;
+            const int newL = uni.cand_newL, newS = uni.cand_newS;
+            if (newL >= 0) {
+                const int64_t P0 = tile0_pos + (int64_t)t * T;
+                c_s.lastL = P0 + newL;
+                if (newS >= 0) c_s.lrun_start = P0 + newS;
+            }
+        }
+    };
 
-        bool done = false;
-        bool x_ready = have_x;  // this tile's samples were requested during the previous tile
-        have_x = false;
-        if (streamable(t) && uni.ok) {
-            int n_meas = 0, n_coarse = 0;  // repeats of this tile: with measured guesses, with a coarser fixed-point step
-            for (;;) {
+    // The tile loop is split in two so that nothing but `t` lives across the rare paths (their calls and double
+    // arithmetic would otherwise push the streamed loop's counters into local memory): an inner loop that only
+    // streams, and a cold part around it that recomputes what it needs from `t`.
+    enum { WHY_NONE = 0, WHY_SNAP, WHY_EXACT, WHY_VERIFY };
+    int t = 0;
+    while (t < ntiles) {
+        const int t_entry = t;
+        {
+            bool snap = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) snap = snap || (t == plan.t_snap[j]);
+            if (snap) {
+                if (t == plan.t_snap[0]) snapshot(w.seam_in, w.begin);
+                for (int j = 1; j < 4; j++)
+                    if (t == plan.t_snap[j]) snapshot(w.ckpt_state[j - 1], tile0_pos + (int64_t)t * T);
+                // the interval collapsed: the coming tile's constants follow it
+                if (warp == 0) {
+                    const double lo = uni.ss_lo, hi = uni.ss_hi;
+                    const float tp = uni.tot_prev, ae = uni.a_est;
+                    __syncwarp();
+                    fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
+                }
+                __syncthreads();
+            }
+        }
+        int why = WHY_NONE;
+        {
+            // ------------------------------------------------------------------------ streamed tiles
+            // tiles [t, t_stop) can be streamed back to back: inside the segment, whole, no snapshot due
+            int t_stop = min(next_snap(t), min(plan.t_int_hi, ntiles));
+            if (plan.t_strad >= t) t_stop = min(t_stop, plan.t_strad);
+            if (t < plan.t_int_lo) t_stop = t;
+            // this kernel's slot of the thread's first sample of the tile (warp-contiguous layout)
+            int slot_w = (int)((tile0_pos + (int64_t)t * T + (int64_t)warp * WS + (int64_t)lane * 4) % L);
+            int have_x = 0;  // the tile's samples were requested during the previous tile
+            float n[R][4];
+            // one pass over tile t: classify against the guesses, sums and margins, verdict.  n_meas / n_coarse: repeats
+            // of this tile so far with measured guesses / with a coarser fixed-point step
+            auto tile_pass = [&](int x_ready, int n_meas, int n_coarse) -> int {
+                int verdict;
                 if (STAGED) {
                     if (!x_ready) request_tile(t);
-                    fetch_tile();
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 } else {
                     load_tile(t);
                 }
-                x_ready = false;
-                const float4 kq = *reinterpret_cast<const float4 *>(&uni.q);  // q, invq, invqA, hwf
-                float thL[R], thH[R];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    thL[r] = uni.gTL[warp * R + r];
-                    thH[r] = uni.gTH[warp * R + r];
-                }
+                x_ready = 0;
+                const float invq = uni.invq, invqA = uni.invqA;
                 const bool precise = n_meas > 0;  // a repeated tile is classified sample by sample against the measured sums
-
-                float n[R][4];
-                // ------------------------------------------------------------ phase 1: classify, sums, margins, maps
+                // -------------------------------------------------------- phase 1: classify, sums, margins, maps
                 {
                     int s0 = slot_w;
                     FastRec *rec = &fs.recs[warp * R];
@@ -638,39 +655,37 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            fast_row<false>(xin[r], pv4, thL[r], thH[r], kq.y, kq.z, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, lane, n[r], rec + r,
-                                            bmw + r * 8);
+                            fast_row<false>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
+                                            invqA, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, lane, n[r], rec + r, bmw + r * 8);
                             s0 += FAST_CH;
                             if (s0 >= L) s0 -= L;
                         }
                     } else {
-                        float c0g[R];
-#pragma unroll
-                        for (int r = 0; r < R; r++) c0g[r] = uni.gC0[warp * R + r];
                         const float TLb = uni.TLb, THb = uni.THb;
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            fast_row<true>(xin[r], pv4, thL[r], thH[r], kq.y, kq.z, c0g[r], TLb, THb, plan.loLf, plan.hiLf, lane, n[r],
-                                           rec + r, bmw + r * 8);
+                            fast_row<true>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
+                                           invqA, uni.gC0[warp * R + r], TLb, THb, plan.loLf, plan.hiLf, lane, n[r], rec + r,
+                                           bmw + r * 8);
                             s0 += FAST_CH;
                             if (s0 >= L) s0 -= L;
                         }
                     }
                 }
                 // next tile's samples on their way while this one is settled
-                if (t + 1 < ntiles && streamable(t + 1)) {
+                if (t + 1 < t_stop) {
                     request_tile(t + 1);
-                    have_x = STAGED;
+                    have_x = STAGED ? 1 : 0;
                 }
                 __syncthreads();
 
                 if (warp == 0) {
-                    // -------------------------------------------------------- phase 2a (warp 0): the sums, lane = chunk
+                    // ---------------------------------------------------- phase 2a (warp 0): the sums, lane = chunk
                     const uint4 r0 = *reinterpret_cast<const uint4 *>(&fs.recs[lane]);
                     const int S = (int)r0.x, A = (int)r0.y;
                     const float mL = __uint_as_float(r0.z), mH = __uint_as_float(r0.w);
-                    const float q = kq.x, hwf = kq.w;
+                    const float q = uni.q, hwf = uni.hwf;
                     const float loLf = plan.loLf, hiLf = plan.hiLf;
                     // window sum at each chunk's first sample, relative to the midpoint of the tile's start interval
                     const float Sf = (float)S * q;
@@ -752,151 +767,164 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     maps_phase(t);
                 }
                 __syncthreads();
-                int verdict = uni.verdict;
+                verdict = uni.verdict;
                 if (uni.st2 && verdict != FV_SLOW) {
                     verdict = FV_SLOW;
                     if (threadIdx.x == 0) uni.stats[FS_ST2]++;
                 }
-                if (verdict == FV_VERIFY) {
-                    // ------------------------------------------------------------ exact fix-point from the precise pass
-                    // Every sample's class is recomputed from its own exact window sum under the current classes, until
-                    // nothing changes: a self-consistent assignment is the sequential answer (the recurrence is causal).
-                    make_exact();  // c_s.ss0: the exact window sum at the tile's first sample
-                    const double ss0 = c_s.ss0;
-                    load_tile(t);  // the staging buffer already holds the coming tile
-                    unsigned cls = 0u;  // two bits per sample: 0 LOW, 1 MID, 2 HIGH
+                return verdict;
+            };
+            for (;;) {
+                if (t >= t_stop || !uni.ok) {
+                    bool snap = false;
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8]);
-                        const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8 + 4]);
-                        const unsigned nlw[4] = {nl.x, nl.y, nl.z, nl.w}, hw[4] = {hh.x, hh.y, hh.z, hh.w};
-#pragma unroll
-                        for (int j = 0; j < 4; j++) cls |= (((nlw[j] >> lane) & 1u) + ((hw[j] >> lane) & 1u)) << (2 * (r * 4 + j));
-                    }
-                    bool settled = false;
-                    double total = 0.0;
-                    for (int it = 0; it < 8 && !settled; it++) {
-                        double lane_ex[R];
-                        int s0 = slot_w;
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
-                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                            double tot = 0.0;
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) tot += (double)xs[j] - (double)ps[j];
-                            double inc = tot;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const double v = __shfl_up_sync(FULL, inc, o);
-                                if (lane >= o) inc += v;
-                            }
-                            lane_ex[r] = inc - tot;
-                            if (lane == 31) fs.vtot[warp * R + r] = inc;
-                            s0 += FAST_CH;
-                            if (s0 >= L) s0 -= L;
-                        }
-                        __syncthreads();
-                        const double ct = fs.vtot[lane];
-                        double cinc = ct;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const double v = __shfl_up_sync(FULL, cinc, o);
-                            if (lane >= o) cinc += v;
-                        }
-                        const double chunk_ex = cinc - ct;
-                        total = __shfl_sync(FULL, cinc, 31);
-                        unsigned ncls = 0u;
-                        s0 = slot_w;
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
-                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                            double ssj = ss0 + __shfl_sync(FULL, chunk_ex, warp * R + r) + lane_ex[r];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                ncls |= (unsigned)(classify(xs[j], ssj, p) + 1) << (2 * (r * 4 + j));
-                                if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) ssj += (double)xs[j] - (double)ps[j];
-                            }
-                            s0 += FAST_CH;
-                            if (s0 >= L) s0 -= L;
-                        }
-                        const bool changed = ncls != cls;
-                        cls = ncls;
-                        settled = !__syncthreads_or((int)changed);  // also: vtot may be written again
-                    }
-                    if (settled) {
-                        // ---- the tile's outputs from the settled classes
-                        int s0 = slot_w;
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
-                            const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-                            unsigned NLm[4], Hm[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const unsigned code = (cls >> (2 * (r * 4 + j))) & 3u;
-                                NLm[j] = __ballot_sync(FULL, code != 0u);
-                                Hm[j] = __ballot_sync(FULL, code == 2u);
-                                n[r][j] = code == 1u ? xs[j] : ps[j];
-                            }
-                            if (lane == 0) {
-                                uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[(warp * R + r) * 8]);
-                                bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
-                                bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
-                            }
-                            s0 += FAST_CH;
-                            if (s0 >= L) s0 -= L;
-                        }
-                        __syncthreads();
-                        if (warp == 0) {
-                            const float ae = uni.a_est;
-                            __syncwarp();
-                            fast_prepare<NC>(uni, ss0 + total, ss0 + total, (float)total, ae, p.loL, p.hiL, lane);
-                        } else if (warp == 1) {
-                            maps_phase(t);
-                        }
-                        __syncthreads();
-                        verdict = uni.st2 ? FV_SLOW : FV_ACCEPT;  // a HIGH sample the hysteresis may hold back: val is not the class
-                        if (verdict == FV_SLOW && threadIdx.x == 0) uni.stats[FS_ST2]++;
-                    } else {
-                        verdict = FV_SLOW;
-                        if (threadIdx.x == 0) uni.stats[FS_VER]++;
-                    }
-                }
-                if (verdict == FV_ACCEPT) {
-                    // ---- ring update, bitmap out, carries
-                    int s0 = slot_w;
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        *reinterpret_cast<float4 *>(ring + s0) = make_float4(n[r][0], n[r][1], n[r][2], n[r][3]);
-                        s0 += FAST_CH;
-                        if (s0 >= L) s0 -= L;
-                    }
-                    if (t >= plan.t_emit && lane < R * 8)
-                        plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
-                    __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
-                    if (threadIdx.x == 0) {
-                        uni.stats[FS_FAST]++;
-                        c_s.last_val = uni.cand_last_val;
-                        const int newL = uni.cand_newL, newS = uni.cand_newS;
-                        if (newL >= 0) {
-                            const int64_t P0 = tile0_pos + (int64_t)t * T;
-                            c_s.lastL = P0 + newL;
-                            if (newS >= 0) c_s.lrun_start = P0 + newS;
-                        }
-                    }
-                    done = true;
+                    for (int j = 0; j < 4; j++) snap = snap || (t == plan.t_snap[j]);
+                    why = (snap && t != t_entry) ? WHY_SNAP : WHY_EXACT;
                     break;
                 }
-                have_x = false;  // xin is needed for this tile again, or the exact path reloads
-                if (verdict == FV_SLOW) break;
-                if (verdict == FV_REDO) n_meas++;
-                else n_coarse++;
+                const int x_ready = have_x;
+                have_x = 0;
+                int verdict = tile_pass(x_ready, 0, 0);
+                if (verdict != FV_ACCEPT) {
+                    int n_meas = 0, n_coarse = 0;
+                    for (;;) {
+                        have_x = 0;  // the samples are needed for this tile again, or the exact path reloads
+                        if (verdict == FV_REDO) n_meas++;
+                        else if (verdict == FV_REDO_COARSE) n_coarse++;
+                        else break;
+                        verdict = tile_pass(0, n_meas, n_coarse);
+                        if (verdict == FV_ACCEPT) break;
+                    }
+                    if (verdict != FV_ACCEPT) {
+                        why = verdict == FV_VERIFY ? WHY_VERIFY : WHY_EXACT;
+                        break;
+                    }
+                }
+                commit(n, t, slot_w);
+                slot_w += slot_step;
+                if (slot_w >= L) slot_w -= L;
+                t++;
+            }
+        }
+        if (t >= ntiles) break;
+        if (why == WHY_SNAP) continue;
+
+        // ---------------------------------------------------------------------------- tile t the hard way (rare)
+        bool done = false;
+        if (why == WHY_VERIFY) {
+            // ---------------------------------------------------------------- exact fix-point from the precise pass
+            // Every sample's class is recomputed from its own exact window sum under the current classes, until
+            // nothing changes: a self-consistent assignment is the sequential answer (the recurrence is causal).
+            const int slot_w = (int)((tile0_pos + (int64_t)t * T + (int64_t)warp * WS + (int64_t)lane * 4) % L);
+            make_exact();  // c_s.ss0: the exact window sum at the tile's first sample
+            const double ss0 = c_s.ss0;
+            load_tile(t);  // the staging buffer already holds the coming tile
+            unsigned cls = 0u;  // two bits per sample: 0 LOW, 1 MID, 2 HIGH
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8]);
+                const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[(warp * R + r) * 8 + 4]);
+                const unsigned nlw[4] = {nl.x, nl.y, nl.z, nl.w}, hw[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) cls |= (((nlw[j] >> lane) & 1u) + ((hw[j] >> lane) & 1u)) << (2 * (r * 4 + j));
+            }
+            bool settled = false;
+            double total = 0.0;
+            for (int it = 0; it < 8 && !settled; it++) {
+                double lane_ex[R];
+                int s0 = slot_w;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                    const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    double tot = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) tot += (double)xs[j] - (double)ps[j];
+                    double inc = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double v = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    lane_ex[r] = inc - tot;
+                    if (lane == 31) fs.vtot[warp * R + r] = inc;
+                    s0 += FAST_CH;
+                    if (s0 >= L) s0 -= L;
+                }
+                __syncthreads();
+                const double ct = fs.vtot[lane];
+                double cinc = ct;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double v = __shfl_up_sync(FULL, cinc, o);
+                    if (lane >= o) cinc += v;
+                }
+                const double chunk_ex = cinc - ct;
+                total = __shfl_sync(FULL, cinc, 31);
+                unsigned ncls = 0u;
+                s0 = slot_w;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                    const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    double ssj = ss0 + __shfl_sync(FULL, chunk_ex, warp * R + r) + lane_ex[r];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        ncls |= (unsigned)(classify(xs[j], ssj, p) + 1) << (2 * (r * 4 + j));
+                        if (((cls >> (2 * (r * 4 + j))) & 3u) == 1u) ssj += (double)xs[j] - (double)ps[j];
+                    }
+                    s0 += FAST_CH;
+                    if (s0 >= L) s0 -= L;
+                }
+                const bool changed = ncls != cls;
+                cls = ncls;
+                settled = !__syncthreads_or((int)changed);  // also: vtot may be written again
+            }
+            if (settled) {
+                // ---- the tile's outputs from the settled classes
+                float n[R][4];
+                int s0 = slot_w;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                    const float xs[4] = {xin[r].x, xin[r].y, xin[r].z, xin[r].w};
+                    const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+                    unsigned NLm[4], Hm[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const unsigned code = (cls >> (2 * (r * 4 + j))) & 3u;
+                        NLm[j] = __ballot_sync(FULL, code != 0u);
+                        Hm[j] = __ballot_sync(FULL, code == 2u);
+                        n[r][j] = code == 1u ? xs[j] : ps[j];
+                    }
+                    if (lane == 0) {
+                        uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[(warp * R + r) * 8]);
+                        bw[0] = make_uint4(NLm[0], NLm[1], NLm[2], NLm[3]);
+                        bw[1] = make_uint4(Hm[0], Hm[1], Hm[2], Hm[3]);
+                    }
+                    s0 += FAST_CH;
+                    if (s0 >= L) s0 -= L;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    const float ae = uni.a_est;
+                    __syncwarp();
+                    fast_prepare<NC>(uni, ss0 + total, ss0 + total, (float)total, ae, p.loL, p.hiL, lane);
+                } else if (warp == 1) {
+                    maps_phase(t);
+                }
+                __syncthreads();
+                if (uni.st2) {  // a HIGH sample the hysteresis may hold back: val is not the class
+                    if (threadIdx.x == 0) uni.stats[FS_ST2]++;
+                } else {
+                    commit(n, t, slot_w);
+                    done = true;
+                }
+            } else {
+                if (threadIdx.x == 0) uni.stats[FS_VER]++;
             }
         }
         if (!done) {
@@ -904,6 +932,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             make_exact();
             const double ss_before = c_s.ss0;
             const int64_t P0 = tile0_pos + (int64_t)t * T;
+            const int slot_x = (int)((P0 + (int64_t)threadIdx.x * 4) % L);  // exact_tile's slot of this thread's first sample of a row
             __syncthreads();
 #pragma unroll 1
             for (int r = 0; r < XR; r++) {
@@ -920,13 +949,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 if (lane == 0) uni.stats[FS_SLOW]++;
                 fast_prepare<NC>(uni, ss1, ss1, (float)(ss1 - ss_before), ae, p.loL, p.hiL, lane);
             }
-            have_x = false;
             __syncthreads();
         }
-        slot_x += slot_step;
-        if (slot_x >= L) slot_x -= L;
-        slot_w += slot_step;
-        if (slot_w >= L) slot_w -= L;
+        t++;
     }
 
     // ---- exit: exactness audit and final state
