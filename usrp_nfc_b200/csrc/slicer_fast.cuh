@@ -126,6 +126,7 @@ struct __align__(16) FastPlan {
     int t_snap[4];                    // tiles before which a state snapshot is due (seam, three checkpoints), or -1
     int nb;                           // chunks a LOW sample can reach forward through the hysteresis
     float loLf, hiLf;
+    float invLo, invHi;               // slightly less than 1 / loLf, 1 / hiLf
 };
 
 template <int NT, int R>
@@ -200,7 +201,8 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
 // One chunk (row r of this warp) of phase 1.  PRECISE: the repeat pass, every sample against its own guessed ss.
 template <bool PRECISE>
 __device__ __forceinline__ void fast_row(const float4 x4, const float4 pv4, float thL, float thH, float invq, float invqA, float c0g,
-                                         float TLb, float THb, float loLf, float hiLf, int lane, float (&n)[4], FastRec *rec, uint32_t *bmw) {
+                                         float TLb, float THb, float loLf, float hiLf, float invLo, float invHi, int lane, float (&n)[4], FastRec *rec,
+                                         uint32_t *bmw) {
     unsigned NLm[4], Hm[4];
     unsigned long long s2 = 0ull;
     float a = 0.0f, mL = INFINITY, mH = INFINITY;
@@ -223,7 +225,6 @@ __device__ __forceinline__ void fast_row(const float4 x4, const float4 pv4, floa
         // in order inside the lane; the margins are now against per-sample thresholds, in ss units.
         const float base = c0g + PA;
         const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
-        const float invLo = (1.0f - 0x1p-20f) / loLf, invHi = (1.0f - 0x1p-20f) / hiLf;
         const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
         const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
         float run = 0.0f, wmin = INFINITY;
@@ -282,7 +283,11 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     static_assert(NC == 32, "one lane per chunk record");
     static_assert(T % SUB == 0, "tile is a whole number of exact rows");
     static_assert(R == 4 || R == 2, "bitmap words of a warp are written by its first R * 8 lanes");
-    static_assert(NW >= 2, "warps 0 and 1 share the verification");
+    static_assert(NW >= 8, "warps 0 and 1 share the verification, another keeps the carries");
+#ifndef NFC_CARRY_THREAD
+#define NFC_CARRY_THREAD 128
+#endif
+    constexpr int CARRY_THREAD = NFC_CARRY_THREAD;  // not in warp 0: that one has the longest way to the next barrier already
     extern __shared__ __align__(16) float ring[];
     __shared__ BlockShared<NT, 1> sh;  // exact_tile's scratch
     __shared__ FastShared<NT, R> fs;
@@ -400,6 +405,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             pl.nb = (p.mx + FAST_CH) / FAST_CH;
             pl.loLf = (float)p.loL;
             pl.hiLf = (float)p.hiL;
+            pl.invLo = (1.0f - 0x1p-20f) / pl.loLf;
+            pl.invHi = (1.0f - 0x1p-20f) / pl.hiLf;
             fs.plan = pl;
         }
         if (warp == 0) fast_prepare<NC>(uni, ss0, ss0, 0.0f, -1.0f, p.loL, p.hiL, lane);
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         if (t >= plan.t_emit && lane < R * 8)
             plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
         __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == CARRY_THREAD) {
             uni.stats[FS_FAST]++;
             c_s.last_val = uni.cand_last_val;
             const int newL = uni.cand_newL, newS = uni.cand_newS;
@@ -656,7 +663,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         for (int r = 0; r < R; r++) {
                             const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
                             fast_row<false>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
-                                            invqA, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, lane, n[r], rec + r, bmw + r * 8);
+                                            invqA, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, lane, n[r], rec + r, bmw + r * 8);
                             s0 += FAST_CH;
                             if (s0 >= L) s0 -= L;
                         }
@@ -666,8 +673,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         for (int r = 0; r < R; r++) {
                             const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
                             fast_row<true>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
-                                           invqA, uni.gC0[warp * R + r], TLb, THb, plan.loLf, plan.hiLf, lane, n[r], rec + r,
-                                           bmw + r * 8);
+                                           invqA, uni.gC0[warp * R + r], TLb, THb, plan.loLf, plan.hiLf, plan.invLo, plan.invHi, lane, n[r],
+                                           rec + r, bmw + r * 8);
                             s0 += FAST_CH;
                             if (s0 >= L) s0 -= L;
                         }
@@ -887,6 +894,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 // ---- the tile's outputs from the settled classes
                 float n[R][4];
                 int s0 = slot_w;
+                int emin = 1 << 30, emax = 0;  // the admitted samples enter the exactness audit
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
@@ -899,6 +907,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         NLm[j] = __ballot_sync(FULL, code != 0u);
                         Hm[j] = __ballot_sync(FULL, code == 2u);
                         n[r][j] = code == 1u ? xs[j] : ps[j];
+                        if (code == 1u) exp_track(xs[j], emin, emax);
                     }
                     if (lane == 0) {
                         uint4 *bw = reinterpret_cast<uint4 *>(&fs.bm[(warp * R + r) * 8]);
@@ -908,6 +917,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     s0 += FAST_CH;
                     if (s0 >= L) s0 -= L;
                 }
+                emin = __reduce_min_sync(FULL, emin);
+                emax = __reduce_max_sync(FULL, emax);
+                if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
                 __syncthreads();
                 if (warp == 0) {
                     const float ae = uni.a_est;
