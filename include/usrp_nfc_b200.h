@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 2
+#define NFC_ABI_VERSION 3
 
 /* what a pushed item is */
 enum {
@@ -112,6 +112,27 @@ int64_t nfc_stream_pending_frame_bits(nfc_stream *s); /* bytes the next full dra
 int64_t nfc_stream_view_frames(nfc_stream *s, const nfc_frame **frames, const uint8_t **bits_tag, int64_t *n_bits_tag,
                                const uint8_t **bits_reader, int64_t *n_bits_reader);
 int nfc_stream_release_frames(nfc_stream *s);
+
+/* What fsm.process_bits does to a frame before any protocol logic, for a batch of frames on the device:
+ * fsm._fix_ending (fsm.py:51-66), fsm._check_parity (fsm.py:28-49), fsm._print_enc (fsm.py:114-131) and
+ * utilities.CRC.check_crc with CRC_14443_A (utilities.py:26-46).  Crypto1 traffic must be decrypted before its parity
+ * and CRC mean anything (fsm.py:133-160, host side); for plain traffic the verdicts are final. */
+typedef struct {
+    int32_t nbits;     /* length after _fix_ending: a multiple of 9 */
+    int32_t nbytes;    /* nbits / 9: what _print_enc prints, what _check_parity returns when it accepts */
+    int64_t byte_off;  /* of the frame's bytes in `bytes` / `parity_flags` */
+    int8_t fix_flag;   /* 0, 1 = _fix_ending printed "EXTRA ERROR", 2 = "MANY MORE ERROR" */
+    int8_t parity_ok;  /* 1: _check_parity returns a non-empty list; 0: process_bits prints PARITY ERROR (fsm.py:226-228) */
+    int8_t crc_ok;     /* CRC.check_crc(bytes) for nbytes >= 2, else 0 */
+    int8_t pad[5];
+} nfc_frame_tail;
+/* frames[i].bit_off indexes bits_tag (type 0) or bits_reader (type 1), as nfc_stream_view_frames returns them (pass the one
+ * buffer of nfc_stream_drain_frames twice); all pointers are host memory.  bytes[k] / parity_flags[k]: the k-th byte of the
+ * batch, LSB first, and 1 where _print_enc appends '!' (parity violated).  Returns the number of bytes written, < 0 on
+ * error (bytes_cap too small: sum of (nbits + 1) / 9 always suffices). */
+int64_t nfc_frames_tail(int device, const nfc_frame *frames, int64_t n_frames, const uint8_t *bits_tag, int64_t n_bits_tag,
+                        const uint8_t *bits_reader, int64_t n_bits_reader, nfc_frame_tail *tails, uint8_t *bytes,
+                        uint8_t *parity_flags, int64_t bytes_cap);
 
 /* Implicit streaming state of the reference objects (transition_sink.py:20-34,102-106; decoder and
  * PacketProcessor attributes), for checkpointing and for stitching time-sharded captures. */

@@ -614,6 +614,27 @@ int32_t nfc_print_enc(const uint8_t *bits, int32_t n, uint8_t *bytes_out, uint8_
     return nb;
 }
 
+void nfc_crc_a(const uint8_t *data, int32_t n, uint8_t out[2]) {
+    /* utilities.py:26-41, cktp = CRC_14443_A */
+    uint32_t wcrc = 0x6363;
+    for (int32_t i = 0; i < n; i++) {
+        uint32_t b = data[i];
+        b = b ^ (wcrc & 0xFF);
+        b = b ^ ((b << 4) & 0xFF); /* `b ^ (b << 4) & 0xFF`: & binds tighter than ^ */
+        wcrc = (wcrc >> 8) ^ (b << 8) ^ (b << 3) ^ (b >> 4);
+    }
+    out[0] = (uint8_t)(wcrc & 0xFF);
+    out[1] = (uint8_t)((wcrc >> 8) & 0xFF);
+}
+
+int nfc_check_crc(const uint8_t *data, int32_t n) {
+    /* utilities.py:43-46; the reference indexes data[-2], data[-1]: n >= 2 */
+    uint8_t crc[2];
+    if (n < 2) return 0;
+    nfc_crc_a(data, n - 2, crc);
+    return crc[0] == data[n - 2] && crc[1] == data[n - 1];
+}
+
 /* ----------------------------------------------------------------- encoders */
 int32_t nfc_miller_encode(const uint8_t *bits, int32_t n, int8_t *level, double *dur_us) {
     /* miller.py:200-233 */

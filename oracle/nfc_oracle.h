@@ -95,6 +95,9 @@ int32_t nfc_fix_ending(const uint8_t *bits, int32_t n, int type, uint8_t *out, i
 /* _check_parity: returns the byte count, or -1 where the reference returns None.
  * (fsm.process_bits treats an empty list like None: "PARITY ERROR", fsm.py:226-228.) */
 int32_t nfc_check_parity(const uint8_t *bits, int32_t n, uint8_t *bytes_out);
+/* utilities.CRC.calculate_crc / check_crc with CRC_14443_A (utilities.py:26-46). */
+void nfc_crc_a(const uint8_t *data, int32_t n, uint8_t out[2]);
+int nfc_check_crc(const uint8_t *data, int32_t n);
 /* _print_enc: bytes followed by a 9th bit, and whether each is flagged '!'. Returns count. */
 int32_t nfc_print_enc(const uint8_t *bits, int32_t n, uint8_t *bytes_out, uint8_t *flag_out);
 

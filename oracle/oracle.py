@@ -69,6 +69,10 @@ def lib():
         L.nfc_check_parity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.nfc_print_enc.restype = C.c_int32
         L.nfc_print_enc.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.nfc_crc_a.restype = None
+        L.nfc_crc_a.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.nfc_check_crc.restype = C.c_int
+        L.nfc_check_crc.argtypes = [C.c_void_p, C.c_int32]
         L.nfc_miller_encode.restype = C.c_int32
         L.nfc_miller_encode.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.nfc_manchester_encode.restype = C.c_int32
@@ -224,6 +228,19 @@ def print_enc(bits):
     fl = np.zeros(b.size // 8 + 2, dtype=np.uint8)
     n = lib().nfc_print_enc(b.ctypes.data, b.size, out.ctypes.data, fl.ctypes.data)
     return out[:n].copy(), fl[:n].copy()
+
+
+def crc_a(data):
+    """utilities.CRC.calculate_crc(data) -> [lo, hi]."""
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.zeros(2, dtype=np.uint8)
+    lib().nfc_crc_a(d.ctypes.data, d.size, out.ctypes.data)
+    return [int(out[0]), int(out[1])]
+
+
+def check_crc(data):
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    return bool(lib().nfc_check_crc(d.ctypes.data, d.size))
 
 
 def _encode(fn, bits):

@@ -46,6 +46,31 @@ def test_decoder_block_hands_frames_to_fsm():
     assert [t for t, _ in got] == case["ftype"].tolist()
 
 
+def test_decoder_block_hands_frame_bytes_from_the_device_tail():
+    """on_frame_bytes: what fsm.process_bits derives first (fsm.py:28-66,114-131; utilities.py:26-46), per frame, next to
+    the bit lists of the same frames."""
+    from oracle import oracle
+    from usrp_nfc_b200.decoder import decoder
+    case = H.load_case("surrogate_classic1k")
+    frames, tails = [], []
+    d = decoder(src=case["pcm"], samp_rate=2e6, on_frame=lambda bits, t: frames.append((t, bits)),
+                on_frame_bytes=lambda by, fl, tl, t: tails.append((t, by, fl, tl.copy())))
+    d.run()
+    assert len(frames) == len(tails) == len(case["fpos"])
+    for (t, bits), (t2, by, fl, tl) in zip(frames, tails):
+        assert t == t2
+        fixed, flag = oracle.fix_ending(bits, t)
+        eb, ef = oracle.print_enc(fixed)
+        assert by == eb.tolist() and fl == ef.tolist() and int(tl["fix_flag"]) == flag and int(tl["nbits"]) == fixed.size
+        par = oracle.check_parity(fixed)
+        assert bool(tl["parity_ok"]) == (par is not None and par.size > 0)
+    # bytes only, no fsm module anywhere: the bit lists are never built
+    only = []
+    d2 = decoder(src=case["pcm"], samp_rate=2e6, on_frame_bytes=lambda by, fl, tl, t: only.append(by))
+    d2.run()
+    assert only == [by for _, by, _, _ in tails]
+
+
 def test_decoder_block_with_fake_fsm_and_emulator():
     from usrp_nfc_b200.decoder import decoder
 

@@ -147,6 +147,16 @@ def test_fsm_tail_known_answers():
         assert [[int(b), int(f)] for b, f in zip(by, fl)] == rec["enc"]
 
 
+def test_crc_a_known_answers():
+    """CRC_A against the reference's utilities.CRC (fixture: oracle/gen_golden_crc.py)."""
+    cases = H.load_json("crc_a.json")
+    assert cases[0]["data"] == [0x50, 0x00] and cases[0]["crc"] == [0x57, 0xCD]  # HLTA, the one every trace shows
+    for rec in cases:
+        assert oracle.crc_a(rec["data"]) == rec["crc"]
+        assert oracle.check_crc(rec["data"] + rec["crc"]) == rec["check_good"] is True
+        assert oracle.check_crc(rec["bad"]) == rec["check_bad"]
+
+
 def test_empty_and_tiny_inputs():
     ts = oracle.TransitionSink(2e6)
     used, ev = ts.work(np.zeros(0, np.float32))

@@ -20,6 +20,8 @@ OUT_ALL = OUT_EVENTS | OUT_SYMBOLS | OUT_FRAMES | OUT_DROPPED_EVENTS
 EVENT_DTYPE = np.dtype([("pos", "<i8"), ("d", "<i4"), ("v", "i1"), ("type", "i1"), ("pad", "<i2")])
 SYMBOL_DTYPE = np.dtype([("pos", "<i8"), ("type", "i1"), ("val", "i1"), ("pad", "<i2"), ("pad2", "<i4")])
 FRAME_DTYPE = np.dtype([("pos", "<i8"), ("bit_off", "<i8"), ("nbits", "<i4"), ("type", "<i4")])
+FRAME_TAIL_DTYPE = np.dtype([("nbits", "<i4"), ("nbytes", "<i4"), ("byte_off", "<i8"), ("fix_flag", "i1"), ("parity_ok", "i1"),
+                             ("crc_ok", "i1"), ("pad", "i1", (5,))])
 
 
 class Params(C.Structure):
@@ -72,6 +74,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_int32)]),
     "nfc_synth_render": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                    C.c_float, C.c_float, C.c_float, C.c_double, C.c_uint64, C.c_int, C.c_int]),
+    "nfc_frames_tail": (C.c_int64, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_last_error": (C.c_char_p, []),
     "nfc_abi_version": (C.c_int, []),
     "nfc_device_count": (C.c_int, []),
@@ -279,6 +283,27 @@ class Stream(object):
 
     def cuda_stream(self):
         return lib().nfc_stream_cuda_stream(self._h)
+
+
+def frames_tail(frames, bits_tag, bits_reader=None, device=0):
+    """fsm._fix_ending / _check_parity / _print_enc / CRC_A for a batch of frames on the device (csrc/frametail.cu).
+
+    frames: FRAME_DTYPE records whose bit_off index bits_tag (type 0) / bits_reader (type 1); with bits_reader None both
+    types index bits_tag (the single buffer of drain_frames_flat).  Returns (tails, bytes, parity_flags).
+    """
+    frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+    b0 = np.ascontiguousarray(bits_tag, dtype=np.uint8)
+    b1 = b0 if bits_reader is None else np.ascontiguousarray(bits_reader, dtype=np.uint8)
+    n = int(frames.size)
+    tails = np.zeros(n, dtype=FRAME_TAIL_DTYPE)
+    cap = int(((frames["nbits"].astype(np.int64) + 1) // 9).sum()) if n else 0
+    by = np.zeros(max(cap, 1), dtype=np.uint8)
+    fl = np.zeros(max(cap, 1), dtype=np.uint8)
+    got = lib().nfc_frames_tail(int(device), frames.ctypes.data, n, b0.ctypes.data, b0.size, b1.ctypes.data, b1.size,
+                                tails.ctypes.data, by.ctypes.data, fl.ctypes.data, cap)
+    if got < 0:
+        raise NfcError("nfc_frames_tail: " + last_error())
+    return tails, by[:got], fl[:got]
 
 
 def build_tables(samp_rate, max_len, which):

@@ -21,18 +21,29 @@ class frame_sink(gr.sync_block):
     path (raw samples, squared on the device) and complex64 for UHD."""
 
     def __init__(self, samp_rate, on_frame, reader=True, tag=True, hi_val=1.1, lo_val=0.1, av_window=2000, max_len=50,
-                 input_kind=_cabi.IN_REAL_F32, device=0):
+                 input_kind=_cabi.IN_REAL_F32, device=0, on_frame_bytes=None):
         in_type = {_cabi.IN_IQ_F32: numpy.complex64, _cabi.IN_PCM_S16: numpy.int16}.get(input_kind, numpy.float32)
         gr.sync_block.__init__(self, name="nfc_frame_sink", in_sig=[in_type], out_sig=None)
         self._on_frame = on_frame
+        self._on_frame_bytes = on_frame_bytes
+        self._device = device
         self._stream = _cabi.Stream(samp_rate, lo_val, hi_val, av_window, max_len, reader=reader, tag=tag,
                                     input_kind=input_kind, outputs=_cabi.OUT_FRAMES, device=device)
 
     def work(self, input_items, output_items):
         consumed, _ = self._stream.push(input_items[0])
-        records, bits = self._stream.drain_frames()
-        for rec, b in zip(records, bits):
-            self._on_frame(b.tolist(), int(rec["type"]))
+        records, flat = self._stream.drain_frames_flat()
+        if self._on_frame is not None:
+            for rec in records:
+                o = int(rec["bit_off"])
+                self._on_frame(flat[o: o + int(rec["nbits"])].tolist(), int(rec["type"]))
+        if self._on_frame_bytes is not None and len(records):
+            # what fsm.process_bits computes first for every frame (_fix_ending, _check_parity / _print_enc, CRC_A), as
+            # one device pass over the batch: on_frame_bytes(bytes, parity_flags, tail_record, packet_type)
+            tails, by, fl = _cabi.frames_tail(records, flat, device=self._device)
+            for rec, tl in zip(records, tails):
+                o, n = int(tl["byte_off"]), int(tl["nbytes"])
+                self._on_frame_bytes(by[o: o + n].tolist(), fl[o: o + n].tolist(), tl, int(rec["type"]))
         return consumed
 
     def stream(self):
@@ -52,13 +63,15 @@ def _load_fsm(fsm_module):
 
 class decoder(gr.hier_block2):
     def __init__(self, src="uhd", dst=None, repeat=False, reader=True, tag=True, samp_rate=2e6, emulator=None,
-                 fsm=None, on_frame=None, device=0, **sink_kwargs):
+                 fsm=None, on_frame=None, device=0, on_frame_bytes=None, **sink_kwargs):
         gr.hier_block2.__init__(self, "decoder",
                                 gr.io_signature(0, 0, 0),  # Input signature
                                 gr.io_signature(0, 0, 0))  # Output signature
         fsm_mod = _load_fsm(fsm)
         if on_frame is not None:
             self._on_frame = on_frame
+        elif fsm_mod is None and on_frame_bytes is not None:
+            self._on_frame = None  # bytes only: the device does the frame tail, nobody wants the bit lists
         elif fsm_mod is not None:  # packets.py:81-92
             if emulator:
                 self._fsm = fsm_mod.fsm(emulator.process_packet)
@@ -83,7 +96,7 @@ class decoder(gr.hier_block2):
             kind = {numpy.dtype(numpy.int16): _cabi.IN_PCM_S16,
                     numpy.dtype(numpy.complex64): _cabi.IN_IQ_F32}.get(src.dtype, _cabi.IN_REAL_F32)
         self._trans = frame_sink(samp_rate, self._on_frame, reader=reader, tag=tag, hi_val=hi_val, input_kind=kind,
-                                 device=device, **sink_kwargs)
+                                 device=device, on_frame_bytes=on_frame_bytes, **sink_kwargs)
         if HAVE_GNURADIO and isinstance(src, str):  # pragma: no cover - needs GNU Radio
             if src == "uhd":
                 import usrp_src  # the reference's own source wrapper (usrp_src.py), minus its mag^2 block
