@@ -580,7 +580,18 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             }
     };
 
-    // ring update, bitmap out and carries of an accepted tile
+    // the tile's bitmap words to global memory.  Streamed tiles: by the last four warps while warps 0 and 1 judge the
+    // tile (a tile that is repeated or settled another way simply overwrites them).
+    auto bitmap_out = [&](int t, int first_warp) {
+        if (t >= plan.t_emit) {
+            static_assert(NC * 8 == 4 * 64, "four warps, two words per lane");
+            uint32_t *dst = plan.bm_base + (size_t)t * (NC * 8);
+            const int i = (warp - first_warp) * 64 + lane;
+            dst[i] = fs.bm[i];
+            dst[i + 32] = fs.bm[i + 32];
+        }
+    };
+    // ring update and carries of an accepted tile
     auto commit = [&](const float (&n)[R][4], int t, int slot) {
         int s0 = slot;
 #pragma unroll
@@ -589,9 +600,6 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             s0 += FAST_CH;
             if (s0 >= L) s0 -= L;
         }
-        if (t >= plan.t_emit && lane < R * 8)
-            plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
-        __syncwarp();  // lane 0 writes the next tile's words only after every lane has read this tile's
         if (threadIdx.x == CARRY_THREAD) {
             uni.stats[FS_FAST]++;
             c_s.last_val = uni.cand_last_val;
@@ -772,6 +780,8 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     }
                 } else if (warp == 1) {
                     maps_phase(t);
+                } else if (warp >= NW - 4) {
+                    bitmap_out(t, NW - 4);
                 }
                 __syncthreads();
                 verdict = uni.verdict;
@@ -932,6 +942,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 if (uni.st2) {  // a HIGH sample the hysteresis may hold back: val is not the class
                     if (threadIdx.x == 0) uni.stats[FS_ST2]++;
                 } else {
+                    if (warp < 4) bitmap_out(t, 0);  // the words were rewritten from the settled classes (barriers since)
                     commit(n, t, slot_w);
                     done = true;
                 }
