@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
 
     // the tile's bitmap words to global memory.  Streamed tiles: by the last four warps while warps 0 and 1 judge the
     // tile (a tile that is repeated or settled another way simply overwrites them).
-    auto bitmap_out = [&](int t, int first_warp) {
+    auto bitmap_out = [&](int t, int first_warp) {  // between the two barriers of a pass
         if (t >= plan.t_emit) {
             static_assert(NC * 8 == 4 * 64, "four warps, two words per lane");
             uint32_t *dst = plan.bm_base + (size_t)t * (NC * 8);
@@ -942,7 +942,11 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 if (uni.st2) {  // a HIGH sample the hysteresis may hold back: val is not the class
                     if (threadIdx.x == 0) uni.stats[FS_ST2]++;
                 } else {
-                    if (warp < 4) bitmap_out(t, 0);  // the words were rewritten from the settled classes (barriers since)
+                    // the words were rewritten from the settled classes: every warp stores its own (no barrier follows
+                    // before the next tile's words are written, by lane 0 of the same warp)
+                    if (t >= plan.t_emit && lane < R * 8)
+                        plan.bm_base[(size_t)t * (NC * 8) + warp * (R * 8) + lane] = fs.bm[warp * (R * 8) + lane];
+                    __syncwarp();
                     commit(n, t, slot_w);
                     done = true;
                 }
