@@ -91,6 +91,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def same_frames(ra, rb):
+    """Two decodes of one capture: identical frame records (closing position, type, length) and identical frame bits."""
+    (fa, a0, a1), (fb, b0, b1) = ra, rb
+    if len(fa) != len(fb) or len(a0) != len(b0) or len(a1) != len(b1):
+        return False
+    return bool(np.array_equal(fa["pos"], fb["pos"]) and np.array_equal(fa["type"], fb["type"]) and
+                np.array_equal(fa["nbits"], fb["nbits"]) and np.array_equal(a0, b0) and np.array_equal(a1, b1))
+
+
 def cpu_baseline(x_host_pieces, params, threads):
     """The reference algorithm (oracle port, C) on the host cores: one independent piece per thread."""
     from oracle import oracle
@@ -180,6 +189,7 @@ def main():
     ap.add_argument("--seg-len", type=int, default=0)
     ap.add_argument("--halo", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the untimed full-size self-check (second decode with another segmentation)")
     ap.add_argument("--rate", type=float, default=RATE, help="13.56e6 (configs[2]) or 20e6 (configs[4])")
     ap.add_argument("--halo-windows", type=int, default=16, help="speculative halo of a time shard, in av_windows")
     ap.add_argument("--batch", type=int, default=0, help="configs[3]: decode a batch of this many independent captures instead")
@@ -327,6 +337,31 @@ def main():
         dist.all_reduce(rp)
         repaired_ranks = int(rp.item())
 
+    # ---- full-size self-check (untimed).  The slicer's answer is unique (the recurrence is causal), so it may not depend
+    # on how the capture was cut: decode once more with other slab and segment lengths (other speculative starts, seams,
+    # edge tiles) and compare every frame record and every frame bit on the host.
+    selfcheck = None
+    if world == 1 and rank == 0 and not args.no_selfcheck:
+        def grab(st_):
+            st_.reset()
+            st_.push_all(x)
+            fr_v, b0_v, b1_v = st_.view_frames()
+            out = (fr_v.copy(), b0_v.copy(), b1_v.copy())
+            st_.release_frames()
+            return out
+        ra = grab(s)
+        s2 = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+        alt = dict(seg_len=1703936, halo=args.halo, slab_len=3 << 28)
+        s2.set_tuning(**alt)
+        rb = grab(s2)
+        st2 = s2.stats()
+        s2.close()
+        selfcheck = {"property": "frames (closing position, type, length, bits) do not depend on the segmentation: default tuning "
+                                 "against seg_len %d, slab_len %d" % (alt["seg_len"], alt["slab_len"]),
+                     "identical": same_frames(ra, rb), "frames": int(len(ra[0])), "frame_bits": int(len(ra[1]) + len(ra[2])),
+                     "segments_alt": int(st2["segments"]), "seam_mismatches_alt": int(st2["seam_mismatches"])}
+        del ra, rb
+
     # ---- e2e: host (pinned) buffers through the same ABI call, H2D inside the timed region.  The host buffer holds what
     # the reference's source block reads from a recording: 16-bit PCM (decoder.py:25 wavfile_source); normalisation and
     # envelope run on the device (NFC_IN_PCM_S16).  Same capture, same frames as the float path.
@@ -420,7 +455,7 @@ def main():
                          "ranks_redone_last_step": repaired_ranks} if world > 1 else None,
             "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
-            "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments")},
+            "selfcheck": selfcheck, "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
