@@ -1264,9 +1264,18 @@ static bool fast_wide() {
     return w;
 }
 
+static bool fast_two() {  // experiment: two CTAs per SM with 128 registers per thread
+    static const bool w = getenv("NFC_SLICER_CTAS") && getenv("NFC_SLICER_CTAS")[0] == '2';
+    return w;
+}
+
 template <int KIND>
 static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
-    if (fast_wide()) {
+    if (fast_two()) {
+        auto k = slicer_fast_kernel<256, 4, 2, KIND>;
+        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+    } else if (fast_wide()) {
         auto k = slicer_fast_kernel<512, 2, 2, KIND>;
         NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<n_works, 512, smem, stream>>>(d_works, d_params);
@@ -1322,7 +1331,10 @@ int slicer_resident_ctas(int L, bool vec_ok) {
     cudaError_t e;
     if (slicer_streaming_ok(L, vec_ok)) {
         const size_t fsm = fast_smem(L, IN_ENVELOPE_F32);
-        if (fast_wide()) {
+        if (fast_two()) {
+            per = 2;
+            e = cudaSuccess;
+        } else if (fast_wide()) {
             cudaFuncSetAttribute(slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, 512, fsm);
         } else {
