@@ -282,9 +282,11 @@ def main():
             s.release_frames()
             return nfr
         res = sharding.decode_time_sharded(s, lambda a, b: x[a - base: b - base], total, L, _cabi.State, dist=dist,
-                                           device="cuda", halo_windows=args.halo_windows, flat=True)
+                                           device="cuda", halo_windows=args.halo_windows, flat="view")
         shard_info.update(repaired=res["repaired"], seam_ok=res["seam_ok"])
-        return res["n_frames"]
+        nfr = res["n_frames"]
+        s.release_frames()
+        return nfr
 
     def barrier():
         torch.cuda.synchronize()

@@ -116,6 +116,9 @@ def _broadcast(vec, src, dist, group, device):
 
 
 def _drain(engine, flat):
+    if flat == "view" and hasattr(engine, "view_frames"):
+        rec, b0, b1 = engine.view_frames()  # zero-copy: the caller releases them (engine.release_frames())
+        return rec, (b0, b1), True
     if flat and hasattr(engine, "drain_frames_flat"):
         try:
             rec, bits = engine.drain_frames_flat(reuse=True)  # views of the engine's buffers: no allocation per shard
@@ -126,13 +129,24 @@ def _drain(engine, flat):
     return rec, bits, False
 
 
+def _discard(engine):
+    """Frames closed inside the halo belong to the previous shard."""
+    if hasattr(engine, "view_frames") and hasattr(engine, "release_frames"):
+        engine.view_frames()
+        engine.release_frames()
+    else:
+        engine.drain_frames()
+
+
 def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, group=None, device="cpu",
                         halo_windows=16, strict_dur=False, flat=False):
     """Decode this rank's time shard of a `total`-sample capture.
 
     fetch(a, b) returns samples [a, b) (numpy array, or a CUDA tensor for a device-resident capture).
     Returns dict(frames=[(abs_pos, type, bits)], repaired=bool, seam_ok=[...], bounds=(begin, end)).
-    With flat=True the frames stay in the engine's bulk form: dict(records, bits, pos_offset, n_frames).
+    With flat=True the frames stay in the engine's bulk form: dict(records, bits, pos_offset, n_frames); with
+    flat="view" they are not even copied: bits = (bits_tag, bits_reader) as Stream.view_frames returns them, valid until
+    the caller's engine.release_frames().
     """
     rank = dist.get_rank(group) if dist is not None else 0
     world = dist.get_world_size(group) if dist is not None else 1
@@ -145,10 +159,10 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
         base = begin - halo - L
         if begin > base:
             engine.push_all(fetch(base, begin))
-        engine.drain_frames()  # frames closed inside the halo belong to the previous shard
+        _discard(engine)
     elif rank > 0:
         engine.push_all(fetch(0, begin))  # shard too close to the stream start: decode from the true start
-        engine.drain_frames()
+        _discard(engine)
     assumed = SeamState.from_engine(engine, base, L) if rank > 0 else None
     if end > begin:
         engine.push_all(fetch(begin, end))
@@ -158,9 +172,11 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
     final = SeamState.from_engine(engine, base, L) if begin < end or rank == 0 else assumed
     repaired, seam_ok = False, [True] * world
     if world > 1:
-        finals = [SeamState(v, L) for v in _all_gather(final.vec, dist, group, device)]
         zero = np.zeros(SeamState.size(L))
-        assumes = [SeamState(v, L) for v in _all_gather(assumed.vec if assumed is not None else zero, dist, group, device)]
+        both = _all_gather(np.concatenate([final.vec, assumed.vec if assumed is not None else zero]), dist, group, device)
+        nv = SeamState.size(L)
+        finals = [SeamState(np.ascontiguousarray(v[:nv]), L) for v in both]
+        assumes = [SeamState(np.ascontiguousarray(v[nv:]), L) for v in both]
         for k in range(1, world):
             ok = finals[k - 1].equal(assumes[k], strict_dur)
             seam_ok[k] = ok
