@@ -211,12 +211,48 @@ struct CountSink {
 };
 
 // ---- frame-boundary search: the state at a chunk start from the nearest reset before it ------------
-// An event whose duration is out of range resets its decoder whatever the state was (tables.cpp,
-// reset_*): scan backwards to the nearest such event of each direction, then replay forward from there.
-// start[c] = R state | G state << 8.  Chunks that find no reset within LOOKBACK_LIMIT events raise *unresolved
+// An event whose duration is out of range resets its decoder whatever the state was (tables.cpp, reset_*).
+// Pass 1 (chunk_summary_kernel): every chunk walks its own events once from an unknown state; after the first reset
+// of a direction its state is known, and so is the state the chunk leaves behind.  summary[c] = R state | known << 5 |
+// G state << 8 | known << 12.
+// Pass 2 (chunk_start_kernel): a chunk looks back over the *summaries* for the nearest chunk that leaves a known state
+// (per direction) and replays only the events between that chunk's end and its own start (none when it is the previous
+// chunk).  start[c] = R state | G state << 8.  Chunks that find nothing within LOOKBACK_LIMIT events raise *unresolved
 // (the host then takes the transfer-function scan below for the slab).
+__global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+                                     uint16_t *__restrict__ summary, uint32_t n_chunks) {
+    NFC_TABLE_SMEM
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int rs = 0, gs = 0;
+    bool kR = false, kG = false;
+    NullSink sink;
+    const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    for (uint32_t i = i0; i < i1; i += 8) {
+        EventRec e8[8];
+        load8(ev, i, e8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (i + k >= i1) continue;
+            const EventRec e = e8[k];
+            int dummy = 0;
+            if (e.type == 1 && tv.use_reader) {
+                const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
+                if (r != 0xFF) { rs = r; kR = true; }
+                else if (kR) step_event(e, tv, rs, dummy, sink);
+            } else if (e.type == 0 && tv.use_tag) {
+                const uint8_t r = lt.reset_manch[(int)tv.dcg[e.d] * 4 + (e.v + 1)];
+                if (r != 0xFF) { gs = r; kG = true; }
+                else if (kG) step_event(e, tv, dummy, gs, sink);
+            }
+        }
+    }
+    summary[c] = (uint16_t)((rs & 31) | (kR ? 32 : 0) | ((gs & 15) << 8) | (kG ? 4096 : 0));
+}
+
 __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt, DecCarry carry,
-                                   uint16_t *__restrict__ start, uint32_t n_chunks, int *__restrict__ unresolved) {
+                                   const uint16_t *__restrict__ summary, uint16_t *__restrict__ start, uint32_t n_chunks,
+                                   int *__restrict__ unresolved) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
@@ -224,30 +260,15 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     int gs = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
     const int64_t i0 = (int64_t)c * CHUNK;
     bool foundR = !tv.use_reader, foundG = !tv.use_tag;
-    int64_t iR = -1, iG = -1;  // index of the reset event found (-1: replay from event 0 with the carry)
-    int64_t i = i0 - 1;  // next event to look at, going backwards (i0 is a multiple of 8)
-    int steps = 0;
-    while (i >= 0 && !(foundR && foundG) && steps < LOOKBACK_LIMIT) {
-        EventRec e8[8];
-        const int64_t base = i & ~(int64_t)7;
-        load8(ev, base, e8);
-#pragma unroll
-        for (int k = 7; k >= 0; k--) {
-            if (base + k <= i && !(foundR && foundG)) {
-                const EventRec e = e8[k];
-                if (!foundR && e.type == 1) {
-                    const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
-                    if (r != 0xFF) { foundR = true; iR = base + k; rs = r; }
-                } else if (!foundG && e.type == 0) {
-                    const uint8_t r = lt.reset_manch[(int)tv.dcg[e.d] * 4 + (e.v + 1)];
-                    if (r != 0xFF) { foundG = true; iG = base + k; gs = r; }
-                }
-            }
-        }
-        steps += (int)(i - base) + 1;
-        i = base - 1;
+    int64_t iR = -1, iG = -1;  // last event already accounted for (-1: replay from event 0 with the carry)
+    int64_t cc = (int64_t)c - 1;
+    const int64_t cmin = max((int64_t)0, (int64_t)c - LOOKBACK_LIMIT / CHUNK);
+    for (; cc >= cmin && !(foundR && foundG); cc--) {
+        const unsigned sm = summary[cc];
+        if (!foundR && (sm & 32u)) { foundR = true; iR = (cc + 1) * CHUNK - 1; rs = (int)(sm & 31u); }
+        if (!foundG && (sm & 4096u)) { foundG = true; iG = (cc + 1) * CHUNK - 1; gs = (int)((sm >> 8) & 15u); }
     }
-    if (i >= 0 && !(foundR && foundG)) {
+    if (cc >= 0 && !(foundR && foundG)) {  // gave up before the first chunk: the carry cannot be used either
         atomicOr(unresolved, 1);
         start[c] = 0;
         return;
@@ -395,12 +416,14 @@ size_t linecode_scratch_bytes(uint32_t n_chunks) {
 }
 
 // Start states by frame-boundary search; *d_unresolved != 0 afterwards means the caller must use the scan path.
-int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_start,
-                          int *d_unresolved, cudaStream_t stream) {
+int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_summary,
+                          uint16_t *d_start, int *d_unresolved, cudaStream_t stream) {
     const uint32_t nc = linecode_chunks(n_ev);
     if (nc == 0) return 0;
     NFC_CUDA_CHECK(cudaMemsetAsync(d_unresolved, 0, sizeof(int), stream));
-    chunk_start_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, carry, d_start, nc, d_unresolved);
+    chunk_summary_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_summary, nc);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    chunk_start_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, carry, d_summary, d_start, nc, d_unresolved);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -47,8 +47,8 @@ size_t linecode_map_bytes();
 size_t linecode_cnt_bytes();
 size_t linecode_emission_bytes();
 size_t linecode_scratch_bytes(uint32_t n_chunks);
-int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_start,
-                          int *d_unresolved, cudaStream_t);
+int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_summary,
+                          uint16_t *d_start, int *d_unresolved, cudaStream_t stream);
 int launch_linecode_start_scan(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
                                void *d_prefix, void *d_scratch, uint16_t *d_start, cudaStream_t);
 int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start, void *d_cnts,
@@ -156,7 +156,7 @@ struct Stream {
     DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
         seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
         line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
-        redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr;
+        redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr, summ_d;
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     // results come back into one of two pinned buffers; a worker thread turns the previous slab's records into the
     // output vectors while the device works on the next slab
@@ -310,7 +310,7 @@ void Stream::destroy() {
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
                      &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
-                     &ex_counts, &ex_offsets, &ex_scr};
+                     &ex_counts, &ex_offsets, &ex_scr, &summ_d};
     for (DevBuf *b : all) b->release();
     finish_pending();
     if (marshal_thr.joinable()) marshal_thr.join();
@@ -1108,15 +1108,17 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
     uint32_t *d_pend = reinterpret_cast<uint32_t *>(carry_d.as<char>() + 128);
     const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
     if (nc > 0 && want_line) {
-        if (start_d.ensure((size_t)nc * 2 + 64) || cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
+        if (start_d.ensure((size_t)nc * 2 + 64) || summ_d.ensure((size_t)nc * 2 + 64) || cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
             cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) || line_scr.ensure(linecode_scratch_bytes(nc) + 256))
             return -1;
         int *d_unres = reinterpret_cast<int *>(totals_d.as<char>() + 128);
-        if (launch_linecode_start(events_d.as<EventRec>(), M, lt, dec_carry, start_d.as<uint16_t>(), d_unres, cs)) return -1;
+        if (launch_linecode_start(events_d.as<EventRec>(), M, lt, dec_carry, summ_d.as<uint16_t>(), start_d.as<uint16_t>(), d_unres,
+                                  cs))
+            return -1;
         if (launch_linecode_count(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p,
                                   totals_d.as<char>() + 64, cs))
             return -1;
-        stats.launches += 5;
+        stats.launches += 6;
         int unres = 0;
         NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(&unres, d_unres, sizeof(int), cudaMemcpyDeviceToHost, cs));
