@@ -63,16 +63,18 @@ struct RunView {
     __device__ __forceinline__ int64_t p(uint32_t r) const { return r == 0 ? w0 - dur0 : (int64_t)trans_pos(tr[r - 1]); }
     __device__ __forceinline__ int64_t e(uint32_t r) const { return r < R ? (int64_t)trans_pos(tr[r]) : w1; }
 
+    // run lengths stay below 2^31 (a slab is at most 2^30 samples, the carried-in run adds at most max_len): all the
+    // divisions by max_len are 32-bit
     __device__ __forceinline__ bool tmo_at_last(int64_t pp, int64_t ee) const {
-        const int64_t ell = ee - pp;
-        return (ell - 1) >= mx && ((ell - 1) % mx) == 0;
+        const uint32_t ell1 = (uint32_t)(ee - pp - 1);
+        return ell1 >= (uint32_t)mx && (ell1 % (uint32_t)mx) == 0u;
     }
     // first timeout position q = p + k*mx (k >= 1), q >= w0, or -1 when none falls before e
     __device__ __forceinline__ int64_t first_tmo(uint32_t r, int64_t pp, int64_t ee) const {
         int64_t k = 1;
         if (r == 0) {
-            const int64_t need = w0 - pp;  // = dur0
-            k = (need + mx - 1) / mx;
+            const uint32_t need = (uint32_t)(w0 - pp);  // = dur0
+            k = (int64_t)((need + (uint32_t)mx - 1u) / (uint32_t)mx);
             if (k < 1) k = 1;
         }
         const int64_t q = pp + k * mx;
@@ -118,8 +120,8 @@ __device__ __forceinline__ void run_events(const RunView &V, uint32_t r, bool ke
         else se = any_tmo ? 0 : s_begin;
         const int un = trans_val(V.tr[r]);
         const int st_after = un == -1 ? 2 : (un == 1 ? 1 : se);
-        const int64_t ell = ee - pp;
-        const int d = se == 0 ? V.mx : (int)((ell - 1) % V.mx) + 1;
+        const uint32_t ell1 = (uint32_t)(ee - pp - 1);
+        const int d = se == 0 ? V.mx : (int)(ell1 % (uint32_t)V.mx) + 1;
         if (keep_dropped || st_after != 0) emit((uint32_t)ee, uu + (st_after == 2 ? 1 : 0), d, st_after - 1);
     }
 }
@@ -153,7 +155,7 @@ __global__ void run_write_kernel(RunView V, int keep_dropped, const uint32_t *__
         if (V.w1 > V.w0) {
             c.st = V.s_end(r);
             c.last_bit = V.u(r);
-            c.dur = (int)((V.w1 - 1 - V.p(r)) % V.mx) + 1;
+            c.dur = (int)((uint32_t)(V.w1 - 1 - V.p(r)) % (uint32_t)V.mx) + 1;
         } else {
             c.st = V.st0; c.last_bit = V.lb0; c.dur = V.dur0;
         }

@@ -403,7 +403,8 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
     }
     if (called_back) *called_back = 1;
     int64_t done = 0;
-    const int64_t slab = slab_len > 0 ? slab_len : (int64_t)1 << 28;
+    // transition records hold positions relative to the slab in 30 bits
+    const int64_t slab = slab_len > 0 ? std::min<int64_t>(slab_len, (int64_t)1 << 30) : (int64_t)1 << 28;
     // Host input goes through two staging buffers: the copy of slab k+1 (stream cs3) runs beside the kernels of slab k.
     const bool host_in = mem == NFC_MEM_HOST;
     auto stage_host = [&](int64_t off, int64_t m, int64_t a, int buf) -> int {
