@@ -905,6 +905,22 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         if (compare(nseg)) return -1;
     }
     NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
+    // The transition count of the bitmap is queued behind the seam check so that one synchronisation serves both; it
+    // stands when no segment has to be redone (the usual case).  The previous slab's carries are needed for it: its
+    // records were copied back beside this slab's kernel.
+    if (finish_pending()) return -1;
+    const size_t nblk = extract_blocks(bm_pos0, a, b);
+    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
+    uint32_t R = 0;
+    auto count_transitions = [&]() -> int {
+        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
+                                 ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
+            return -1;
+        stats.launches += 4;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
+        return 0;
+    };
+    if (count_transitions()) return -1;
     NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
     kernel_time();
     int st_all = 0;
@@ -913,6 +929,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         *fell_back = true;  // caller redoes the slab with the sequential kernel
         return 0;
     }
+    bool bitmap_changed = false;
 
     // ---- repair: redo a wrong segment from its predecessor's true final state, checkpoint by checkpoint; the
     // redo overwrites the bitmap in place and stops at the first checkpoint of the speculative run it reproduces
@@ -923,6 +940,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         nbad += bad[(size_t)k];
     }
     for (int guard = 0; nbad > 0 && guard < nseg + 2; guard++) {
+        bitmap_changed = true;
         std::vector<int> ks;
         for (int k = 1; k < nseg; k++)
             if (bad[(size_t)k] && !bad[(size_t)k - 1]) ks.push_back(k);
@@ -1035,16 +1053,10 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         }
     }
     // ---- bitmap -> dense ordered transitions (the first sample is compared with the previous slab's last val)
-    if (finish_pending()) return -1;
-    const size_t nblk = extract_blocks(bm_pos0, a, b);
-    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
-    if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
-                             ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
-        return -1;
-    stats.launches += 4;
-    uint32_t R = 0;
-    NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if (bitmap_changed) {  // segments were redone: count again
+        if (count_transitions()) return -1;
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    }
     if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
     if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
                              trans_dense.as<TransRec>(), R, cs))
