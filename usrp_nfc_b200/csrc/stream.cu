@@ -1272,15 +1272,15 @@ int Stream::finish_pending() {
             const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
             const uint8_t *nb[2] = {(const uint8_t *)(hp + off_b0), (const uint8_t *)(hp + off_b1)};
             const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
+            // hbits[t]: bits of a frame still open at the end of the previous slab; the slab's new bits follow them
             const size_t old[2] = {hbits[0].size(), hbits[1].size()};
-            for (int t = 0; t < 2; t++) hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
             size_t last_end[2] = {0, 0};
             bool any[2] = {false, false};
             const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
             out_frames.reserve(out_frames.size() + tot.nemit);
             for (uint32_t i = 0; i < tot.nemit; i++) {
                 const int t = em[i].type;
-                const size_t end = old[t] + em[i].bit_end;  // index into hbits[t]
+                const size_t end = old[t] + em[i].bit_end;  // index into (open bits ++ new bits)
                 any[t] = true;
                 last_end[t] = end;
                 if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
@@ -1295,11 +1295,20 @@ int Stream::finish_pending() {
                 f.type = t;
                 out_frames.push_back(f);
             }
-            for (int t = 0; t < 2; t++)
-                if (any[t]) {
-                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
-                    hbits[t].erase(hbits[t].begin(), hbits[t].begin() + (long)last_end[t]);
+            for (int t = 0; t < 2; t++) {
+                if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
+                    const size_t used_new = last_end[t] - old[t];
+                    if (used_new > nnew[t]) {
+                        marshal_err = 1;
+                        return;
+                    }
+                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
+                    out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
+                    hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
+                } else {
+                    hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
                 }
+            }
         }
     });
     if (timing)
@@ -1489,6 +1498,13 @@ int64_t nfc_stream_view_frames(nfc_stream *h, const nfc_frame **frames, const ui
     if (!h || !frames || !bits_tag || !n_bits_tag || !bits_reader || !n_bits_reader) {
         nfc::set_error("null argument");
         return -1;
+    }
+    if (getenv("NFC_TIMING")) {
+        const double t0 = nfc::now_ms();
+        if (h->s.finish_pending()) return -1;
+        const double t1 = nfc::now_ms();
+        if (h->s.join_marshal()) return -1;
+        fprintf(stderr, "view_frames: last slab's records %.2f ms, its marshalling %.2f ms\n", t1 - t0, nfc::now_ms() - t1);
     }
     if (h->s.settle()) return -1;
     Stream &s = h->s;
