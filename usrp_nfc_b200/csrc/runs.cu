@@ -55,39 +55,39 @@ __global__ void gather_pieces_kernel(const TransRec *const *__restrict__ src, co
 struct RunView {
     const TransRec *tr;  // dense transitions of the window, ascending
     uint32_t R;          // number of transitions (runs = R + 1; run 0 is the carried-in run)
-    int64_t w0, w1;      // window, relative to the slab origin
+    int32_t w0, w1;      // window, relative to the slab origin (a slab is at most 2^30 samples: 32-bit positions)
     int st0, lb0, dur0;  // reference's (cur_state, last_bit, dur) at w0
     int mx;
 
     __device__ __forceinline__ int u(uint32_t r) const { return r == 0 ? lb0 : trans_val(tr[r - 1]); }
-    __device__ __forceinline__ int64_t p(uint32_t r) const { return r == 0 ? w0 - dur0 : (int64_t)trans_pos(tr[r - 1]); }
-    __device__ __forceinline__ int64_t e(uint32_t r) const { return r < R ? (int64_t)trans_pos(tr[r]) : w1; }
+    __device__ __forceinline__ int32_t p(uint32_t r) const { return r == 0 ? w0 - dur0 : (int32_t)trans_pos(tr[r - 1]); }
+    __device__ __forceinline__ int32_t e(uint32_t r) const { return r < R ? (int32_t)trans_pos(tr[r]) : w1; }
 
     // run lengths stay below 2^31 (a slab is at most 2^30 samples, the carried-in run adds at most max_len): all the
     // divisions by max_len are 32-bit
-    __device__ __forceinline__ bool tmo_at_last(int64_t pp, int64_t ee) const {
+    __device__ __forceinline__ bool tmo_at_last(int32_t pp, int32_t ee) const {
         const uint32_t ell1 = (uint32_t)(ee - pp - 1);
         return ell1 >= (uint32_t)mx && (ell1 % (uint32_t)mx) == 0u;
     }
     // first timeout position q = p + k*mx (k >= 1), q >= w0, or -1 when none falls before e
-    __device__ __forceinline__ int64_t first_tmo(uint32_t r, int64_t pp, int64_t ee) const {
-        int64_t k = 1;
+    __device__ __forceinline__ int32_t first_tmo(uint32_t r, int32_t pp, int32_t ee) const {
+        int32_t k = 1;
         if (r == 0) {
             const uint32_t need = (uint32_t)(w0 - pp);  // = dur0
-            k = (int64_t)((need + (uint32_t)mx - 1u) / (uint32_t)mx);
+            k = (int32_t)((need + (uint32_t)mx - 1u) / (uint32_t)mx);
             if (k < 1) k = 1;
         }
-        const int64_t q = pp + k * mx;
+        const int32_t q = pp + k * mx;
         return q < ee ? q : -1;
     }
     // cur_state after the last sample of a run with val != 0
-    __device__ __forceinline__ int s_end_nz(uint32_t r, int uu, int64_t pp, int64_t ee) const {
+    __device__ __forceinline__ int s_end_nz(uint32_t r, int uu, int32_t pp, int32_t ee) const {
         if (r == 0 && ee == w0) return st0;
         return tmo_at_last(pp, ee) ? 0 : (uu == -1 ? 2 : 1);
     }
     __device__ int s_end(uint32_t r) const {
         const int uu = u(r);
-        const int64_t pp = p(r), ee = e(r);
+        const int32_t pp = p(r), ee = e(r);
         if (r == 0 && ee == w0) return st0;
         if (uu != 0) return s_end_nz(r, uu, pp, ee);
         if (first_tmo(r, pp, ee) >= 0) return 0;
@@ -100,9 +100,9 @@ struct RunView {
 template <class Emit>
 __device__ __forceinline__ void run_events(const RunView &V, uint32_t r, bool keep_dropped, Emit emit) {
     const int uu = V.u(r);
-    const int64_t pp = V.p(r), ee = V.e(r);
+    const int32_t pp = V.p(r), ee = V.e(r);
     const int s_begin = r == 0 ? V.st0 : V.s_end(r - 1);
-    int64_t q = V.first_tmo(r, pp, ee);
+    int32_t q = V.first_tmo(r, pp, ee);
     bool first = true;
     bool any_tmo = false;
     while (q >= 0 && q < ee) {  // timeouts (transition_sink.py:95-99)
@@ -188,7 +188,7 @@ int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, R
                      uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total,
                      cudaStream_t stream) {
     RunView V;
-    V.tr = d_tr; V.R = R; V.w0 = w0; V.w1 = w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
+    V.tr = d_tr; V.R = R; V.w0 = (int32_t)w0; V.w1 = (int32_t)w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
     const uint32_t nrun = R + 1;
     run_count_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_counts);
     NFC_CUDA_CHECK(cudaGetLastError());
@@ -199,7 +199,7 @@ int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, R
                      const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, RunCarry *d_carry_out,
                      cudaStream_t stream) {
     RunView V;
-    V.tr = d_tr; V.R = R; V.w0 = w0; V.w1 = w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
+    V.tr = d_tr; V.R = R; V.w0 = (int32_t)w0; V.w1 = (int32_t)w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
     const uint32_t nrun = R + 1;
     run_write_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_offsets, d_events, cap, d_carry_out);
     NFC_CUDA_CHECK(cudaGetLastError());
