@@ -61,7 +61,8 @@ struct CombineCnt {
 
 struct TabView {
     const uint8_t *dcm, *dcg;       // duration classes (global)
-    const TabEntry *tm, *tg;        // tables (shared memory copies)
+    const TabEntry *tab;            // tables (one shared memory copy: Miller, then Manchester at goff)
+    int goff;
     int use_reader, use_tag;
 };
 
@@ -82,22 +83,24 @@ __device__ __forceinline__ void framer_put(int &started, int o, int type, uint32
     }
 }
 
-// one event through the machine it belongs to; rs/gs are the R and G machine states
+// one event through the machine it belongs to; rs/gs are the R and G machine states.  One code path for both
+// directions (table offset, state width and duration classes selected by the event's type): the lanes of a warp walk
+// different chunks, so reader and tag events meet in every step and separate branches would both be executed.
 template <class Sink>
 __device__ __forceinline__ void step_event(const EventRec &ev, const TabView &tv, int &rs, int &gs, Sink &sink) {
-    if (ev.type == 1 && tv.use_reader) {
-        const TabEntry e = tv.tm[((int)tv.dcm[ev.d] * 4 + (ev.v + 1)) * MILLER_STATES + (rs & 15)];
-        int started = rs >> 4;
-        const int n = tab_nout(e);
-        if (n > 0) framer_put(started, tab_out0(e), 1, ev.rel_pos, sink);
-        if (n > 1) framer_put(started, tab_out1(e), 1, ev.rel_pos, sink);
-        rs = tab_next(e) | (started << 4);
-    } else if (ev.type == 0 && tv.use_tag) {
-        const TabEntry e = tv.tg[((int)tv.dcg[ev.d] * 4 + (ev.v + 1)) * MANCH_STATES + (gs & 7)];
-        int started = gs >> 3;
-        if (tab_nout(e) > 0) framer_put(started, tab_out0(e), 0, ev.rel_pos, sink);
-        gs = (tab_next(e) & 7) | (started << 3);
-    }
+    const bool is_r = ev.type == 1;
+    if (!(is_r ? tv.use_reader != 0 : (ev.type == 0 && tv.use_tag != 0))) return;
+    const uint8_t *dc = is_r ? tv.dcm : tv.dcg;
+    const int nst = is_r ? MILLER_STATES : MANCH_STATES, sh = is_r ? 4 : 3;
+    const int st = is_r ? rs : gs;
+    const TabEntry e = tv.tab[(is_r ? 0 : tv.goff) + ((int)dc[ev.d] * 4 + (ev.v + 1)) * nst + (st & (nst - 1))];
+    int started = st >> sh;
+    const int n = tab_nout(e), type = is_r ? 1 : 0;
+    if (n > 0) framer_put(started, tab_out0(e), type, ev.rel_pos, sink);
+    if (n > 1 && is_r) framer_put(started, tab_out1(e), type, ev.rel_pos, sink);  // only the Miller decoder emits two symbols
+    const int nx = (tab_next(e) & (nst - 1)) | (started << sh);
+    rs = is_r ? nx : rs;
+    gs = is_r ? gs : nx;
 }
 
 // eight events at once (one 64-byte line): the loops below are chains of dependent loads otherwise.
@@ -126,19 +129,18 @@ struct NullSink {
     __device__ __forceinline__ void bit(int, int) {}
 };
 
-__device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, TabEntry *sg) {
+__device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, TabEntry *sg) {  // sg follows sm
     for (int i = threadIdx.x; i < lt.n_dclass_miller * 4 * MILLER_STATES; i += blockDim.x) sm[i] = lt.miller[i];
     for (int i = threadIdx.x; i < lt.n_dclass_manch * 4 * MANCH_STATES; i += blockDim.x) sg[i] = lt.manch[i];
     __syncthreads();
 }
 
 #define NFC_TABLE_SMEM                                              \
-    __shared__ TabEntry s_tm[MAX_DCLASS * 4 * MILLER_STATES];       \
-    __shared__ TabEntry s_tg[MAX_DCLASS * 4 * MANCH_STATES];        \
-    load_tables(lt, s_tm, s_tg);                                    \
+    __shared__ TabEntry s_tab[MAX_DCLASS * 4 * (MILLER_STATES + MANCH_STATES)]; \
+    load_tables(lt, s_tab, s_tab + MAX_DCLASS * 4 * MILLER_STATES); \
     TabView tv;                                                     \
     tv.dcm = lt.dclass_miller; tv.dcg = lt.dclass_manch;            \
-    tv.tm = s_tm; tv.tg = s_tg;                                     \
+    tv.tab = s_tab; tv.goff = MAX_DCLASS * 4 * MILLER_STATES;        \
     tv.use_reader = lt.decode_reader; tv.use_tag = lt.decode_tag;
 
 // ---- pass A: transfer function of every chunk -------------------------------------------------
