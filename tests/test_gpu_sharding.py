@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def _worker(rank, world, port, halo_windows, rate, q):
+def _worker(rank, world, port, halo_windows, rate, q, view=False):
     import torch.distributed as dist
     from oracle import oracle
     from usrp_nfc_b200 import _cabi, sharding, synth
@@ -26,8 +26,19 @@ def _worker(rank, world, port, halo_windows, rate, q):
     eng = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_FRAMES, **p)
     eng.set_tuning(seg_len=16 * p["av_window"], halo=4 * p["av_window"])
     res = sharding.decode_time_sharded(eng, lambda a, b: x[a:b], x.size, p["av_window"], _cabi.State, dist=dist,
-                                       halo_windows=halo_windows)
-    merged = sharding.gather_frames(res["frames"], dist)
+                                       halo_windows=halo_windows, flat="view" if view else False)
+    if view:  # zero-copy bulk form (what bench.py uses): records + the engine's own bit buffers, released by the caller
+        b0, b1 = res["bits"]
+        mine = []
+        for r in res["records"]:
+            buf = b0 if int(r["type"]) == 0 else b1
+            mine.append((int(r["pos"]) + res["pos_offset"], int(r["type"]),
+                         buf[int(r["bit_off"]): int(r["bit_off"]) + int(r["nbits"])].copy()))
+        assert len(mine) == res["n_frames"]
+        eng.release_frames()
+    else:
+        mine = res["frames"]
+    merged = sharding.gather_frames(mine, dist)
     if rank == 0:
         want = oracle.decode_capture(x, rate, hi_val=1.09, **p)
         ok = len(merged) == len(want["frames"])
@@ -39,13 +50,14 @@ def _worker(rank, world, port, halo_windows, rate, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,halo_windows,rate", [(2, 16, 2e6), (3, 1, 2e6), (2, 2, 13.56e6)])
-def test_gpu_time_shards_stitch_exactly(world, halo_windows, rate):
+@pytest.mark.parametrize("world,halo_windows,rate,view", [(2, 16, 2e6, False), (3, 1, 2e6, False), (2, 2, 13.56e6, False),
+                                                          (3, 2, 13.56e6, True)])
+def test_gpu_time_shards_stitch_exactly(world, halo_windows, rate, view):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200) + world * 11 + halo_windows
-    procs = [ctx.Process(target=_worker, args=(r, world, port, halo_windows, rate, q)) for r in range(world)]
+    port = 29700 + (os.getpid() % 200) + world * 11 + halo_windows + (400 if view else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, halo_windows, rate, q, view)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=600) for _ in range(world + 1)]

@@ -1218,7 +1218,20 @@ __global__ void seam_compare_kernel(const SlicerHdr *const *__restrict__ truth, 
     int bad = 0;
     const uint32_t *ra = reinterpret_cast<const uint32_t *>(state_ring(a));
     const uint32_t *rb = reinterpret_cast<const uint32_t *>(state_ring(b));
-    for (int i = threadIdx.x; i < p.L; i += blockDim.x) bad |= (ra[i] != rb[i]);
+    if ((((uintptr_t)ra | (uintptr_t)rb) & 15) == 0 && (p.L & 3) == 0) {  // 128-bit loads, two in flight per thread
+        const uint4 *va = reinterpret_cast<const uint4 *>(ra), *vb = reinterpret_cast<const uint4 *>(rb);
+        const int n4 = p.L >> 2;
+        for (int i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+            const int j = i + blockDim.x;
+            const uint4 x0 = __ldg(va + i), y0 = __ldg(vb + i);
+            uint4 x1 = x0, y1 = y0;
+            if (j < n4) { x1 = __ldg(va + j); y1 = __ldg(vb + j); }
+            bad |= (x0.x != y0.x) | (x0.y != y0.y) | (x0.z != y0.z) | (x0.w != y0.w) | (x1.x != y1.x) | (x1.y != y1.y) |
+                   (x1.z != y1.z) | (x1.w != y1.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < p.L; i += blockDim.x) bad |= (ra[i] != rb[i]);
+    }
     if (threadIdx.x == 0) {
         if (__double_as_longlong(a->ss) != __double_as_longlong(b->ss)) bad = 1;
         if (a->last_val != b->last_val || a->pos != b->pos) bad = 1;
