@@ -108,6 +108,8 @@ struct __align__(16) FastUni {
     int ok;                           // the coming tile may be streamed (ss > 0, step representable)
     int verdict;                      // warp 0: what the sums say
     int st2, cand_last_val, cand_newL, cand_newS;  // warp 1: hysteresis risk; the carries the tile would leave
+    unsigned redo_mask;               // repeat: the chunks classified again, sample by sample (bit = chunk)
+    int pad_[3];
     float gTL[32], gTH[32];           // guessed thresholds per chunk of the coming tile (or of the repeat), at the chunk's middle
     float gMid[32];                   // the guessed ss behind them (relative to the interval's midpoint)
     float gC0[32];                    // repeat: the measured ss at the chunk's first sample (relative to the midpoint) the guess assumes
@@ -676,13 +678,17 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                             if (s0 >= L) s0 -= L;
                         }
                     } else {
+                        // only the chunks the verdict named: the others keep their records, maps and ring values
                         const float TLb = uni.TLb, THb = uni.THb;
+                        const unsigned mine = uni.redo_mask >> (warp * R);
 #pragma unroll
                         for (int r = 0; r < R; r++) {
-                            const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
-                            fast_row<true>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
-                                           invqA, uni.gC0[warp * R + r], TLb, THb, plan.loLf, plan.hiLf, plan.invLo, plan.invHi, lane, n[r],
-                                           rec + r, bmw + r * 8);
+                            if ((mine >> r) & 1u) {
+                                const float4 pv4 = *reinterpret_cast<const float4 *>(ring + s0);
+                                fast_row<true>(STAGED ? staged_row(r) : xin[r], pv4, uni.gTL[warp * R + r], uni.gTH[warp * R + r], invq,
+                                               invqA, uni.gC0[warp * R + r], TLb, THb, plan.loLf, plan.hiLf, plan.invLo, plan.invHi,
+                                               lane, n[r], rec + r, bmw + r * 8);
+                            }
                             s0 += FAST_CH;
                             if (s0 >= L) s0 -= L;
                         }
@@ -722,7 +728,10 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     const float slack = (hwf + Ef) * 1.001f;
                     const float gl = uni.gTL[lane], gh = uni.gTH[lane];
                     bool fine;
-                    if (precise) {
+                    // a repeat: chunks classified sample by sample (the mask of the last verdict) are judged by their lanes'
+                    // slack, the others as in the first pass -- with the chunk starts as they are now
+                    const bool lane_precise = precise && ((uni.redo_mask >> lane) & 1u);
+                    if (lane_precise) {
                         // the lanes' slack must cover what the chunk's start is off the assumed one by, and the interval
                         const float need = (fabsf(c0 - uni.gC0[lane]) + slack) * (1.0f + 0x1p-18f) + uni.TLb * (0x1p-21f / loLf);
                         fine = (mL > need) && (gl > 0.0f);
@@ -735,10 +744,13 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                         // the guess is proven when no sample lies between it and any value the true threshold can take
                         fine = (mL > rl) && (mH > rh) && (gl - rl > 0.0f);
                     }
-                    const bool all_fine = __all_sync(FULL, fine);
+                    const unsigned failing = __ballot_sync(FULL, !fine);
+                    const bool all_fine = failing == 0u;
                     if (!all_fine || bad) {
-                        const bool redo = bad ? n_coarse < 3 : n_meas < 1;
-                        if (redo && !bad) {  // go round again with the measured window sums as the guess
+                        // first the failing chunks alone, then (if that does not settle it) every chunk
+                        const bool redo = bad ? n_coarse < 3 : n_meas < 2;
+                        const unsigned again = n_meas == 0 ? failing : FULL;
+                        if (redo && !bad && ((again >> lane) & 1u)) {  // go round again with the measured window sums as the guess
                             const float mid = c0 + 0.5f * Sf;  // measured window sum at the chunk's middle
                             uni.gTL[lane] = fmaf(mid, loLf, uni.TLb);
                             uni.gTH[lane] = fmaf(mid, hiLf, uni.THb);
@@ -746,6 +758,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                             uni.gC0[lane] = c0;
                         }
                         if (lane == 0) {
+                            uni.redo_mask = again;
                             // a precise pass that cannot prove itself is checked sample by sample in exact arithmetic
                             int v = redo ? (bad ? FV_REDO_COARSE : FV_REDO) : ((precise && !bad) ? FV_VERIFY : FV_SLOW);
                             if (bad && redo) {  // a lane's sum did not fit: coarser fixed-point step
@@ -806,9 +819,14 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     int n_meas = 0, n_coarse = 0;
                     for (;;) {
                         have_x = 0;  // the samples are needed for this tile again, or the exact path reloads
-                        if (verdict == FV_REDO) n_meas++;
-                        else if (verdict == FV_REDO_COARSE) n_coarse++;
-                        else break;
+                        if (verdict == FV_REDO) {
+                            n_meas++;
+                        } else if (verdict == FV_REDO_COARSE) {  // other fixed-point step: every chunk's sums again
+                            n_coarse++;
+                            n_meas = 0;
+                        } else {
+                            break;
+                        }
                         verdict = tile_pass(0, n_meas, n_coarse);
                         if (verdict == FV_ACCEPT) break;
                     }
