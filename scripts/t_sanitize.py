@@ -16,3 +16,32 @@ for kind, data in ((_cabi.IN_ENVELOPE_F32, x), (_cabi.IN_PCM_S16, pcm)):
     st = s.stats()
     print("kind", kind, "events", len(ev), "frames", len(fr), {k: st[k] for k in ("segments", "seam_mismatches", "fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles")})
     s.close()
+
+# a stream that provokes the rare paths too: samples hovering around the HIGH threshold (fix-point pass), spikes right
+# after pauses (hysteresis -> exact path), level steps (coarser fixed-point step)
+rng = np.random.default_rng(11)
+L, mx, n = 8192, 50, 260000
+y = (0.25 * (1 + 0.01 * rng.standard_normal(n))).astype(np.float32)
+i = L + 10
+while i < n - 4 * mx - 10:
+    kind = rng.integers(0, 5)
+    ln = min(int(rng.choice([1, 2, mx, 2 * mx + 1, 6, 700])), n - i - 1)
+    if kind == 0:
+        y[i:i + ln] = 1e-4
+        i += ln
+        if rng.random() < 0.7:
+            k = int(rng.integers(0, mx + 4))
+            y[i + k: i + k + 2] = 0.4
+    elif kind == 2:
+        y[i:i + ln] = 0.2725 * (1 + 0.002 * rng.standard_normal(ln))
+        i += ln
+    elif kind == 3 and rng.random() < 0.05:
+        y[i:] *= np.float32(rng.choice([0.7, 1.4]))
+    i += int(rng.integers(1, 6 * mx))
+s = _cabi.Stream(13.56e6, hi_val=1.09, outputs=_cabi.OUT_ALL, av_window=L, max_len=mx)
+s.set_tuning(seg_len=65536, halo=4 * L)
+s.push_all(y)
+ev = s.drain_events(); fr, bits = s.drain_frames()
+st = s.stats()
+print("corner events", len(ev), "frames", len(fr), {k: st[k] for k in ("segments", "seam_mismatches", "fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles")})
+s.close()

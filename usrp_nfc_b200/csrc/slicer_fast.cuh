@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                             uni.gMid[lane] = mid;
                             uni.gC0[lane] = c0;
                         }
+                        __syncwarp();  // every lane has read the step and the mask this pass was judged with
                         if (lane == 0) {
                             uni.redo_mask = again;
                             // a precise pass that cannot prove itself is checked sample by sample in exact arithmetic
