@@ -246,12 +246,14 @@ def test_large_synthetic_stream(rate, n_sessions):
     print("samples %d frames %d stats %s" % (x.size, len(want["frames"]), got["stream"].stats()))
 
 
-@pytest.mark.parametrize("n,seg_len", [(48_000_000, 0), (20_000_000, 1_200_000)])
-def test_bench_workload_matches_oracle(n, seg_len):
+@pytest.mark.parametrize("n,seg_len,super_slab", [(48_000_000, 0, 1), (20_000_000, 1_200_000, 1), (20_000_000, 1_200_000, 2)])
+def test_bench_workload_matches_oracle(n, seg_len, super_slab, monkeypatch):
     """The bench.py traffic (dense frames, 5 % fade: many samples close to the HIGH threshold, repeated tiles, exact-path
-    tiles, seam repairs) rendered on the device, decoded by the streaming kernel and by the oracle."""
+    tiles, seam repairs) rendered on the device, decoded by the streaming kernel and by the oracle.  super_slab = 2: the
+    slicer runs over two slabs per launch, the second slab's transitions come from the bitmap it left."""
     import torch
     import bench
+    monkeypatch.setenv("NFC_SUPER_SLAB", str(super_slab))
     rate = 13.56e6
     codes, lens, p = bench.build_schedule(rate, 2024)
     x = torch.empty(n, dtype=torch.float32, device="cuda")

@@ -201,11 +201,19 @@ struct Stream {
     int settle() { return finish_pending() || join_marshal() ? -1 : 0; }
     int64_t push(const void *items, int64_t n, int mem, int *called_back);
     int finish_warmup();
-    int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b);
+    int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, int64_t slicer_end);
     int run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial, uint32_t *R_out,
                    bool *fell_back);
-    int run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, uint32_t *R_out,
-                      bool *fell_back);
+    int run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b_post, int64_t b,
+                      uint32_t *R_out, bool *fell_back);
+    int extract_only(int64_t a, int64_t b, uint32_t *R_out);
+    // the class bitmap holds stream positions [bm_lo, bm_hi) (chunk 0 at bm_origin): the streaming slicer may run ahead of the
+    // slab that is being turned into events
+    int64_t bm_lo = 0, bm_hi = 0, bm_origin = 0;
+    // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB=2: segments twice as long, the kernel
+    // alone gains 9 %; off by default because the slabs after the first then wait for the previous slab's carries on the host
+    // with no slicer launch to hide behind)
+    int64_t super_slab = 1;
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
@@ -302,6 +310,7 @@ int Stream::init(const nfc_params *p) {
     if (carry_d.ensure(256)) return -1;
     if (totals_d.ensure(256)) return -1;
     resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok()) : 1;
+    if (const char *e = getenv("NFC_SUPER_SLAB")) super_slab = std::max(1, std::min(8, atoi(e)));
     return 0;
 }
 
@@ -428,6 +437,7 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
         const int64_t in_pos0 = a - (a & 3);
         const void *d_in = nullptr;
         int64_t in_begin = in_pos0;
+        int64_t slicer_end = b;
         const char *src = (const char *)items + (size_t)done * ib;
         const size_t padb = (size_t)(a - in_pos0) * ib;
         if (host_in) {
@@ -440,12 +450,15 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
         } else if ((((uintptr_t)src - padb) & 15) == 0) {
             d_in = src - padb;  // usable in place: item with stream index in_pos0 would sit 16-byte aligned
             in_begin = a;       // ... but nothing before the caller's pointer is read
+            // device-resident input: the streaming slicer may run over several slabs at once (only positions relative to a
+            // slab are limited to 30 bits, and the slicer writes none)
+            slicer_end = std::min(pos + (n - done), a + super_slab * slab);
         } else {
             if (staging.ensure(padb + (size_t)m * ib + 64)) return -1;
             NFC_CUDA_CHECK(cudaMemcpyAsync(staging.as<char>() + padb, src, (size_t)m * ib, cudaMemcpyDeviceToDevice, cs));
             d_in = staging.p;
         }
-        if (process_slab(d_in, in_pos0, in_begin, b, a, b)) return -1;
+        if (process_slab(d_in, in_pos0, in_begin, std::max(b, slicer_end), a, b, slicer_end)) return -1;
         pos = b;
         done += m;
         stats.samples += m;
@@ -786,10 +799,12 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
     return -1;
 }
 
-// The streaming kernel over [a, b): class bitmap of the slab (fixed-rate output, no per-segment lists), seams
-// verified and repaired like run_slicer, then the dense ordered transitions extracted from the bitmap.
-int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, uint32_t *R_out,
-                          bool *fell_back) {
+// The streaming kernel over [a, b): class bitmap (fixed-rate output, no per-segment lists), seams verified and repaired like
+// run_slicer, then the dense ordered transitions of [a, b_post) extracted from the bitmap (b_post <= b: the slicer may cover
+// several slabs at once -- longer segments, relatively shorter speculative starts; extract_only serves the rest).
+int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b_post, int64_t b,
+                          uint32_t *R_out, bool *fell_back) {
+    bm_hi = bm_lo = 0;
     const int L = sp.L;
     const int T = tile();
     *fell_back = false;
@@ -802,9 +817,10 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         int64_t S = seg_len;
         if (S <= 0) {
             const int64_t n = b - a, res = std::max(1, resident_ctas);
-            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)256 * L, s_min);
-            int64_t k = 1;
-            while (n / (res * (k + 1)) >= s_min) k++;
+            // one segment per resident CTA if that keeps them below s_max, else the fewest waves that do: the longer the
+            // segments, the smaller the share of the speculative starts
+            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)512 * L, s_min);
+            const int64_t k = std::max<int64_t>(1, (n + res * s_max - 1) / (res * s_max));
             S = n / (res * k);
             if (S < s_min) S = s_min;
             if (S > s_max) S = s_max;
@@ -909,11 +925,11 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
     // stands when no segment has to be redone (the usual case).  The previous slab's carries are needed for it: its
     // records were copied back beside this slab's kernel.
     if (finish_pending()) return -1;
-    const size_t nblk = extract_blocks(bm_pos0, a, b);
+    const size_t nblk = extract_blocks(bm_pos0, a, b_post);
     if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
     uint32_t R = 0;
     auto count_transitions = [&]() -> int {
-        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
+        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b_post, run_carry.last_bit, ex_counts.as<uint32_t>(),
                                  ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
             return -1;
         stats.launches += 4;
@@ -1058,11 +1074,35 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
     }
     if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
-    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
+    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b_post, run_carry.last_bit, ex_offsets.as<uint32_t>(),
                              trans_dense.as<TransRec>(), R, cs))
         return -1;
     stats.launches++;
     NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
+    bm_lo = a;
+    bm_hi = b;
+    bm_origin = bm_pos0;
+    *R_out = R;
+    return 0;
+}
+
+// Transitions of [a, b) from a bitmap the slicer has already filled.
+int Stream::extract_only(int64_t a, int64_t b, uint32_t *R_out) {
+    if (finish_pending()) return -1;  // run_carry.last_bit: the val before sample a
+    const size_t nblk = extract_blocks(bm_origin, a, b);
+    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
+    if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_origin, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
+                             ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
+        return -1;
+    stats.launches += 4;
+    uint32_t R = 0;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
+    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
+                             trans_dense.as<TransRec>(), R, cs))
+        return -1;
+    stats.launches++;
     *R_out = R;
     return 0;
 }
@@ -1071,7 +1111,8 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b) {
+int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b,
+                         int64_t slicer_end) {
     static const bool timing = getenv("NFC_TIMING") != nullptr;
     const double t0 = now_ms();
     double t1 = t0, t2 = t0;
@@ -1081,12 +1122,15 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
     uint32_t R = 0;
     bool fell_back = false;
     const bool par = parallel_ok();
-    if (streaming_ok()) {
-        if (run_slicer_bm(d_in, in_pos0, in_begin, in_end, a, b, &R, &fell_back)) return -1;
+    if (streaming_ok() && a >= bm_lo && b <= bm_hi) {
+        if (extract_only(a, b, &R)) return -1;  // the slicer ran over this slab together with the one before
+    } else if (streaming_ok()) {
+        if (run_slicer_bm(d_in, in_pos0, in_begin, in_end, a, b, std::max(b, slicer_end), &R, &fell_back)) return -1;
     } else if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) {
         return -1;
     }
     if (fell_back) {
+        bm_lo = bm_hi = 0;
         serial_mode = true;  // sums are no longer exactly representable: stay on the sequential kernel
         if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, true, &R, &fell_back)) return -1;
     }
@@ -1395,6 +1439,7 @@ int nfc_stream_reset(nfc_stream *h) {
     s.pos = 0;
     s.stable = false;
     s.serial_mode = false;
+    s.bm_lo = s.bm_hi = 0;
     s.warm.clear();
     s.run_carry = nfc::RunCarry{0, 0, 0, 0};
     s.dec_carry = nfc::DecCarry{0, 0, {0, 0}};
@@ -1581,6 +1626,7 @@ int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, 
         return -1;
     }
     Stream &s = h->s;
+    s.bm_lo = s.bm_hi = 0;
     if (s.settle()) return -1;
     if (!st->stable || !ring) {
         nfc::set_error("set_state needs a stable state with its ring");
