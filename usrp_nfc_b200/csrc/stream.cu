@@ -6,11 +6,13 @@
 // The ordered transitions of the slab go through runs.cu (events) and linecode.cu (symbols, frames);
 // only records leave the device.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -158,13 +160,16 @@ struct Stream {
         line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
         redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr, summ_d;
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
-    // results come back into one of two pinned buffers; a worker thread turns the previous slab's records into the
-    // output vectors while the device works on the next slab
-    void *pinned[2] = {nullptr, nullptr};
-    size_t pinned_cap[2] = {0, 0};
-    int pin_idx = 0;
+    // results come back into one of three pinned buffers.  The carries of a slab (256 bytes) are copied first and are all
+    // the next slab waits for; the records behind them are awaited by a worker thread, which turns them into the output
+    // vectors while the device works on the following slabs (the threads form a chain: each joins its predecessor first).
+    static const int NPIN = 3;
+    void *pinned[NPIN] = {nullptr, nullptr, nullptr};
+    size_t pinned_cap[NPIN] = {0, 0, 0};
+    long long slabs_enqueued = 0;               // slabs whose records were put on their way
+    std::atomic<long long> slabs_marshalled{0};  // slabs whose records are in the output vectors
     std::thread marshal_thr;
-    int marshal_err = 0;
+    std::atomic<int> marshal_err{0};
     // a slab whose records are on their way to the host: completed (carries taken over, marshalling started) right
     // before the next slab needs its carries, or when the caller looks at results
     struct Pending {
@@ -175,9 +180,10 @@ struct Stream {
         int64_t a = 0, b = 0;
         bool want_ev = false, want_sym = false, want_fr = false, have_line = false;
         double t0 = 0, t1 = 0, t2 = 0;
-        int ei = 0;
+        int ei = 0, pi = 0;
     } pend;
-    cudaEvent_t ev_d = nullptr;
+    cudaEvent_t ev_d[NPIN] = {nullptr, nullptr, nullptr};  // all records of the slab that used pinned[i] have arrived
+    cudaEvent_t ev_carry = nullptr;                         // the carries of the pending slab have arrived
 
     // results
     std::vector<nfc_event> out_events;
@@ -210,10 +216,9 @@ struct Stream {
     // the class bitmap holds stream positions [bm_lo, bm_hi) (chunk 0 at bm_origin): the streaming slicer may run ahead of the
     // slab that is being turned into events
     int64_t bm_lo = 0, bm_hi = 0, bm_origin = 0;
-    // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB=2: segments twice as long, the kernel
-    // alone gains 9 %; off by default because the slabs after the first then wait for the previous slab's carries on the host
-    // with no slicer launch to hide behind)
-    int64_t super_slab = 1;
+    // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB, 1..8): segments twice as long halve
+    // the share of the speculative starts; the slabs after the first take their transitions from the bitmap (extract_only)
+    int64_t super_slab = 2;
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
@@ -230,9 +235,8 @@ int Stream::ensure_pinned(int idx, size_t bytes) {
 // waits for the records of the previous slab to be in the output vectors
 int Stream::join_marshal() {
     if (marshal_thr.joinable()) marshal_thr.join();
-    if (marshal_err) {
-        marshal_err = 0;
-        set_error("internal: frame longer than the retained bits");
+    if (const int err = marshal_err.exchange(0)) {
+        set_error(err == 2 ? "copying a slab's records to the host failed" : "internal: frame longer than the retained bits");
         return -1;
     }
     return 0;
@@ -261,7 +265,8 @@ int Stream::init(const nfc_params *p) {
         NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_c[i]));
     }
-    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
+    for (int i = 0; i < NPIN; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming));
+    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_carry, cudaEventDisableTiming));
     factor = 1e6 / p->samp_rate;  // transition_sink.py:21
     sp.lo = p->lo_val;
     sp.hi = p->hi_val;
@@ -323,7 +328,7 @@ void Stream::destroy() {
     for (DevBuf *b : all) b->release();
     finish_pending();
     if (marshal_thr.joinable()) marshal_thr.join();
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < NPIN; i++)
         if (pinned[i]) cudaFreeHost(pinned[i]);
     for (int i = 0; i < 2; i++) {
         if (ev_a[i]) cudaEventDestroy(ev_a[i]);
@@ -338,7 +343,9 @@ void Stream::destroy() {
         if (ev_h[i]) cudaEventDestroy(ev_h[i]);
         staging2[i].release();
     }
-    if (ev_d) cudaEventDestroy(ev_d);
+    for (int i = 0; i < NPIN; i++)
+        if (ev_d[i]) cudaEventDestroy(ev_d[i]);
+    if (ev_carry) cudaEventDestroy(ev_carry);
     if (cs) cudaStreamDestroy(cs);
 }
 
@@ -1226,11 +1233,14 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         off_b0 = place(tot.nbit0);
         off_b1 = place(tot.nbit1);
     }
-    pin_idx ^= 1;  // the worker may still be reading the other buffer
-    if (ensure_pinned(pin_idx, total)) return -1;
-    char *hp = (char *)pinned[pin_idx];
+    const int pi = (int)(slabs_enqueued % NPIN);
+    // the slab that used this buffer last (three slabs ago) must be in the output vectors: long done, normally
+    while (slabs_marshalled.load(std::memory_order_acquire) < slabs_enqueued - (NPIN - 1)) std::this_thread::yield();
+    if (ensure_pinned(pi, total)) return -1;
+    char *hp = (char *)pinned[pi];
     NFC_CUDA_CHECK(cudaStreamWaitEvent(cs2, ev_c[ei], 0));
     NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_c, carry_d.p, 256, cudaMemcpyDeviceToHost, cs2));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_carry, cs2));
     if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d.p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
     if (want_sym && tot.nsym)
         NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d.p, (size_t)tot.nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
@@ -1240,7 +1250,9 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         if (tot.nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d.p, tot.nbit0, cudaMemcpyDeviceToHost, cs2));
         if (tot.nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d.p, tot.nbit1, cudaMemcpyDeviceToHost, cs2));
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_d, cs2));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_d[pi], cs2));
+    slabs_enqueued++;
+    pend.pi = pi;
     pend.active = true;
     pend.hp = hp;
     pend.off_ev = off_ev; pend.off_sym = off_sym; pend.off_em = off_em; pend.off_b0 = off_b0; pend.off_b1 = off_b1;
@@ -1258,7 +1270,7 @@ int Stream::finish_pending() {
     if (!pend.active) return 0;
     static const bool timing = getenv("NFC_TIMING") != nullptr;
     pend.active = false;
-    NFC_CUDA_CHECK(cudaEventSynchronize(ev_d));
+    NFC_CUDA_CHECK(cudaEventSynchronize(ev_carry));  // the carries only: the records behind them are the worker's business
     const double t3 = now_ms();
     char *hp = pend.hp;
     const size_t off_ev = pend.off_ev, off_sym = pend.off_sym, off_em = pend.off_em, off_b0 = pend.off_b0, off_b1 = pend.off_b1,
@@ -1282,9 +1294,18 @@ int Stream::finish_pending() {
         pending[0] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[0];
         pending[1] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[1];
     }
-    // ---- marshal records (absolute positions) on the worker thread
-    if (join_marshal()) return -1;
-    marshal_thr = std::thread([this, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, totc, a, want_ev, want_sym, want_fr]() {
+    // ---- marshal records (absolute positions) on a worker thread: it waits for its predecessor (the output vectors are
+    // filled in slab order), then for the slab's records to arrive
+    if (marshal_err.load()) return join_marshal();
+    auto prev = std::make_shared<std::thread>(std::move(marshal_thr));
+    const cudaEvent_t evd = ev_d[pend.pi];
+    const int dev = prm.device;
+    marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, totc, a, want_ev, want_sym,
+                               want_fr]() {
+      if (prev->joinable()) prev->join();
+      cudaSetDevice(dev);
+      if (cudaEventSynchronize(evd) != cudaSuccess) marshal_err = 2;
+      else [&]() {
         const Totals &tot = totc;
         // ---- marshal records (absolute positions)
         if (want_ev) {
@@ -1354,6 +1375,8 @@ int Stream::finish_pending() {
                 }
             }
         }
+      }();
+      slabs_marshalled.fetch_add(1, std::memory_order_release);
     });
     if (timing)
         fprintf(stderr, "slab %lld..%lld: slicer %.2f ms (dev %.2f), runs+linecode %.2f (dev %.2f), completed %.2f ms after enqueue\n",
