@@ -1342,16 +1342,44 @@ int Stream::finish_pending() {
             size_t last_end[2] = {0, 0};
             bool any[2] = {false, false};
             const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
+            // the last closing of each type says how many of the new bits go out: known before the frames are walked, so the
+            // bits can be copied by a helper thread meanwhile (different containers)
+            for (uint32_t i = tot.nemit; i > 0 && !(any[0] && any[1]); i--) {
+                const int t = em[i - 1].type;
+                if (!any[t]) {
+                    any[t] = true;
+                    last_end[t] = old[t] + em[i - 1].bit_end;  // index into (open bits ++ new bits)
+                }
+            }
+            for (int t = 0; t < 2; t++)
+                if (any[t] && last_end[t] - old[t] > nnew[t]) {
+                    marshal_err = 1;
+                    return;
+                }
+            auto copy_bits = [&]() {
+                for (int t = 0; t < 2; t++) {
+                    if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
+                        const size_t used_new = last_end[t] - old[t];
+                        out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
+                        out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
+                        hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
+                    } else {
+                        hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
+                    }
+                }
+            };
+            std::thread helper;
+            if (tot.nemit > 20000) helper = std::thread(copy_bits);
+            else copy_bits();
+            bool bad_frame = false;
             out_frames.reserve(out_frames.size() + tot.nemit);
             for (uint32_t i = 0; i < tot.nemit; i++) {
                 const int t = em[i].type;
-                const size_t end = old[t] + em[i].bit_end;  // index into (open bits ++ new bits)
-                any[t] = true;
-                last_end[t] = end;
+                const size_t end = old[t] + em[i].bit_end;
                 if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
                 if (em[i].nbits > end) {
-                    marshal_err = 1;
-                    return;
+                    bad_frame = true;
+                    break;
                 }
                 nfc_frame f;
                 f.pos = a + (int64_t)em[i].rel_pos;
@@ -1360,19 +1388,10 @@ int Stream::finish_pending() {
                 f.type = t;
                 out_frames.push_back(f);
             }
-            for (int t = 0; t < 2; t++) {
-                if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
-                    const size_t used_new = last_end[t] - old[t];
-                    if (used_new > nnew[t]) {
-                        marshal_err = 1;
-                        return;
-                    }
-                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
-                    out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
-                    hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
-                } else {
-                    hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
-                }
+            if (helper.joinable()) helper.join();
+            if (bad_frame) {
+                marshal_err = 1;
+                return;
             }
         }
       }();
