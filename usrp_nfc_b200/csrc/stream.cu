@@ -218,7 +218,7 @@ struct Stream {
     int64_t bm_lo = 0, bm_hi = 0, bm_origin = 0;
     // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB, 1..8): segments twice as long halve
     // the share of the speculative starts; the slabs after the first take their transitions from the bitmap (extract_only)
-    int64_t super_slab = 2;
+    int64_t super_slab = 4;
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
@@ -826,7 +826,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             const int64_t n = b - a, res = std::max(1, resident_ctas);
             // one segment per resident CTA if that keeps them below s_max, else the fewest waves that do: the longer the
             // segments, the smaller the share of the speculative starts
-            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)512 * L, s_min);
+            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)1024 * L, s_min);
             const int64_t k = std::max<int64_t>(1, (n + res * s_max - 1) / (res * s_max));
             S = n / (res * k);
             if (S < s_min) S = s_min;
