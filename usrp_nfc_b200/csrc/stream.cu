@@ -219,6 +219,7 @@ struct Stream {
     // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB, 1..8): segments twice as long halve
     // the share of the speculative starts; the slabs after the first take their transitions from the bitmap (extract_only)
     int64_t super_slab = 4;
+    bool super_balance = true;  // NFC_SUPER_BALANCE=0: every launch but the last takes super_slab slabs
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
 
@@ -316,6 +317,7 @@ int Stream::init(const nfc_params *p) {
     if (totals_d.ensure(256)) return -1;
     resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok()) : 1;
     if (const char *e = getenv("NFC_SUPER_SLAB")) super_slab = std::max(1, std::min(8, atoi(e)));
+    if (const char *e = getenv("NFC_SUPER_BALANCE")) super_balance = atoi(e) != 0;
     return 0;
 }
 
@@ -459,7 +461,14 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
             in_begin = a;       // ... but nothing before the caller's pointer is read
             // device-resident input: the streaming slicer may run over several slabs at once (only positions relative to a
             // slab are limited to 30 bits, and the slicer writes none)
-            slicer_end = std::min(pos + (n - done), a + super_slab * slab);
+            // ... over equally many slabs per launch (ten slabs at four per launch go 4 + 3 + 3, not 4 + 4 + 2: the
+            // segments of a short last launch would be short too)
+            int64_t take = super_slab;
+            if (super_balance) {
+                const int64_t left = (n - done + slab - 1) / slab, launches = (left + super_slab - 1) / super_slab;
+                take = (left + launches - 1) / launches;
+            }
+            slicer_end = std::min(pos + (n - done), a + take * slab);
         } else {
             if (staging.ensure(padb + (size_t)m * ib + 64)) return -1;
             NFC_CUDA_CHECK(cudaMemcpyAsync(staging.as<char>() + padb, src, (size_t)m * ib, cudaMemcpyDeviceToDevice, cs));
