@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
-        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+        self.index, self.rows, self._stop_evt, self.proc, self.first = index, [], threading.Event(), None, threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -64,21 +64,33 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+                self.first.set()
                 if self._stop_evt.is_set():
                     break
         except Exception:
             pass
+        self.first.set()
 
-    def stop(self):
+    def wait_running(self, timeout=3.0):
+        """nvidia-smi needs ~0.1 s to start: the step is shorter than that, so the caller waits for the first row."""
+        self.first.wait(timeout)
+
+    def stop(self, t_load=None, t0=None, t1=None):
+        """Rows inside the timed region [t0, t1] if there are any, else the rows since the load began (t_load: the warm-up steps
+        in front of the timed region run the same work); `window` says which."""
         self._stop_evt.set()
         if self.proc:
             self.proc.terminate()
+        rows = list(self.rows)
+        timed = [r for t, r in rows if t0 is not None and t0 <= t <= t1]
+        load = [r for t, r in rows if t_load is not None and t_load <= t <= t1]
+        use, window = (timed, "timed region") if timed else ((load, "warm-up + timed region") if load else ([r for _, r in rows], "whole run"))
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in use:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -88,7 +100,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window, "samples_timed": len(timed)}
 
 
 def same_frames(ra, rb):
@@ -295,12 +307,14 @@ def main():
         torch.cuda.synchronize()
 
     frames = 0
-    for _ in range(args.warmup):
-        frames = step()
-    s.reset_stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_running()
+    t_load = time.perf_counter()
+    for _ in range(args.warmup):
+        frames = step()
+    s.reset_stats()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -311,7 +325,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     st = s.stats()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_load, t0, t0 + wall) if rank == 0 else None
     # device time of the step on the library's own stream (CUDA events inside the library bracket every slab)
     dev_ms = st["kernel_ms"] / args.steps
     wall_ms = wall * 1e3 / args.steps

@@ -36,7 +36,7 @@ def full():
             "lts__t_bytes.sum ", "sm__pipe_fp64_cycles_active.avg.pct", "smsp__thread_inst_executed.sum"]
     with open("profiles/%s_slicer_ncu.txt" % tag, "w") as f:
         f.write("# %s %s\n# ncu --set full --clock-control none --import-source on -k regex:slicer_fast -s 1 -c 1; "
-                "python bench.py --samples 2.1e9 --steps 1 --warmup 1 (the timed step: one launch of the streaming slicer over two slabs)\n" % (tag, note))
+                "python bench.py --samples 5.3e9 --steps 1 --warmup 1 (the timed step: one launch of the streaming slicer over five slabs)\n" % (tag, note))
         for h, v in zip(hdr, vals):
             if any(w in h for w in want) and "pcsamp" not in h:
                 f.write("%s = %s\n" % (h, v))

@@ -246,11 +246,13 @@ def test_large_synthetic_stream(rate, n_sessions):
     print("samples %d frames %d stats %s" % (x.size, len(want["frames"]), got["stream"].stats()))
 
 
-@pytest.mark.parametrize("n,seg_len,super_slab", [(48_000_000, 0, 1), (20_000_000, 1_200_000, 1), (20_000_000, 1_200_000, 2)])
-def test_bench_workload_matches_oracle(n, seg_len, super_slab, monkeypatch):
+@pytest.mark.parametrize("n,seg_len,super_slab,slab_len", [(48_000_000, 0, 1, 1 << 23), (20_000_000, 1_200_000, 1, 1 << 23),
+                                                            (20_000_000, 1_200_000, 2, 1 << 23), (20_000_000, 1_200_000, 4, 1 << 21)])
+def test_bench_workload_matches_oracle(n, seg_len, super_slab, slab_len, monkeypatch):
     """The bench.py traffic (dense frames, 5 % fade: many samples close to the HIGH threshold, repeated tiles, exact-path
     tiles, seam repairs) rendered on the device, decoded by the streaming kernel and by the oracle.  super_slab = 2: the
-    slicer runs over two slabs per launch, the second slab's transitions come from the bitmap it left."""
+    slicer runs over two slabs per launch, the second slab's transitions come from the bitmap it left; super_slab = 4 with
+    ten slabs: launches over 4 + 3 + 3 slabs."""
     import torch
     import bench
     monkeypatch.setenv("NFC_SUPER_SLAB", str(super_slab))
@@ -262,7 +264,7 @@ def test_bench_workload_matches_oracle(n, seg_len, super_slab, monkeypatch):
     torch.cuda.synchronize()
     s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_ALL, **p)
     if seg_len:
-        s.set_tuning(seg_len=seg_len, halo=4 * p["av_window"], slab_len=1 << 23)
+        s.set_tuning(seg_len=seg_len, halo=4 * p["av_window"], slab_len=slab_len)
     s.push_all(x)
     got = dict(events=s.drain_events(), symbols=s.drain_symbols())
     got["frames"], got["frame_bits"] = s.drain_frames()

@@ -218,7 +218,7 @@ struct Stream {
     int64_t bm_lo = 0, bm_hi = 0, bm_origin = 0;
     // slabs per launch of the streaming slicer on device-resident input (NFC_SUPER_SLAB, 1..8): segments twice as long halve
     // the share of the speculative starts; the slabs after the first take their transitions from the bitmap (extract_only)
-    int64_t super_slab = 4;
+    int64_t super_slab = 5;
     bool super_balance = true;  // NFC_SUPER_BALANCE=0: every launch but the last takes super_slab slabs
     bool streaming_ok() const { return parallel_ok() && slicer_streaming_ok(sp.L, vec_ok()); }
 };
