@@ -151,7 +151,8 @@ def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, 
     tuning = dict(seg_len=0, halo=0, slab_len=1 << 28)
 
     def step():
-        res = batch.decode_batch(caps, RATE, plist, device=local_rank, workers=args.batch_workers, tuning=tuning)
+        res = batch.decode_batch(caps, RATE, plist, device=local_rank, workers=args.batch_workers, tuning=tuning,
+                                 blocking_wait=not args.batch_spin)
         return sum(len(fr) for fr, _ in res)
 
     frames = 0
@@ -179,7 +180,8 @@ def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, 
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "batch of %d independent synthetic captures of %.3g samples at %.2f MS/s, hi_val 1.05..1.10 per capture, "
-                                       "round-robin over %d GPU(s), %d streams in flight per GPU" % (args.batch, ns, RATE / 1e6, world, args.batch_workers),
+                                       "round-robin over %d GPU(s), %d streams in flight per GPU (%s waits)" % (args.batch, ns, RATE / 1e6, world, args.batch_workers,
+                                                                                                              "spinning" if args.batch_spin else "blocking"),
                            "samp_rate": RATE, **params},
                 "frames_per_step": int(frames)}
         print(json.dumps(line))
@@ -207,6 +209,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="configs[3]: decode a batch of this many independent captures instead")
     ap.add_argument("--batch-samples", type=float, default=4e6, help="samples per capture of the batch")
     ap.add_argument("--batch-workers", type=int, default=8)
+    ap.add_argument("--batch-spin", action="store_true", help="batch: spinning waits (the library's default for a single stream)")
     ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
     ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()

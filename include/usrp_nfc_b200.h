@@ -157,6 +157,10 @@ int nfc_stream_set_state(nfc_stream *s, const nfc_state *st, const float *ring, 
  * tiles; 0 = automatic), slab_len = samples processed per kernel wave, force_serial = use the strictly
  * sequential kernel for everything (the on-device cross-check). */
 int nfc_stream_set_tuning(nfc_stream *s, int64_t seg_len, int64_t halo, int64_t slab_len, int force_serial);
+/* blocking != 0: host threads that wait for this stream's results sleep in the driver (blocking-sync events) instead of
+ * spinning.  For many streams driven by many host threads -- one per independent capture, each its own transition_sink
+ * (code/transition_sink.py:12-34) -- where spinning waiters would outnumber the cores; the default (0) has the lower latency. */
+int nfc_stream_set_wait_mode(nfc_stream *s, int blocking);
 
 /* Counters since creation: kernel time measured with CUDA events on the stream's CUDA stream. */
 typedef struct {

@@ -67,6 +67,7 @@ SIGNATURES = {
     "nfc_stream_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_tuning": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "nfc_stream_set_wait_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "nfc_stream_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "nfc_stream_reset_stats": (C.c_int, [C.c_void_p]),
     "nfc_stream_cuda_stream": (C.c_void_p, [C.c_void_p]),
@@ -272,6 +273,11 @@ class Stream(object):
 
     def set_tuning(self, seg_len=0, halo=0, slab_len=0, force_serial=False):
         lib().nfc_stream_set_tuning(self._h, int(seg_len), int(halo), int(slab_len), int(bool(force_serial)))
+
+    def set_wait_mode(self, blocking=True):
+        """Waiting host threads sleep instead of spinning (many streams on many threads: usrp_nfc_b200/batch.py)."""
+        if lib().nfc_stream_set_wait_mode(self._h, int(bool(blocking))) != 0:
+            raise NfcError(last_error())
 
     def stats(self):
         st = Stats()

@@ -13,7 +13,7 @@ import numpy as np
 from . import _cabi
 
 
-def _decode_one(x, samp_rate, params, device, tuning, outputs, kind, cache):
+def _decode_one(x, samp_rate, params, device, tuning, outputs, kind, cache, blocking=True):
     """One capture through one nfc_stream; a worker keeps one stream per window geometry and only changes its thresholds
     between captures (device buffers are not reallocated)."""
     key = tuple(sorted((k, v) for k, v in params.items() if k not in ("lo_val", "hi_val")))
@@ -22,6 +22,7 @@ def _decode_one(x, samp_rate, params, device, tuning, outputs, kind, cache):
         s = _cabi.Stream(samp_rate, device=device, outputs=outputs, input_kind=kind, **params)
         if tuning:
             s.set_tuning(**tuning)
+        s.set_wait_mode(blocking)
         cache[key] = s
     else:
         s.reset()
@@ -32,11 +33,13 @@ def _decode_one(x, samp_rate, params, device, tuning, outputs, kind, cache):
 
 
 def decode_batch(captures, samp_rate, params, device=0, workers=8, tuning=None, outputs=_cabi.OUT_FRAMES,
-                 kind=_cabi.IN_ENVELOPE_F32):
+                 kind=_cabi.IN_ENVELOPE_F32, blocking_wait=True):
     """Decode independent captures on one GPU.
 
     captures: sequence of sample arrays (numpy, or CUDA tensors on `device`); params: one dict of Stream keyword
     arguments per capture (hi_val, av_window, max_len, ...) or a single dict for all.
+    blocking_wait: the workers sleep while they wait for their stream (nfc_stream_set_wait_mode) instead of spinning --
+    with spinning waits, the workers and each stream's marshalling thread outnumber the host cores.
     Returns a list of (frame records, flat frame bits) in capture order.
     """
     n = len(captures)
@@ -62,7 +65,7 @@ def decode_batch(captures, samp_rate, params, device=0, workers=8, tuning=None, 
             if i >= n:
                 return
             try:
-                out[i] = _decode_one(captures[i], samp_rate, plist[i], device, tuning, outputs, kind, cache)
+                out[i] = _decode_one(captures[i], samp_rate, plist[i], device, tuning, outputs, kind, cache, blocking_wait)
             except Exception as exc:  # surfaced to the caller below
                 errors.append((i, exc))
                 return

@@ -169,6 +169,16 @@ struct Stream {
     long long slabs_enqueued = 0;               // slabs whose records were put on their way
     std::atomic<long long> slabs_marshalled{0};  // slabs whose records are in the output vectors
     std::thread marshal_thr;
+    // wait mode (nfc_stream_set_wait_mode): host threads sleep in the driver instead of spinning while they wait for this
+    // stream -- for many streams driven by many host threads (batches of captures), where spinning threads outnumber the cores
+    bool blocking_wait = false;
+    cudaEvent_t ev_blk = nullptr;
+    cudaError_t sync_cs() {
+        if (!blocking_wait) return cudaStreamSynchronize(cs);
+        const cudaError_t e = cudaEventRecord(ev_blk, cs);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_blk);
+    }
+    int set_wait_mode(bool blocking);
     std::atomic<int> marshal_err{0};
     // a slab whose records are on their way to the host: completed (carries taken over, marshalling started) right
     // before the next slab needs its carries, or when the caller looks at results
@@ -348,6 +358,7 @@ void Stream::destroy() {
     for (int i = 0; i < NPIN; i++)
         if (ev_d[i]) cudaEventDestroy(ev_d[i]);
     if (ev_carry) cudaEventDestroy(ev_carry);
+    if (ev_blk) cudaEventDestroy(ev_blk);
     if (cs) cudaStreamDestroy(cs);
 }
 
@@ -372,6 +383,23 @@ static float host_env(const void *items, int64_t i, int kind, float pcm_scale) {
             return r;
         }
     }
+}
+
+int Stream::set_wait_mode(bool blocking) {
+    if (settle()) return -1;
+    NFC_CUDA_CHECK(cudaSetDevice(prm.device));
+    const unsigned flags = cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0);
+    for (int i = 0; i < NPIN; i++) {
+        if (ev_d[i]) cudaEventDestroy(ev_d[i]);
+        ev_d[i] = nullptr;
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], flags));
+    }
+    if (ev_carry) cudaEventDestroy(ev_carry);
+    ev_carry = nullptr;
+    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_carry, flags));
+    if (blocking && !ev_blk) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming | cudaEventBlockingSync));
+    blocking_wait = blocking;
+    return 0;
 }
 
 int Stream::finish_warmup() {
@@ -437,7 +465,7 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
     int hbuf = 0;
     if (host_in && n > 0) {
         // the buffers may still be read by kernels of an earlier push: those are complete once the stream is idle
-        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        NFC_CUDA_CHECK(sync_cs());
         if (stage_host(0, std::min(slab, n), pos, hbuf)) return -1;
     }
     while (done < n) {
@@ -621,7 +649,7 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
         }
         NFC_CUDA_CHECK(cudaMemcpyAsync(counts.data(), seg_counts.p, sizeof(uint32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
-        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        NFC_CUDA_CHECK(sync_cs());
         int st_all = 0;
         bool over = false;
         for (int k = 0; k < nseg; k++) {
@@ -718,7 +746,7 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
                 if (compare(nw)) return -1;
                 std::vector<uint32_t> rc((size_t)nr * 2);
                 NFC_CUDA_CHECK(cudaMemcpyAsync(rc.data(), redo_counts.p, sizeof(uint32_t) * 2 * (size_t)nr, cudaMemcpyDeviceToHost, cs));
-                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+                NFC_CUDA_CHECK(sync_cs());
                 for (int q = 0; q < nw; q++) {
                     const int i = who[(size_t)q], k = ks[(size_t)i];
                     const uint32_t got = rc[(size_t)i];
@@ -761,7 +789,7 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
                     pidx[q] = 0;
                 }
                 if (compare((int)unk.size())) return -1;
-                NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+                NFC_CUDA_CHECK(sync_cs());
                 for (size_t q = 0; q < unk.size(); q++) bad[(size_t)unk[q]] = mism[q] ? 1 : 0;
             }
             nbad = 0;
@@ -805,7 +833,7 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
         stats.launches++;
         // the slab's final state becomes the stream's state
         NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
-        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));  // pieces may live in buffers released below
+        NFC_CUDA_CHECK(sync_cs());  // pieces may live in buffers released below
         for (DevBuf &kb : kept_bufs) kb.release();
         kept_bufs.clear();
         *R_out = (uint32_t)R;
@@ -953,7 +981,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         return 0;
     };
     if (count_transitions()) return -1;
-    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    NFC_CUDA_CHECK(sync_cs());
     kernel_time();
     int st_all = 0;
     for (int k = 0; k < nseg; k++) st_all |= status[(size_t)k];
@@ -1021,7 +1049,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             if (compare(nw)) return -1;
             std::vector<int32_t> rst((size_t)nr, 0);
             NFC_CUDA_CHECK(cudaMemcpyAsync(rst.data(), redo_counts.p, sizeof(int32_t) * (size_t)nr, cudaMemcpyDeviceToHost, cs));
-            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            NFC_CUDA_CHECK(sync_cs());
             kernel_time();
             for (int q = 0; q < nw; q++) {
                 const int i = who[(size_t)q], k = ks[(size_t)i];
@@ -1051,7 +1079,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
                 pidx[q] = 0;
             }
             if (compare((int)unk.size())) return -1;
-            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            NFC_CUDA_CHECK(sync_cs());
             for (size_t q = 0; q < unk.size(); q++) bad[(size_t)unk[q]] = mism[q] ? 1 : 0;
         }
         nbad = 0;
@@ -1087,7 +1115,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
     // ---- bitmap -> dense ordered transitions (the first sample is compared with the previous slab's last val)
     if (bitmap_changed) {  // segments were redone: count again
         if (count_transitions()) return -1;
-        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        NFC_CUDA_CHECK(sync_cs());
     }
     if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
     if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b_post, run_carry.last_bit, ex_offsets.as<uint32_t>(),
@@ -1113,7 +1141,7 @@ int Stream::extract_only(int64_t a, int64_t b, uint32_t *R_out) {
     stats.launches += 4;
     uint32_t R = 0;
     NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    NFC_CUDA_CHECK(sync_cs());
     if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
     if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
                              trans_dense.as<TransRec>(), R, cs))
@@ -1164,7 +1192,7 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
     stats.launches += 3;
     uint32_t M = 0;
     NFC_CUDA_CHECK(cudaMemcpyAsync(&M, totals_d.p, 4, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+    NFC_CUDA_CHECK(sync_cs());
     if (events_d.ensure(((size_t)M + 16) * sizeof(EventRec))) return -1;
     RunCarry *d_rc = carry_d.as<RunCarry>();
     if (launch_run_write(trans_dense.as<TransRec>(), R, 0, b - a, run_carry, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
@@ -1195,7 +1223,7 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
         int unres = 0;
         NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(&unres, d_unres, sizeof(int), cudaMemcpyDeviceToHost, cs));
-        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        NFC_CUDA_CHECK(sync_cs());
         if (unres) {
             // some chunk saw no decoder reset within the search limit: compose chunk transfer functions instead
             stats.linecode_scan_fallbacks++;
@@ -1208,7 +1236,7 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
                 return -1;
             stats.launches += 9;
             NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
-            NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+            NFC_CUDA_CHECK(sync_cs());
         }
         const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
         if ((want_sym && sym_d.ensure(((size_t)tot.nsym + 16) * sizeof(SymbolRec))) || bits0_d.ensure((size_t)tot.nbit0 + 16) ||
@@ -1524,7 +1552,7 @@ int nfc_stream_set_thresholds(nfc_stream *h, double lo_val, double hi_val) {
     s.sp.cls_ss0_x0 = nfc::classify_ratio_host(1.0, s.sp.lo, s.sp.hi);
     s.sp.cls_ss0_xn = nfc::classify_ratio_host(s.sp.hi + 0.1, s.sp.lo, s.sp.hi);
     NFC_CUDA_CHECK(cudaMemcpyAsync(s.params_d.p, &s.sp, sizeof(s.sp), cudaMemcpyHostToDevice, s.cs));
-    NFC_CUDA_CHECK(cudaStreamSynchronize(s.cs));
+    NFC_CUDA_CHECK(s.sync_cs());
     return 0;
 }
 
@@ -1730,6 +1758,11 @@ int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, 
         o += (size_t)st->pending[t];
     }
     return 0;
+}
+
+int nfc_stream_set_wait_mode(nfc_stream *h, int blocking) {
+    if (!h) return -1;
+    return h->s.set_wait_mode(blocking != 0);
 }
 
 int nfc_stream_set_tuning(nfc_stream *h, int64_t seg_len, int64_t halo, int64_t slab_len, int force_serial) {
