@@ -1,6 +1,7 @@
 #!/bin/bash
-# end-of-round artefacts: bench line + launch list + ncu --set full of the streaming slicer, then compute-sanitizer
-bash scripts/gpu_art.sh
-( timeout 500 compute-sanitizer --tool racecheck --racecheck-report analysis python scripts/t_sanitize.py 2>&1 | grep -E "^kind|RACECHECK SUMMARY|hazard" | head -20
-  timeout 500 compute-sanitizer --tool memcheck python scripts/t_sanitize.py 2>&1 | grep -E "^kind|ERROR SUMMARY|Invalid" | head -20 ) > gpurun_out/sanitizer.txt 2>&1
-cat gpurun_out/sanitizer.txt
+# end-of-round confirmation: GPU parity tests, smoke, the default bench line
+bash scripts/gpu_check.sh
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"; python -c "import json; b=json.load(open('gpurun_out/bench.json')); print(b['value'], b['ms_per_step'], b['clocks'], b['roofline']['frac'], b['selfcheck']['identical'], b['e2e']['value'])"
+timeout 300 python bench.py --batch 512 --steps 2 --warmup 1 > gpurun_out/bench_batch.json 2> gpurun_out/bench_batch.err
+echo "batch exit $?"; tail -c 400 gpurun_out/bench_batch.json

@@ -414,7 +414,8 @@ int Stream::finish_warmup() {
     h->lrun_start = NO_POS;
     h->last_val = 0;
     memcpy(state_ring(h), warm.data(), (size_t)sp.L * 4);
-    NFC_CUDA_CHECK(cudaMemcpy(state.p, blk.data(), blk.size(), cudaMemcpyHostToDevice));
+    NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, blk.data(), blk.size(), cudaMemcpyHostToDevice, cs));
+    NFC_CUDA_CHECK(sync_cs());  // blk is a local buffer
     run_carry.st = 0;
     run_carry.last_bit = 0;
     run_carry.dur = sp.L % sp.mx;
@@ -438,7 +439,9 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
             const void *src = items;
             if (mem == NFC_MEM_DEVICE) {
                 tmp.resize((size_t)can * ib);
-                NFC_CUDA_CHECK(cudaMemcpy(tmp.data(), items, (size_t)can * ib, cudaMemcpyDeviceToHost));
+                // on the stream's own CUDA stream: a copy on the default stream would queue behind other streams' work
+                NFC_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), items, (size_t)can * ib, cudaMemcpyDeviceToHost, cs));
+                NFC_CUDA_CHECK(sync_cs());
                 src = tmp.data();
             }
             for (int64_t i = 0; i < can; i++) warm.push_back(host_env(src, i, sp.input_kind, sp.pcm_scale));
