@@ -184,10 +184,30 @@ def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, 
                                                                                                               "spinning" if args.batch_spin else "blocking"),
                            "samp_rate": RATE, **params},
                 "frames_per_step": int(frames)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Everything libraries write to stdout while the bench runs (NCCL prints its version there) goes to stderr; the one JSON
+    line is written to the real stdout by emit()."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -213,6 +233,7 @@ def main():
     ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
     ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()
+    quiet_stdout()
     globals()["RATE"] = args.rate
 
     rank = int(os.environ.get("RANK", "0"))
@@ -260,7 +281,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ this repo's CUDA path
@@ -476,7 +497,7 @@ def main():
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
             "selfcheck": selfcheck, "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
