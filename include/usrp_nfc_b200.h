@@ -95,7 +95,8 @@ int nfc_stream_set_thresholds(nfc_stream *s, double lo_val, double hi_val);
  * Like the reference, the call that completes the warm-up consumes only the warm-up part and
  * reports *called_back = 0; afterwards every call consumes everything and reports 1 (the reference
  * invokes its callback exactly once per work_stable call, even with an empty list).  The samples are
- * copied (or fully processed) before the call returns.  mem = NFC_MEM_HOST or NFC_MEM_DEVICE. */
+ * copied (or fully processed) before the call returns.  mem = NFC_MEM_HOST or NFC_MEM_DEVICE.  Device items are read on
+ * the handle's own CUDA stream: the work that produces them must have completed when the call is made. */
 int64_t nfc_stream_push(nfc_stream *s, const void *items, int64_t n, int mem, int *called_back);
 
 /* Results accumulated since the last drain, in stream order.  Each call copies up to cap records

@@ -114,6 +114,10 @@ def _ptr_and_mem(items, itemsize_expected=None):
     """(address, count, mem kind, keepalive) of a numpy array or a torch tensor."""
     if hasattr(items, "data_ptr") and hasattr(items, "is_cuda"):  # torch tensor
         t = items.contiguous()
+        if t.is_cuda:
+            # the library reads device items on its own CUDA stream: whatever produced them on torch's stream must be done
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
         return t.data_ptr(), t.numel(), (MEM_DEVICE if t.is_cuda else MEM_HOST), t
     a = np.ascontiguousarray(items)
     return a.ctypes.data, a.size, MEM_HOST, a
