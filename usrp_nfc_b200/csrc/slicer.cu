@@ -22,6 +22,7 @@
 //    reference's warm-up) `halo` samples early; the state they reach at their first emitted
 //    sample is compared bit for bit with the predecessor's final state (seam_compare_kernel)
 //    and the segment is redone from the true state when it differs.
+#include <atomic>
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -1294,7 +1295,14 @@ static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *
         k<<<n_works, 512, smem, stream>>>(d_works, d_params);
     } else {
         auto k = slicer_fast_kernel<256, 4, 3, KIND>;
-        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the attribute is raised once per device and size, not on every launch (many streams launch this kernel concurrently)
+        static std::atomic<size_t> smem_set[64];
+        int dev = 0;
+        NFC_CUDA_CHECK(cudaGetDevice(&dev));
+        if (smem_set[dev & 63].load() < smem) {
+            NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[dev & 63].store(smem);
+        }
         k<<<n_works, 256, smem, stream>>>(d_works, d_params);
     }
     NFC_CUDA_CHECK(cudaGetLastError());
