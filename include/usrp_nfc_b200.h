@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 3
+#define NFC_ABI_VERSION 4
 
 /* what a pushed item is */
 enum {
@@ -184,6 +184,10 @@ typedef struct {
     int64_t exact_rounds;     /* fix-point rounds of the exact path (first-generation kernel) */
     double slicer_kernel_ms;  /* CUDA-event time of the streaming slicer kernel's launches alone */
     int64_t slicer_kernel_launches;
+    /* the pipelined mode of the streaming kernel (device-wide counters, like the tile counters above) */
+    int64_t pipe_tiles;       /* tiles proven while the workers ran ahead of the verdicts (subset of fast_tiles) */
+    int64_t pipe_runs;        /* runs of consecutive tiles entered in that mode */
+    int64_t pipe_aborts;      /* runs ended by a tile the pipelined mode could not prove (settled by the synchronous loop) */
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
 int nfc_stream_reset_stats(nfc_stream *s);
@@ -206,6 +210,9 @@ int nfc_synth_render(void *dev_out_f32, int64_t n, int64_t first_index, const in
 
 const char *nfc_last_error(void);
 int nfc_abi_version(void);
+/* sizeof of the structs above as this library was compiled, for bindings to check their own layouts against:
+ * which = 0 nfc_params, 1 nfc_event, 2 nfc_symbol, 3 nfc_frame, 4 nfc_frame_tail, 5 nfc_state, 6 nfc_stats; -1 otherwise */
+int nfc_abi_sizeof(int which);
 int nfc_device_count(void);
 
 #ifdef __cplusplus

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_cabi.LIB_PATH)
     for name in _declared():
         assert hasattr(raw, name), name
-    assert L.nfc_abi_version() == 3
+    assert L.nfc_abi_version() == 4
 
 
 def test_default_params_match_reference_constructors():
@@ -40,8 +40,21 @@ def test_default_params_match_reference_constructors():
 
 
 def test_struct_layouts():
-    assert ctypes.sizeof(_cabi.Params) == 64 or ctypes.sizeof(_cabi.Params) % 8 == 0
-    assert _cabi.EVENT_DTYPE.itemsize == 16 and _cabi.SYMBOL_DTYPE.itemsize == 16 and _cabi.FRAME_DTYPE.itemsize == 24
+    """Every struct of the binding has exactly the size the library was compiled with (nfc_abi_sizeof), and the field
+    offsets the header implies for the records that are read as numpy arrays."""
+    L = _cabi.lib()
+    sizes = {0: ctypes.sizeof(_cabi.Params), 1: _cabi.EVENT_DTYPE.itemsize, 2: _cabi.SYMBOL_DTYPE.itemsize,
+             3: _cabi.FRAME_DTYPE.itemsize, 4: _cabi.FRAME_TAIL_DTYPE.itemsize, 5: ctypes.sizeof(_cabi.State),
+             6: ctypes.sizeof(_cabi.Stats)}
+    for which, size in sizes.items():
+        assert L.nfc_abi_sizeof(which) == size, (which, L.nfc_abi_sizeof(which), size)
+    assert L.nfc_abi_sizeof(99) == -1
+    assert (sizes[0], sizes[1], sizes[2], sizes[3], sizes[4]) == (56, 16, 16, 24, 24)
+    assert [_cabi.EVENT_DTYPE.fields[k][1] for k in ("pos", "d", "v", "type")] == [0, 8, 12, 13]
+    assert [_cabi.SYMBOL_DTYPE.fields[k][1] for k in ("pos", "type", "val")] == [0, 8, 9]
+    assert [_cabi.FRAME_DTYPE.fields[k][1] for k in ("pos", "bit_off", "nbits", "type")] == [0, 8, 16, 20]
+    assert [_cabi.FRAME_TAIL_DTYPE.fields[k][1] for k in ("nbits", "nbytes", "byte_off", "fix_flag", "parity_ok", "crc_ok")] == [0, 4, 8, 16, 17, 18]
+    assert _cabi.Params.pcm_scale.offset == 52 and _cabi.State.lastL.offset == 64 and _cabi.Stats.slicer_kernel_ms.offset == 160
 
 
 def test_creation_fails_loudly_without_a_gpu():

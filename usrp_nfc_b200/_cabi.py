@@ -46,7 +46,8 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("fast_tiles", C.c_int64),
                 ("exact_tiles", C.c_int64), ("repeated_passes", C.c_int64), ("fixpoint_tiles", C.c_int64),
                 ("st2_tiles", C.c_int64), ("unproven_tiles", C.c_int64), ("ring_resums", C.c_int64),
-                ("exact_rounds", C.c_int64), ("slicer_kernel_ms", C.c_double), ("slicer_kernel_launches", C.c_int64)]
+                ("exact_rounds", C.c_int64), ("slicer_kernel_ms", C.c_double), ("slicer_kernel_launches", C.c_int64),
+                ("pipe_tiles", C.c_int64), ("pipe_runs", C.c_int64), ("pipe_aborts", C.c_int64)]
 
 
 # every symbol include/usrp_nfc_b200.h declares: (restype, argtypes)
@@ -79,6 +80,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_last_error": (C.c_char_p, []),
     "nfc_abi_version": (C.c_int, []),
+    "nfc_abi_sizeof": (C.c_int, [C.c_int]),
     "nfc_device_count": (C.c_int, []),
 }
 
@@ -110,9 +112,18 @@ def last_error():
     return (lib().nfc_last_error() or b"").decode()
 
 
-def _ptr_and_mem(items, itemsize_expected=None):
-    """(address, count, mem kind, keepalive) of a numpy array or a torch tensor."""
+def _torch_dtype_name(input_kind):
+    return {IN_ENVELOPE_F32: "float32", IN_REAL_F32: "float32", IN_IQ_F32: "complex64", IN_PCM_S16: "int16"}[input_kind]
+
+
+def _ptr_and_mem(items, input_kind=None):
+    """(address, item count, mem kind, keepalive) of a numpy array or a torch tensor.  A tensor must already hold items of the
+    stream's input kind (one element = one item): the kernels read t.numel() items of that size behind the pointer."""
     if hasattr(items, "data_ptr") and hasattr(items, "is_cuda"):  # torch tensor
+        if input_kind is not None:
+            want = _torch_dtype_name(input_kind)
+            if str(items.dtype).replace("torch.", "") != want:
+                raise TypeError("stream input kind %d takes %s items, got a tensor of %s" % (input_kind, want, items.dtype))
         t = items.contiguous()
         if t.is_cuda:
             # the library reads device items on its own CUDA stream: whatever produced them on torch's stream must be done
@@ -163,7 +174,7 @@ class Stream(object):
         """-> (consumed, called_back): transition_sink.work semantics (transition_sink.py:37-125)."""
         if not (hasattr(items, "data_ptr") and hasattr(items, "is_cuda")):
             items = np.ascontiguousarray(items, dtype=_KIND_DTYPES[self.input_kind])
-        addr, n, mem, keep = _ptr_and_mem(items)
+        addr, n, mem, keep = _ptr_and_mem(items, self.input_kind)
         cb = C.c_int(0)
         used = lib().nfc_stream_push(self._h, addr, n, mem, C.byref(cb))
         del keep
@@ -190,6 +201,8 @@ class Stream(object):
         out = np.zeros(n, dtype=dtype)
         if n:
             got = fn(self._h, out.ctypes.data, n)
+            if got < 0:
+                raise NfcError(last_error())
             out = out[:got]
         return out
 
@@ -204,10 +217,14 @@ class Stream(object):
         L = lib()
         n = L.nfc_stream_drain_frames(self._h, None, 0, None, 0)
         nb = L.nfc_stream_pending_frame_bits(self._h)
+        if n < 0 or nb < 0:
+            raise NfcError(last_error())
         fr = np.zeros(n, dtype=FRAME_DTYPE)
         bits = np.zeros(max(nb, 1), dtype=np.uint8)
         if n:
             got = L.nfc_stream_drain_frames(self._h, fr.ctypes.data, n, bits.ctypes.data, nb)
+            if got < 0:
+                raise NfcError(last_error())
             fr = fr[:got]
         return fr, [bits[f["bit_off"]: f["bit_off"] + f["nbits"]].copy() for f in fr]
 
@@ -217,6 +234,8 @@ class Stream(object):
         L = lib()
         n = L.nfc_stream_drain_frames(self._h, None, 0, None, 0)
         nb = L.nfc_stream_pending_frame_bits(self._h)
+        if n < 0 or nb < 0:
+            raise NfcError(last_error())
         if reuse:
             if getattr(self, "_fr_buf", None) is None or self._fr_buf.size < n:
                 self._fr_buf = np.zeros(int(n * 1.25) + 16, dtype=FRAME_DTYPE)
@@ -273,10 +292,12 @@ class Stream(object):
             raise NfcError(last_error())
 
     def reset(self):
-        lib().nfc_stream_reset(self._h)
+        if lib().nfc_stream_reset(self._h) != 0:
+            raise NfcError("nfc_stream_reset: " + last_error())
 
     def set_tuning(self, seg_len=0, halo=0, slab_len=0, force_serial=False):
-        lib().nfc_stream_set_tuning(self._h, int(seg_len), int(halo), int(slab_len), int(bool(force_serial)))
+        if lib().nfc_stream_set_tuning(self._h, int(seg_len), int(halo), int(slab_len), int(bool(force_serial))) != 0:
+            raise NfcError("nfc_stream_set_tuning: " + last_error())
 
     def set_wait_mode(self, blocking=True):
         """Waiting host threads sleep instead of spinning (many streams on many threads: usrp_nfc_b200/batch.py)."""
@@ -285,11 +306,13 @@ class Stream(object):
 
     def stats(self):
         st = Stats()
-        lib().nfc_stream_get_stats(self._h, C.byref(st))
+        if lib().nfc_stream_get_stats(self._h, C.byref(st)) != 0:
+            raise NfcError("nfc_stream_get_stats: " + last_error())
         return {k: getattr(st, k) for k, _ in Stats._fields_}
 
     def reset_stats(self):
-        lib().nfc_stream_reset_stats(self._h)
+        if lib().nfc_stream_reset_stats(self._h) != 0:
+            raise NfcError("nfc_stream_reset_stats: " + last_error())
 
     def cuda_stream(self):
         return lib().nfc_stream_cuda_stream(self._h)

@@ -23,6 +23,9 @@
 //    sample is compared bit for bit with the predecessor's final state (seam_compare_kernel)
 //    and the segment is redone from the true state when it differs.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -33,6 +36,29 @@ static const unsigned FULL = 0xffffffffu;
 // 5 repeated passes, 6 hysteresis risk, 7 fix-point pass gave up, 8 exact-path rounds, 9/10 first-generation kernel: refined / refine failed
 __device__ unsigned long long g_tile_stats[16];
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
+
+// Barrier over the first NT threads of the CTA (named barrier 1).  The streaming kernel's CTAs carry two more warps
+// (judge and mapper of the pipelined mode, slicer_pipe.cuh) that take no part in the segment's block-wide steps; for
+// kernels whose CTAs have exactly NT threads this is __syncthreads().
+template <int NT>
+__device__ __forceinline__ void cta_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+template <int NT>
+__device__ __forceinline__ int cta_sync_or(int pred) {
+    int r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, 1, %2, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"(pred), "n"(NT)
+        : "memory");
+    return r;
+}
 
 // ---------------------------------------------------------------- sample loading / envelope
 __device__ __forceinline__ float env_real(float s) { return __fmul_rn(s, s); }  // float_to_complex + mag^2, im = 0
@@ -189,7 +215,7 @@ __device__ __forceinline__ double block_excl_scan(double v, double &total, doubl
         if (lane >= o) inc += n;
     }
     if (lane == 31) wsum[buf][warp] = inc;
-    __syncthreads();
+    cta_sync<NT>();
     double wbase = 0.0, tot = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) {
@@ -211,7 +237,7 @@ __device__ __forceinline__ int block_excl_scan_int(int v, int &total, int (*wcnt
         if (lane >= o) inc += n;
     }
     if (lane == 31) wcnt[buf][warp] = inc;
-    __syncthreads();
+    cta_sync<NT>();
     int wbase = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) {
@@ -309,7 +335,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
         f = __reduce_or_sync(FULL, f);
         if (lane == 0 && f) atomicOr(&sh.flags[fb], f);
         if (lane == 31) sh.wlastcls[warp] = act[K - 1] ? cls[K - 1] : 2;  // 2 = "no sample"
-        __syncthreads();
+        cta_sync<NT>();
         unsigned flags = sh.flags[fb];
         c.round_no++;
 
@@ -354,7 +380,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
             int exL = __shfl_up_sync(FULL, incL, 1), exS = __shfl_up_sync(FULL, incS, 1);
             if (lane == 0) { exL = -1; exS = -1; }
             if (lane == 31) { sh.wmaxL[warp] = incL; sh.wmaxS[warp] = incS; }
-            __syncthreads();
+            cta_sync<NT>();
             for (int ww = 0; ww < warp; ww++) {
                 exL = max(exL, sh.wmaxL[ww]);
                 exS = max(exS, sh.wmaxS[ww]);
@@ -376,7 +402,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
             if (tid == 0) sh.flags[(c.round_no + 1u) % 3u] = 0u;
             f2 = __reduce_or_sync(FULL, f2);
             if (lane == 0 && f2) atomicOr(&sh.flags[fb2], f2);
-            __syncthreads();
+            cta_sync<NT>();
             flags |= sh.flags[fb2] & 1u;
             c.round_no++;
             had_slow = true;
@@ -388,7 +414,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
             for (int j = 0; j < K; j++) {
                 if (forced[j]) { f2 = 1u; forced[j] = false; }
             }
-            if (__syncthreads_or((int)f2)) flags |= 1u;
+            if (cta_sync_or<NT>((int)f2)) flags |= 1u;
             had_slow = false;
         }
         if (!(flags & 1u)) {  // converged: `total` belongs to the final classes
@@ -433,7 +459,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
         if (!has) wl = 3;
         if (lane == 0) sh.wlastcls[warp] = wl;  // reuse: last defined val of the warp (3 = none)
     }
-    __syncthreads();
+    cta_sync<NT>();
     if (pv == 3) {
         pv = last_val;
         for (int ww = warp - 1; ww >= 0; ww--) {
@@ -519,7 +545,7 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
         atomicMax(&sh.emax, emax);
     }
     if (tid == 0) *cs = c;
-    __syncthreads();  // carry, ring writes and shared scratch settle before the next tile reads them
+    cta_sync<NT>();  // carry, ring writes and shared scratch settle before the next tile reads them
 }
 
 // ---------------------------------------------------------------- the segment kernel
@@ -1250,74 +1276,107 @@ __global__ void seam_compare_kernel(const SlicerHdr *const *__restrict__ truth, 
 int slicer_rows(int L) { return L >= 8192 ? 4 : (L >= 4096 ? 2 : 1); }
 int slicer_tile(int L, bool vec_ok) { return (vec_ok && L >= 1024) ? 1024 * slicer_rows(L) : 256; }
 
+static int raise_dynamic_smem(const void *fn, size_t smem);
+
 template <int NT, int K, int R>
 static int launch_one(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
     auto k = slicer_kernel<NT, K, R>;
-    NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (raise_dynamic_smem((const void *)k, smem)) return -1;
     k<<<n_works, NT, smem, stream>>>(d_works, d_params);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-// the streaming kernel needs two tiles of 4096 samples to fit into the window; NFC_SLICER_OLD=1 keeps the first kernel
-bool slicer_streaming_ok(int L, bool vec_ok) {
-    static const bool old = getenv("NFC_SLICER_OLD") && getenv("NFC_SLICER_OLD")[0] == '1';
-    return vec_ok && L >= 8192 && !old;
+// ---- variants of the streaming kernel.  Default: the pipelined one (slicer_pipe.cuh), two CTAs of 8 + 2 warps per SM with
+// three stages of 4096 samples (NFC_SLICER_STAGES=2: two); windows too long for that (20 MS/s: 80 KB ring) take 16 + 2 warps,
+// one CTA per SM.  NFC_SLICER_PIPE=0: the synchronous loop only (three CTAs of 8 warps per SM, round 1's kernel).
+struct FastVariant {
+    const void *fn;
+    int threads;
+    size_t smem;  // dynamic: the ring, then the stages (or the one staging buffer of the synchronous loop)
+};
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && v[0]) ? atoi(v) : dflt;
 }
-
-// dynamic shared memory of the streaming kernel: the ring, then the staging buffer of one tile of input
-static size_t fast_smem(int L, int kind) {
-    const size_t ring = ((size_t)L * 4 + 15) / 16 * 16;
-    const size_t item = kind == IN_IQ_F32 ? 0 : (kind == IN_PCM_S16 ? 2 : 4);
-    return ring + 4096 * item;
+static size_t smem_optin_limit() {
+    int dev = 0, lim = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return (size_t)lim;
 }
-
-// NFC_SLICER_WIDE=1: 512 threads per segment, two chunks per warp (experiment: more warps per SM, fewer registers per thread)
-static bool fast_wide() {
-    static const bool w = getenv("NFC_SLICER_WIDE") && getenv("NFC_SLICER_WIDE")[0] == '1';
-    return w;
-}
-
-static bool fast_two() {  // experiment: two CTAs per SM with 128 registers per thread
-    static const bool w = getenv("NFC_SLICER_CTAS") && getenv("NFC_SLICER_CTAS")[0] == '2';
-    return w;
-}
+static const size_t FAST_STATIC_SMEM = 10 * 1024;  // upper bound of the kernels' static shared memory
 
 template <int KIND>
-static int launch_fast(const SegWork *d_works, int n_works, const SlicerParams *d_params, size_t smem, cudaStream_t stream) {
-    if (fast_two()) {
-        auto k = slicer_fast_kernel<256, 4, 2, KIND>;
-        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
-    } else if (fast_wide()) {
-        auto k = slicer_fast_kernel<512, 2, 2, KIND>;
-        NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<n_works, 512, smem, stream>>>(d_works, d_params);
-    } else {
-        auto k = slicer_fast_kernel<256, 4, 3, KIND>;
-        // the attribute is raised once per device and size, not on every launch (many streams launch this kernel concurrently)
-        static std::atomic<size_t> smem_set[64];
-        int dev = 0;
-        NFC_CUDA_CHECK(cudaGetDevice(&dev));
-        if (smem_set[dev & 63].load() < smem) {
-            NFC_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set[dev & 63].store(smem);
+static FastVariant fast_variant(int L) {
+    static const int pipe = env_int("NFC_SLICER_PIPE", 1), stages = env_int("NFC_SLICER_STAGES", 3);
+    const size_t ring = ((size_t)L * 4 + 15) / 16 * 16;
+    const size_t item = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
+    const size_t one = KIND == IN_IQ_F32 ? 0 : 4096 * item;  // staging buffer of the synchronous loop (IQ tiles are not staged)
+    const size_t stg = KIND == IN_PCM_S16 ? 4096 * 6 : 4096 * 4;  // a stage of the pipelined mode (PipeStage): samples, undo log
+    const size_t half = smem_optin_limit() / 2;               // two CTAs per SM
+    FastVariant v;
+    if (pipe && KIND != IN_IQ_F32) {
+        if (stages >= 3 && ring + 3 * stg + FAST_STATIC_SMEM <= half) {
+            v.fn = (const void *)slicer_fast_kernel<256, 4, 2, KIND, 3>;
+            v.threads = 320;
+            v.smem = ring + 3 * stg;
+        } else if (ring + 2 * stg + FAST_STATIC_SMEM <= half) {
+            v.fn = (const void *)slicer_fast_kernel<256, 4, 2, KIND, 2>;
+            v.threads = 320;
+            v.smem = ring + 2 * stg;
+        } else {
+            v.fn = (const void *)slicer_fast_kernel<512, 2, 1, KIND, 3>;
+            v.threads = 576;
+            v.smem = ring + 3 * stg;
         }
-        k<<<n_works, 256, smem, stream>>>(d_works, d_params);
+    } else {
+        v.fn = (const void *)slicer_fast_kernel<256, 4, 3, KIND, 0>;
+        v.threads = 256;
+        v.smem = ring + one;
     }
-    NFC_CUDA_CHECK(cudaGetLastError());
+    return v;
+}
+static FastVariant fast_variant_of(int L, int kind) {
+    switch (kind) {
+        case IN_ENVELOPE_F32: return fast_variant<IN_ENVELOPE_F32>(L);
+        case IN_REAL_F32: return fast_variant<IN_REAL_F32>(L);
+        case IN_IQ_F32: return fast_variant<IN_IQ_F32>(L);
+        default: return fast_variant<IN_PCM_S16>(L);
+    }
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel is only ever raised (streams with different windows share the
+// kernels, and setting the attribute before every launch serialises the launching threads)
+static int raise_dynamic_smem(const void *fn, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> have;
+    int dev = 0;
+    NFC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = have[std::make_pair(fn, dev)];
+    if (cur < smem) {
+        NFC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
     return 0;
+}
+
+// the streaming kernel needs two tiles of 4096 samples to fit into the window (and the window, a tile and the kernel's
+// own scratch into one CTA's shared memory); NFC_SLICER_OLD=1 keeps the first-generation kernel
+bool slicer_streaming_ok(int L, bool vec_ok) {
+    static const bool old = getenv("NFC_SLICER_OLD") && getenv("NFC_SLICER_OLD")[0] == '1';
+    if (!(vec_ok && L >= 8192 && !old)) return false;
+    return fast_variant_of(L, IN_IQ_F32).smem + 16384 + FAST_STATIC_SMEM <= smem_optin_limit();
 }
 
 int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t stream) {
     if (n_works <= 0) return 0;
-    const size_t smem = fast_smem(L, kind);
-    switch (kind) {
-        case IN_ENVELOPE_F32: return launch_fast<IN_ENVELOPE_F32>(d_works, n_works, d_params, smem, stream);
-        case IN_REAL_F32: return launch_fast<IN_REAL_F32>(d_works, n_works, d_params, smem, stream);
-        case IN_IQ_F32: return launch_fast<IN_IQ_F32>(d_works, n_works, d_params, smem, stream);
-        default: return launch_fast<IN_PCM_S16>(d_works, n_works, d_params, smem, stream);
-    }
+    const FastVariant v = fast_variant_of(L, kind);
+    if (raise_dynamic_smem(v.fn, v.smem)) return -1;
+    void *args[2] = {(void *)&d_works, (void *)&d_params};
+    NFC_CUDA_CHECK(cudaLaunchKernel(v.fn, dim3((unsigned)n_works), dim3((unsigned)v.threads), args, v.smem, stream));
+    return 0;
 }
 
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok,
@@ -1344,42 +1403,30 @@ int slicer_tile_stats(unsigned long long *out4, bool reset) {
 }
 
 // CTAs of the slicer kernel that fit on the device at once (for sizing the number of segments)
-int slicer_resident_ctas(int L, bool vec_ok) {
+int slicer_resident_ctas(int L, bool vec_ok, int kind) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = ((size_t)L * 4 + 15) / 16 * 16;
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+    const void *fn;
+    int threads = 256;
+    size_t dyn = smem;
     if (slicer_streaming_ok(L, vec_ok)) {
-        const size_t fsm = fast_smem(L, IN_ENVELOPE_F32);
-        if (fast_two()) {
-            per = 2;
-            e = cudaSuccess;
-        } else if (fast_wide()) {
-            cudaFuncSetAttribute(slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<512, 2, 2, IN_ENVELOPE_F32>, 512, fsm);
-        } else {
-            cudaFuncSetAttribute(slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_fast_kernel<256, 4, 3, IN_ENVELOPE_F32>, 256, fsm);
-        }
+        const FastVariant v = fast_variant_of(L, kind);
+        fn = v.fn;
+        threads = v.threads;
+        dyn = v.smem;
     } else if (vec_ok && L >= 1024) {
         switch (slicer_rows(L)) {
-            case 4:
-                cudaFuncSetAttribute(slicer_kernel<256, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 4>, 256, smem);
-                break;
-            case 2:
-                cudaFuncSetAttribute(slicer_kernel<256, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 2>, 256, smem);
-                break;
-            default:
-                cudaFuncSetAttribute(slicer_kernel<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 4, 1>, 256, smem);
+            case 4: fn = (const void *)slicer_kernel<256, 4, 4>; break;
+            case 2: fn = (const void *)slicer_kernel<256, 4, 2>; break;
+            default: fn = (const void *)slicer_kernel<256, 4, 1>;
         }
     } else {
-        cudaFuncSetAttribute(slicer_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, slicer_kernel<256, 1, 1>, 256, smem);
+        fn = (const void *)slicer_kernel<256, 1, 1>;
     }
+    if (raise_dynamic_smem(fn, dyn) == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, threads, dyn);
     if (e != cudaSuccess || per < 1) per = 1;
     return sms * per;
 }

@@ -33,7 +33,7 @@ struct __align__(16) FastRec {  // one chunk of 128 samples
                     // a lane's sum does not fit the fixed point); precise pass: mL = smallest slack of any lane, in ss units
 };
 enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3, FV_VERIFY = 4 };
-enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_N };
+enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_PIPE_T, FS_PIPE_IN, FS_PIPE_AB, FS_N };
 
 static const int FAST_CH = 128;  // samples per chunk
 
@@ -143,13 +143,17 @@ struct FastShared {
     double vtot[32];  // exact verification: sum of the admitted steps of each chunk
 };
 
+}  // namespace nfc
+#include "slicer_pipe.cuh"
+namespace nfc {
+
 __device__ __forceinline__ uint32_t uniform_stats(const FastUni &u, int k) { return u.stats[k] > 0xffffu ? 0xffffu : u.stats[k]; }
 
 // exact window sum = sum of the ring (any order: exact inside the audited exponent span)
 template <int NT>
 __device__ __noinline__ double ring_sum_exact(const float *ring, int L, double *red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();  // all ring writes of earlier tiles have landed
+    cta_sync<NT>();  // all ring writes of earlier tiles have landed
     double part = 0.0;
     for (int i = tid * 4; i < L; i += NT * 4) {
         const float4 v = *reinterpret_cast<const float4 *>(ring + i);
@@ -158,11 +162,11 @@ __device__ __noinline__ double ring_sum_exact(const float *ring, int L, double *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
     if (lane == 0) red[warp] = part;
-    __syncthreads();
+    cta_sync<NT>();
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < NT / 32; i++) s += red[i];
-    __syncthreads();  // red may be reused
+    cta_sync<NT>();  // red may be reused
     return s;
 }
 
@@ -270,10 +274,11 @@ __device__ __forceinline__ void fast_row(const float4 x4, const float4 pv4, floa
     }
 }
 
-// KIND: InputKind of the segment's samples (compile-time: the load path has no branches)
-template <int NT, int R, int MINB, int KIND>
-__global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__restrict__ works,
-                                                               const SlicerParams *__restrict__ params) {
+// KIND: InputKind of the segment's samples (compile-time: the load path has no branches).  PIPE: stages of the pipelined
+// mode (slicer_pipe.cuh; 0 = synchronous loop only); the CTA then has two more warps than the NT worker threads.
+template <int NT, int R, int MINB, int KIND, int PIPE>
+__global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel(const SegWork *__restrict__ works,
+                                                                                 const SlicerParams *__restrict__ params) {
     constexpr int NW = NT / 32;
     constexpr int NC = NW * R;            // chunks per tile
     constexpr int WS = R * FAST_CH;       // samples per warp per tile
@@ -296,14 +301,24 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     __shared__ SegWork w_s;
     __shared__ SlicerParams p_s;
     __shared__ SegCarry c_s;
+    constexpr bool PIPED = PIPE > 0 && KIND != IN_IQ_F32;
+    constexpr int NT_ALL = NT + (PIPE ? 64 : 0);
+    __shared__ PipeShared<NW, R, (PIPE > 0 ? PIPE : 1)> ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (PIPE > 0 && warp >= NW) {
+        // judge and mapper of the pipelined mode: parked until the workers enter it (everything they read is set up by then)
+        if (PIPED) pipe_aux_main<NW, R, (PIPE > 0 ? PIPE : 1), (KIND == IN_PCM_S16 ? 2 : 4)>(ps, fs.uni, fs.plan, p_s, c_s, ring, warp, lane);
+        else pipe_aux_idle<NW>(ps);
+        return;
+    }
     const long long clk0 = clock64();
     if (threadIdx.x == 0) {
         w_s = works[blockIdx.x];
         p_s = params[w_s.param_idx];
     }
     if (threadIdx.x < FS_N) fs.uni.stats[threadIdx.x] = 0u;
-    __syncthreads();
+    if (threadIdx.x == 0) ps.inited = 0;
+    cta_sync<NT>();
     const SegWork &w = w_s;
     const SlicerParams &p = p_s;
     FastUni &uni = fs.uni;
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 exp_track(v, emin, emax);
             }
             ss0 = w.state_in->ss;
-            __syncthreads();
+            cta_sync<NT>();
         } else {
             // Speculative start.  Any state will do (the seam check decides whether the segment stands); the closer to the
             // true one, the sooner it converges.  The true ring holds admitted samples only, so: the previous L samples,
@@ -338,9 +353,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     a += __shfl_xor_sync(FULL, a, o);
                     b += __shfl_xor_sync(FULL, b, o);
                 }
-                __syncthreads();
+                cta_sync<NT>();
                 if (lane == 0) { sh.red[warp] = a; fs.red[warp] = b; }
-                __syncthreads();
+                cta_sync<NT>();
                 ra = 0.0; rb = 0.0;
                 for (int i = 0; i < NW; i++) { ra += sh.red[i]; rb += fs.red[i]; }
             };
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         }
         if (warp == 0) fast_prepare<NC>(uni, ss0, ss0, 0.0f, -1.0f, p.loL, p.hiL, lane);
     }
-    __syncthreads();
+    cta_sync<NT>();
 
     auto next_snap = [&](int after) -> int {
         int best = INT_MAX;
@@ -503,13 +518,13 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         const double lo = uni.ss_lo, hi = uni.ss_hi;
         double s = lo;
         if (lo != hi) s = ring_sum_exact<NT>(ring, L, fs.red);
-        else __syncthreads();
+        else cta_sync<NT>();
         if (threadIdx.x == 0) {
             if (lo != hi) uni.stats[FS_RESUM]++;
             uni.ss_lo = uni.ss_hi = s;
             c_s.ss0 = s;
         }
-        __syncthreads();
+        cta_sync<NT>();
     };
     auto snapshot = [&](SlicerHdr *dsth, int64_t pos) {
         make_exact();
@@ -617,7 +632,14 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
     // The tile loop is split in two so that nothing but `t` lives across the rare paths (their calls and double
     // arithmetic would otherwise push the streamed loop's counters into local memory): an inner loop that only
     // streams, and a cold part around it that recomputes what it needs from `t`.
-    enum { WHY_NONE = 0, WHY_SNAP, WHY_EXACT, WHY_VERIFY };
+    enum { WHY_NONE = 0, WHY_SNAP, WHY_EXACT, WHY_VERIFY, WHY_PIPE };
+    // pipelined mode: the window must span three tiles (ordering of the ring writes, slicer_pipe.cuh), bulk copies need
+    // 16-byte aligned tiles; entered when a run of PIPE_MIN tiles can be streamed and the last PIPE_COOL tiles of the
+    // synchronous loop were proven at the first attempt (bursts of tiles that need the precise passes stay with it)
+    constexpr int PIPE_MIN = 6, PIPE_COOL = 3;
+    char *const stage0 = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16;
+    const bool pipe_can = PIPED && L >= 3 * T && ((reinterpret_cast<uintptr_t>(plan.xbase) & 15u) == 0u) && plan.bm_base != nullptr;
+    int cool = 0, pipe_K = 0;
     int t = 0;
     while (t < ntiles) {
         const int t_entry = t;
@@ -636,7 +658,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     __syncwarp();
                     fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
                 }
-                __syncthreads();
+                cta_sync<NT>();
             }
         }
         int why = WHY_NONE;
@@ -699,7 +721,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     request_tile(t + 1);
                     have_x = STAGED ? 1 : 0;
                 }
-                __syncthreads();
+                cta_sync<NT>();
 
                 if (warp == 0) {
                     // ---------------------------------------------------- phase 2a (warp 0): the sums, lane = chunk
@@ -797,7 +819,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 } else if (warp >= NW - 4) {
                     bitmap_out(t, NW - 4);
                 }
-                __syncthreads();
+                cta_sync<NT>();
                 verdict = uni.verdict;
                 if (uni.st2 && verdict != FV_SLOW) {
                     verdict = FV_SLOW;
@@ -813,9 +835,19 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     why = (snap && t != t_entry) ? WHY_SNAP : WHY_EXACT;
                     break;
                 }
+                if (pipe_can && cool == 0 && t_stop - t >= PIPE_MIN) {
+                    why = WHY_PIPE;
+                    pipe_K = t_stop - t;
+                    break;
+                }
                 const int x_ready = have_x;
                 have_x = 0;
                 int verdict = tile_pass(x_ready, 0, 0);
+                if (verdict == FV_ACCEPT) {
+                    if (cool > 0) cool--;
+                } else {
+                    cool = PIPE_COOL;
+                }
                 if (verdict != FV_ACCEPT) {
                     int n_meas = 0, n_coarse = 0;
                     for (;;) {
@@ -844,6 +876,34 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         }
         if (t >= ntiles) break;
         if (why == WHY_SNAP) continue;
+        if (PIPED && why == WHY_PIPE) {
+            // ------------------------------------------------------------------------ pipelined run over tiles [t, t + pipe_K)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // a tile requested by the synchronous loop is dropped
+            if (threadIdx.x == 0) {
+                ps.cmd = PIPE_CMD_ENTER;
+                ps.t0 = t;
+                ps.K = pipe_K;
+                uni.stats[FS_PIPE_IN]++;
+            }
+            fence_proxy_async();  // the stages were written through the generic proxy so far
+            named_bar_sync<PIPE_BAR_PARK, NT_ALL>();  // wakes judge and mapper
+            named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // barriers and first guesses are set up
+            const int done = pipe_worker<NW, R, (PIPE > 0 ? PIPE : 1), KIND>(ps, ring, stage0, plan, L, p.pcm_scale, warp, lane);
+            named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
+            t += done;
+            if (done < pipe_K) {
+                cool = PIPE_COOL;
+                if (threadIdx.x == 0) uni.stats[FS_PIPE_AB]++;
+            }
+            if (warp == 0) {  // the coming tile's constants for the synchronous loop
+                const double lo = uni.ss_lo, hi = uni.ss_hi;
+                const float tp = uni.tot_prev, ae = uni.a_est;
+                __syncwarp();
+                fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
+            }
+            cta_sync<NT>();
+            continue;
+        }
 
         // ---------------------------------------------------------------------------- tile t the hard way (rare)
         bool done = false;
@@ -889,7 +949,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                     s0 += FAST_CH;
                     if (s0 >= L) s0 -= L;
                 }
-                __syncthreads();
+                cta_sync<NT>();
                 const double ct = fs.vtot[lane];
                 double cinc = ct;
 #pragma unroll
@@ -917,7 +977,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 }
                 const bool changed = ncls != cls;
                 cls = ncls;
-                settled = !__syncthreads_or((int)changed);  // also: vtot may be written again
+                settled = !cta_sync_or<NT>((int)changed);  // also: vtot may be written again
             }
             if (settled) {
                 // ---- the tile's outputs from the settled classes
@@ -949,7 +1009,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 emin = __reduce_min_sync(FULL, emin);
                 emax = __reduce_max_sync(FULL, emax);
                 if (lane == 0) { atomicMin(&sh.emin, emin); atomicMax(&sh.emax, emax); }
-                __syncthreads();
+                cta_sync<NT>();
                 if (warp == 0) {
                     const float ae = uni.a_est;
                     __syncwarp();
@@ -957,7 +1017,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 } else if (warp == 1) {
                     maps_phase(t);
                 }
-                __syncthreads();
+                cta_sync<NT>();
                 if (uni.st2) {  // a HIGH sample the hysteresis may hold back: val is not the class
                     if (threadIdx.x == 0) uni.stats[FS_ST2]++;
                 } else {
@@ -979,7 +1039,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
             const double ss_before = c_s.ss0;
             const int64_t P0 = tile0_pos + (int64_t)t * T;
             const int slot_x = (int)((P0 + (int64_t)threadIdx.x * 4) % L);  // exact_tile's slot of this thread's first sample of a row
-            __syncthreads();
+            cta_sync<NT>();
 #pragma unroll 1
             for (int r = 0; r < XR; r++) {
                 const int64_t Pr = P0 + (int64_t)r * SUB;
@@ -995,12 +1055,16 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
                 if (lane == 0) uni.stats[FS_SLOW]++;
                 fast_prepare<NC>(uni, ss1, ss1, (float)(ss1 - ss_before), ae, p.loL, p.hiL, lane);
             }
-            __syncthreads();
+            cta_sync<NT>();
         }
         t++;
     }
 
     // ---- exit: exactness audit and final state
+    if (PIPE > 0) {
+        if (threadIdx.x == 0) ps.cmd = PIPE_CMD_QUIT;
+        named_bar_sync<PIPE_BAR_PARK, NT_ALL>();
+    }
     make_exact();
     if (threadIdx.x == 0 && uni.stats[FS_FAST]) {
         int emin = 1 << 30, emax = 0;
@@ -1009,7 +1073,7 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         atomicMin(&sh.emin, emin);
         atomicMax(&sh.emax, emax);
     }
-    __syncthreads();
+    cta_sync<NT>();
     const int emin = sh.emin, emax = sh.emax;
     int status = SEG_OK;
     if (emax >= 255) status |= SEG_NOT_SANE;
@@ -1039,6 +1103,9 @@ __global__ void __launch_bounds__(NT, MINB) slicer_fast_kernel(const SegWork *__
         atomicAdd(&g_tile_stats[6], (unsigned long long)uni.stats[FS_ST2]);
         atomicAdd(&g_tile_stats[7], (unsigned long long)uni.stats[FS_VER]);
         atomicAdd(&g_tile_stats[8], (unsigned long long)c_s.round_no);
+        atomicAdd(&g_tile_stats[11], (unsigned long long)uni.stats[FS_PIPE_T]);
+        atomicAdd(&g_tile_stats[12], (unsigned long long)uni.stats[FS_PIPE_IN]);
+        atomicAdd(&g_tile_stats[13], (unsigned long long)uni.stats[FS_PIPE_AB]);
     }
 }
 

@@ -60,7 +60,7 @@ int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables 
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
                           uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t);
 int slicer_tile(int L, bool vec_ok);
-int slicer_resident_ctas(int L, bool vec_ok);
+int slicer_resident_ctas(int L, bool vec_ok, int kind);
 int slicer_tile_stats(unsigned long long *out4, bool reset);
 int synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens, int64_t n_runs,
                  float carrier, float pause, float tag_high, float noise, float fade, double fade_period, uint64_t seed,
@@ -325,7 +325,7 @@ int Stream::init(const nfc_params *p) {
     if (state.ensure(state_block_bytes(sp.L))) return -1;
     if (carry_d.ensure(256)) return -1;
     if (totals_d.ensure(256)) return -1;
-    resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok()) : 1;
+    resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok(), sp.input_kind) : 1;
     if (const char *e = getenv("NFC_SUPER_SLAB")) super_slab = std::max(1, std::min(8, atoi(e)));
     if (const char *e = getenv("NFC_SUPER_BALANCE")) super_balance = atoi(e) != 0;
     return 0;
@@ -1791,6 +1791,9 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
         h->s.stats.unproven_tiles = (int64_t)(ts[2] + ts[7]);
         h->s.stats.ring_resums = (int64_t)ts[4];
         h->s.stats.exact_rounds = (int64_t)ts[8];
+        h->s.stats.pipe_tiles = (int64_t)ts[11];
+        h->s.stats.pipe_runs = (int64_t)ts[12];
+        h->s.stats.pipe_aborts = (int64_t)ts[13];
     }
     *st = h->s.stats;
     return 0;
@@ -1835,6 +1838,19 @@ int nfc_synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t
 
 const char *nfc_last_error(void) { return nfc::g_err; }
 int nfc_abi_version(void) { return NFC_ABI_VERSION; }
+
+int nfc_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(nfc_params);
+        case 1: return (int)sizeof(nfc_event);
+        case 2: return (int)sizeof(nfc_symbol);
+        case 3: return (int)sizeof(nfc_frame);
+        case 4: return (int)sizeof(nfc_frame_tail);
+        case 5: return (int)sizeof(nfc_state);
+        case 6: return (int)sizeof(nfc_stats);
+        default: return -1;
+    }
+}
 int nfc_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
