@@ -251,7 +251,7 @@ __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, c
         unpack2(a.s2, sa, sb);
         const float ssum = sa + sb;
         float m = a.m;
-        if (!(fabsf(ssum) * invq < 33554432.0f)) m = __int_as_float(0x7fc00000);  // the lane's sum does not fit 2^25 steps (or is NaN)
+        if (!(fabsf(ssum) * invq < 4194304.0f)) m = __int_as_float(0x7fc00000);  // the lane's sum does not fit 2^22 steps (or is NaN)
         const int si = __float2int_rn(ssum * invq);
         const int Ssum = __reduce_add_sync(FULL, si);
         const unsigned amax_u = __reduce_max_sync(FULL, __float_as_uint(a.amax));  // amax >= 0: ordered like its bit pattern
@@ -299,16 +299,25 @@ __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, c
 }
 
 // ---------------------------------------------------------------- judge
-// fixed-point step for sums whose lanes stay below a_est / 32: a power of two near a_est * 2^-30 (as fast_prepare)
+// fixed-point step: a power of two near a_est * 2^-27.  A lane's sum must stay below 2^22 steps (a_est / 32, a_est being an
+// upper bound of the tile's sum of |x - prev| of late: 128 times the lane's share), so that the sums of a tile's chunks fit int32.
 __device__ __forceinline__ bool pipe_step(float a_est, float &q, float &invq) {
     const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;
     const bool ok = ae > 45u && ae < 250u;
-    const unsigned qe = ok ? ae - 30u : 127u;
+    const unsigned qe = ok ? ae - 27u : 127u;
     q = __uint_as_float(qe << 23);
     invq = __uint_as_float((254u - qe) << 23);
     return ok;
 }
 
+// The judge is one warp with a serial job per tile: its instruction count and dependency chains bound how fast the
+// workers may go.  Everything on the way to the verdict is float / int32 (the double-precision window sum is only touched
+// after the verdict is out), per-parity values live in registers and are picked with selects.
+//
+//  * window sum at the tile's first sample: |true - ssm| <= hw (ssm double, hw float rounded up);
+//  * guesses of tile j were made when the judge knew ssm at the start of tile j-1 (ssmG): guessed window sum of chunk c
+//    gss = ssmG + goff[c]; at tile j's start ssm - ssmG = the drift of tile j-1 (dprev; 0 for the run's first tile), so
+//    (window sum at chunk c's first sample) - gss = dprev - goff[c] + c0[c], c0 = exclusive prefix of the chunk sums.
 template <int NW, int R, int S, int ITEM>
 __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, const FastPlan &plan, const double loL, const double hiL,
                                         char *stage0, const int lane) {
@@ -341,33 +350,38 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         }
     }
     // ---- state handed over by the synchronous loop
-    double ss_lo = uni.ss_lo, ss_hi = uni.ss_hi;
+    const double ss_lo0 = uni.ss_lo, ss_hi0 = uni.ss_hi;
+    double ssm = 0.5 * (ss_lo0 + ss_hi0);
+    float hw = (__double2float_ru(__dsub_ru(ss_hi0, ssm)) + __double2float_ru(__dsub_ru(ssm, ss_lo0))) * 1.0001f;
     float drift = uni.tot_prev, a_est = uni.a_est;
-    const float hiLf = plan.hiLf * (1.0f + 0x1p-20f);
-    float thr_min = 3.0e38f, thr_max = 0.0f;
+    if (!(a_est > 0.0f)) a_est = __double2float_rd(ss_lo0) * 0x1p-7f;
+    const float loLf = plan.loLf, hiLf = plan.hiLf, hiLs = plan.hiLf * (1.0f + 0x1p-20f);
     const bool act = lane < NW;
-    double gss[2];
-    float gTL[2], gTH[2], qv[2];
-    // guesses of one tile: the window sum at the middle of chunk c is taken to be ssm + drift * (ofs + (c + 1/2) / NW)
-    auto prepare = [&](int b, double ssm, float dr, float ofs, float a_e) -> bool {
+    const float fc = ((float)lane + 0.5f) * (1.0f / NW);  // the chunk's middle, in tiles
+    float thr_min = 3.0e38f, thr_max = 0.0f;
+    // per parity of the tile: guess offsets, guessed thresholds (LOW; HIGH * 2^-19), fixed-point step, guesses usable
+    float goff0 = 0.0f, goff1 = 0.0f, gTL0 = 0.0f, gTL1 = 0.0f, gTHs0 = 0.0f, gTHs1 = 0.0f, q0 = 1.0f, q1 = 1.0f;
+    bool ok0 = false, ok1 = false;
+    // guesses of one tile from the window sum `sm` known now: chunk c is taken to see sm + dr * (ofs + fc)
+    auto prepare = [&](int b, double sm, float dr, float ofs, float a_e, bool sane) {
         float q, invq;
-        const bool ok = pipe_step(a_e, q, invq);
-        const double g = ssm + (double)(dr * (ofs + ((float)lane + 0.5f) * (1.0f / NW)));
-        const float TL = __double2float_rn(g * loL), TH = __double2float_rn(g * hiL);
+        const bool stepok = pipe_step(a_e, q, invq);
+        const float TLm = __double2float_rn(sm * loL), THm = __double2float_rn(sm * hiL);
+        const float go = dr * (ofs + fc);
+        const float TL = fmaf(go, loLf, TLm), TH = fmaf(go, hiLf, THm);
         const float cg = 0.5f * (TL + TH), rg = 0.5f * (TH - TL);
-        gss[b] = g;
-        gTL[b] = TL;
-        gTH[b] = TH;
-        qv[b] = q;
         if (act) ps.G[b][lane] = make_float4(-cg, rg, invq, 0.0f);
-        return ok && TL > 0.0f;
+        const bool ok = __all_sync(FULL, !act || (TL > 0.0f && rg > 0.0f)) && stepok && sane;
+        if (b) { goff1 = go; gTL1 = TL; gTHs1 = TH * 0x1p-19f; q1 = q; ok1 = ok; }
+        else { goff0 = go; gTL0 = TL; gTHs0 = TH * 0x1p-19f; q0 = q; ok0 = ok; }
     };
-    if (!(a_est > 0.0f)) a_est = __double2float_rd(ss_lo) * 0x1p-7f;
-    double ssm = 0.5 * (ss_lo + ss_hi);
-    float hwf = __double2float_ru(__dsub_ru(ss_hi, ssm)) + __double2float_ru(__dsub_ru(ssm, ss_lo));
-    bool okv[2];  // the guesses of the tile with this parity could be made
-    okv[0] = __all_sync(FULL, prepare(0, ssm, drift, 0.0f, a_est) || !act);
-    okv[1] = __all_sync(FULL, prepare(1, ssm, drift, 1.0f, a_est) || !act);
+    {
+        const float ssf = __double2float_rd(ssm);
+        const bool sane = ssf - hw > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
+        prepare(0, ssm, drift, 0.0f, a_est, sane);
+        prepare(1, ssm, drift, 1.0f, a_est, sane);
+    }
+    float dprev = 0.0f;  // drift of the tile before the one being judged, since its guesses' window sum was known
     if (lane == 0) {
         ps.vfail[0] = ps.vfail[1] = 0;
         ps.vst2[0] = ps.vst2[1] = 0;
@@ -379,72 +393,63 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
     for (; k < K; k++) {
         const int b = k & 1;
         const unsigned par = (unsigned)(k >> 1) & 1u;
+        const float q = b ? q1 : q0, goff = b ? goff1 : goff0, gTL = b ? gTL1 : gTL0, gTHs = b ? gTHs1 : gTHs0;
+        const bool okb = b ? ok1 : ok0;
         mbar_wait(&ps.rec_full[b], par);
+        // ---------------------------------------------------------------- on the way to the verdict
         const PipeRec rc = ps.recs[b][act ? lane : 0];
-        const float q = qv[b];
-        // an upper bound of the chunk's sum of |x - prev|, and its sum of x - prev (exact multiple of q)
-        const float Ahat = act ? rc.amax * ((float)C::CHS * 1.0001f) : 0.0f;
-        const double Sd = act ? (double)rc.S * (double)q : 0.0;
-        double inc = Sd;
+        const int Si = act ? rc.S : 0;
+        const float amax = act ? rc.amax : 0.0f;
+        int inc = Si;
 #pragma unroll
         for (int o = 1; o < NW; o <<= 1) {
-            const double v = __shfl_up_sync(FULL, inc, o);
+            const int v = __shfl_up_sync(FULL, inc, o);
             if (lane >= o) inc += v;
         }
-        const double c0d = inc - Sd;                          // window sum at the chunk's first sample less the tile's
-        const double tot = __shfl_sync(FULL, inc, NW - 1);    // the tile's drift: exact (sums of a few multiples of q below 2^34 q)
-        float totA = Ahat;
-#pragma unroll
-        for (int o = NW / 2; o > 0; o >>= 1) totA += __shfl_xor_sync(FULL, totA, o);
-        totA = __shfl_sync(FULL, totA, 0) * 1.0001f;
+        const int c0i = inc - Si;                            // chunk sums below 2^27 steps each (lane sums below 2^22): no overflow
+        const int toti = __shfl_sync(FULL, inc, NW - 1);
+        const float c0f = (float)c0i * q, Sf = (float)Si * q;
+        // upper bounds of the sums of |x - prev|: of the chunk, of the tile
+        const float Ahat = amax * ((float)C::CHS * 1.0001f);
+        const float totA = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(amax))) * ((float)C::T * 1.0002f);
         // error of the measured sums: conversion (half a step per lane and chunk), float rounding (2^-19 of |x - prev|)
-        const float Ef = ((float)(16 * NW) * q + totA * 0x1p-19f) * 1.01f;
-        const float slack = (hwf + Ef) * 1.001f;
+        const float Ef = fmaf(totA, 0x1p-19f, (float)(16 * NW) * q) * 1.01f;
+        const float slack = (hw + Ef + (fabsf(dprev) + fabsf(goff) + fabsf(c0f)) * 0x1p-21f) * 1.001f;
         // inside the chunk the window sum moves within [V, U] of its start: the sums of the negative / positive steps
-        const float Sf = __double2float_rn(Sd);
-        const float U = 0.5f * (Ahat + Sf) * (1.0f + 0x1p-20f), V = -0.5f * (Ahat - Sf) * (1.0f + 0x1p-20f);
-        const double offd = (ssm + c0d) - gss[b];
-        const double hi_d = offd + (double)(fmaxf(U, 0.0f) + slack), lo_d = offd + (double)(fminf(V, 0.0f) - slack);
-        const float dev = __double2float_ru(fmax(fabs(hi_d), fabs(lo_d)));  // |window sum - guessed window sum| at any sample
+        const float U = fmaxf(0.5f * (Ahat + Sf), 0.0f) * (1.0f + 0x1p-20f), V = fminf(-0.5f * (Ahat - Sf), 0.0f) * (1.0f + 0x1p-20f);
+        const float off = (dprev - goff) + c0f;
+        const float dev = fmaxf(fabsf(off + (U + slack)), fabsf(off + (V - slack))) * (1.0f + 0x1p-20f);  // |window sum - guessed| at any sample
         // the guess is proven when no sample lies between it and any value the true threshold can take
-        const float need = fmaf(dev, hiLf, gTH[b] * 0x1p-19f);
-        const bool fine = !act || ((rc.m > need) && (gTL[b] - need > 0.0f));
-        bool accept = __all_sync(FULL, fine) && okv[b];
-        double ss_lo2 = ss_lo, ss_hi2 = ss_hi, ssm2 = ssm;
-        float hwf2 = hwf, a_new = a_est;
-        if (accept) {
-            ss_lo2 = __dadd_rd(ss_lo, __dadd_rd(tot, -(double)Ef));
-            ss_hi2 = __dadd_ru(ss_hi, __dadd_ru(tot, (double)Ef));
-            ssm2 = 0.5 * (ss_lo2 + ss_hi2);
-            hwf2 = __double2float_ru(__dsub_ru(ss_hi2, ssm2)) + __double2float_ru(__dsub_ru(ssm2, ss_lo2));
-            const float ssf = __double2float_rd(ssm2);
-            a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL[b], 0) * 0x1p-16f);  // follows the traffic, decays slowly
-            accept = ss_lo2 > 0.0 && ssf < 1.0e30f && ssf > 1.0e-30f;
-            if (accept) {
-                // admitted samples lie strictly between the guessed thresholds: one binade of slack either way (exponent audit)
-                thr_min = fminf(thr_min, gTL[b] * 0.5f);
-                thr_max = fmaxf(thr_max, gTH[b] * 2.0f);
-                const float dr = __double2float_rn(tot);
-                // tile k + 2: one tile of the same drift in between; a tile whose guesses could not be made is refused when it arrives
-                okv[b] = __all_sync(FULL, prepare(b, ssm2, dr, 1.0f, a_new) || !act);
-                drift = dr;
-            }
-        }
-        __syncwarp();
+        const float need = fmaf(dev, hiLs, gTHs);
+        const bool fine = !act || ((rc.m > need) && (gTL - need > 0.0f));
+        const bool accept = __all_sync(FULL, fine) && okb;
         if (lane == 0) {
             ps.vfail[b] = accept ? 0 : 1;
             mbar_arrive(&ps.verdict[b]);
         }
+        // ---------------------------------------------------------------- the verdict is out
+        // the window sum after the tile and the guesses of tile k + 2 (published by the verdict on tile k + 1)
+        const double totd = (double)toti * (double)q;  // exact
+        const double ssm2 = ssm + totd;
+        const float ssf = __double2float_rd(ssm2);
+        const float hw2 = (hw + Ef + ssf * 0x1p-50f) * 1.0001f;
+        const float a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL, 0) * 0x1p-16f);  // follows the traffic, decays slowly
+        const float dr = (float)toti * q;
+        const bool sane = ssf - hw2 > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
         mbar_wait(&ps.verdict[b], par);  // the mapper's say
         {
             const volatile int *vs = ps.vst2;
             if (!accept || vs[b]) break;
         }
-        ss_lo = ss_lo2;
-        ss_hi = ss_hi2;
+        // admitted samples lie strictly between the guessed thresholds: one binade of slack either way (exponent audit)
+        thr_min = fminf(thr_min, gTL * 0.5f);
+        thr_max = fmaxf(thr_max, gTHs * 0x1p20f);
         ssm = ssm2;
-        hwf = hwf2;
+        hw = hw2;
         a_est = a_new;
+        drift = dr;
+        dprev = dr;
+        prepare(b, ssm2, dr, 1.0f, a_new, sane);  // tile k + 2: one tile of the same drift in between
         // tile k stands: its stage (the undo log by now) is free for tile k + S
         if (issued < K) {
             if (lane == 0) {
@@ -460,9 +465,9 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
     thr_min = redux_min(thr_min);
     thr_max = -redux_min(-thr_max);
     if (lane == 0) {
-        uni.ss_lo = ss_lo;
-        uni.ss_hi = ss_hi;
         if (k > 0) {
+            uni.ss_lo = __dadd_rd(ssm, -(double)hw);
+            uni.ss_hi = __dadd_ru(ssm, (double)hw);
             uni.tot_prev = drift;
             uni.a_est = a_est;
             uni.thr_min = fminf(uni.thr_min, thr_min);

@@ -866,7 +866,7 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             const int64_t n = b - a, res = std::max(1, resident_ctas);
             // one segment per resident CTA if that keeps them below s_max, else the fewest waves that do: the longer the
             // segments, the smaller the share of the speculative starts
-            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)1024 * L, s_min);
+            const int64_t s_min = 6 * H, s_max = std::max<int64_t>((int64_t)4096 * L, s_min);
             const int64_t k = std::max<int64_t>(1, (n + res * s_max - 1) / (res * s_max));
             S = n / (res * k);
             if (S < s_min) S = s_min;
