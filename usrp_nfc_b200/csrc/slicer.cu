@@ -35,6 +35,9 @@ static const unsigned FULL = 0xffffffffu;
 // tile counters (device-wide): 0 streamed, 1 exact path, 2 coarse-step retries exhausted, 3 exact fix-point pass, 4 ring resums,
 // 5 repeated passes, 6 hysteresis risk, 7 fix-point pass gave up, 8 exact-path rounds, 9/10 first-generation kernel: refined / refine failed
 __device__ unsigned long long g_tile_stats[16];
+// pipelined mode of the streaming kernel: shortest run worth entering (tiles), tiles the synchronous loop must prove at the
+// first attempt before the pipeline is entered again (NFC_PIPE_MIN / NFC_PIPE_COOL set them per process, for experiments)
+__device__ int g_pipe_tune[4] = {6, 2, 0, 0};
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
 
 // Barrier over the first NT threads of the CTA (named barrier 1).  The streaming kernel's CTAs carry two more warps
@@ -1370,8 +1373,26 @@ bool slicer_streaming_ok(int L, bool vec_ok) {
     return fast_variant_of(L, IN_IQ_F32).smem + 16384 + FAST_STATIC_SMEM <= smem_optin_limit();
 }
 
+static int apply_pipe_tuning() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    NFC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev & 63]) return 0;
+    done[dev & 63] = true;
+    if (getenv("NFC_PIPE_MIN") || getenv("NFC_PIPE_COOL")) {
+        int t[4] = {env_int("NFC_PIPE_MIN", 6), env_int("NFC_PIPE_COOL", 2), 0, 0};
+        if (t[0] < 3) t[0] = 3;
+        if (t[1] < 0) t[1] = 0;
+        NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_pipe_tune, t, sizeof(t)));
+    }
+    return 0;
+}
+
 int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t stream) {
     if (n_works <= 0) return 0;
+    if (apply_pipe_tuning()) return -1;
     const FastVariant v = fast_variant_of(L, kind);
     if (raise_dynamic_smem(v.fn, v.smem)) return -1;
     void *args[2] = {(void *)&d_works, (void *)&d_params};

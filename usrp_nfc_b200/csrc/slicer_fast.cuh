@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     // pipelined mode: the window must span three tiles (ordering of the ring writes, slicer_pipe.cuh), bulk copies need
     // 16-byte aligned tiles; entered when a run of PIPE_MIN tiles can be streamed and the last PIPE_COOL tiles of the
     // synchronous loop were proven at the first attempt (bursts of tiles that need the precise passes stay with it)
-    constexpr int PIPE_MIN = 6, PIPE_COOL = 3;
+    const int PIPE_MIN = g_pipe_tune[0], PIPE_COOL = g_pipe_tune[1];
     char *const stage0 = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16;
     const bool pipe_can = PIPED && L >= 3 * T && ((reinterpret_cast<uintptr_t>(plan.xbase) & 15u) == 0u) && plan.bm_base != nullptr;
     int cool = 0, pipe_K = 0;
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
             t += done;
             if (done < pipe_K) {
-                cool = PIPE_COOL;
+                cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
                 if (threadIdx.x == 0) uni.stats[FS_PIPE_AB]++;
             }
             if (warp == 0) {  // the coming tile's constants for the synchronous loop

@@ -315,9 +315,12 @@ __device__ __forceinline__ bool pipe_step(float a_est, float &q, float &invq) {
 // after the verdict is out), per-parity values live in registers and are picked with selects.
 //
 //  * window sum at the tile's first sample: |true - ssm| <= hw (ssm double, hw float rounded up);
-//  * guesses of tile j were made when the judge knew ssm at the start of tile j-1 (ssmG): guessed window sum of chunk c
-//    gss = ssmG + goff[c]; at tile j's start ssm - ssmG = the drift of tile j-1 (dprev; 0 for the run's first tile), so
-//    (window sum at chunk c's first sample) - gss = dprev - goff[c] + c0[c], c0 = exclusive prefix of the chunk sums.
+//  * the guesses of tile j+2 are published with the verdict on tile j (the workers start tile j+2 without waiting for
+//    anything after that verdict).  They are made from ssm at the start of tile j (known before tile j's records arrive,
+//    so its products with lo/L and hi/L are ready) and the drift of tile j (dr): the guessed window sum of chunk c is
+//    gss = ssm_j + goff[c], goff[c] = dr * (2 + (c + 1/2) / NW); at tile j+2's start ssm - ssm_j is the drift of tiles j and
+//    j+1 (d1 + d2), so (window sum at chunk c's first sample) - gss = (d1 + d2) - goff[c] + c0[c], c0 = exclusive prefix
+//    of the chunk sums.  The first two tiles of a run are guessed from the window sum at its start.
 template <int NW, int R, int S, int ITEM>
 __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, const FastPlan &plan, const double loL, const double hiL,
                                         char *stage0, const int lane) {
@@ -362,11 +365,11 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
     // per parity of the tile: guess offsets, guessed thresholds (LOW; HIGH * 2^-19), fixed-point step, guesses usable
     float goff0 = 0.0f, goff1 = 0.0f, gTL0 = 0.0f, gTL1 = 0.0f, gTHs0 = 0.0f, gTHs1 = 0.0f, q0 = 1.0f, q1 = 1.0f;
     bool ok0 = false, ok1 = false;
-    // guesses of one tile from the window sum `sm` known now: chunk c is taken to see sm + dr * (ofs + fc)
-    auto prepare = [&](int b, double sm, float dr, float ofs, float a_e, bool sane) {
+    // guesses of one tile from a window sum known now, whose products with lo/L and hi/L are TLm and THm: chunk c is taken
+    // to see that window sum + dr * (ofs + fc)
+    auto prepare = [&](int b, float TLm, float THm, float dr, float ofs, float a_e, bool sane) {
         float q, invq;
         const bool stepok = pipe_step(a_e, q, invq);
-        const float TLm = __double2float_rn(sm * loL), THm = __double2float_rn(sm * hiL);
         const float go = dr * (ofs + fc);
         const float TL = fmaf(go, loLf, TLm), TH = fmaf(go, hiLf, THm);
         const float cg = 0.5f * (TL + TH), rg = 0.5f * (TH - TL);
@@ -375,13 +378,15 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         if (b) { goff1 = go; gTL1 = TL; gTHs1 = TH * 0x1p-19f; q1 = q; ok1 = ok; }
         else { goff0 = go; gTL0 = TL; gTHs0 = TH * 0x1p-19f; q0 = q; ok0 = ok; }
     };
+    float TLm = __double2float_rn(ssm * loL), THm = __double2float_rn(ssm * hiL);  // of ssm at the start of the tile being judged
+    bool sane;  // the window sum at the start of the tile being judged is positive and in range
     {
         const float ssf = __double2float_rd(ssm);
-        const bool sane = ssf - hw > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
-        prepare(0, ssm, drift, 0.0f, a_est, sane);
-        prepare(1, ssm, drift, 1.0f, a_est, sane);
+        sane = ssf - hw > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
+        prepare(0, TLm, THm, drift, 0.0f, a_est, sane);
+        prepare(1, TLm, THm, drift, 1.0f, a_est, sane);
     }
-    float dprev = 0.0f;  // drift of the tile before the one being judged, since its guesses' window sum was known
+    float d1 = 0.0f, d2 = 0.0f;  // drifts of the two tiles before the one being judged (0 before the run's start)
     if (lane == 0) {
         ps.vfail[0] = ps.vfail[1] = 0;
         ps.vst2[0] = ps.vst2[1] = 0;
@@ -414,42 +419,50 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         const float totA = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(amax))) * ((float)C::T * 1.0002f);
         // error of the measured sums: conversion (half a step per lane and chunk), float rounding (2^-19 of |x - prev|)
         const float Ef = fmaf(totA, 0x1p-19f, (float)(16 * NW) * q) * 1.01f;
-        const float slack = (hw + Ef + (fabsf(dprev) + fabsf(goff) + fabsf(c0f)) * 0x1p-21f) * 1.001f;
+        const float dsince = k < 2 ? d1 : d1 + d2;  // ssm - (the window sum the guesses were made from)
+        const float slack = (hw + Ef + (fabsf(d1) + fabsf(d2) + fabsf(goff) + fabsf(c0f)) * 0x1p-21f) * 1.001f;
         // inside the chunk the window sum moves within [V, U] of its start: the sums of the negative / positive steps
         const float U = fmaxf(0.5f * (Ahat + Sf), 0.0f) * (1.0f + 0x1p-20f), V = fminf(-0.5f * (Ahat - Sf), 0.0f) * (1.0f + 0x1p-20f);
-        const float off = (dprev - goff) + c0f;
+        const float off = (dsince - goff) + c0f;
         const float dev = fmaxf(fabsf(off + (U + slack)), fabsf(off + (V - slack))) * (1.0f + 0x1p-20f);  // |window sum - guessed| at any sample
         // the guess is proven when no sample lies between it and any value the true threshold can take
         const float need = fmaf(dev, hiLs, gTHs);
         const bool fine = !act || ((rc.m > need) && (gTL - need > 0.0f));
         const bool accept = __all_sync(FULL, fine) && okb;
+        // the guesses of tile k + 2, from the window sum at this tile's start: this tile's drift, as much again for tile k + 1
+        const float dr = (float)toti * q;
+        const float a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL, 0) * 0x1p-16f);  // follows the traffic, decays slowly
+        const float gTL_k = gTL, gTHs_k = gTHs;
+        if (accept) prepare(b, TLm, THm, dr, 2.0f, a_new, sane);
+        __syncwarp();
         if (lane == 0) {
             ps.vfail[b] = accept ? 0 : 1;
             mbar_arrive(&ps.verdict[b]);
         }
         // ---------------------------------------------------------------- the verdict is out
-        // the window sum after the tile and the guesses of tile k + 2 (published by the verdict on tile k + 1)
+        // the window sum after the tile
         const double totd = (double)toti * (double)q;  // exact
         const double ssm2 = ssm + totd;
         const float ssf = __double2float_rd(ssm2);
-        const float hw2 = (hw + Ef + ssf * 0x1p-50f) * 1.0001f;
-        const float a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL, 0) * 0x1p-16f);  // follows the traffic, decays slowly
-        const float dr = (float)toti * q;
-        const bool sane = ssf - hw2 > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
+        const float hw2 = hw + (Ef + ssf * 0x1p-50f + hw * 0x1p-22f) * 1.001f;
+        const float TLm2 = __double2float_rn(ssm2 * loL), THm2 = __double2float_rn(ssm2 * hiL);
         mbar_wait(&ps.verdict[b], par);  // the mapper's say
         {
             const volatile int *vs = ps.vst2;
             if (!accept || vs[b]) break;
         }
         // admitted samples lie strictly between the guessed thresholds: one binade of slack either way (exponent audit)
-        thr_min = fminf(thr_min, gTL * 0.5f);
-        thr_max = fmaxf(thr_max, gTHs * 0x1p20f);
+        thr_min = fminf(thr_min, gTL_k * 0.5f);
+        thr_max = fmaxf(thr_max, gTHs_k * 0x1p20f);
         ssm = ssm2;
         hw = hw2;
+        TLm = TLm2;
+        THm = THm2;
+        sane = ssf - hw2 > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
         a_est = a_new;
         drift = dr;
-        dprev = dr;
-        prepare(b, ssm2, dr, 1.0f, a_new, sane);  // tile k + 2: one tile of the same drift in between
+        d2 = d1;
+        d1 = dr;
         // tile k stands: its stage (the undo log by now) is free for tile k + S
         if (issued < K) {
             if (lane == 0) {
