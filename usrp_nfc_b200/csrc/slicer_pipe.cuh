@@ -16,13 +16,18 @@
 //  * The mapper warp (lane = 128 samples) derives from the bitmap what the hysteresis needs: whether a HIGH sample
 //    follows a LOW sample closely enough for cur_state == 2 to matter (then val != class and the tile is not ours),
 //    and the carries (val of the last sample, last LOW sample, start of its run).
-//  * Any tile that cannot be proven ends the pipelined run at that tile: nothing of it (or of the tile the workers
-//    classified ahead) has been written to the ring, and the synchronous loop settles it (measured guesses, exact
-//    fix-point, exact path) before the pipeline is entered again.
+//  * The ring slots are rewritten while a tile is classified; what they held goes to the tile's stage in place of the
+//    samples (an undo log), so that a refused tile -- and the tile classified ahead of its verdict -- can be taken back.
+//  * A tile whose guess cannot be proven (a sample too close to a threshold for what is known about the window sum) is
+//    taken back and classified again inside the pipeline by the precise pass (every sample against its own guessed
+//    window sum: the chunk's measured start + the steps before the sample), which the judge checks the same way.
+//  * What the precise pass cannot prove either, and tiles where the hysteresis may matter, end the pipelined run at
+//    that tile: the ring is as before it, and the synchronous loop settles it (exact fix-point, exact path) before
+//    the pipeline is entered again.
 //
-// Ordering of the ring: the slots tile k writes are read next by tiles >= k + L/T - 1.  A worker writes tile k-1's slots
-// before it arrives on rec_full[k]; a worker starts tile k' after the verdict on k'-2, i.e. after every worker's
-// arrival on rec_full[k'-2], i.e. after every write of tiles <= k'-3.  Hence L >= 3T is required (checked by the caller).
+// Ordering of the ring: the slots tile k writes are read next by tiles >= k + L/T - 1 >= k + 2 (L >= 3T is required by
+// the caller).  A worker starts tile k' after the verdict on k'-2, i.e. after every worker's arrival on rec_full[k'-2],
+// i.e. after every ring write of tiles <= k'-2.
 #pragma once
 
 namespace nfc {
@@ -42,14 +47,21 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned b
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(b)), "r"(bytes)
                  : "memory");
 }
+// Waits for the phase of the given parity to complete.  A wait that does not end (a protocol error: each try_wait already
+// suspends the thread for a while) traps instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
         "PIPE_WAIT:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra PIPE_DONE;\n\t"
-        "bra PIPE_WAIT;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x400000;\n\t"
+        "@p bra PIPE_WAIT;\n\t"
+        "trap;\n\t"
         "PIPE_DONE:\n\t"
         "}" ::"r"(smem_u32(b)),
         "r"(parity)
@@ -91,13 +103,15 @@ __device__ __forceinline__ float max3_abs(float m, float a, float b) {
 
 // ---------------------------------------------------------------- shared state of the pipelined mode
 struct __align__(16) PipeRec {  // one warp's chunk (R * 128 samples) of one tile
-    int S;       // round(sum of admitted (x - prev) / q), summed over the lanes
-    float amax;  // max |x - prev| over the admitted samples
-    float m;     // min over the samples of the distance to the nearer guessed threshold (NaN: not usable)
+    int S;       // round(sum of admitted (x - prev) / q), summed over the lanes (and rows)
+    float amax;  // cheap pass: max |x - prev| over the admitted samples; precise pass: sum of |x - prev|, in steps, rounded up
+    float m;     // cheap pass: min over the samples of the distance to the nearer guessed threshold; precise pass: the smallest
+                 // slack of any lane, in window-sum units (NaN: not usable)
     int pad;
 };
 
 enum { PIPE_CMD_ENTER = 1, PIPE_CMD_QUIT = 2 };
+enum { PV_ACCEPT = 0, PV_ABORT = 1, PV_REDO = 2 };
 static const int PIPE_BAR_RUN = 2, PIPE_BAR_PARK = 3;  // named barriers over all threads of the CTA (workers + judge + mapper)
 template <int ID, int N>
 __device__ __forceinline__ void named_bar_sync() {
@@ -106,15 +120,20 @@ __device__ __forceinline__ void named_bar_sync() {
 
 template <int NW, int R, int S>
 struct __align__(16) PipeShared {
-    unsigned long long x_full[S];  // stage s holds the samples of tile k, k % S == s
-    unsigned long long rec_full[2];  // all workers have published tile k (k & 1), written tile k-1's ring slots, and are done reading tile k's stage
+    unsigned long long x_full[S];    // stage s holds the samples of tile k, k % S == s
+    unsigned long long rec_full[2];  // all workers have published tile k (k & 1) -- its cheap pass, or its precise pass
     unsigned long long verdict[2];   // judge and mapper have judged tile k (k & 1); the guesses of tile k+2 are published
     float4 G[2][NW];                 // per warp of tile k (k & 1): -centre and radius of the guessed thresholds, 1/q
     PipeRec recs[2][NW];
     uint32_t bm[2][NW * R * 8];      // the tile's bitmap words, chunk of 128 samples major (as FastShared::bm)
-    int vfail[2], vst2[2];
+    int vjudge[2], vjudge2[2];       // the judge's verdict (PV_*) on the cheap pass / on the precise pass of tile k (k & 1)
+    int vst2[2], vst2b[2];           // the mapper's: the hysteresis may matter
+    // what the precise pass of a refused tile assumes (judge -> workers)
+    float redo_c0[NW];               // measured window sum at each chunk's first sample, less the tile's
+    float redo_TLb, redo_THb;        // thresholds at the window sum of the tile's first sample
+    float redo_q, redo_invq;
     int cmd, t0, K, done;            // command to the parked warps; first tile and number of tiles of the run; tiles proven
-    int inited, pad_[3];
+    int inited, redone, pad_[2];
 };
 
 // A stage: the tile's samples, overwritten in place by the undo log (what the ring slots held) while the tile is classified.
@@ -158,9 +177,67 @@ __device__ __forceinline__ void pipe_pair(float x0, float x1, float p0, float p1
     a.amax = max3_abs(a.amax, d0, d1);
 }
 
+// One row (128 samples) of the precise pass (as fast_row<true> of the synchronous loop): every sample against its own
+// guessed window sum, c0g (the row's first sample, less the tile's) + the steps of the lanes before it + the steps before
+// it inside the lane.  TLb / THb: thresholds at the window sum of the tile's first sample.  Returns the row's fixed-point
+// sum of n - prev, of |n - prev| (rounded up), and the smallest slack of any lane in window-sum units (NaN: not usable).
+__device__ __forceinline__ void pipe_row_precise(const float4 x4, const float4 pv4, const float c0g, const float TLb, const float THb,
+                                                 const float loLf, const float hiLf, const float invLo, const float invHi, const float invq,
+                                                 const int lane, float4 &n4, unsigned (&NLm)[4], unsigned (&Hm)[4], int &S, int &A,
+                                                 float &slack) {
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+    // first the steps under the classes the thresholds at the row's first sample give
+    const float thL = fmaf(c0g, loLf, TLb), thH = fmaf(c0g, hiLf, THb);
+    float s1 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool adm = xs[j] > thL && !(xs[j] > thH);
+        s1 += adm ? xs[j] - ps[j] : 0.0f;
+    }
+    float incA = s1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(FULL, incA, o);
+        if (lane >= o) incA += v;
+    }
+    const float PA = incA - s1;
+    // ... then every sample against its own guessed window sum, in order inside the lane; margins in window-sum units
+    const float base = c0g + PA;
+    const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
+    float run = 0.0f, wmin = INFINITY, a = 0.0f;
+    float nn[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
+        const bool pnl = xs[j] > tl, ph = xs[j] > th;
+        NLm[j] = __ballot_sync(FULL, pnl);
+        Hm[j] = __ballot_sync(FULL, ph);
+        nn[j] = (pnl && !ph) ? xs[j] : ps[j];
+        const float d = nn[j] - ps[j];
+        run += d;
+        a += fabsf(d);
+        wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
+    }
+    n4 = make_float4(nn[0], nn[1], nn[2], nn[3]);
+    float incB = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(FULL, incB, o);
+        if (lane >= o) incB += v;
+    }
+    // slack of the lane: its margin less what the second classification moved the steps before it by
+    float mL = wmin - fabsf((incB - run) - PA) * 1.001f;
+    const float af = a * (invq * (1.0f + 0x1p-20f));
+    if (!(af < 4194304.0f)) mL = __int_as_float(0x7fc00000);  // the lane's sums do not fit 2^22 steps (or are NaN)
+    const int si = __float2int_rn(run * invq);
+    const int ai = __float2int_ru(fminf(af, 4194304.0f));
+    S = __reduce_add_sync(FULL, si);
+    A = __reduce_add_sync(FULL, ai);
+    slack = redux_min_nan(mL);
+}
+
 // Returns the number of tiles of the run that were proven (K when the whole run was); the ring holds exactly those.
-// The ring slots are rewritten while a tile is classified; what they held goes to the tile's stage in place of the samples
-// (an undo log), so that a refused tile -- and the tile classified ahead of its verdict -- can be taken back.
 template <int NW, int R, int S, int KIND>
 __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, char *stage0, const FastPlan &plan, const int L,
                                         const float pcm_scale, const int warp, const int lane) {
@@ -168,13 +245,16 @@ __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, c
     constexpr int ITEM = KIND == IN_PCM_S16 ? 2 : 4;
     constexpr int stage_bytes = PipeStage<NW, R, ITEM>::bytes;
     constexpr int log_ofs = PipeStage<NW, R, ITEM>::log_ofs;
+    constexpr int tile_bytes = C::T * ITEM;
     const int t0 = ps.t0, K = ps.K;
     int slot_w = (int)((plan.tile0_pos + (int64_t)t0 * C::T + (int64_t)warp * C::CHS + (int64_t)lane * 4) % L);
     const int slot_step = C::T % L;
-    char *const xs = stage0 + (warp * C::CHS + lane * 4) * ITEM;   // this thread's samples inside a stage
+    const int xoff = (warp * C::CHS + lane * 4) * ITEM;                  // this thread's first sample inside a tile of the input
+    char *const xs = stage0 + xoff;                                       // ... inside a stage
     char *const ls = stage0 + log_ofs + (warp * C::CHS + lane * 4) * 4;  // this thread's part of the undo log
     uint32_t *bm_g = plan.bm_base + (size_t)t0 * (C::NC * 8) + warp * (R * 8) + lane;
     const int emit_from = plan.t_emit - t0;  // tiles of the run from this one on are written to the bitmap
+    const char *src0 = plan.xbase + (int64_t)t0 * tile_bytes + xoff;
 
     auto undo = [&](int stage, int slot) {  // the ring slots of a tile as they were before it
         const char *lg = ls + stage * stage_bytes;
@@ -185,117 +265,179 @@ __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, c
             if (slot >= L) slot -= L;
         }
     };
-
-    int slot_prev = 0, st_prev = 0;
-    int st = 0;
-    unsigned xph = 0u;
-    int k = 0;
-#pragma unroll 1
-    for (; k < K; k++) {
-        const int b = k & 1;
-        mbar_wait(&ps.x_full[st], xph);
-        const float4 g = ps.G[b][warp];
-        const unsigned long long ncg2 = pack2(g.x, g.x);
-        const float rg = g.y, nrg = -g.y, invq = g.z;
-        const char *xrow = xs + st * stage_bytes;
-        char *lrow = ls + st * stage_bytes;
-        uint32_t *bms = &ps.bm[b][warp * (R * 8)];
-        PipeAcc a;
-        a.s2 = 0ull;
-        a.amax = 0.0f;
-        a.m = INFINITY;
-        // all loads of the tile first: the rows' dependency chains overlap (the compiler cannot move a load above a store
-        // to shared memory that may alias it)
-        float4 xv[R], pv[R];
-        int sl[R];
-        {
-            int s0 = slot_w;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                sl[r] = s0;
-                if (KIND == IN_PCM_S16) {
-                    const short4 sv = *reinterpret_cast<const short4 *>(xrow + r * (FAST_CH * 2));
-                    xv[r] = make_float4((float)sv.x, (float)sv.y, (float)sv.z, (float)sv.w);
-                } else {
-                    xv[r] = *reinterpret_cast<const float4 *>(xrow + r * (FAST_CH * 4));
-                }
-                pv[r] = *reinterpret_cast<const float4 *>(ring + s0);
-                s0 += FAST_CH;
-                if (s0 >= L) s0 -= L;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            float4 x4 = xv[r];
-            if (KIND == IN_PCM_S16) {
-                x4 = make_float4(env_real(__fdiv_rn(x4.x, pcm_scale)), env_real(__fdiv_rn(x4.y, pcm_scale)),
-                                 env_real(__fdiv_rn(x4.z, pcm_scale)), env_real(__fdiv_rn(x4.w, pcm_scale)));
-            } else if (KIND == IN_REAL_F32) {
-                x4.x = env_real(x4.x); x4.y = env_real(x4.y); x4.z = env_real(x4.z); x4.w = env_real(x4.w);
-            }
-            const float4 p4 = pv[r];
-            unsigned NL[4], H[4];
-            float4 n4;
-            pipe_pair(x4.x, x4.y, p4.x, p4.y, ncg2, rg, nrg, a, NL[0], NL[1], H[0], H[1], n4.x, n4.y);
-            pipe_pair(x4.z, x4.w, p4.z, p4.w, ncg2, rg, nrg, a, NL[2], NL[3], H[2], H[3], n4.z, n4.w);
-            *reinterpret_cast<float4 *>(ring + sl[r]) = n4;
-            *reinterpret_cast<float4 *>(lrow + r * (FAST_CH * 4)) = p4;
-            if (lane == 0) {
-                uint4 *bw = reinterpret_cast<uint4 *>(bms + r * 8);
-                bw[0] = make_uint4(NL[0], NL[1], NL[2], NL[3]);
-                bw[1] = make_uint4(H[0], H[1], H[2], H[3]);
-            }
-        }
-        // the warp's record
-        float sa, sb;
-        unpack2(a.s2, sa, sb);
-        const float ssum = sa + sb;
-        float m = a.m;
-        if (!(fabsf(ssum) * invq < 4194304.0f)) m = __int_as_float(0x7fc00000);  // the lane's sum does not fit 2^22 steps (or is NaN)
-        const int si = __float2int_rn(ssum * invq);
-        const int Ssum = __reduce_add_sync(FULL, si);
-        const unsigned amax_u = __reduce_max_sync(FULL, __float_as_uint(a.amax));  // amax >= 0: ordered like its bit pattern
-        m = redux_min_nan(m);
-        // the verdict on tile k-1: no tile is started two ahead of an open verdict (ring ordering, depth of the undo logs)
-        if (k > 0) {
-            mbar_wait(&ps.verdict[b ^ 1], (unsigned)((k - 1) >> 1) & 1u);
-            const volatile int *vf = ps.vfail, *vs = ps.vst2;
-            if (vf[b ^ 1] | vs[b ^ 1]) {
-                undo(st, slot_w);
-                undo(st_prev, slot_prev);
-                return k - 1;
-            }
-        }
+    unsigned xph = 0u, vph = 0u;  // bit s / bit b: the parity of the phase to wait for next on x_full[s] / verdict[b]
+    // the verdict on the tile with parity b (the cheap pass's, or the precise pass's)
+    auto wait_verdict = [&](int b, bool second) -> int {
+        mbar_wait(&ps.verdict[b], (vph >> b) & 1u);
+        vph ^= 1u << b;
+        const volatile int *vj = second ? ps.vjudge2 : ps.vjudge, *vs = second ? ps.vst2b : ps.vst2;
+        return vs[b] ? (int)PV_ABORT : vj[b];
+    };
+    // record, bitmap words and the arrival of tile k
+    auto publish = [&](int k, int b, int Ssum, float amax, float m) {
         if (lane == 0) {
             PipeRec rc;
             rc.S = Ssum;
-            rc.amax = __uint_as_float(amax_u);
+            rc.amax = amax;
             rc.m = m;
             rc.pad = 0;
             ps.recs[b][warp] = rc;
         }
         __syncwarp();
-        if (k >= emit_from && lane < R * 8) bm_g[(size_t)k * (C::NC * 8)] = bms[lane];
+        if (k >= emit_from && lane < R * 8) bm_g[(size_t)k * (C::NC * 8)] = ps.bm[b][warp * (R * 8) + lane];
         if (lane == 0) mbar_arrive(&ps.rec_full[b]);
+    };
+
+    int slot_prev = 0, st_prev = 0, st = 0, k = 0;
+    bool pending = false;  // tile k-1 awaits its verdict
+#pragma unroll 1
+    for (;;) {
+        const int b = k & 1;
+        int Ssum = 0;
+        unsigned amax_u = 0u;
+        float m = 0.0f;
+        if (k < K) {
+            // ------------------------------------------------------------ tile k against its guesses
+            mbar_wait(&ps.x_full[st], (xph >> st) & 1u);
+            xph ^= 1u << st;
+            const float4 g = ps.G[b][warp];
+            const unsigned long long ncg2 = pack2(g.x, g.x);
+            const float rg = g.y, nrg = -g.y, invq = g.z;
+            const char *xrow = xs + st * stage_bytes;
+            char *lrow = ls + st * stage_bytes;
+            uint32_t *bms = &ps.bm[b][warp * (R * 8)];
+            PipeAcc a;
+            a.s2 = 0ull;
+            a.amax = 0.0f;
+            a.m = INFINITY;
+            // all loads of the tile first: the rows' dependency chains overlap (the compiler cannot move a load above a
+            // store to shared memory that may alias it)
+            float4 xv[R], pv[R];
+            int sl[R];
+            {
+                int s0 = slot_w;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    sl[r] = s0;
+                    if (KIND == IN_PCM_S16) {
+                        const short4 sv = *reinterpret_cast<const short4 *>(xrow + r * (FAST_CH * 2));
+                        xv[r] = make_float4((float)sv.x, (float)sv.y, (float)sv.z, (float)sv.w);
+                    } else {
+                        xv[r] = *reinterpret_cast<const float4 *>(xrow + r * (FAST_CH * 4));
+                    }
+                    pv[r] = *reinterpret_cast<const float4 *>(ring + s0);
+                    s0 += FAST_CH;
+                    if (s0 >= L) s0 -= L;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float4 x4 = xv[r];
+                if (KIND == IN_PCM_S16) {
+                    x4 = make_float4(env_real(__fdiv_rn(x4.x, pcm_scale)), env_real(__fdiv_rn(x4.y, pcm_scale)),
+                                     env_real(__fdiv_rn(x4.z, pcm_scale)), env_real(__fdiv_rn(x4.w, pcm_scale)));
+                } else if (KIND == IN_REAL_F32) {
+                    x4.x = env_real(x4.x); x4.y = env_real(x4.y); x4.z = env_real(x4.z); x4.w = env_real(x4.w);
+                }
+                const float4 p4 = pv[r];
+                unsigned NL[4], H[4];
+                float4 n4;
+                pipe_pair(x4.x, x4.y, p4.x, p4.y, ncg2, rg, nrg, a, NL[0], NL[1], H[0], H[1], n4.x, n4.y);
+                pipe_pair(x4.z, x4.w, p4.z, p4.w, ncg2, rg, nrg, a, NL[2], NL[3], H[2], H[3], n4.z, n4.w);
+                *reinterpret_cast<float4 *>(ring + sl[r]) = n4;
+                *reinterpret_cast<float4 *>(lrow + r * (FAST_CH * 4)) = p4;
+                if (lane == 0) {
+                    uint4 *bw = reinterpret_cast<uint4 *>(bms + r * 8);
+                    bw[0] = make_uint4(NL[0], NL[1], NL[2], NL[3]);
+                    bw[1] = make_uint4(H[0], H[1], H[2], H[3]);
+                }
+            }
+            // the warp's record
+            float sa, sb;
+            unpack2(a.s2, sa, sb);
+            const float ssum = sa + sb;
+            m = a.m;
+            if (!(fabsf(ssum) * invq < 4194304.0f)) m = __int_as_float(0x7fc00000);  // the lane's sum does not fit 2^22 steps (or is NaN)
+            const int si = __float2int_rn(ssum * invq);
+            Ssum = __reduce_add_sync(FULL, si);
+            amax_u = __reduce_max_sync(FULL, __float_as_uint(a.amax));  // amax >= 0: ordered like its bit pattern
+            m = redux_min_nan(m);
+        }
+        if (pending) {
+            // ------------------------------------------------------------ the verdict on tile k-1
+            // (no tile is announced two ahead of an open verdict: ring ordering, depth of the undo logs)
+            const int bp = b ^ 1;
+            int v = wait_verdict(bp, false);
+            if (v != PV_ACCEPT) {
+                if (k < K) undo(st, slot_w);
+                undo(st_prev, slot_prev);
+                if (v != PV_REDO) return k - 1;
+                // ---- the precise pass over tile k-1: the samples come from global memory again (the stage holds the log)
+                const float TLb = ps.redo_TLb, THb = ps.redo_THb, rq = ps.redo_q, rinvq = ps.redo_invq;
+                float c0g = ps.redo_c0[warp];
+                const char *src = src0 + (int64_t)(k - 1) * tile_bytes;
+                char *lrow = ls + st_prev * stage_bytes;
+                uint32_t *bms = &ps.bm[bp][warp * (R * 8)];
+                int Stot = 0, Atot = 0, sp = slot_prev;
+                float mslack = INFINITY;
+                float4 xv[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (KIND == IN_PCM_S16) {
+                        const short4 sv = __ldg(reinterpret_cast<const short4 *>(src + r * (FAST_CH * 2)));
+                        xv[r] = make_float4(env_real(__fdiv_rn((float)sv.x, pcm_scale)), env_real(__fdiv_rn((float)sv.y, pcm_scale)),
+                                            env_real(__fdiv_rn((float)sv.z, pcm_scale)), env_real(__fdiv_rn((float)sv.w, pcm_scale)));
+                    } else {
+                        xv[r] = ldg_stream4(reinterpret_cast<const float4 *>(src + r * (FAST_CH * 4)));
+                        if (KIND == IN_REAL_F32) {
+                            xv[r].x = env_real(xv[r].x); xv[r].y = env_real(xv[r].y); xv[r].z = env_real(xv[r].z); xv[r].w = env_real(xv[r].w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float4 p4 = *reinterpret_cast<const float4 *>(ring + sp);
+                    unsigned NL[4], H[4];
+                    float4 n4;
+                    int Sr, Ar;
+                    float mr;
+                    pipe_row_precise(xv[r], p4, c0g, TLb, THb, plan.loLf, plan.hiLf, plan.invLo, plan.invHi, rinvq, lane, n4, NL, H, Sr, Ar, mr);
+                    *reinterpret_cast<float4 *>(ring + sp) = n4;
+                    *reinterpret_cast<float4 *>(lrow + r * (FAST_CH * 4)) = p4;
+                    if (lane == 0) {
+                        uint4 *bw = reinterpret_cast<uint4 *>(bms + r * 8);
+                        bw[0] = make_uint4(NL[0], NL[1], NL[2], NL[3]);
+                        bw[1] = make_uint4(H[0], H[1], H[2], H[3]);
+                    }
+                    Stot += Sr;
+                    Atot += Ar;
+                    mslack = fmin_nan(mslack, mr);
+                    c0g += (float)Sr * rq;  // the next row starts where the judge's sums will put it
+                    sp += FAST_CH;
+                    if (sp >= L) sp -= L;
+                }
+                publish(k - 1, bp, Stot, (float)Atot, mslack);
+                v = wait_verdict(bp, true);
+                if (v != PV_ACCEPT) {
+                    undo(st_prev, slot_prev);
+                    return k - 1;
+                }
+                pending = false;
+                if (k >= K) return K;
+                continue;  // tile k again: the judge has its samples copied again and new guesses made
+            }
+            pending = false;
+        }
+        if (k >= K) return K;
+        publish(k, b, Ssum, __uint_as_float(amax_u), m);
+        pending = true;
         slot_prev = slot_w;
         st_prev = st;
         slot_w += slot_step;
         if (slot_w >= L) slot_w -= L;
-        if (++st == S) {
-            st = 0;
-            xph ^= 1u;
-        }
+        if (++st == S) st = 0;
+        k++;
     }
-    // the last tile of the run
-    mbar_wait(&ps.verdict[(K - 1) & 1], (unsigned)((K - 1) >> 1) & 1u);
-    {
-        const volatile int *vf = ps.vfail, *vs = ps.vst2;
-        if (vf[(K - 1) & 1] | vs[(K - 1) & 1]) {
-            undo(st_prev, slot_prev);
-            return K - 1;
-        }
-    }
-    return K;
 }
 
 // ---------------------------------------------------------------- judge
@@ -320,15 +462,23 @@ __device__ __forceinline__ bool pipe_step(float a_est, float &q, float &invq) {
 //    so its products with lo/L and hi/L are ready) and the drift of tile j (dr): the guessed window sum of chunk c is
 //    gss = ssm_j + goff[c], goff[c] = dr * (2 + (c + 1/2) / NW); at tile j+2's start ssm - ssm_j is the drift of tiles j and
 //    j+1 (d1 + d2), so (window sum at chunk c's first sample) - gss = (d1 + d2) - goff[c] + c0[c], c0 = exclusive prefix
-//    of the chunk sums.  The first two tiles of a run are guessed from the window sum at its start.
+//    of the chunk sums.  The first two tiles of a run (and after a precise pass) are guessed from the window sum known then.
 template <int NW, int R, int S, int ITEM>
 __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, const FastPlan &plan, const double loL, const double hiL,
-                                        char *stage0, const int lane) {
+                                        char *stage0, const int lane, const int allow_redo) {
     typedef PipeConsts<NW, R> C;
     constexpr unsigned stage_bytes = PipeStage<NW, R, ITEM>::bytes, tile_bytes = C::T * ITEM;
     const int t0 = ps.t0, K = ps.K;
     const char *src0 = plan.xbase + (int64_t)t0 * tile_bytes;
-    int issued = 0;
+    unsigned xused = 0u, xlast = 0u;  // bit s: a copy was issued into stage s; the parity of the phase the latest one completes
+    auto issue = [&](int tile, int stage) {  // the samples of `tile` into `stage` (all lanes call, one issues)
+        if (lane == 0) {
+            mbar_expect_tx(&ps.x_full[stage], tile_bytes);
+            bulk_g2s(stage0 + (size_t)stage * stage_bytes, src0 + (size_t)tile * tile_bytes, tile_bytes, &ps.x_full[stage]);
+        }
+        if (xused & (1u << stage)) xlast ^= 1u << stage;
+        xused |= 1u << stage;
+    };
     if (lane == 0) {
         if (ps.inited) {  // barriers of the previous run: nobody waits on them any more
             for (int s = 0; s < S; s++) mbar_inval(&ps.x_full[s]);
@@ -346,12 +496,8 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    for (; issued < S && issued < K; issued++) {
-        if (lane == 0) {
-            mbar_expect_tx(&ps.x_full[issued], tile_bytes);
-            bulk_g2s(stage0 + (size_t)issued * stage_bytes, src0 + (size_t)issued * tile_bytes, tile_bytes, &ps.x_full[issued]);
-        }
-    }
+    int issued = 0;
+    for (; issued < S && issued < K; issued++) issue(issued, issued);
     // ---- state handed over by the synchronous loop
     const double ss_lo0 = uni.ss_lo, ss_hi0 = uni.ss_hi;
     double ssm = 0.5 * (ss_lo0 + ss_hi0);
@@ -386,21 +532,22 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         prepare(0, TLm, THm, drift, 0.0f, a_est, sane);
         prepare(1, TLm, THm, drift, 1.0f, a_est, sane);
     }
-    float d1 = 0.0f, d2 = 0.0f;  // drifts of the two tiles before the one being judged (0 before the run's start)
+    float d1 = 0.0f, d2 = 0.0f;  // drifts of the two tiles before the one being judged, as far as its guesses did not know them
     if (lane == 0) {
-        ps.vfail[0] = ps.vfail[1] = 0;
-        ps.vst2[0] = ps.vst2[1] = 0;
+        ps.vjudge[0] = ps.vjudge[1] = ps.vjudge2[0] = ps.vjudge2[1] = 0;
+        ps.vst2[0] = ps.vst2[1] = ps.vst2b[0] = ps.vst2b[1] = 0;
     }
     named_bar_sync<PIPE_BAR_RUN, (NW + 2) * 32>();  // barriers, guesses and flags are set up
 
-    int k = 0, st = 0;
+    unsigned rph = 0u, vph = 0u;  // bit b: the parity of the phase to wait for next on rec_full[b] / verdict[b]
+    int k = 0, st = 0, redone = 0;
 #pragma unroll 1
     for (; k < K; k++) {
         const int b = k & 1;
-        const unsigned par = (unsigned)(k >> 1) & 1u;
         const float q = b ? q1 : q0, goff = b ? goff1 : goff0, gTL = b ? gTL1 : gTL0, gTHs = b ? gTHs1 : gTHs0;
         const bool okb = b ? ok1 : ok0;
-        mbar_wait(&ps.rec_full[b], par);
+        mbar_wait(&ps.rec_full[b], (rph >> b) & 1u);
+        rph ^= 1u << b;
         // ---------------------------------------------------------------- on the way to the verdict
         const PipeRec rc = ps.recs[b][act ? lane : 0];
         const int Si = act ? rc.S : 0;
@@ -412,14 +559,14 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
             if (lane >= o) inc += v;
         }
         const int c0i = inc - Si;                            // chunk sums below 2^27 steps each (lane sums below 2^22): no overflow
-        const int toti = __shfl_sync(FULL, inc, NW - 1);
+        int toti = __shfl_sync(FULL, inc, NW - 1);
         const float c0f = (float)c0i * q, Sf = (float)Si * q;
         // upper bounds of the sums of |x - prev|: of the chunk, of the tile
         const float Ahat = amax * ((float)C::CHS * 1.0001f);
-        const float totA = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(amax))) * ((float)C::T * 1.0002f);
+        float totA = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(amax))) * ((float)C::T * 1.0002f);
         // error of the measured sums: conversion (half a step per lane and chunk), float rounding (2^-19 of |x - prev|)
-        const float Ef = fmaf(totA, 0x1p-19f, (float)(16 * NW) * q) * 1.01f;
-        const float dsince = k < 2 ? d1 : d1 + d2;  // ssm - (the window sum the guesses were made from)
+        float Ef = fmaf(totA, 0x1p-19f, (float)(16 * NW) * q) * 1.01f;
+        const float dsince = d1 + d2;  // ssm - (the window sum the guesses were made from)
         const float slack = (hw + Ef + (fabsf(d1) + fabsf(d2) + fabsf(goff) + fabsf(c0f)) * 0x1p-21f) * 1.001f;
         // inside the chunk the window sum moves within [V, U] of its start: the sums of the negative / positive steps
         const float U = fmaxf(0.5f * (Ahat + Sf), 0.0f) * (1.0f + 0x1p-20f), V = fminf(-0.5f * (Ahat - Sf), 0.0f) * (1.0f + 0x1p-20f);
@@ -430,51 +577,122 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         const bool fine = !act || ((rc.m > need) && (gTL - need > 0.0f));
         const bool accept = __all_sync(FULL, fine) && okb;
         // the guesses of tile k + 2, from the window sum at this tile's start: this tile's drift, as much again for tile k + 1
-        const float dr = (float)toti * q;
-        const float a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL, 0) * 0x1p-16f);  // follows the traffic, decays slowly
+        float dr = (float)toti * q;
+        float a_new = fmaxf(fmaxf(totA, 0.25f * a_est), __shfl_sync(FULL, gTL, 0) * 0x1p-16f);  // follows the traffic, decays slowly
         const float gTL_k = gTL, gTHs_k = gTHs;
-        if (accept) prepare(b, TLm, THm, dr, 2.0f, a_new, sane);
+        // a refused tile goes through the precise pass if its records are numbers (no sample is NaN, the sums fit the fixed point)
+        const bool redo = !accept && allow_redo && okb && sane && __all_sync(FULL, !act || rc.m == rc.m);
+        if (accept) {
+            prepare(b, TLm, THm, dr, 2.0f, a_new, sane);
+        } else if (redo) {
+            if (act) ps.redo_c0[lane] = c0f;
+            if (lane == 0) {
+                ps.redo_TLb = TLm;
+                ps.redo_THb = THm;
+                ps.redo_q = q;
+                ps.redo_invq = __uint_as_float((254u << 23) - __float_as_uint(q));  // q is a power of two
+            }
+        }
         __syncwarp();
         if (lane == 0) {
-            ps.vfail[b] = accept ? 0 : 1;
+            ps.vjudge[b] = accept ? PV_ACCEPT : (redo ? PV_REDO : PV_ABORT);
             mbar_arrive(&ps.verdict[b]);
         }
         // ---------------------------------------------------------------- the verdict is out
+        mbar_wait(&ps.verdict[b], (vph >> b) & 1u);  // the mapper's say
+        vph ^= 1u << b;
+        {
+            const volatile int *vs = ps.vst2;
+            if (vs[b] || !(accept || redo)) break;
+        }
+        bool reprime = false;
+        if (!accept) {
+            // ------------------------------------------------------------ the precise pass's records
+            mbar_wait(&ps.rec_full[b], (rph >> b) & 1u);
+            rph ^= 1u << b;
+            const PipeRec r2 = ps.recs[b][act ? lane : 0];
+            const int S2 = act ? r2.S : 0;
+            const float A2 = act ? r2.amax : 0.0f;  // sum of |x - prev| in steps
+            int inc2 = S2;
+            float incA2 = A2;
+#pragma unroll
+            for (int o = 1; o < NW; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, inc2, o);
+                const float va = __shfl_xor_sync(FULL, incA2, o);
+                if (lane >= o) inc2 += v;
+                incA2 += va;
+            }
+            const float c0n = (float)(inc2 - S2) * q;  // the window sum at the chunk's first sample (less the tile's) as it is now
+            toti = __shfl_sync(FULL, inc2, NW - 1);
+            totA = __shfl_sync(FULL, incA2, 0) * q * 1.0002f;
+            // error of the sums: conversion (half a step per lane and row), float rounding
+            Ef = fmaf(totA, 0x1p-19f, (float)(16 * NW * R) * q) * 1.01f;
+            const float slack2 = (hw + Ef + fabsf(c0n) * 0x1p-21f) * 1.001f;
+            // the lanes' slack must cover what the chunk's start is off the assumed one by, the interval, and the rounding
+            // of the per-sample thresholds
+            const float need2 = (fabsf(c0n - c0f) + slack2) * (1.0f + 0x1p-18f) + TLm * (0x1p-21f / loLf);
+            const bool fine2 = !act || (r2.m > need2);
+            const bool accept2 = __all_sync(FULL, fine2) && TLm > 0.0f;
+            dr = (float)toti * q;
+            a_new = fmaxf(fmaxf(totA, 0.25f * a_est), TLm * 0x1p-16f);
+            // the window sum after the tile; the coming two tiles are guessed from it
+            const double ssmr = ssm + (double)toti * (double)q;
+            const float ssfr = __double2float_rd(ssmr);
+            const float hwr = hw + (Ef + ssfr * 0x1p-50f + hw * 0x1p-22f) * 1.001f;
+            const float TLr = __double2float_rn(ssmr * loL), THr = __double2float_rn(ssmr * hiL);
+            const bool saner = ssfr - hwr > 0.0f && ssfr < 1.0e30f && ssfr > 1.0e-30f;
+            if (accept2) {
+                prepare(b ^ 1, TLr, THr, dr, 0.0f, a_new, saner);
+                prepare(b, TLr, THr, dr, 1.0f, a_new, saner);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ps.vjudge2[b] = accept2 ? PV_ACCEPT : PV_ABORT;
+                mbar_arrive(&ps.verdict[b]);
+            }
+            mbar_wait(&ps.verdict[b], (vph >> b) & 1u);  // the mapper's second say
+            vph ^= 1u << b;
+            {
+                const volatile int *vs = ps.vst2b;
+                if (vs[b] || !accept2) break;
+            }
+            redone++;
+            reprime = true;
+        }
+        // ---------------------------------------------------------------- tile k stands
         // the window sum after the tile
         const double totd = (double)toti * (double)q;  // exact
         const double ssm2 = ssm + totd;
         const float ssf = __double2float_rd(ssm2);
         const float hw2 = hw + (Ef + ssf * 0x1p-50f + hw * 0x1p-22f) * 1.001f;
-        const float TLm2 = __double2float_rn(ssm2 * loL), THm2 = __double2float_rn(ssm2 * hiL);
-        mbar_wait(&ps.verdict[b], par);  // the mapper's say
-        {
-            const volatile int *vs = ps.vst2;
-            if (!accept || vs[b]) break;
-        }
         // admitted samples lie strictly between the guessed thresholds: one binade of slack either way (exponent audit)
-        thr_min = fminf(thr_min, gTL_k * 0.5f);
-        thr_max = fmaxf(thr_max, gTHs_k * 0x1p20f);
+        thr_min = fminf(thr_min, (reprime ? TLm : gTL_k) * 0.5f);
+        thr_max = fmaxf(thr_max, reprime ? THm * 2.0f : gTHs_k * 0x1p20f);
         ssm = ssm2;
         hw = hw2;
-        TLm = TLm2;
-        THm = THm2;
+        TLm = __double2float_rn(ssm2 * loL);
+        THm = __double2float_rn(ssm2 * hiL);
         sane = ssf - hw2 > 0.0f && ssf < 1.0e30f && ssf > 1.0e-30f;
         a_est = a_new;
         drift = dr;
-        d2 = d1;
-        d1 = dr;
-        // tile k stands: its stage (the undo log by now) is free for tile k + S
+        if (reprime) {
+            d1 = 0.0f;  // the coming tiles were guessed from the window sum after this tile
+            d2 = 0.0f;
+            if (k + 1 < K) issue(k + 1, st + 1 == S ? 0 : st + 1);  // its samples again: its stage holds the log of the tile taken back
+        } else {
+            d2 = d1;
+            d1 = dr;
+        }
+        // its stage (the undo log by now) is free for tile k + S
         if (issued < K) {
-            if (lane == 0) {
-                mbar_expect_tx(&ps.x_full[st], tile_bytes);
-                bulk_g2s(stage0 + (size_t)st * stage_bytes, src0 + (size_t)issued * tile_bytes, tile_bytes, &ps.x_full[st]);
-            }
+            issue(issued, st);
             issued++;
         }
         if (++st == S) st = 0;
     }
     // ---- hand the state back: the interval after the last proven tile
-    for (int j = max(issued - S, 0); j < issued; j++) mbar_wait(&ps.x_full[j % S], (unsigned)(j / S) & 1u);  // no copy in flight
+    for (int s = 0; s < S; s++)  // no copy in flight
+        if (xused & (1u << s)) mbar_wait(&ps.x_full[s], (xlast >> s) & 1u);
     thr_min = redux_min(thr_min);
     thr_max = -redux_min(-thr_max);
     if (lane == 0) {
@@ -487,6 +705,7 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
             uni.thr_max = fmaxf(uni.thr_max, thr_max);
             uni.stats[FS_FAST] += (unsigned)k;
             uni.stats[FS_PIPE_T] += (unsigned)k;
+            uni.stats[FS_PIPE_RD] += (unsigned)redone;
         }
         ps.done = k;
     }
@@ -502,67 +721,91 @@ __device__ __noinline__ void pipe_mapper(PipeShared<NW, R, S> &ps, SegCarry &cs,
     int last_val = cs.last_val;
     const bool act = lane < C::NC;
     named_bar_sync<PIPE_BAR_RUN, (NW + 2) * 32>();
+    unsigned rph = 0u, vph = 0u;
     int k = 0;
 #pragma unroll 1
     for (; k < K; k++) {
         const int b = k & 1;
-        const unsigned par = (unsigned)(k >> 1) & 1u;
-        mbar_wait(&ps.rec_full[b], par);
-        uint4 nl = make_uint4(FULL, FULL, FULL, FULL), hh = make_uint4(0u, 0u, 0u, 0u);
-        if (act) {
-            nl = *reinterpret_cast<const uint4 *>(&ps.bm[b][lane * 8]);
-            hh = *reinterpret_cast<const uint4 *>(&ps.bm[b][lane * 8 + 4]);
-        }
-        const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
-        const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
-        const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
         const int64_t P0 = plan.tile0_pos + (int64_t)(t0 + k) * C::T;
-        // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
         bool st2 = false;
-        if (Hmask) {
-            const int nb = plan.nb;
-            const int lo_c = max(lane - nb, 0);
-            const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
-            bool risk = hasH && win != 0u;
-            if (hasH && lastL != NO_POS) {
-                const int64_t dist = P0 + (int64_t)lane * FAST_CH - lastL;  // first sample of the chunk to the carried LOW
-                if (dist <= (int64_t)mx + 1) risk = true;
+        int newL = -1, newS = -1, lv_new = 0;
+        // the class maps of the tile as the workers left them in ps.bm[b]
+        auto maps = [&]() {
+            uint4 nl = make_uint4(FULL, FULL, FULL, FULL), hh = make_uint4(0u, 0u, 0u, 0u);
+            if (act) {
+                nl = *reinterpret_cast<const uint4 *>(&ps.bm[b][lane * 8]);
+                hh = *reinterpret_cast<const uint4 *>(&ps.bm[b][lane * 8 + 4]);
             }
-            st2 = __any_sync(FULL, risk);
-        }
-        // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
-        int newL = -1, newS = -1;
-        if (Lmask) {
-            int prevlast = __shfl_up_sync(FULL, lastc, 1);
-            if (lane == 0) prevlast = last_val + 1;  // class code of the sample before the tile
-            int candL = -1, candS = -1;
-            if (hasL && (lastc == 0 || lane >= C::NC - plan.nb)) {
-                const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w};
-                int bestL = -1, bestS = -1;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const unsigned lw = ~NLw[j];
-                    const unsigned pw = j == 0 ? ((NLw[3] << 1) & ~1u) : NLw[j - 1];  // predecessor not LOW
-                    const unsigned sw = lw & pw;
-                    if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
-                    if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
+            const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
+            const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
+            const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
+            // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
+            st2 = false;
+            if (Hmask) {
+                const int nb = plan.nb;
+                const int lo_c = max(lane - nb, 0);
+                const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
+                bool risk = hasH && win != 0u;
+                if (hasH && lastL != NO_POS) {
+                    const int64_t dist = P0 + (int64_t)lane * FAST_CH - lastL;  // first sample of the chunk to the carried LOW
+                    if (dist <= (int64_t)mx + 1) risk = true;
                 }
-                candL = lane * FAST_CH + bestL;
-                if (bestS >= 0) candS = lane * FAST_CH + bestS;
-                if (firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
+                st2 = __any_sync(FULL, risk);
             }
-            newL = __reduce_max_sync(FULL, candL);
-            newS = __reduce_max_sync(FULL, candS);
-        }
-        const int lv_new = __shfl_sync(FULL, lastc, C::NC - 1) - 1;
+            // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
+            newL = -1;
+            newS = -1;
+            if (Lmask) {
+                int prevlast = __shfl_up_sync(FULL, lastc, 1);
+                if (lane == 0) prevlast = last_val + 1;  // class code of the sample before the tile
+                int candL = -1, candS = -1;
+                if (hasL && (lastc == 0 || lane >= C::NC - plan.nb)) {
+                    const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w};
+                    int bestL = -1, bestS = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const unsigned lw = ~NLw[j];
+                        const unsigned pw = j == 0 ? ((NLw[3] << 1) & ~1u) : NLw[j - 1];  // predecessor not LOW
+                        const unsigned sw = lw & pw;
+                        if (lw) bestL = max(bestL, ((31 - __clz(lw)) << 2) | j);
+                        if (sw) bestS = max(bestS, ((31 - __clz(sw)) << 2) | j);
+                    }
+                    candL = lane * FAST_CH + bestL;
+                    if (bestS >= 0) candS = lane * FAST_CH + bestS;
+                    if (firstc == 0 && prevlast != 0) candS = max(candS, lane * FAST_CH);  // a LOW run starts at the chunk's first sample
+                }
+                newL = __reduce_max_sync(FULL, candL);
+                newS = __reduce_max_sync(FULL, candS);
+            }
+            lv_new = __shfl_sync(FULL, lastc, C::NC - 1) - 1;
+        };
+        mbar_wait(&ps.rec_full[b], (rph >> b) & 1u);
+        rph ^= 1u << b;
+        maps();
         if (lane == 0) {
             ps.vst2[b] = st2 ? 1 : 0;
             mbar_arrive(&ps.verdict[b]);
         }
-        mbar_wait(&ps.verdict[b], par);  // the judge's say
+        mbar_wait(&ps.verdict[b], (vph >> b) & 1u);  // the judge's say
+        vph ^= 1u << b;
+        int vj;
         {
-            const volatile int *vf = ps.vfail;
-            if (st2 || vf[b]) break;
+            const volatile int *v = ps.vjudge;
+            vj = v[b];
+        }
+        if (st2 || vj == PV_ABORT) break;
+        if (vj == PV_REDO) {  // the maps of the precise pass
+            mbar_wait(&ps.rec_full[b], (rph >> b) & 1u);
+            rph ^= 1u << b;
+            maps();
+            if (lane == 0) {
+                ps.vst2b[b] = st2 ? 1 : 0;
+                mbar_arrive(&ps.verdict[b]);
+            }
+            mbar_wait(&ps.verdict[b], (vph >> b) & 1u);
+            vph ^= 1u << b;
+            const volatile int *v2 = ps.vjudge2;
+            if (st2 || v2[b] != PV_ACCEPT) break;
         }
         last_val = lv_new;
         if (newL >= 0) {
@@ -593,12 +836,12 @@ __device__ __forceinline__ void pipe_aux_idle(PS &ps) {
 // The two extra warps of a CTA: parked until the segment's workers enter the pipelined mode (or finish the segment).
 template <int NW, int R, int S, int ITEM>
 __device__ __forceinline__ void pipe_aux_main(PipeShared<NW, R, S> &ps, FastUni &uni, const FastPlan &plan, const SlicerParams &p, SegCarry &cs,
-                                              float *ring, const int warp, const int lane) {
+                                              float *ring, const int warp, const int lane, const int allow_redo) {
     for (;;) {
         named_bar_sync<PIPE_BAR_PARK, (NW + 2) * 32>();
         if (*(volatile int *)&ps.cmd == PIPE_CMD_QUIT) return;
         char *stage0 = reinterpret_cast<char *>(ring) + (((size_t)p.L * 4 + 15) / 16) * 16;  // the stages follow the ring
-        if (warp == NW) pipe_judge<NW, R, S, ITEM>(ps, uni, plan, p.loL, p.hiL, stage0, lane);
+        if (warp == NW) pipe_judge<NW, R, S, ITEM>(ps, uni, plan, p.loL, p.hiL, stage0, lane, allow_redo);
         else pipe_mapper<NW, R, S>(ps, cs, plan, p.mx, lane);
         named_bar_sync<PIPE_BAR_RUN, (NW + 2) * 32>();  // the run is over, the state handed back
     }
