@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libusrp_nfc_b200.so")
+# USRP_NFC_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("USRP_NFC_B200_LIB") or os.path.join(_HERE, "libusrp_nfc_b200.so")
 
 IN_ENVELOPE_F32, IN_REAL_F32, IN_IQ_F32, IN_PCM_S16 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -891,6 +891,12 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             const int done = pipe_worker<NW, R, (PIPE > 0 ? PIPE : 1), KIND>(ps, ring, stage0, plan, L, p.pcm_scale, warp, lane);
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
             t += done;
+            if (threadIdx.x == 0 && done > 0) {  // the window sum after the last proven tile: the mapper's middle, the judge's half width
+                const double m = ps.ssm_out, h = (double)ps.hw_out;
+                uni.ss_lo = __dadd_rd(m, -h);
+                uni.ss_hi = __dadd_ru(m, h);
+            }
+            cta_sync<NT>();
             if (done < pipe_K) {
                 cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
                 if (threadIdx.x == 0) uni.stats[FS_PIPE_AB]++;
