@@ -188,7 +188,6 @@ typedef struct {
     int64_t pipe_tiles;       /* tiles proven while the workers ran ahead of the verdicts (subset of fast_tiles) */
     int64_t pipe_runs;        /* runs of consecutive tiles entered in that mode */
     int64_t pipe_aborts;      /* runs ended by a tile the pipelined mode could not prove (settled by the synchronous loop) */
-    int64_t pipe_redone;      /* tiles taken back and settled by the precise pass inside the pipeline */
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
 int nfc_stream_reset_stats(nfc_stream *s);

@@ -37,7 +37,7 @@ static const unsigned FULL = 0xffffffffu;
 __device__ unsigned long long g_tile_stats[16];
 // pipelined mode of the streaming kernel: shortest run worth entering (tiles), tiles the synchronous loop must prove at the
 // first attempt before the pipeline is entered again (NFC_PIPE_MIN / NFC_PIPE_COOL set them per process, for experiments)
-__device__ int g_pipe_tune[4] = {6, 2, 1, 0};  // [2]: refused tiles go through the precise pass inside the pipeline (NFC_PIPE_REDO=0: off)
+__device__ int g_pipe_tune[4] = {6, 2, 0, 0};
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
 
 // Barrier over the first NT threads of the CTA (named barrier 1).  The streaming kernel's CTAs carry two more warps
@@ -1381,8 +1381,8 @@ static int apply_pipe_tuning() {
     std::lock_guard<std::mutex> lock(mu);
     if (done[dev & 63]) return 0;
     done[dev & 63] = true;
-    if (getenv("NFC_PIPE_MIN") || getenv("NFC_PIPE_COOL") || getenv("NFC_PIPE_REDO")) {
-        int t[4] = {env_int("NFC_PIPE_MIN", 6), env_int("NFC_PIPE_COOL", 2), env_int("NFC_PIPE_REDO", 1), 0};
+    if (getenv("NFC_PIPE_MIN") || getenv("NFC_PIPE_COOL")) {
+        int t[4] = {env_int("NFC_PIPE_MIN", 6), env_int("NFC_PIPE_COOL", 2), 0, 0};
         if (t[0] < 3) t[0] = 3;
         if (t[1] < 0) t[1] = 0;
         NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_pipe_tune, t, sizeof(t)));

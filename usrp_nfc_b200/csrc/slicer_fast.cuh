@@ -33,7 +33,7 @@ struct __align__(16) FastRec {  // one chunk of 128 samples
                     // a lane's sum does not fit the fixed point); precise pass: mL = smallest slack of any lane, in ss units
 };
 enum { FV_ACCEPT = 0, FV_REDO = 1, FV_SLOW = 2, FV_REDO_COARSE = 3, FV_VERIFY = 4 };
-enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_PIPE_T, FS_PIPE_IN, FS_PIPE_AB, FS_PIPE_RD, FS_N };
+enum { FS_FAST = 0, FS_SLOW, FS_BAD, FS_UNC, FS_RESUM, FS_REDO, FS_ST2, FS_VER, FS_PIPE_T, FS_PIPE_IN, FS_PIPE_AB, FS_N };
 
 static const int FAST_CH = 128;  // samples per chunk
 
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (PIPE > 0 && warp >= NW) {
         // judge and mapper of the pipelined mode: parked until the workers enter it (everything they read is set up by then)
-        if (PIPED) pipe_aux_main<NW, R, (PIPE > 0 ? PIPE : 1), (KIND == IN_PCM_S16 ? 2 : 4)>(ps, fs.uni, fs.plan, p_s, c_s, ring, warp, lane, g_pipe_tune[2]);
+        if (PIPED) pipe_aux_main<NW, R, (PIPE > 0 ? PIPE : 1), (KIND == IN_PCM_S16 ? 2 : 4)>(ps, fs.uni, fs.plan, p_s, c_s, ring, warp, lane);
         else pipe_aux_idle<NW>(ps);
         return;
     }
@@ -891,12 +891,6 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             const int done = pipe_worker<NW, R, (PIPE > 0 ? PIPE : 1), KIND>(ps, ring, stage0, plan, L, p.pcm_scale, warp, lane);
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
             t += done;
-            if (threadIdx.x == 0 && done > 0) {  // the window sum after the last proven tile: the mapper's middle, the judge's half width
-                const double m = ps.ssm_out, h = (double)ps.hw_out;
-                uni.ss_lo = __dadd_rd(m, -h);
-                uni.ss_hi = __dadd_ru(m, h);
-            }
-            cta_sync<NT>();
             if (done < pipe_K) {
                 cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
                 if (threadIdx.x == 0) uni.stats[FS_PIPE_AB]++;
@@ -1112,7 +1106,6 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
         atomicAdd(&g_tile_stats[11], (unsigned long long)uni.stats[FS_PIPE_T]);
         atomicAdd(&g_tile_stats[12], (unsigned long long)uni.stats[FS_PIPE_IN]);
         atomicAdd(&g_tile_stats[13], (unsigned long long)uni.stats[FS_PIPE_AB]);
-        atomicAdd(&g_tile_stats[14], (unsigned long long)uni.stats[FS_PIPE_RD]);
     }
 }
 

@@ -1794,7 +1794,6 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
         h->s.stats.pipe_tiles = (int64_t)ts[11];
         h->s.stats.pipe_runs = (int64_t)ts[12];
         h->s.stats.pipe_aborts = (int64_t)ts[13];
-        h->s.stats.pipe_redone = (int64_t)ts[14];
     }
     *st = h->s.stats;
     return 0;
