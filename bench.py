@@ -146,14 +146,31 @@ def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, 
         pool.append(x)
     torch.cuda.synchronize()
     his = [1.05, 1.06, 1.07, 1.08, 1.09, 1.10]
-    caps = [pool[i % uniq] for i in mine]
     plist = [dict(hi_val=his[i % len(his)], **params) for i in mine]
     tuning = dict(seg_len=0, halo=0, slab_len=1 << 28)
+    state = {}
+    if args.batch_legacy:
+        caps = [pool[i % uniq] for i in mine]
 
-    def step():
-        res = batch.decode_batch(caps, RATE, plist, device=local_rank, workers=args.batch_workers, tuning=tuning,
-                                 blocking_wait=not args.batch_spin)
-        return sum(len(fr) for fr, _ in res)
+        def step():
+            res = batch.decode_batch(caps, RATE, plist, device=local_rank, workers=args.batch_workers, tuning=tuning,
+                                     blocking_wait=not args.batch_spin)
+            return sum(len(fr) for fr, _ in res)
+    else:
+        # one pass over the rank's share (nfc_stream_push_batch): the captures side by side in HBM, one threshold per capture
+        x2d = torch.empty((len(mine), ns), dtype=torch.float32, device="cuda")
+        for k, i in enumerate(mine):
+            x2d[k].copy_(pool[i % uniq])
+        hv = np.array([his[i % len(his)] for i in mine], dtype=np.float64)
+        del pool
+        torch.cuda.synchronize()
+
+        def step():
+            res = batch.decode_batch_onepass(x2d, RATE, params, hi_vals=hv, device=local_rank, stream=state.get("s"))
+            state["s"] = res["stream"]
+            if res.get("per_capture") is not None:
+                return sum(len(fr) for fr, _ in res["per_capture"])
+            return len(res["frames"])
 
     frames = 0
     for _ in range(args.warmup):
@@ -180,8 +197,9 @@ def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, 
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "batch of %d independent synthetic captures of %.3g samples at %.2f MS/s, hi_val 1.05..1.10 per capture, "
-                                       "round-robin over %d GPU(s), %d streams in flight per GPU (%s waits)" % (args.batch, ns, RATE / 1e6, world, args.batch_workers,
-                                                                                                              "spinning" if args.batch_spin else "blocking"),
+                                       "round-robin over %d GPU(s), %s" % (args.batch, ns, RATE / 1e6, world,
+                                                                          ("%d streams in flight per GPU (%s waits)" % (args.batch_workers, "spinning" if args.batch_spin else "blocking"))
+                                                                          if args.batch_legacy else "one pass per GPU (nfc_stream_push_batch)"),
                            "samp_rate": RATE, **params},
                 "frames_per_step": int(frames)}
         emit(line)
@@ -230,6 +248,7 @@ def main():
     ap.add_argument("--batch-samples", type=float, default=4e6, help="samples per capture of the batch")
     ap.add_argument("--batch-workers", type=int, default=8)
     ap.add_argument("--batch-spin", action="store_true", help="batch: spinning waits (the library's default for a single stream)")
+    ap.add_argument("--batch-legacy", action="store_true", help="batch: one nfc_stream per capture on worker threads instead of one pass")
     ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
     ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()

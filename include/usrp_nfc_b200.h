@@ -99,6 +99,20 @@ int nfc_stream_set_thresholds(nfc_stream *s, double lo_val, double hi_val);
  * the handle's own CUDA stream: the work that produces them must have completed when the call is made. */
 int64_t nfc_stream_push(nfc_stream *s, const void *items, int64_t n, int mem, int *called_back);
 
+/* A batch of independent captures in one pass: n_captures captures of items_per_capture items each, capture c starting
+ * at items + c * stride_items.  In the reference every capture is its own decoder (decoder.py:16-33): its own
+ * transition_sink with its own warm-up and lo_val / hi_val (transition_sink.py:12-34,109-125; lo_vals / hi_vals: one value
+ * per capture, NULL = the stream's), its own background thread, Miller / Manchester decoders and PacketProcessors
+ * (background.py:17-25).  The stream must be new or reset; its outputs afterwards are those of all captures, positions
+ * in one space: capture = pos / *pitch, item index inside the capture = pos % *pitch (*pitch: items_per_capture rounded
+ * up to whole tiles).  Events and symbols at indices below av_window or from items_per_capture on belong to no capture
+ * (they flush the decoders between captures) and are to be skipped by the consumer; frames never carry such positions.
+ * NFC_OUT_DROPPED_EVENTS is not available in this mode.  Needs av_window >= 8192 (a multiple of 4) and 16-byte aligned
+ * captures.  Returns n_captures; -1 on error; -3 when some capture has to take the sequential path (negative or widely
+ * spread samples): decode the captures one by one with nfc_stream_push then.  The stream takes no further items until reset. */
+int64_t nfc_stream_push_batch(nfc_stream *s, const void *items, int mem, int64_t n_captures, int64_t items_per_capture,
+                              int64_t stride_items, const double *lo_vals, const double *hi_vals, int64_t *pitch);
+
 /* Results accumulated since the last drain, in stream order.  Each call copies up to cap records
  * and removes them from the stream.  Pass cap = 0 to query the number available. */
 int64_t nfc_stream_drain_events(nfc_stream *s, nfc_event *out, int64_t cap);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "nfc_stream_reset": (C.c_int, [C.c_void_p]),
     "nfc_stream_set_thresholds": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "nfc_stream_push": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
+    "nfc_stream_push_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_int64)]),
     "nfc_stream_drain_events": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_symbols": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_frames": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
@@ -90,6 +92,10 @@ _lib = None
 
 class NfcError(RuntimeError):
     pass
+
+
+class BatchNeedsSequential(NfcError):
+    """nfc_stream_push_batch returned -3: some capture has to take the sequential path; decode the captures one by one."""
 
 
 def lib():
@@ -182,6 +188,44 @@ class Stream(object):
         if used < 0:
             raise NfcError("nfc_stream_push: " + last_error())
         return int(used), bool(cb.value)
+
+    def push_batch(self, items, lo_vals=None, hi_vals=None):
+        """A batch of independent captures in one pass: items is a 2-D array / tensor [captures, items per capture] of the
+        stream's input kind (every row its own transition_sink + decoders in the reference, decoder.py:16-33); lo_vals /
+        hi_vals: per-capture thresholds.  Returns the pitch of the position space the results use (capture = pos // pitch,
+        index inside the capture = pos % pitch).  Raises BatchNeedsSequential when a capture must take the sequential path."""
+        if hasattr(items, "data_ptr") and hasattr(items, "is_cuda"):
+            if items.dim() != 2:
+                raise ValueError("push_batch takes a 2-D tensor")
+            want = _torch_dtype_name(self.input_kind)
+            if str(items.dtype).replace("torch.", "") != want:
+                raise TypeError("stream input kind %d takes %s items, got a tensor of %s" % (self.input_kind, want, items.dtype))
+            keep = items if items.stride(1) == 1 else items.contiguous()
+            if keep.is_cuda:
+                import torch
+                torch.cuda.current_stream(keep.device).synchronize()  # the library reads the items on its own CUDA stream
+            ncap, n, stride = int(keep.shape[0]), int(keep.shape[1]), int(keep.stride(0))
+            addr, mem = keep.data_ptr(), (MEM_DEVICE if keep.is_cuda else MEM_HOST)
+        else:
+            keep = np.ascontiguousarray(items, dtype=_KIND_DTYPES[self.input_kind])
+            if keep.ndim != 2:
+                raise ValueError("push_batch takes a 2-D array")
+            ncap, n, stride = int(keep.shape[0]), int(keep.shape[1]), int(keep.shape[1])
+            addr, mem = keep.ctypes.data, MEM_HOST
+        lo = None if lo_vals is None else np.ascontiguousarray(lo_vals, dtype=np.float64)
+        hi = None if hi_vals is None else np.ascontiguousarray(hi_vals, dtype=np.float64)
+        for v in (lo, hi):
+            if v is not None and v.size != ncap:
+                raise ValueError("one threshold per capture")
+        pitch = C.c_int64(0)
+        rc = lib().nfc_stream_push_batch(self._h, addr, mem, ncap, n, stride, None if lo is None else lo.ctypes.data,
+                                         None if hi is None else hi.ctypes.data, C.byref(pitch))
+        del keep
+        if rc == -3:
+            raise BatchNeedsSequential(last_error())
+        if rc < 0:
+            raise NfcError("nfc_stream_push_batch: " + last_error())
+        return int(pitch.value)
 
     def push_all(self, items, chunk=None):
         """Feed everything, re-offering what a call did not consume (the GNU Radio scheduler's job)."""

@@ -80,6 +80,63 @@ def decode_batch(captures, samp_rate, params, device=0, workers=8, tuning=None, 
     return out
 
 
+def decode_batch_onepass(captures, samp_rate, params, lo_vals=None, hi_vals=None, device=0, outputs=_cabi.OUT_FRAMES,
+                         kind=_cabi.IN_ENVELOPE_F32, stream=None):
+    """A batch of equally long captures in one pass over the device (nfc_stream_push_batch): one launch of the slicer with
+    one segment per capture, extraction / runs / line code over the whole batch, no host work per capture.
+
+    captures: 2-D array or CUDA tensor [captures, items]; params: the Stream keyword arguments all captures share
+    (av_window, max_len, ...); lo_vals / hi_vals: one threshold per capture (transition_sink's constructor arguments,
+    transition_sink.py:12).  stream: a Stream to reuse (it is reset).  Returns dict(pitch, frames, bits_tag, bits_reader,
+    stream): frame records with positions in the batch's position space (capture = pos // pitch, index inside the
+    capture = pos % pitch), bit_off into bits_tag (type 0) / bits_reader (type 1); views valid until the stream is used
+    again.  Falls back to decode_batch when a capture needs the sequential path (the same results, capture by capture)."""
+    s = stream
+    if s is None:
+        s = _cabi.Stream(samp_rate, device=device, outputs=outputs, input_kind=kind, **params)
+    else:
+        s.release_frames()
+        s.reset()
+    try:
+        pitch = s.push_batch(captures, lo_vals=lo_vals, hi_vals=hi_vals)
+    except _cabi.BatchNeedsSequential:
+        n = len(captures)
+        plist = []
+        for i in range(n):
+            p = dict(params)
+            if lo_vals is not None:
+                p["lo_val"] = float(lo_vals[i])
+            if hi_vals is not None:
+                p["hi_val"] = float(hi_vals[i])
+            plist.append(p)
+        res = decode_batch([captures[i] for i in range(n)], samp_rate, plist, device=device, outputs=outputs, kind=kind)
+        return dict(pitch=None, per_capture=res, stream=s)
+    fr, b0, b1 = s.view_frames()
+    return dict(pitch=pitch, frames=fr, bits_tag=b0, bits_reader=b1, stream=s)
+
+
+def split_captures(res, n_captures):
+    """Result of decode_batch_onepass -> [(frame records, flat frame bits)] per capture, as decode_batch returns them:
+    positions relative to the capture, bit_off into the capture's own bit array."""
+    if res.get("per_capture") is not None:
+        return res["per_capture"]
+    fr, pitch = res["frames"], res["pitch"]
+    cap = fr["pos"] // pitch
+    out = []
+    for c in range(n_captures):
+        sel = fr[cap == c].copy()
+        bits = []
+        off = 0
+        for r in sel:
+            src = res["bits_tag"] if r["type"] == 0 else res["bits_reader"]
+            bits.append(np.array(src[int(r["bit_off"]): int(r["bit_off"]) + int(r["nbits"])], dtype=np.uint8))
+            r["bit_off"] = off
+            off += int(r["nbits"])
+        sel["pos"] -= c * pitch
+        out.append((sel, np.concatenate(bits) if bits else np.zeros(0, np.uint8)))
+    return out
+
+
 def rank_share(n_captures, rank, world):
     """Indices of the captures rank `rank` decodes (round-robin)."""
     return list(range(rank, n_captures, world))

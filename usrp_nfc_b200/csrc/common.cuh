@@ -145,6 +145,12 @@ struct LineTables {
     const uint8_t *reset_manch;
     int n_dclass_miller, n_dclass_manch;
     int decode_reader, decode_tag;
+    // A batch of independent captures decoded as one event stream (every capture its own transition_sink, decoders and
+    // PacketProcessors in the reference: transition_sink.py:12-34, background.py:17-25): capture k of a slab owns the
+    // slab-relative positions [k * batch_pitch, (k + 1) * batch_pitch); only events at offsets [batch_skip, batch_len) of it
+    // are the capture's (before: its warm-up, transition_sink.py:109-125; behind: padding), the others are ignored; the first
+    // event of a capture finds both decoders and both PacketProcessors as new.  batch_pitch == 0: one stream.
+    uint32_t batch_pitch, batch_skip, batch_len;
 };
 
 struct DecCarry {

@@ -64,7 +64,20 @@ struct TabView {
     const TabEntry *tab;            // tables (one shared memory copy: Miller, then Manchester at goff)
     int goff;
     int use_reader, use_tag;
+    uint32_t pitch, skip, len;      // batches of captures (LineTables::batch_*); pitch == 0: one stream
 };
+
+// Batches of captures: which capture an event belongs to, and whether it is one of the capture's own events.
+static const uint32_t NO_CAPTURE = 0xffffffffu;
+__device__ __forceinline__ uint32_t batch_capture(const TabView &tv, uint32_t rel_pos, bool &inside) {
+    const uint32_t cap = rel_pos / tv.pitch, off = rel_pos - cap * tv.pitch;
+    inside = off >= tv.skip && off < tv.len;
+    return cap;
+}
+// the capture of the event before event i (NO_CAPTURE before the slab's first event: a slab starts with a capture)
+__device__ __forceinline__ uint32_t batch_capture_before(const TabView &tv, const EventRec *__restrict__ ev, int64_t i) {
+    return i > 0 ? ev[i - 1].rel_pos / tv.pitch : NO_CAPTURE;
+}
 
 // one symbol into a PacketProcessor (packets.py:67-79); returns 1 when a frame is closed
 template <class Sink>
@@ -103,6 +116,24 @@ __device__ __forceinline__ void step_event(const EventRec &ev, const TabView &tv
     gs = is_r ? gs : nx;
 }
 
+// the same for a stream that may be a batch of captures: a capture's first event finds everything as new
+// (background.py:17-25, packets.py:63-65), events outside a capture's own range are ignored
+template <class Sink>
+__device__ __forceinline__ void step_event_batch(const EventRec &ev, const TabView &tv, int &rs, int &gs, Sink &sink, uint32_t &cap_prev) {
+    if (tv.pitch) {
+        bool inside;
+        const uint32_t cap = batch_capture(tv, ev.rel_pos, inside);
+        if (cap != cap_prev) {
+            cap_prev = cap;
+            rs = 0;
+            gs = 0;
+            sink.new_capture();
+        }
+        if (!inside) return;
+    }
+    step_event(ev, tv, rs, gs, sink);
+}
+
 // eight events at once (one 64-byte line): the loops below are chains of dependent loads otherwise.
 // `base` is a multiple of 8; the event buffer is padded, so reading a little past n_ev is safe.
 __device__ __forceinline__ void load8(const EventRec *__restrict__ ev, int64_t base, EventRec (&e)[8]) {
@@ -127,6 +158,7 @@ struct NullSink {
     __device__ __forceinline__ void symbol(uint32_t, int, int) {}
     __device__ __forceinline__ void emission(uint32_t, int) {}
     __device__ __forceinline__ void bit(int, int) {}
+    __device__ __forceinline__ void new_capture() {}
 };
 
 __device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, TabEntry *sg) {  // sg follows sm
@@ -141,7 +173,8 @@ __device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, 
     TabView tv;                                                     \
     tv.dcm = lt.dclass_miller; tv.dcg = lt.dclass_manch;            \
     tv.tab = s_tab; tv.goff = MAX_DCLASS * 4 * MILLER_STATES;        \
-    tv.use_reader = lt.decode_reader; tv.use_tag = lt.decode_tag;
+    tv.use_reader = lt.decode_reader; tv.use_tag = lt.decode_tag;   \
+    tv.pitch = lt.batch_pitch; tv.skip = lt.batch_skip; tv.len = lt.batch_len;
 
 // ---- pass A: transfer function of every chunk -------------------------------------------------
 __global__ void chunk_map_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
@@ -155,8 +188,19 @@ __global__ void chunk_map_kernel(const EventRec *__restrict__ ev, uint32_t n_ev,
     for (int s = 0; s < GSTATES; s++) g[s] = (uint8_t)s;
     bool r_flat = false, g_flat = false;  // all start states already lead to the same state
     NullSink sink;
+    uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i++) {
         const EventRec e = ev[i];
+        if (tv.pitch) {
+            bool inside;
+            const uint32_t cap = batch_capture(tv, e.rel_pos, inside);
+            if (cap != cap_prev) {  // a new capture: every state leads to the initial one
+                cap_prev = cap;
+                r[0] = 0; g[0] = 0;
+                r_flat = g_flat = true;
+            }
+            if (!inside) continue;
+        }
         if (e.type == 1 && tv.use_reader) {
             if (r_flat) {
                 int rs = r[0], gs = 0;
@@ -210,6 +254,10 @@ struct CountSink {
     __device__ __forceinline__ void bit(int type, int) {
         if (type == 0) { c.nbit0++; c.tail0++; } else { c.nbit1++; c.tail1++; }
     }
+    __device__ __forceinline__ void new_capture() {  // the bits appended so far belong to no later frame
+        c.has0 = 1; c.tail0 = 0;
+        c.has1 = 1; c.tail1 = 0;
+    }
 };
 
 // ---- frame-boundary search: the state at a chunk start from the nearest reset before it ------------
@@ -230,6 +278,7 @@ __global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, uint32_t n
     bool kR = false, kG = false;
     NullSink sink;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
         EventRec e8[8];
         load8(ev, i, e8);
@@ -238,6 +287,16 @@ __global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, uint32_t n
             if (i + k >= i1) continue;
             const EventRec e = e8[k];
             int dummy = 0;
+            if (tv.pitch) {
+                bool inside;
+                const uint32_t cap = batch_capture(tv, e.rel_pos, inside);
+                if (cap != cap_prev) {  // a new capture: both machines are known to be in their initial state
+                    cap_prev = cap;
+                    rs = 0; kR = true;
+                    gs = 0; kG = true;
+                }
+                if (!inside) continue;
+            }
             if (e.type == 1 && tv.use_reader) {
                 const uint8_t r = lt.reset_miller[(int)tv.dcm[e.d] * 4 + (e.v + 1)];
                 if (r != 0xFF) { rs = r; kR = true; }
@@ -279,6 +338,7 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     // replay from the earliest point a still-unknown machine needs (a disabled direction needs nothing)
     const int64_t fromR = tv.use_reader ? iR + 1 : i0, fromG = tv.use_tag ? iG + 1 : i0;
     const int64_t from = fromR < fromG ? fromR : fromG;
+    uint32_t cap_prev = (tv.pitch && from < i0) ? batch_capture_before(tv, ev, from) : 0u;
     for (int64_t base = from & ~(int64_t)7; base < i0; base += 8) {
         EventRec e8[8];
         load8(ev, base, e8);
@@ -288,6 +348,16 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
             if (kk < from || kk >= i0) continue;
             const EventRec e = e8[k];
             int dummy_r = 0, dummy_g = 0;
+            if (tv.pitch) {
+                bool inside;
+                const uint32_t cap = batch_capture(tv, e.rel_pos, inside);
+                if (cap != cap_prev) {  // a new capture behind the point a machine's state was known at: initial state
+                    cap_prev = cap;
+                    if (kk > iR) rs = 0;
+                    if (kk > iG) gs = 0;
+                }
+                if (!inside) continue;
+            }
             if (e.type == 1) {
                 if (kk > iR) step_event(e, tv, rs, dummy_g, sink);
             } else if (e.type == 0) {
@@ -317,12 +387,13 @@ __global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     CountSink sink;
     sink.c = ChunkCnt{0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
         EventRec e[8];
         load8(ev, i, e);
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (i + k < i1) step_event(e[k], tv, rs, gs, sink);
+            if (i + k < i1) step_event_batch(e[k], tv, rs, gs, sink, cap_prev);
     }
     cnts[c] = sink.c;
 }
@@ -365,6 +436,7 @@ struct WriteSink {
         if (type == 0) { if (ib0 < cap_b0) bits0[ib0] = (uint8_t)o; ib0++; pend0++; }
         else { if (ib1 < cap_b1) bits1[ib1] = (uint8_t)o; ib1++; pend1++; }
     }
+    __device__ __forceinline__ void new_capture() { pend0 = 0; pend1 = 0; }
 };
 
 struct LineOut {
@@ -391,12 +463,13 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     sink.pend0 = pc.has0 ? pc.tail0 : out.pending0 + pc.tail0;
     sink.pend1 = pc.has1 ? pc.tail1 : out.pending1 + pc.tail1;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
         EventRec e[8];
         load8(ev, i, e);
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (i + k < i1) step_event(e[k], tv, rs, gs, sink);
+            if (i + k < i1) step_event_batch(e[k], tv, rs, gs, sink, cap_prev);
     }
     if (c == n_chunks - 1) {
         DecCarry co;

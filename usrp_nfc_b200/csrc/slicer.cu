@@ -500,8 +500,10 @@ __device__ __noinline__ void exact_tile(const SegWork *wp, const SlicerParams *p
             unsigned wv = 0u;
 #pragma unroll
             for (int j = 0; j < K; j++) {
+                // samples of the chunk outside [begin, end) are written as val == 0: a single stream masks them by position
+                // (extract.cu), in a batch of captures they are the warm-up / padding around the capture
                 const bool on = val[j] != 3 && (p0 + j >= w.begin);
-                const unsigned bn = __ballot_sync(FULL, on && val[j] != -1), bh = __ballot_sync(FULL, on && val[j] == 1);
+                const unsigned bn = __ballot_sync(FULL, !on || val[j] != -1), bh = __ballot_sync(FULL, on && val[j] == 1);
                 if (lane == j) wv = bn;
                 if (lane == 4 + j) wv = bh;
             }
@@ -1450,6 +1452,66 @@ int slicer_resident_ctas(int L, bool vec_ok, int kind) {
     if (raise_dynamic_smem(fn, dyn) == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, threads, dyn);
     if (e != cudaSuccess || per < 1) per = 1;
     return sms * per;
+}
+
+// ---------------------------------------------------------------- batches of independent captures
+// The reference gives every capture its own transition_sink (transition_sink.py:12-34): the first av_window items fill the
+// ring unconditionally, _sum is their left-to-right double sum (transition_sink.py:109-125).  One block per capture writes
+// that state as a state block; the ring is laid out by stream position of the batch (capture c starts at c * pitch).
+__global__ void __launch_bounds__(256) batch_warm_kernel(const char *__restrict__ items, int64_t stride_bytes, int64_t pitch,
+                                                         const SlicerParams *__restrict__ params, char *__restrict__ states,
+                                                         size_t state_bytes) {
+    extern __shared__ float warm_s[];
+    const int64_t c = blockIdx.x;
+    const SlicerParams p = params[c];
+    const int L = p.L;
+    SlicerHdr *h = reinterpret_cast<SlicerHdr *>(states + (size_t)c * state_bytes);
+    float *ring = state_ring(h);
+    const int64_t B = c * pitch;
+    const void *in = items + c * stride_bytes;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float v = load_one(in, i, p);
+        warm_s[i] = v;
+        ring[(int)((B + i) % L)] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < L; i++) s += (double)warm_s[i];  // sum(ar), left to right (transition_sink.py:122)
+        SlicerHdr hh;
+        hh.ss = s;
+        hh.pos = B + L;
+        hh.lastL = NO_POS;
+        hh.lrun_start = NO_POS;
+        hh.last_val = 0;
+        hh.emin = 0; hh.emax = 0; hh.status = 0; hh.count = 0; hh.pad = 0;
+        *h = hh;
+    }
+}
+
+// class bitmap of positions no segment writes (warm-ups, padding behind the captures): val == 0 everywhere
+__global__ void bitmap_fill_kernel(uint4 *__restrict__ bm, size_t n_chunks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunks) return;
+    bm[2 * i] = make_uint4(FULL, FULL, FULL, FULL);
+    bm[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int launch_batch_warm(const void *d_items, int64_t stride_bytes, int64_t pitch, int n_cap, int L, const SlicerParams *d_params,
+                      void *d_states, size_t state_bytes, cudaStream_t stream) {
+    if (n_cap <= 0) return 0;
+    const size_t smem = (size_t)L * 4;
+    if (raise_dynamic_smem((const void *)batch_warm_kernel, smem)) return -1;
+    batch_warm_kernel<<<n_cap, 256, smem, stream>>>((const char *)d_items, stride_bytes, pitch, d_params, (char *)d_states, state_bytes);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_bitmap_fill(uint32_t *d_bm, size_t n_chunks, cudaStream_t stream) {
+    if (!n_chunks) return 0;
+    bitmap_fill_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(reinterpret_cast<uint4 *>(d_bm), n_chunks);
+    NFC_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,

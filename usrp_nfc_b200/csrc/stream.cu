@@ -62,6 +62,9 @@ int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables 
 int slicer_tile(int L, bool vec_ok);
 int slicer_resident_ctas(int L, bool vec_ok, int kind);
 int slicer_tile_stats(unsigned long long *out4, bool reset);
+int launch_batch_warm(const void *d_items, int64_t stride_bytes, int64_t pitch, int n_cap, int L, const SlicerParams *d_params,
+                      void *d_states, size_t state_bytes, cudaStream_t stream);
+int launch_bitmap_fill(uint32_t *d_bm, size_t n_chunks, cudaStream_t stream);
 int synth_render(void *dev_out, int64_t n, int64_t first_index, const int8_t *codes, const int64_t *lens, int64_t n_runs,
                  float carrier, float pause, float tag_high, float noise, float fade, double fade_period, uint64_t seed,
                  int as_envelope, cudaStream_t);
@@ -216,6 +219,11 @@ struct Stream {
     int finish_pending();
     int settle() { return finish_pending() || join_marshal() ? -1 : 0; }
     int64_t push(const void *items, int64_t n, int mem, int *called_back);
+    int64_t push_batch(const void *items, int mem, int64_t n_cap, int64_t cap_len, int64_t stride_items, const double *lo_vals,
+                       const double *hi_vals, int64_t *pitch_out);
+    // layout of the class bitmap a batch was filled for (positions no segment writes hold val == 0 and stay so)
+    int64_t batch_fill_pitch = 0, batch_fill_caps = 0, batch_fill_len = 0;
+    DevBuf batch_states, batch_stage;
     int finish_warmup();
     int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, int64_t slicer_end);
     int run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial, uint32_t *R_out,
@@ -320,6 +328,9 @@ int Stream::init(const nfc_params *p) {
     lt.n_dclass_manch = ht.n_dclass_manch;
     lt.decode_reader = p->decode_reader;
     lt.decode_tag = p->decode_tag;
+    lt.batch_pitch = 0;
+    lt.batch_skip = 0;
+    lt.batch_len = 0;
 
     warm.reserve((size_t)sp.L);
     if (state.ensure(state_block_bytes(sp.L))) return -1;
@@ -332,7 +343,7 @@ int Stream::init(const nfc_params *p) {
 }
 
 void Stream::destroy() {
-    DevBuf *all[] = {&params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
+    DevBuf *all[] = {&batch_states, &batch_stage, &params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
                      &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
@@ -511,6 +522,162 @@ int64_t Stream::push(const void *items, int64_t n, int mem, int *called_back) {
         stats.samples += m;
     }
     return n;
+}
+
+// A batch of independent captures in one pass (BASELINE.json configs[3]).  The reference gives every capture its own
+// transition_sink (own warm-up, own lo_val / hi_val: transition_sink.py:12-34,109-125), background thread, decoders and
+// PacketProcessors (decoder.py:29-33).  Here capture c owns the stream positions [c * pitch, c * pitch + cap_len) of one
+// position space (pitch: cap_len rounded up to tiles); one launch of the streaming slicer runs one segment per capture
+// from the capture's own warm-up state (computed on the device), and extraction / runs / line code walk the batch as one
+// stream in which a capture's first event finds decoders and PacketProcessors as new (linecode.cu).  Frames come out with
+// positions of that space: capture = pos / pitch, index in the capture = pos % pitch.
+// Returns n_cap, -1 on error, -3 when a capture leaves the exactly-summable regime (the caller decodes captures one by
+// one then: nfc_stream_push takes the sequential path for such input).
+int64_t Stream::push_batch(const void *items, int mem, int64_t n_cap, int64_t cap_len, int64_t stride_items, const double *lo_vals,
+                           const double *hi_vals, int64_t *pitch_out) {
+    NFC_CUDA_CHECK(cudaSetDevice(prm.device));
+    const int L = sp.L;
+    const int T = tile();
+    const size_t ib = item_bytes(sp.input_kind);
+    if (pos != 0 || stable || !warm.empty()) {
+        set_error("push_batch: the stream has consumed samples; reset it first");
+        return -1;
+    }
+    if (!streaming_ok()) {
+        set_error("push_batch: needs the streaming slicer (av_window >= 8192, a multiple of 4)");
+        return -1;
+    }
+    if (n_cap <= 0 || cap_len <= (int64_t)L + 2 * sp.mx || stride_items < cap_len || L <= sp.mx + 1) {
+        set_error("push_batch: bad shape (captures %lld, items %lld, stride %lld, av_window %d)", (long long)n_cap, (long long)cap_len,
+                  (long long)stride_items, L);
+        return -1;
+    }
+    if (prm.outputs & NFC_OUT_DROPPED_EVENTS) {
+        set_error("push_batch: type -1 events are not reproduced across capture boundaries (NFC_OUT_DROPPED_EVENTS)");
+        return -1;
+    }
+    if (((size_t)stride_items * ib) % 16 != 0 || ((uintptr_t)items % 16) != 0) {
+        set_error("push_batch: captures must start 16-byte aligned");
+        return -1;
+    }
+    const int64_t pitch = (cap_len + T - 1) / T * T;
+    if (pitch >= ((int64_t)1 << 30)) {
+        set_error("push_batch: capture too long for one slab");
+        return -1;
+    }
+    if (pitch_out) *pitch_out = pitch;
+    const void *d_items = items;
+    if (mem == NFC_MEM_HOST) {
+        const size_t bytes = ((size_t)(n_cap - 1) * (size_t)stride_items + (size_t)cap_len) * ib;
+        if (batch_stage.ensure(bytes + 64)) return -1;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(batch_stage.p, items, bytes, cudaMemcpyHostToDevice, cs));
+        stats.h2d_bytes += (int64_t)bytes;
+        d_items = batch_stage.p;
+    }
+    // ---- per-capture parameters (transition_sink's lo_val / hi_val constructor arguments)
+    std::vector<SlicerParams> ps((size_t)n_cap, sp);
+    for (int64_t c = 0; c < n_cap; c++) {
+        SlicerParams &q = ps[(size_t)c];
+        if (lo_vals) q.lo = lo_vals[c];
+        if (hi_vals) q.hi = hi_vals[c];
+        q.loL = q.lo / q.Ld;
+        q.hiL = q.hi / q.Ld;
+        q.cls_ss0_x0 = classify_ratio_host(1.0, q.lo, q.hi);
+        q.cls_ss0_xn = classify_ratio_host(q.hi + 0.1, q.lo, q.hi);
+        if (!(q.lo > 0.0) || !(q.hi > q.lo)) {
+            set_error("push_batch: capture %lld: thresholds must satisfy 0 < lo_val < hi_val", (long long)c);
+            return -1;
+        }
+    }
+    if (params_d.ensure(sizeof(SlicerParams) * (size_t)n_cap)) return -1;
+    NFC_CUDA_CHECK(cudaMemcpyAsync(params_d.p, ps.data(), sizeof(SlicerParams) * (size_t)n_cap, cudaMemcpyHostToDevice, cs));
+    // ---- warm-up states, bitmap, one segment per capture
+    const size_t sblk = state_block_bytes(L);
+    if (batch_states.ensure(sblk * (size_t)n_cap) || seg_status.ensure(sizeof(int32_t) * (size_t)n_cap) ||
+        works_d.ensure(sizeof(SegWork) * (size_t)n_cap))
+        return -1;
+    const int64_t total = n_cap * pitch;
+    const size_t n_chunks = (size_t)(total / 128);
+    const size_t bm_cap_before = bitmap_d.cap;
+    if (bitmap_d.ensure((n_chunks + 64) * 32)) return -1;
+    if (bitmap_d.cap != bm_cap_before || batch_fill_pitch != pitch || batch_fill_caps < n_cap || batch_fill_len != cap_len) {
+        if (launch_bitmap_fill(bitmap_d.as<uint32_t>(), n_chunks, cs)) return -1;
+        batch_fill_pitch = pitch;
+        batch_fill_caps = n_cap;
+        batch_fill_len = cap_len;
+        stats.launches++;
+    }
+    if (launch_batch_warm(d_items, (int64_t)((size_t)stride_items * ib), pitch, (int)n_cap, L, params_d.as<SlicerParams>(), batch_states.p,
+                          sblk, cs))
+        return -1;
+    stats.launches++;
+    std::vector<SegWork> works((size_t)n_cap);
+    for (int64_t c = 0; c < n_cap; c++) {
+        SegWork &w = works[(size_t)c];
+        memset(&w, 0, sizeof(w));
+        const int64_t B = c * pitch;
+        w.in = (const char *)d_items + (size_t)c * (size_t)stride_items * ib;
+        w.in_pos0 = B;
+        w.in_begin = B;
+        w.in_end = B + cap_len;
+        w.warm_begin = B + L;
+        w.begin = B + L;
+        w.end = B + cap_len;
+        w.slab_pos0 = 0;
+        w.state_in = reinterpret_cast<const SlicerHdr *>(batch_states.as<char>() + sblk * (size_t)c);
+        for (int j = 0; j < 3; j++) w.ckpt_pos[j] = INT64_MAX;
+        w.status = seg_status.as<int32_t>() + c;
+        w.param_idx = (int32_t)c;
+        w.bitmap = bitmap_d.as<uint32_t>();
+        w.bm_pos0 = 0;
+    }
+    NFC_CUDA_CHECK(cudaMemcpyAsync(works_d.p, works.data(), sizeof(SegWork) * (size_t)n_cap, cudaMemcpyHostToDevice, cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_k0, cs));
+    if (launch_slicer_streaming(works_d.as<SegWork>(), (int)n_cap, params_d.as<SlicerParams>(), L, sp.input_kind, cs)) return -1;
+    NFC_CUDA_CHECK(cudaEventRecord(ev_k1, cs));
+    stats.launches++;
+    stats.slicer_launches++;
+    stats.segments += n_cap;
+    std::vector<int32_t> status((size_t)n_cap);
+    NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)n_cap, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(sync_cs());
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev_k0, ev_k1) == cudaSuccess) {
+            stats.slicer_kernel_ms += ms;
+            stats.slicer_kernel_launches++;
+        }
+    }
+    for (int64_t c = 0; c < n_cap; c++)
+        if (status[(size_t)c] & (SEG_INEXACT | SEG_NOT_SANE)) {
+            set_error("push_batch: capture %lld is outside the exactly-summable regime: decode the captures one by one", (long long)c);
+            return -3;
+        }
+    // ---- extraction, runs, line code: slabs of whole captures
+    stable = true;
+    bm_lo = 0;
+    bm_hi = total;
+    bm_origin = 0;
+    lt.batch_pitch = (uint32_t)pitch;
+    lt.batch_skip = (uint32_t)L;
+    lt.batch_len = (uint32_t)cap_len;
+    const int64_t per_slab = std::max<int64_t>(1, ((int64_t)1 << 30) / pitch);
+    int rc = 0;
+    for (int64_t c0 = 0; c0 < n_cap && !rc; c0 += per_slab) {
+        const int64_t c1 = std::min(n_cap, c0 + per_slab);
+        if (finish_pending()) { rc = -1; break; }
+        run_carry = RunCarry{0, 0, L % sp.mx, 0};  // whatever the slab before left: the first capture's warm-up flushes it
+        if (process_slab(nullptr, c0 * pitch, c0 * pitch, c1 * pitch, c0 * pitch, c1 * pitch, c1 * pitch)) rc = -1;
+        pos = c1 * pitch;
+        stats.samples += (c1 - c0) * cap_len;
+    }
+    if (!rc && finish_pending()) rc = -1;
+    lt.batch_pitch = 0;
+    bm_lo = bm_hi = 0;
+    // the parameter block of a single stream again
+    cudaMemcpyAsync(params_d.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, cs);
+    if (sync_cs() != cudaSuccess && !rc) rc = -1;
+    return rc ? rc : n_cap;
 }
 
 // Runs the slicer over [a, b) and leaves the dense ordered transitions in trans_dense (count in *R_out) and the
@@ -1565,6 +1732,16 @@ int64_t nfc_stream_push(nfc_stream *h, const void *items, int64_t n, int mem, in
         return -1;
     }
     return h->s.push(items, n, mem, called_back);
+}
+
+int64_t nfc_stream_push_batch(nfc_stream *h, const void *items, int mem, int64_t n_captures, int64_t items_per_capture,
+                              int64_t stride_items, const double *lo_vals, const double *hi_vals, int64_t *pitch) {
+    if (!h || !items) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    if (h->s.settle()) return -1;
+    return h->s.push_batch(items, mem, n_captures, items_per_capture, stride_items, lo_vals, hi_vals, pitch);
 }
 
 int64_t nfc_stream_drain_events(nfc_stream *h, nfc_event *out, int64_t cap) {
