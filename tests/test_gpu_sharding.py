@@ -51,7 +51,7 @@ def _worker(rank, world, port, halo_windows, rate, q, view=False):
 
 
 @pytest.mark.parametrize("world,halo_windows,rate,view", [(2, 16, 2e6, False), (3, 1, 2e6, False), (2, 2, 13.56e6, False),
-                                                          (3, 2, 13.56e6, True)])
+                                                          (3, 2, 13.56e6, True), (2, 2, 20e6, True)])
 def test_gpu_time_shards_stitch_exactly(world, halo_windows, rate, view):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

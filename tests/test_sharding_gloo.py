@@ -110,12 +110,22 @@ def _worker(rank, world, port, halo_windows, q):
     res = sharding.decode_time_sharded(eng, lambda a, b: x[a:b], x.size, 2000, _cabi.State, dist=dist,
                                        halo_windows=halo_windows)
     merged = sharding.gather_frames(res["frames"], dist)
+    # the frame offsets alone, as fixed-size records (what bench.py times at N > 1)
+    mine = np.zeros(len(res["frames"]), dtype=_cabi.FRAME_DTYPE)
+    for i, (pp, tt, bb) in enumerate(res["frames"]):
+        mine[i] = (pp, 0, len(bb), tt)
+    index = sharding.gather_frame_records(mine, 0, res["bounds"][0], dist)
     if rank == 0:
         want = oracle.decode_capture(x, 2e6, hi_val=1.09)
         ok = len(merged) == len(want["frames"])
         ok = ok and all(p == int(w["pos"]) and t == int(w["type"]) and np.array_equal(b, wb)
                         for (p, t, b), w, wb in zip(merged, want["frames"], want["frame_bits"]))
-        q.put((ok, len(merged), len(want["frames"])))
+        ok = ok and len(index) == len(want["frames"]) and np.array_equal(index["pos"], want["frames"]["pos"])
+        ok = ok and np.array_equal(index["nbits"], want["frames"]["nbits"]) and np.array_equal(index["type"], want["frames"]["type"])
+        ok = ok and (np.diff(index["shard"]) >= 0).all() and index["shard"].max() == world - 1
+        q.put((bool(ok), len(merged), len(want["frames"])))
+    else:
+        assert index is None
     q.put(("rank", rank, res["repaired"], res["seam_ok"]))
     dist.barrier()
     dist.destroy_process_group()
@@ -150,3 +160,15 @@ def test_plan_alignment():
         for a, b in bounds[:-1]:
             assert a % L == 0 and b % L == 0 and a % 4 == 0
         assert halo % L == 0 and halo % 4 == 0 and halo >= 16 * L
+
+
+def test_packed_records_round_trip():
+    from usrp_nfc_b200 import _cabi, sharding
+    rec = np.zeros(5, dtype=_cabi.FRAME_DTYPE)
+    rec["pos"], rec["nbits"], rec["type"] = [10, 10, 4000000000, 4000000007, 2 ** 33], [7, 163, 9, 0, 18], [1, 0, 1, 0, 1]
+    packed = sharding.pack_records(rec[:4], 100, 50)
+    assert packed.dtype.itemsize == 8
+    back = sharding.unpack_records([packed, sharding.pack_records(rec[:0], 0, 0)], [50, 999])
+    assert back["pos"].tolist() == (rec["pos"][:4] + 100).tolist() and back["nbits"].tolist() == [7, 163, 9, 0]
+    with pytest.raises(ValueError):
+        sharding.pack_records(rec, 0, 0)  # a gap of more than 2^32 samples between two frames of one shard

@@ -16,7 +16,7 @@ usrp_nfc_b200._cabi.Stream; the gloo tests on CPU pass an oracle-backed stand-in
 import numpy as np
 
 INT64_MIN = -(2 ** 63)
-PEND_CAP = 8192  # bits of an unfinished frame carried across a seam (a frame holds at most a few hundred)
+PEND_CAP = 1024  # bits of an unfinished frame carried across a seam (a frame holds at most a few hundred)
 
 
 def plan(total, world, av_window, halo_windows=16):
@@ -32,7 +32,9 @@ def plan(total, world, av_window, halo_windows=16):
 
 
 class SeamState(object):
-    """Engine state in absolute stream coordinates, as one flat float64 vector (for all_gather)."""
+    """Engine state in absolute stream coordinates as one flat byte vector (for all_gather): a header of sixteen 64-bit
+    slots (positions and counters as int64, ss as the bits of its double), the ring as float32, the bits of an unfinished
+    frame.  `overflow` (more than PEND_CAP open bits) travels with it, so that every rank raises after the collective."""
     NH = 16
 
     def __init__(self, vec, L):
@@ -40,63 +42,76 @@ class SeamState(object):
 
     @staticmethod
     def size(L):
-        return SeamState.NH + L + PEND_CAP
+        return SeamState.NH * 8 + L * 4 + PEND_CAP
+
+    @staticmethod
+    def zeros(L):
+        return SeamState(np.zeros(SeamState.size(L), dtype=np.uint8), L)
+
+    def _hdr(self):
+        return self.vec[: self.NH * 8].view(np.int64)
+
+    def _ring(self):
+        return self.vec[self.NH * 8: self.NH * 8 + self.L * 4].view(np.float32)
+
+    def _pend(self):
+        return self.vec[self.NH * 8 + self.L * 4:]
 
     @staticmethod
     def from_engine(engine, base, L):
         st, ring, pend = engine.state()
-        v = np.zeros(SeamState.size(L), dtype=np.float64)
-        v[0] = st.pos + base
-        v[1] = np.float64(st.ss)
-        v[2:5] = (st.cur_state, st.last_bit, st.dur)
-        v[5:7] = (st.miller_state, st.manch_state)
-        v[7:9] = (st.started[0], st.started[1])
-        v[9:11] = (st.pending[0], st.pending[1])
-        v[11] = st.serial_mode
-        if len(pend) > PEND_CAP:
-            raise ValueError("unfinished frame longer than PEND_CAP bits at a seam")
-        v[SeamState.NH: SeamState.NH + L] = ring
-        v[SeamState.NH + L: SeamState.NH + L + len(pend)] = pend
-        return SeamState(v, L)
+        out = SeamState.zeros(L)
+        h = out._hdr()
+        h[0] = st.pos + base
+        h[1] = np.array([st.ss], dtype=np.float64).view(np.int64)[0]
+        h[2:5] = (st.cur_state, st.last_bit, st.dur)
+        h[5:7] = (st.miller_state, st.manch_state)
+        h[7:9] = (st.started[0], st.started[1])
+        h[9:11] = (st.pending[0], st.pending[1])
+        h[11] = st.serial_mode
+        h[12] = 1 if len(pend) > PEND_CAP else 0
+        out._ring()[:] = np.asarray(ring, dtype=np.float32)
+        n = min(len(pend), PEND_CAP)
+        out._pend()[:n] = np.asarray(pend[:n], dtype=np.uint8)
+        return out
+
+    def overflow(self):
+        return bool(self._hdr()[12])
 
     def npend(self):
-        return int(self.vec[9] + self.vec[10])
+        h = self._hdr()
+        return int(min(h[9] + h[10], PEND_CAP))
 
     def equal(self, other, strict_dur=False):
-        a, b = self.vec, other.vec
-        if a[0] != b[0] or a[1].tobytes() != b[1].tobytes():
+        a, b = self._hdr(), other._hdr()
+        if a[0] != b[0] or a[1] != b[1]:  # position; ss bit for bit
             return False
         if not np.array_equal(a[2:4], b[2:4]) or not np.array_equal(a[5:11], b[5:11]):
             return False
         idle = a[2] == 0 and a[3] == 0  # dur then only phases the dropped type -1 events
         if (strict_dur or not idle) and a[4] != b[4]:
             return False
-        L = self.L
-        ra = a[self.NH: self.NH + L].astype(np.float32).view(np.uint32)
-        rb = b[self.NH: self.NH + L].astype(np.float32).view(np.uint32)
-        if not np.array_equal(ra, rb):
+        if not np.array_equal(self._ring().view(np.uint32), other._ring().view(np.uint32)):
             return False
         n = self.npend()
-        return np.array_equal(a[self.NH + L: self.NH + L + n], b[self.NH + L: self.NH + L + n])
+        return np.array_equal(self._pend()[:n], other._pend()[:n])
 
     def apply(self, engine, state_cls):
         """Load into a freshly reset engine, in absolute coordinates (base 0)."""
-        v, L = self.vec, self.L
+        h, L = self._hdr(), self.L
         st = state_cls()
-        st.pos = int(v[0])
-        st.ss = float(v[1])
-        st.cur_state, st.last_bit, st.dur = int(v[2]), int(v[3]), int(v[4])
-        st.index = int(v[0]) % L
+        st.pos = int(h[0])
+        st.ss = float(np.array([h[1]], dtype=np.int64).view(np.float64)[0])
+        st.cur_state, st.last_bit, st.dur = int(h[2]), int(h[3]), int(h[4])
+        st.index = int(h[0]) % L
         st.stable = 1
-        st.miller_state, st.manch_state = int(v[5]), int(v[6])
-        st.started[0], st.started[1] = int(v[7]), int(v[8])
-        st.pending[0], st.pending[1] = int(v[9]), int(v[10])
-        st.serial_mode = int(v[11])
+        st.miller_state, st.manch_state = int(h[5]), int(h[6])
+        st.started[0], st.started[1] = int(h[7]), int(h[8])
+        st.pending[0], st.pending[1] = int(h[9]), int(h[10])
+        st.serial_mode = int(h[11])
         st.lastL = INT64_MIN  # derived from (cur_state, last_bit, dur) by set_state
         st.lrun_start = INT64_MIN
-        ring = v[self.NH: self.NH + L].astype(np.float32)
-        pend = v[self.NH + L: self.NH + L + self.npend()].astype(np.uint8)
-        engine.set_state(st, ring, pend)
+        engine.set_state(st, self._ring().copy(), self._pend()[: self.npend()].copy())
 
 
 def _all_gather(vec, dist, group, device):
@@ -172,11 +187,13 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
     final = SeamState.from_engine(engine, base, L) if begin < end or rank == 0 else assumed
     repaired, seam_ok = False, [True] * world
     if world > 1:
-        zero = np.zeros(SeamState.size(L))
+        zero = SeamState.zeros(L).vec
         both = _all_gather(np.concatenate([final.vec, assumed.vec if assumed is not None else zero]), dist, group, device)
         nv = SeamState.size(L)
         finals = [SeamState(np.ascontiguousarray(v[:nv]), L) for v in both]
         assumes = [SeamState(np.ascontiguousarray(v[nv:]), L) for v in both]
+        if any(f.overflow() for f in finals) or any(a.overflow() for a in assumes):  # the same verdict on every rank
+            raise ValueError("unfinished frame longer than PEND_CAP bits at a seam")
         for k in range(1, world):
             ok = finals[k - 1].equal(assumes[k], strict_dur)
             seam_ok[k] = ok
@@ -195,11 +212,83 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
                 repaired = True
                 vec = final.vec
             else:
-                vec = np.zeros(SeamState.size(L))
+                vec = SeamState.zeros(L).vec
             finals[k] = SeamState(_broadcast(vec, k, dist, group, device), L)
     out = dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo, n_frames=len(rec))
     if frames is None:
         out.update(records=rec, bits=bits, pos_offset=pos_offset)
+    return out
+
+
+REC_DTYPE = np.dtype([("dpos", "<u4"), ("nbits", "<u2"), ("type", "u1"), ("pad", "u1")])
+
+
+def pack_records(rec, pos_offset, begin):
+    """Frame records of one shard as 8 bytes each: closing position as the distance from the frame before (the first from
+    the shard's first sample), length, type.  bit_off is not sent: frames of one type are back to back."""
+    out = np.zeros(len(rec), dtype=REC_DTYPE)
+    if len(rec):
+        pos = rec["pos"].astype(np.int64) + pos_offset
+        d = np.diff(np.concatenate(([begin], pos)))
+        if (d < 0).any() or (d >= 1 << 32).any():
+            raise ValueError("frame positions of a shard must ascend within 2^32 samples of each other")
+        out["dpos"], out["nbits"], out["type"] = d, rec["nbits"], rec["type"]
+    return out
+
+
+def gather_frame_records(rec, pos_offset, begin, dist=None, group=None, device="cpu", state=None):
+    """The frame offsets of all shards on rank 0 in stream order (the order the reference hands frames to fsm.process_bits,
+    packets.py:94-98): one all_gather of the counts, one gather of the packed records (8 bytes per frame, device tensors
+    over NCCL or host tensors over gloo), read back into host memory on rank 0.  Returns on rank 0 an array with absolute
+    closing position, length, type and shard of every frame; None elsewhere.  `state`: a dict that keeps the staging
+    tensors between calls."""
+    import torch
+    if dist is None or dist.get_world_size(group) == 1:
+        return unpack_records([pack_records(rec, pos_offset, begin)], [begin])
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    packed = pack_records(rec, pos_offset, begin)
+    state = state if state is not None else {}
+    cnt = torch.tensor([len(packed), begin], dtype=torch.int64, device=device)
+    cnts = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    meta = torch.stack(cnts).cpu().numpy()
+    nmax = int(meta[:, 0].max())
+    cap = max(1, nmax)
+    if state.get("cap", 0) < cap:
+        state["cap"] = int(cap * 1.25) + 16
+        state["send"] = torch.zeros(state["cap"], dtype=torch.int64, device=device)
+        state["recv"] = [torch.zeros(state["cap"], dtype=torch.int64, device=device) for _ in range(world)] if rank == 0 else None
+        state["host"] = torch.zeros((world, state["cap"]), dtype=torch.int64).pin_memory() if (rank == 0 and str(device) != "cpu") else None
+    send = state["send"]
+    if len(packed):
+        send[: len(packed)].copy_(torch.from_numpy(packed.view(np.int64)), non_blocking=True)
+    dist.gather(send, state["recv"] if rank == 0 else None, dst=0, group=group)
+    if rank != 0:
+        return None
+    if state["host"] is not None:
+        for r in range(world):
+            state["host"][r, : int(meta[r, 0])].copy_(state["recv"][r][: int(meta[r, 0])], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        parts = [state["host"][r, : int(meta[r, 0])].numpy().view(REC_DTYPE) for r in range(world)]
+    else:
+        parts = [state["recv"][r][: int(meta[r, 0])].numpy().view(REC_DTYPE) for r in range(world)]
+    return unpack_records(parts, [int(b) for b in meta[:, 1]])
+
+
+FRAME_INDEX_DTYPE = np.dtype([("pos", "<i8"), ("nbits", "<i4"), ("type", "i1"), ("shard", "i1"), ("pad", "<i2")])
+
+
+def unpack_records(parts, begins):
+    out = np.zeros(sum(len(p) for p in parts), dtype=FRAME_INDEX_DTYPE)
+    o = 0
+    for r, (p, b) in enumerate(zip(parts, begins)):
+        n = len(p)
+        if n:
+            out["pos"][o: o + n] = b + np.cumsum(p["dpos"].astype(np.int64))
+            out["nbits"][o: o + n] = p["nbits"]
+            out["type"][o: o + n] = p["type"]
+            out["shard"][o: o + n] = r
+        o += n
     return out
 
 
