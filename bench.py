@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 
 RATE = 13.56e6  # BASELINE.json configs[2]; --rate 20e6 gives configs[4] (time-sharded 20 MS/s capture)
 HI_VAL = 1.09
+# the reference's own Python loop (transition_sink.work_stable + decoders), measured per core in the build container where
+# /root/reference can be imported; the GPU box has no /root/reference, so the arm below times the C port
+PY_REF_NOTE = "the reference's Python 2 loop does 2.3-3.6 Msamples/s per core (BASELINE.md 2, SURVEY.md 6: 0.91 published); kind 'port' is its C restatement, ~60x faster per core"
 
 
 def measured_peak_gbs():
@@ -112,6 +115,42 @@ def same_frames(ra, rb):
                 np.array_equal(fa["nbits"], fb["nbits"]) and np.array_equal(a0, b0) and np.array_equal(a1, b1))
 
 
+def oracle_windows(x, frames, params, k, wlen=6_000_000):
+    """k random windows of the device-resident capture x against the oracle (test infrastructure: the checker, not the
+    thing measured).  frames: (records, tag bits, reader bits) of the CUDA decode of x as view_frames returns them."""
+    from oracle import oracle
+    fr, b0, b1 = frames
+    L = params["av_window"]
+    n = int(x.numel())
+    halo = 24 * L
+    rng = np.random.default_rng(7)
+    starts = sorted(int(v) for v in rng.integers(halo + L, max(halo + L + 1, n - wlen), k))
+    if n > (1 << 30) + wlen:
+        starts[0] = (1 << 30) - wlen // 2  # one window across a slab boundary
+    ok, nfr, nbits = True, 0, 0
+    for w0 in starts:
+        w1 = min(n, w0 + wlen)
+        base = w0 - halo - L
+        want = oracle.decode_capture(x[base:w1].cpu().numpy(), RATE, hi_val=HI_VAL, **params)
+        wpos = want["frames"]["pos"] + base
+        wsel = np.nonzero((wpos >= w0 + 100000) & (wpos < w1))[0]
+        lo, hi = np.searchsorted(fr["pos"], [w0 + 100000, w1])
+        g = fr[lo:hi]
+        same = len(wsel) == len(g) and np.array_equal(wpos[wsel], g["pos"]) and np.array_equal(want["frames"]["type"][wsel], g["type"]) \
+            and np.array_equal(want["frames"]["nbits"][wsel], g["nbits"])
+        if same:
+            for i, r in zip(wsel, g):
+                bits = b0 if r["type"] == 0 else b1
+                if not np.array_equal(want["frame_bits"][i], bits[r["bit_off"]: r["bit_off"] + r["nbits"]]):
+                    same = False
+                    break
+                nbits += int(r["nbits"])
+        ok = ok and bool(same)
+        nfr += len(wsel)
+    return {"windows": len(starts), "samples_each": wlen, "frames_compared": int(nfr), "frame_bits_compared": int(nbits),
+            "identical": bool(ok), "starts": starts}
+
+
 def cpu_baseline(x_host_pieces, params, threads):
     """The reference algorithm (oracle port, C) on the host cores: one independent piece per thread."""
     from oracle import oracle
@@ -130,6 +169,205 @@ def cpu_baseline(x_host_pieces, params, threads):
     dt = time.perf_counter() - t0
     n = sum(len(p) for p in x_host_pieces)
     return n / dt / 1e6, dt, res
+
+
+def chan_for(rate, args):
+    """Amplitude model of SURVEY.md 8(d) at a sample rate (the fade period is 20 ms of samples)."""
+    return dict(carrier=0.5, pause=0.015, tag_high=args.tag_high, noise=0.003, fade=args.fade, fade_period=round(rate * 0.02))
+
+
+def step_frac(samples_per_gpu, ms, peak):
+    """Whole-step fraction of the HBM roofline: 4 algorithmic bytes per sample over the step's wall time."""
+    return 4.0 * samples_per_gpu / (ms * 1e-3) / 1e9 / peak if ms and ms > 0 else None
+
+
+def leg_stream(torch, _cabi, rate, n, local_rank, args, peak, steps=2, warmup=2):
+    """One device-resident capture of n samples at `rate` with that rate's parameters through one
+    nfc_stream on this GPU: the N1 row (2 / 13.56 / 20 MS/s) beside the headline.  Own timing, roofline fractions, clocks."""
+    codes, lens, params = build_schedule(rate, 2024)
+    L = params["av_window"]
+    n = int(n) - int(n) % (L * 4 // np.gcd(L, 4))
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    _cabi.synth_render(x, codes, lens, seed=99, as_envelope=True, device=local_rank, first_index=0, **chan_for(rate, args))
+    torch.cuda.synchronize()
+    s = _cabi.Stream(rate, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_running()
+    t_load = time.perf_counter()
+
+    def step():
+        s.reset()
+        s.push_all(x)
+        fr = s.view_frames()[0]
+        k = len(fr)
+        s.release_frames()
+        return k
+    for _ in range(warmup):
+        step()
+    s.reset_stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        frames = step()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st = s.stats()
+    clocks = sampler.stop(t_load, t0, t0 + wall)
+    s.close()
+    del x
+    torch.cuda.empty_cache()
+    ms = wall * 1e3 / steps
+    kern = st["slicer_kernel_ms"] / steps
+    return {"workload": "synthetic ISO 14443A reader+tag traffic, %.3g samples at %.2f MS/s on one GPU" % (n, rate / 1e6),
+            "samp_rate": rate, **params, "hi_val": HI_VAL, "steps": steps, "warmup": warmup, "ms": ms,
+            "value": n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "frac": step_frac(n, ms, peak),
+            "kernel_ms": kern, "kernel_frac": step_frac(n, kern, peak) if kern > 0 else None,
+            "slicer_stage_ms": st["slicer_ms"] / steps, "device_ms": st["kernel_ms"] / steps, "frames": int(frames),
+            "streaming_tiles": int(st["fast_tiles"]), "pipelined_tiles": int(st["pipe_tiles"]), "exact_tiles": int(st["exact_tiles"]),
+            "clocks": clocks}
+
+
+def leg_batch(torch, _cabi, dist, rank, world, local_rank, args, peak, per_rank_captures, ns, rate, steps=2, warmup=2):
+    """BASELINE.json configs[3] (C4): per_rank_captures independent captures per GPU (4096 over eight GPUs = 512 each), mixed
+    Ultralight / Classic traffic, hi_val per capture from 1.05..1.10, decoded in one pass per GPU (nfc_stream_push_batch);
+    frame records stay per rank, their counts are all-reduced.  Weak in N: value = all captures / max-over-ranks time."""
+    from usrp_nfc_b200 import batch
+    codes, lens, params = build_schedule(rate, 2024)
+    chan = chan_for(rate, args)
+    uniq = 8
+    his = [1.05, 1.06, 1.07, 1.08, 1.09, 1.10]
+    mine = [rank * per_rank_captures + k for k in range(per_rank_captures)]
+    x2d = torch.empty((len(mine), ns), dtype=torch.float32, device="cuda")
+    for u in range(uniq):
+        _cabi.synth_render(x2d[u], codes, lens, seed=500 + u, as_envelope=True, device=local_rank, first_index=u * 7919 * 4096, **chan)
+    for k, i in enumerate(mine):
+        if k >= uniq:
+            x2d[k].copy_(x2d[k % uniq])
+    hv = np.array([his[i % len(his)] for i in mine], dtype=np.float64)
+    torch.cuda.synchronize()
+    state = {}
+
+    def step():
+        res = batch.decode_batch_onepass(x2d, rate, params, hi_vals=hv, device=local_rank, stream=state.get("s"))
+        state["s"] = res["stream"]
+        if res.get("per_capture") is not None:
+            return sum(len(fr) for fr, _ in res["per_capture"])
+        return len(res["frames"])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_running()
+    t_load = time.perf_counter()
+    for _ in range(warmup):
+        frames = step()
+    state["s"].reset_stats()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        frames = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    st = state["s"].stats()
+    clocks = sampler.stop(t_load, t0, t0 + wall) if rank == 0 else None
+    t = torch.tensor([wall * 1e3 / steps, float(frames), st["slicer_kernel_ms"] / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx, sm = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, frames, kern = float(mx[0]), int(sm[1]), float(mx[2])
+    else:
+        ms, frames, kern = float(t[0]), int(t[1]), float(t[2])
+    state["s"].release_frames()
+    state["s"].close()
+    del x2d
+    torch.cuda.empty_cache()
+    n_rank = per_rank_captures * ns
+    return {"workload": "batch of %d independent synthetic captures (%d per GPU) of %.3g samples at %.2f MS/s, mixed Ultralight / "
+                        "Classic sessions, hi_val 1.05..1.10 per capture, one pass per GPU (nfc_stream_push_batch)" % (
+                            per_rank_captures * world, per_rank_captures, ns, rate / 1e6),
+            "samp_rate": rate, **params, "n_gpus": world, "scaling": "weak", "steps": steps, "warmup": warmup, "ms": ms,
+            "value": world * n_rank / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "frac": step_frac(n_rank, ms, peak),
+            "kernel_ms": kern, "kernel_frac": step_frac(n_rank, kern, peak) if kern > 0 else None, "frames": frames, "clocks": clocks}
+
+
+def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate, piece, buf=None):
+    """BASELINE.json configs[4] (C5): ONE capture of `total` samples at 20 MS/s, strong-scaled: time shards with a halo
+    (sharding.plan), every rank decodes total / N samples.  The capture never exists as a whole: each rank renders its shard
+    piece by piece (`piece` samples, one reused buffer: 1e11 samples are 400 GB) and pushes the piece into its stream, which
+    carries the state on -- the slabbed regenerate-and-decode loop of SURVEY.md 7.7.  Rendering is not timed (the clock stops
+    while a piece is rendered); seam verification (all_gather of the seam states), any repair and the gather of the frame
+    offsets to rank 0 (fixed 8-byte records over NCCL) are."""
+    from usrp_nfc_b200 import sharding
+    codes, lens, params = build_schedule(rate, 2024)
+    chan = chan_for(rate, args)
+    L = params["av_window"]
+    q = L * 4 // np.gcd(L, 4)
+    total = int(total) - int(total) % (q * world)
+    piece = int(piece) - int(piece) % q
+    if buf is None or buf.numel() < piece:
+        buf = torch.empty(piece, dtype=torch.float32, device="cuda")
+    s = _cabi.Stream(rate, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+    clock = {"on": None, "sum": 0.0, "render": 0.0}
+
+    def fetch(a, b):
+        t = time.perf_counter()
+        if clock["on"] is not None:
+            clock["sum"] += t - clock["on"]
+        _cabi.synth_render(buf[: b - a], codes, lens, seed=99, as_envelope=True, device=local_rank, first_index=a, **chan)
+        torch.cuda.synchronize()
+        clock["on"] = time.perf_counter()
+        clock["render"] += clock["on"] - t
+        return buf[: b - a]
+    # warm-up: the first piece of rank 0's shard (allocations, first launches), untimed
+    s.reset()
+    s.push_all(fetch(0, min(piece, total // world)))
+    s.view_frames()
+    s.release_frames()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_running()
+    gstate = {}
+    s.reset_stats()
+    clock.update(on=time.perf_counter(), sum=0.0, render=0.0)
+    t_begin = clock["on"]
+    res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
+                                       halo_windows=args.halo_windows, flat="view", piece=piece)
+    index = sharding.gather_frame_records(res["records"], res["pos_offset"], res["bounds"][0], dist if world > 1 else None,
+                                          device="cuda", state=gstate)
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    clock["sum"] += t_end - clock["on"]
+    st = s.stats()
+    n_frames_rank = int(res["n_frames"])
+    s.release_frames()
+    s.close()
+    clocks = sampler.stop(t_begin, t_begin, t_end) if rank == 0 else None
+    t = torch.tensor([clock["sum"] * 1e3, clock["render"] * 1e3, float(res["repaired"]), st["slicer_kernel_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        ms, render_ms, repaired, kern = float(mx[0]), float(mx[1]), int(mx[2]), float(mx[3])
+    else:
+        ms, render_ms, repaired, kern = float(t[0]), float(t[1]), int(t[2]), float(t[3])
+    per_gpu = total // world
+    return {"workload": "ONE synthetic capture of %.3g samples at %.2f MS/s, time shards of %.3g samples with a halo of %d av_windows, "
+                        "rendered and decoded in pieces of %.3g samples (400 GB never resident)" % (
+                            total, rate / 1e6, per_gpu, args.halo_windows, piece),
+            "samp_rate": rate, **params, "n_gpus": world, "scaling": "strong", "steps": 1, "warmup": "one piece",
+            "ms": ms, "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "frac": step_frac(per_gpu, ms, peak),
+            "kernel_ms": kern, "kernel_frac": step_frac(per_gpu, kern, peak) if kern > 0 else None,
+            "render_ms_untimed": render_ms, "frames": int(len(index)) if index is not None else n_frames_rank,
+            "frame_offsets_gathered_bytes": int(len(index)) * 8 if index is not None else 0,
+            "ranks_redone": repaired, "clocks": clocks}
 
 
 def bench_batch(args, rank, world, local_rank, codes, lens, params, chan, dist, torch, _cabi):
@@ -249,6 +487,11 @@ def main():
     ap.add_argument("--batch-workers", type=int, default=8)
     ap.add_argument("--batch-spin", action="store_true", help="batch: spinning waits (the library's default for a single stream)")
     ap.add_argument("--batch-legacy", action="store_true", help="batch: one nfc_stream per capture on worker threads instead of one pass")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-runs of the other BASELINE.json configs (2 / 20 MS/s, batch, C5)")
+    ap.add_argument("--c5-total", type=float, default=1e11, help="configs[4]: samples of the one strong-scaled 20 MS/s capture")
+    ap.add_argument("--c5-piece", type=float, default=1e10, help="configs[4]: samples rendered and pushed at a time")
+    ap.add_argument("--c4-per-gpu", type=int, default=512, help="configs[3] leg: captures per GPU (4096 over eight GPUs)")
+    ap.add_argument("--parity-windows", type=int, default=4, help="windows of the timed capture decoded again by the oracle (untimed)")
     ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
     ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()
@@ -296,8 +539,9 @@ def main():
         line = {"impl": "reference", "metric": "decoded_msamples_per_s", "value": v, "unit": "Msamples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, workload=workload + " (bounded CPU sample per step)"),
-                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+                "config": config, "sample_note": "bounded CPU sample per step: " + sample,
+                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample,
+                                 "python_reference": PY_REF_NOTE},
                 "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -327,6 +571,7 @@ def main():
     s = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
     s.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(args.slab))
     shard_info = {}
+    gather_state = {}
 
     def step():
         if world == 1:
@@ -340,6 +585,11 @@ def main():
                                            device="cuda", halo_windows=args.halo_windows, flat="view")
         shard_info.update(repaired=res["repaired"], seam_ok=res["seam_ok"])
         nfr = res["n_frames"]
+        # the frame offsets of all shards on rank 0, in stream order (packets.py:94-98): fixed 8-byte records over NCCL
+        index = sharding.gather_frame_records(res["records"], res["pos_offset"], res["bounds"][0], dist, device="cuda", state=gather_state)
+        if index is not None:
+            shard_info.update(gathered_frames=int(len(index)), gathered_bytes=int(len(index)) * 8,
+                              in_order=bool((np.diff(index["pos"]) >= 0).all()) if len(index) > 1 else True)
         s.release_frames()
         return nfr
 
@@ -419,6 +669,13 @@ def main():
                                  "against seg_len %d, slab_len %d" % (alt["seg_len"], alt["slab_len"]),
                      "identical": same_frames(ra, rb), "frames": int(len(ra[0])), "frame_bits": int(len(ra[1]) + len(ra[2])),
                      "segments_alt": int(st2["segments"]), "seam_mismatches_alt": int(st2["seam_mismatches"])}
+        # ---- windows of the timed capture decoded by the oracle (untimed): cold-started 24 av_windows early, its state has
+        # converged to the stream's long before the window begins; every frame closing inside the window must be the CUDA path's
+        if args.parity_windows > 0:
+            try:
+                selfcheck["parity_windows"] = oracle_windows(x, ra, params, args.parity_windows)
+            except Exception as exc:
+                selfcheck["parity_windows"] = {"error": str(exc)[:200]}
         del ra, rb
 
     # ---- e2e: host (pinned) buffers through the same ABI call, H2D inside the timed region.  The host buffer holds what
@@ -435,6 +692,43 @@ def main():
         xh.copy_(pcm_d)
         del pcm_d
         torch.cuda.synchronize()
+        # the host -> device ceiling of this box for the same pinned buffer: rank 0 alone, then all ranks at once (the e2e
+        # number cannot exceed samples = bytes / 2 over these)
+        h2d = {}
+        try:
+            dev_buf = torch.empty_like(xh, device="cuda")
+
+            def copy_gbs():
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dev_buf.copy_(xh, non_blocking=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    dev_buf.copy_(xh, non_blocking=True)
+                e1.record()
+                torch.cuda.synchronize()
+                return 3 * xh.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            if world > 1:
+                dist.barrier()
+                alone = copy_gbs() if rank == 0 else 0.0
+                dist.barrier()
+            else:
+                alone = copy_gbs()
+            mine_gbs = copy_gbs()
+            tg = torch.tensor([mine_gbs, alone], dtype=torch.float64, device="cuda")
+            if world > 1:
+                allg = [torch.empty_like(tg) for _ in range(world)]
+                dist.all_gather(allg, tg)
+                per = [float(a[0]) for a in allg]
+                alone = float(allg[0][1])
+            else:
+                per = [mine_gbs]
+            h2d = {"one_gpu_alone_gbs": alone, "all_gpus_at_once_gbs_per_rank": per, "all_gpus_at_once_gbs_sum": float(sum(per)),
+                   "e2e_ceiling_msamples_per_s": float(sum(per)) * 1e3 / 2.0,
+                   "note": "pinned int16 host buffer -> device, torch copy, 3 repetitions; all ranks copy at the same time"}
+            del dev_buf
+        except Exception as exc:
+            h2d = {"error": str(exc)[:200]}
         se = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, input_kind=_cabi.IN_PCM_S16, **params)
         se.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(min(args.slab, 1 << 28)))
         xh_np = xh.numpy()
@@ -462,18 +756,48 @@ def main():
         e2e = {"value": world * ne / float(tt[0]) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(est["h2d_bytes"] / esteps), "d2h_bytes_per_step": int(est["d2h_bytes"] / esteps),
                "samples_per_step_per_gpu": ne, "ms_per_step": float(tt[0]) * 1e3, "frames_per_step": int(n_fr_e),
-               "host_buffer": "int16 PCM (pinned), what wavfile_source reads; normalised and squared on the device"}
+               "host_buffer": "int16 PCM (pinned), what wavfile_source reads; normalised and squared on the device",
+               "h2d_ceiling": h2d}
         se.close()
         del xh
     except Exception as exc:  # pinned allocation can fail on small hosts
         e2e = {"value": None, "unit": "Msamples/s", "error": str(exc)[:200]}
+
+    peak, peak_src = measured_peak_gbs()
+    cpu_pieces = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = max(1, cores)
+        piece = int(min(args.cpu_piece, (1 << 31) / threads, n // max(1, threads)))
+        piece -= piece % 4
+        host = x[: piece * threads].cpu().numpy()
+        cpu_pieces = [host[i * piece: (i + 1) * piece] for i in range(threads)]
+
+    # ---- the other BASELINE.json configs, each with its own timing, roofline fractions and clocks (none of them enters `value`)
+    configs = None
+    if not args.no_configs:
+        s.close()
+        del x
+        torch.cuda.empty_cache()
+        configs = {}
+
+        def leg(name, fn):
+            try:
+                configs[name] = fn()
+            except Exception as exc:
+                configs[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+        leg("c4_batch", lambda: leg_batch(torch, _cabi, dist, rank, world, local_rank, args, peak, args.c4_per_gpu,
+                                          int(args.batch_samples), 13.56e6))
+        leg("c5_one_capture_20MS_strong", lambda: leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, args.c5_total,
+                                                         20e6, min(args.c5_piece, args.c5_total / world)))
+        if world == 1:
+            leg("n1_2MS_reference_defaults", lambda: leg_stream(torch, _cabi, 2e6, 2e9, local_rank, args, peak))
+            leg("n1_20MS", lambda: leg_stream(torch, _cabi, 20e6, 4e9, local_rank, args, peak))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak_gbs()
     # the dominant kernel alone: CUDA events around every launch of the streaming slicer kernel, on the library's stream
     k_launches = max(1, st["slicer_kernel_launches"])
     alg_bytes_per_launch = 4.0 * n * args.steps / k_launches
@@ -492,30 +816,32 @@ def main():
                 "algorithmic_bytes_per_sample": 4, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": kern_ms * args.steps / k_launches, "launches_per_step": k_launches / args.steps,
                 "slicer_stage_ms_per_step": slicer_ms,
+                "step_frac": step_frac(n, wall_ms, peak), "step_ms": wall_ms,
+                "step_note": "step_frac = 4 B x samples per GPU / wall time of the whole step (slicer, extraction, runs, line code, "
+                             "framing, records to the host" + (", seam verification, gather of the frame offsets)" if world > 1 else ")"),
                 "note": "achieved = 4 B x samples / CUDA-event time of the streaming slicer kernel's launches per step; the slicer "
                         "stage (kernel, seam checks and repairs, bitmap -> transition extraction) is slicer_stage_ms_per_step"}
 
     cpu = None
-    if not args.no_cpu_baseline:
-        threads = max(1, cores)
-        piece = int(min(args.cpu_piece, (1 << 31) / threads, n // max(1, threads)))
-        piece -= piece % 4
-        host = x[: piece * threads].cpu().numpy()
-        pieces = [host[i * piece: (i + 1) * piece] for i in range(threads)]
-        v, dt, _ = cpu_baseline(pieces, params, threads)
+    if cpu_pieces is not None:
+        threads = len(cpu_pieces)
+        v, dt, _ = cpu_baseline(cpu_pieces, params, threads)
         cpu = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
                "sample": "%d consecutive pieces of %d samples of rank 0's capture, one per host thread, %.1f s" % (
-                   threads, piece, dt)}
+                   threads, len(cpu_pieces[0]), dt),
+               "python_reference": PY_REF_NOTE}
 
     line = {"metric": "decoded_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "sharding": {"kind": "time shards of one capture, halo %d av_windows, seam states all_gathered and verified" % args.halo_windows,
-                         "ranks_redone_last_step": repaired_ranks} if world > 1 else None,
+            "sharding": {"kind": "time shards of one capture, halo %d av_windows, seam states all_gathered and verified, frame "
+                                 "offsets gathered to rank 0 inside the timed step" % args.halo_windows,
+                         "ranks_redone_last_step": repaired_ranks, "frame_offsets_gathered": shard_info.get("gathered_frames"),
+                         "gathered_bytes_per_step": shard_info.get("gathered_bytes"), "gathered_in_stream_order": shard_info.get("in_order")} if world > 1 else None,
             "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
             "selfcheck": selfcheck, "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments", "pipe_tiles", "pipe_runs", "pipe_aborts")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "configs": configs}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

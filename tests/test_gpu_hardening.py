@@ -111,3 +111,23 @@ def test_synthesis_kernel_renders_the_host_schedule():
     _cabi.synth_render(y, codes, lens, carrier=0.5, pause=0.02, tag_high=1.08, noise=0.0, fade=0.0, as_envelope=False, first_index=n - 1234)
     ref = synth.pcm_to_float(np.concatenate([pcm, pcm]))[n - 1234: n - 1234 + 5000]
     assert np.array_equal(y.cpu().numpy(), ref)
+
+
+def test_queued_slab_chain_is_done_again_when_its_buffers_are_too_small():
+    """Slabs after the first are queued with buffers sized from the slabs before (no host round trip per slab).  Calm
+    slabs first, then a stretch where val changes with every sample: the chain of that slab finds its buffers too small,
+    raises the flag in its context block, and the host does it (and the slab queued behind it) again with exact sizes."""
+    rate, L, mx = 13.56e6, 13560, 339
+    frames = synth.load_sessions()["ultralight"]
+    pcm = synth.capture(frames, rate, 5, av_window=L, sessions=24)
+    x = synth.envelope(synth.pcm_to_float(pcm)).copy()
+    slab = 1 << 20
+    assert x.size > 5 * slab
+    lvl = float(np.median(x[:L]))
+    a = 3 * slab + 70000
+    x[a: a + 400000: 2] = np.float32(lvl * 1.3)  # HIGH on every other sample: 400k transitions in one slab
+    want = oracle.decode_capture(x, rate, hi_val=1.09, av_window=L, max_len=mx)
+    got = gpu_decode(x, rate, hi_val=1.09, av_window=L, max_len=mx, tuning=dict(slab_len=slab))
+    check_against_oracle(got, want)
+    st = got["stream"].stats()
+    assert st["fast_tiles"] > 0 and st["overflow_retries"] > 0

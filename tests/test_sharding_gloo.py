@@ -108,7 +108,7 @@ def _worker(rank, world, port, halo_windows, q):
     x = synth.envelope(synth.pcm_to_float(pcm))
     eng = OracleEngine(2e6, 1.09, 2000, 50)
     res = sharding.decode_time_sharded(eng, lambda a, b: x[a:b], x.size, 2000, _cabi.State, dist=dist,
-                                       halo_windows=halo_windows)
+                                       halo_windows=halo_windows, piece=50021 if halo_windows == 1 else None)
     merged = sharding.gather_frames(res["frames"], dist)
     # the frame offsets alone, as fixed-size records (what bench.py times at N > 1)
     mine = np.zeros(len(res["frames"]), dtype=_cabi.FRAME_DTYPE)

@@ -115,6 +115,11 @@ struct SegWork {
     int64_t bm_pos0;      // multiple of 128
 };
 
+// ---- a slab's post-slicer chain (extraction -> runs -> line code) queued without host round trips ----
+// Flags the kernels raise in device memory when a buffer sized from the slabs before turns out too small (the host then
+// does the slab again with exact sizes), or when the frame-boundary search finds no reset (scan fallback).
+enum PostFlags { POST_OVF_TRANS = 1, POST_OVF_EVENTS = 2, POST_UNRESOLVED = 4 };
+
 // ---- run -> event carry (the reference's cur_state / last_bit / dur at a window start) ----
 struct RunCarry {
     int32_t st, last_bit, dur;

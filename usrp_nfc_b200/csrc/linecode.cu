@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <algorithm>
+
 namespace nfc {
 
 #ifndef NFC_LC_CHUNK
@@ -57,6 +59,15 @@ struct CombineCnt {
         c.tail1 = b.has1 ? b.tail1 : a.tail1 + b.tail1;
         return c;
     }
+};
+
+// The number of events of a slab is read from device memory (left there by the run kernels' scan), so that the host can
+// queue the line-code kernels without waiting for it; cap sizes grids and buffers (more events than that: POST_OVF_EVENTS,
+// raised by run_write_kernel, and the host does the slab again).
+struct EvCount {
+    const uint32_t *d_M;
+    uint32_t cap;
+    __device__ __forceinline__ uint32_t n() const { return min(*d_M, cap); }
 };
 
 struct TabView {
@@ -177,12 +188,13 @@ __device__ __forceinline__ void load_tables(const LineTables &lt, TabEntry *sm, 
     tv.pitch = lt.batch_pitch; tv.skip = lt.batch_skip; tv.len = lt.batch_len;
 
 // ---- pass A: transfer function of every chunk -------------------------------------------------
-__global__ void chunk_map_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
-                                 ChunkMap *__restrict__ maps, uint32_t n_chunks) {
+__global__ void chunk_map_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
+                                 ChunkMap *__restrict__ maps, uint32_t cap_chunks) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chunks) return;
-    const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
+    const uint32_t n_ev = evc.n();
+    if (c >= cap_chunks) return;
+    const uint32_t i0 = min(n_ev, c * CHUNK), i1 = min(n_ev, i0 + CHUNK);  // behind the last event: the identity
     uint8_t r[RSTATES], g[GSTATES];
     for (int s = 0; s < RSTATES; s++) r[s] = (uint8_t)s;
     for (int s = 0; s < GSTATES; s++) g[s] = (uint8_t)s;
@@ -269,10 +281,11 @@ struct CountSink {
 // (per direction) and replays only the events between that chunk's end and its own start (none when it is the previous
 // chunk).  start[c] = R state | G state << 8.  Chunks that find nothing within LOOKBACK_LIMIT events raise *unresolved
 // (the host then takes the transfer-function scan below for the slab).
-__global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
-                                     uint16_t *__restrict__ summary, uint32_t n_chunks) {
+__global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
+                                     uint16_t *__restrict__ summary) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_ev = evc.n(), n_chunks = (n_ev + CHUNK - 1) / CHUNK;
     if (c >= n_chunks) return;
     int rs = 0, gs = 0;
     bool kR = false, kG = false;
@@ -311,12 +324,14 @@ __global__ void chunk_summary_kernel(const EventRec *__restrict__ ev, uint32_t n
     summary[c] = (uint16_t)((rs & 31) | (kR ? 32 : 0) | ((gs & 15) << 8) | (kG ? 4096 : 0));
 }
 
-__global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt, DecCarry carry,
-                                   const uint16_t *__restrict__ summary, uint16_t *__restrict__ start, uint32_t n_chunks,
-                                   int *__restrict__ unresolved) {
+__global__ void chunk_start_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
+                                   const DecCarry *__restrict__ carry_in, const uint16_t *__restrict__ summary,
+                                   uint16_t *__restrict__ start, uint32_t *__restrict__ flags) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_ev = evc.n(), n_chunks = (n_ev + CHUNK - 1) / CHUNK;
     if (c >= n_chunks) return;
+    const DecCarry carry = *carry_in;
     int rs = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
     int gs = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
     const int64_t i0 = (int64_t)c * CHUNK;
@@ -330,7 +345,7 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
         if (!foundG && (sm & 4096u)) { foundG = true; iG = (cc + 1) * CHUNK - 1; gs = (int)((sm >> 8) & 15u); }
     }
     if (cc >= 0 && !(foundR && foundG)) {  // gave up before the first chunk: the carry cannot be used either
-        atomicOr(unresolved, 1);
+        atomicOr(flags, (uint32_t)POST_UNRESOLVED);
         start[c] = 0;
         return;
     }
@@ -369,23 +384,29 @@ __global__ void chunk_start_kernel(const EventRec *__restrict__ ev, uint32_t n_e
 }
 
 // start states from the composed transfer functions (fallback path)
-__global__ void chunk_start_from_maps_kernel(const ChunkMap *__restrict__ prefix, DecCarry carry,
+__global__ void chunk_start_from_maps_kernel(const ChunkMap *__restrict__ prefix, const DecCarry *__restrict__ carry_in,
                                              uint16_t *__restrict__ start, uint32_t n_chunks) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
+    const DecCarry carry = *carry_in;
     const int rs0 = (carry.miller_state & 15) | ((carry.started[1] & 1) << 4);
     const int gs0 = (carry.manch_state & 7) | ((carry.started[0] & 1) << 3);
     start[c] = (uint16_t)(prefix[c].r[rs0] | (prefix[c].g[gs0] << 8));
 }
 
-__global__ void chunk_count_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
-                                   const uint16_t *__restrict__ start, ChunkCnt *__restrict__ cnts, uint32_t n_chunks) {
+__global__ void chunk_count_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
+                                   const uint16_t *__restrict__ start, ChunkCnt *__restrict__ cnts, uint32_t cap_chunks) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chunks) return;
-    int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
+    const uint32_t n_ev = evc.n(), n_chunks = (n_ev + CHUNK - 1) / CHUNK;
+    if (c >= cap_chunks) return;
     CountSink sink;
     sink.c = ChunkCnt{0, 0, 0, 0, 0, 0, 0, 0};
+    if (c >= n_chunks) {  // behind the slab's last event: nothing (the scan runs over the capacity)
+        cnts[c] = sink.c;
+        return;
+    }
+    int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
     uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
@@ -444,15 +465,21 @@ struct LineOut {
     uint8_t *bits0, *bits1;
     EmissionRec *em;
     uint32_t cap_sym, cap_b0, cap_b1, cap_em;
-    uint32_t pending0, pending1;  // len(_cur) of each PacketProcessor at the slab start
+    const uint32_t *pending_in;   // len(_cur) of each PacketProcessor at the slab start (device memory: [2])
 };
 
-__global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_ev, LineTables lt,
+__global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
                                    const uint16_t *__restrict__ start,
-                                   const ChunkCnt *__restrict__ cnt_prefix, LineOut out, uint32_t n_chunks,
+                                   const ChunkCnt *__restrict__ cnt_prefix, LineOut out, const DecCarry *__restrict__ carry_in,
                                    DecCarry *__restrict__ carry_out, uint32_t *__restrict__ pending_out) {
     NFC_TABLE_SMEM
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_ev = evc.n(), n_chunks = (n_ev + CHUNK - 1) / CHUNK;
+    if (n_chunks == 0 && c == 0) {  // a slab without events hands the carries on as they came
+        *carry_out = *carry_in;
+        pending_out[0] = out.pending_in[0];
+        pending_out[1] = out.pending_in[1];
+    }
     if (c >= n_chunks) return;
     int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
     const ChunkCnt pc = cnt_prefix[c];
@@ -460,8 +487,8 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, uint32_t n_e
     sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.em = out.em;
     sink.cap_sym = out.cap_sym; sink.cap_b0 = out.cap_b0; sink.cap_b1 = out.cap_b1; sink.cap_em = out.cap_em;
     sink.isym = pc.nsym; sink.ib0 = pc.nbit0; sink.ib1 = pc.nbit1; sink.iem = pc.nemit;
-    sink.pend0 = pc.has0 ? pc.tail0 : out.pending0 + pc.tail0;
-    sink.pend1 = pc.has1 ? pc.tail1 : out.pending1 + pc.tail1;
+    sink.pend0 = pc.has0 ? pc.tail0 : out.pending_in[0] + pc.tail0;
+    sink.pend1 = pc.has1 ? pc.tail1 : out.pending_in[1] + pc.tail1;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
     uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
@@ -490,63 +517,64 @@ size_t linecode_scratch_bytes(uint32_t n_chunks) {
     return scan_scratch_elems(n_chunks) * sizeof(ChunkMap) + scan_scratch_elems(n_chunks) * sizeof(ChunkCnt);
 }
 
-// Start states by frame-boundary search; *d_unresolved != 0 afterwards means the caller must use the scan path.
-int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_summary,
-                          uint16_t *d_start, int *d_unresolved, cudaStream_t stream) {
-    const uint32_t nc = linecode_chunks(n_ev);
-    if (nc == 0) return 0;
-    NFC_CUDA_CHECK(cudaMemsetAsync(d_unresolved, 0, sizeof(int), stream));
-    chunk_summary_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_summary, nc);
+// Start states by frame-boundary search; POST_UNRESOLVED in *d_flags afterwards means the caller must use the scan path.
+// d_M / cap_ev: see EvCount.  d_carry_in: the decoder state the slab before left on the device.
+int launch_linecode_start(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const DecCarry *d_carry_in,
+                          uint16_t *d_summary, uint16_t *d_start, uint32_t *d_flags, cudaStream_t stream) {
+    const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
+    const EvCount evc{d_M, cap_ev};
+    chunk_summary_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_summary);
     NFC_CUDA_CHECK(cudaGetLastError());
-    chunk_start_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, carry, d_summary, d_start, nc, d_unresolved);
+    chunk_start_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_carry_in, d_summary, d_start, d_flags);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 // Start states by composing chunk transfer functions (always applicable).
-int launch_linecode_start_scan(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
-                               void *d_prefix, void *d_scratch, uint16_t *d_start, cudaStream_t stream) {
-    const uint32_t nc = linecode_chunks(n_ev);
-    if (nc == 0) return 0;
+int launch_linecode_start_scan(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt,
+                               const DecCarry *d_carry_in, void *d_maps, void *d_prefix, void *d_scratch, uint16_t *d_start,
+                               cudaStream_t stream) {
+    const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
     ChunkMap *maps = (ChunkMap *)d_maps, *prefix = (ChunkMap *)d_prefix;
     const unsigned nb = (nc + 127) / 128;
-    chunk_map_kernel<<<nb, 128, 0, stream>>>(d_ev, n_ev, lt, maps, nc);
+    const EvCount evc{d_M, cap_ev};
+    chunk_map_kernel<<<nb, 128, 0, stream>>>(d_ev, evc, lt, maps, nc);
     NFC_CUDA_CHECK(cudaGetLastError());
     ChunkMap ident;
     for (int s = 0; s < RSTATES; s++) ident.r[s] = (uint8_t)s;
     for (int s = 0; s < GSTATES; s++) ident.g[s] = (uint8_t)s;
     if (device_exclusive_scan<ChunkMap, ComposeMap>(maps, prefix, nc, ident, ComposeMap(), (ChunkMap *)d_scratch, nullptr, stream))
         return -1;
-    chunk_start_from_maps_kernel<<<nb, 128, 0, stream>>>(prefix, carry, d_start, nc);
+    chunk_start_from_maps_kernel<<<nb, 128, 0, stream>>>(prefix, d_carry_in, d_start, nc);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 // Counts per chunk from the start states, scanned into d_cnt_prefix; totals in *d_total.
-int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start, void *d_cnts,
-                          void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t stream) {
-    const uint32_t nc = linecode_chunks(n_ev);
-    if (nc == 0) return 0;
+int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
+                          void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t stream) {
+    const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
     ChunkCnt *cnts = (ChunkCnt *)d_cnts, *cprefix = (ChunkCnt *)d_cnt_prefix;
-    chunk_count_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_start, cnts, nc);
+    const EvCount evc{d_M, cap_ev};
+    chunk_count_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_start, cnts, nc);
     NFC_CUDA_CHECK(cudaGetLastError());
     ChunkCnt zero = {0, 0, 0, 0, 0, 0, 0, 0};
     return device_exclusive_scan<ChunkCnt, CombineCnt>(cnts, cprefix, nc, zero, CombineCnt(), (ChunkCnt *)d_scratch,
                                                        (ChunkCnt *)d_total, stream);
 }
 
-int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start,
+int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
-                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
-                          uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
-    const uint32_t nc = linecode_chunks(n_ev);
-    if (nc == 0) return 0;
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, const uint32_t *d_pending_in,
+                          const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
+    const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
     LineOut out;
     out.sym = d_sym; out.bits0 = d_bits0; out.bits1 = d_bits1; out.em = (EmissionRec *)d_em;
     out.cap_sym = cap_sym; out.cap_b0 = cap_b0; out.cap_b1 = cap_b1; out.cap_em = cap_em;
-    out.pending0 = pending0; out.pending1 = pending1;
-    chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, n_ev, lt, d_start, (const ChunkCnt *)d_cnt_prefix, out,
-                                                             nc, d_carry_out, d_pending_out);
+    out.pending_in = d_pending_in;
+    const EvCount evc{d_M, cap_ev};
+    chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_start, (const ChunkCnt *)d_cnt_prefix, out,
+                                                             d_carry_in, d_carry_out, d_pending_out);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

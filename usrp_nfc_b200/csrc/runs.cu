@@ -126,17 +126,48 @@ __device__ __forceinline__ void run_events(const RunView &V, uint32_t r, bool ke
     }
 }
 
-__global__ void run_count_kernel(RunView V, int keep_dropped, uint32_t *__restrict__ counts) {
+// What the kernels know about a slab before it runs: the number of transitions and the carry are read from device memory
+// (left there by the extraction and by the slab before), so that the host can queue a slab's whole chain of kernels without
+// waiting for any count.  cap_R sizes the grid and the buffers: more transitions than that raise POST_OVF_TRANS and the
+// host does the slab again with exact sizes.
+struct RunArgs {
+    const TransRec *tr;
+    const uint32_t *d_R;     // transitions of the slab
+    uint32_t cap_R;
+    int32_t w0, w1;
+    const RunCarry *rc_in;   // the reference's (cur_state, last_bit, dur) at w0
+    int mx;
+    uint32_t *flags;
+};
+__device__ __forceinline__ RunView make_view(const RunArgs &A) {
+    RunView V;
+    const RunCarry c = *A.rc_in;
+    V.tr = A.tr;
+    V.R = min(*A.d_R, A.cap_R);
+    V.w0 = A.w0; V.w1 = A.w1;
+    V.st0 = c.st; V.lb0 = c.last_bit; V.dur0 = c.dur;
+    V.mx = A.mx;
+    return V;
+}
+
+// counts[r] for every r <= cap_R (0 behind the slab's last run: the scan runs over the capacity)
+__global__ void run_count_kernel(RunArgs A, int keep_dropped, uint32_t *__restrict__ counts) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > V.R) return;
+    if (r > A.cap_R) return;
+    const RunView V = make_view(A);
+    if (r == 0 && *A.d_R > A.cap_R) atomicOr(A.flags, (uint32_t)POST_OVF_TRANS);
     uint32_t c = 0;
-    run_events(V, r, keep_dropped != 0, [&](uint32_t, int, int, int) { c++; });
+    if (r <= V.R) run_events(V, r, keep_dropped != 0, [&](uint32_t, int, int, int) { c++; });
     counts[r] = c;
 }
 
-__global__ void run_write_kernel(RunView V, int keep_dropped, const uint32_t *__restrict__ offsets,
-                                 EventRec *__restrict__ out, uint32_t cap, RunCarry *__restrict__ carry_out) {
+__global__ void run_write_kernel(RunArgs A, int keep_dropped, const uint32_t *__restrict__ offsets,
+                                 EventRec *__restrict__ out, uint32_t cap, const uint32_t *__restrict__ d_M,
+                                 RunCarry *__restrict__ carry_out) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > A.cap_R) return;
+    const RunView V = make_view(A);
+    if (r == 0 && *d_M > cap) atomicOr(A.flags, (uint32_t)POST_OVF_EVENTS);
     if (r > V.R) return;
     uint32_t idx = offsets[r];
     run_events(V, r, keep_dropped != 0, [&](uint32_t pos, int v, int d, int type) {
@@ -183,25 +214,26 @@ int launch_gather_pieces(const TransRec *const *d_src, const uint32_t *d_n, cons
     return 0;
 }
 
-// Counts the events of every run into d_counts[0..R] and scans them into d_offsets; *d_total = number of events.
-int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
-                     uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total,
-                     cudaStream_t stream) {
-    RunView V;
-    V.tr = d_tr; V.R = R; V.w0 = (int32_t)w0; V.w1 = (int32_t)w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
-    const uint32_t nrun = R + 1;
-    run_count_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_counts);
+// Counts the events of every run into d_counts[0..cap_R] and scans them into d_offsets; *d_total = number of events.
+// d_R, d_rc_in: device memory (see RunArgs).
+int launch_run_count(const TransRec *d_tr, const uint32_t *d_R, uint32_t cap_R, int64_t w0, int64_t w1, const RunCarry *d_rc_in,
+                     int mx, int keep_dropped, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total,
+                     uint32_t *d_flags, cudaStream_t stream) {
+    RunArgs A;
+    A.tr = d_tr; A.d_R = d_R; A.cap_R = cap_R; A.w0 = (int32_t)w0; A.w1 = (int32_t)w1; A.rc_in = d_rc_in; A.mx = mx; A.flags = d_flags;
+    const uint32_t nrun = cap_R + 1;
+    run_count_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(A, keep_dropped, d_counts);
     NFC_CUDA_CHECK(cudaGetLastError());
     return device_exclusive_scan<uint32_t, AddU32>(d_counts, d_offsets, nrun, 0u, AddU32(), d_scratch, d_total, stream);
 }
 
-int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
-                     const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, RunCarry *d_carry_out,
-                     cudaStream_t stream) {
-    RunView V;
-    V.tr = d_tr; V.R = R; V.w0 = (int32_t)w0; V.w1 = (int32_t)w1; V.st0 = carry.st; V.lb0 = carry.last_bit; V.dur0 = carry.dur; V.mx = mx;
-    const uint32_t nrun = R + 1;
-    run_write_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(V, keep_dropped, d_offsets, d_events, cap, d_carry_out);
+int launch_run_write(const TransRec *d_tr, const uint32_t *d_R, uint32_t cap_R, int64_t w0, int64_t w1, const RunCarry *d_rc_in,
+                     int mx, int keep_dropped, const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, const uint32_t *d_M,
+                     RunCarry *d_carry_out, uint32_t *d_flags, cudaStream_t stream) {
+    RunArgs A;
+    A.tr = d_tr; A.d_R = d_R; A.cap_R = cap_R; A.w0 = (int32_t)w0; A.w1 = (int32_t)w1; A.rc_in = d_rc_in; A.mx = mx; A.flags = d_flags;
+    const uint32_t nrun = cap_R + 1;
+    run_write_kernel<<<(nrun + 255) / 256, 256, 0, stream>>>(A, keep_dropped, d_offsets, d_events, cap, d_M, d_carry_out);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <deque>
 #include <vector>
 
 #include "../../include/usrp_nfc_b200.h"
@@ -27,10 +28,10 @@ namespace nfc {
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok, cudaStream_t);
 bool slicer_streaming_ok(int L, bool vec_ok);
 int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t);
-int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, int carry_val, uint32_t *d_block_counts,
-                         uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total, cudaStream_t);
-int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, int carry_val,
-                         const uint32_t *d_block_offsets, TransRec *d_out, uint32_t out_cap, cudaStream_t);
+int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, uint32_t *d_block_counts,
+                         uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total, cudaStream_t stream);
+int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in,
+                         const uint32_t *d_block_offsets, TransRec *d_out, uint32_t out_cap, cudaStream_t stream);
 size_t extract_blocks(int64_t bm_pos0, int64_t a, int64_t b);
 int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,
                          size_t ring_stride, cudaStream_t);
@@ -40,25 +41,28 @@ int launch_gather_transitions(const SegWork *d_works, const uint32_t *d_counts, 
                               TransRec *d_dense, cudaStream_t);
 int launch_gather_pieces(const TransRec *const *d_src, const uint32_t *d_n, const uint32_t *d_off, int n_pieces,
                          TransRec *d_dense, cudaStream_t);
-int launch_run_count(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
-                     uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total, cudaStream_t);
-int launch_run_write(const TransRec *d_tr, uint32_t R, int64_t w0, int64_t w1, RunCarry carry, int mx, int keep_dropped,
-                     const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, RunCarry *d_carry_out, cudaStream_t);
+int launch_run_count(const TransRec *d_tr, const uint32_t *d_R, uint32_t cap_R, int64_t w0, int64_t w1, const RunCarry *d_rc_in,
+                     int mx, int keep_dropped, uint32_t *d_counts, uint32_t *d_offsets, uint32_t *d_scratch, uint32_t *d_total,
+                     uint32_t *d_flags, cudaStream_t stream);
+int launch_run_write(const TransRec *d_tr, const uint32_t *d_R, uint32_t cap_R, int64_t w0, int64_t w1, const RunCarry *d_rc_in,
+                     int mx, int keep_dropped, const uint32_t *d_offsets, EventRec *d_events, uint32_t cap, const uint32_t *d_M,
+                     RunCarry *d_carry_out, uint32_t *d_flags, cudaStream_t stream);
 uint32_t linecode_chunks(uint32_t n_ev);
 size_t linecode_map_bytes();
 size_t linecode_cnt_bytes();
 size_t linecode_emission_bytes();
 size_t linecode_scratch_bytes(uint32_t n_chunks);
-int launch_linecode_start(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, uint16_t *d_summary,
-                          uint16_t *d_start, int *d_unresolved, cudaStream_t stream);
-int launch_linecode_start_scan(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, DecCarry carry, void *d_maps,
-                               void *d_prefix, void *d_scratch, uint16_t *d_start, cudaStream_t);
-int launch_linecode_count(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start, void *d_cnts,
-                          void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t);
-int launch_linecode_write(const EventRec *d_ev, uint32_t n_ev, const LineTables &lt, const uint16_t *d_start,
+int launch_linecode_start(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const DecCarry *d_carry_in,
+                          uint16_t *d_summary, uint16_t *d_start, uint32_t *d_flags, cudaStream_t stream);
+int launch_linecode_start_scan(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt,
+                               const DecCarry *d_carry_in, void *d_maps, void *d_prefix, void *d_scratch, uint16_t *d_start,
+                               cudaStream_t stream);
+int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
+                          void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t stream);
+int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
-                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, uint32_t pending0,
-                          uint32_t pending1, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t);
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, const uint32_t *d_pending_in,
+                          const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream);
 int slicer_tile(int L, bool vec_ok);
 int slicer_resident_ctas(int L, bool vec_ok, int kind);
 int slicer_tile_stats(unsigned long long *out4, bool reset);
@@ -139,8 +143,23 @@ struct Stream {
     cudaEvent_t ev_h[2] = {nullptr, nullptr};
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around a launch of the streaming slicer kernel
     DevBuf staging2[2];
-    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
-    int ev_idx = 0;
+    // A slab's post-slicer chain (extraction -> runs -> line code) is queued on `cs` without waiting for any count: the
+    // kernels read counts and carries from the slab's context block in device memory (ring of NCTX blocks, PostCtx) and from
+    // the block of the slab before; buffers are sized from the slabs before.  The host looks at a slab's context (copied to
+    // pinned memory behind its chain) one slab later -- the next chain is already queued by then -- and only then puts the
+    // records on their way to the host.  A slab whose buffers turn out too small is done again with exact sizes.
+    static const int NCTX = 4;
+    cudaEvent_t ev_a[NCTX] = {}, ev_b[NCTX] = {}, ev_c[NCTX] = {};  // timing: slab begins, transitions ready, chain done
+    cudaEvent_t ev_ctx[NCTX] = {};   // the slab's context block has arrived in ctx_h
+    cudaEvent_t ev_out[2] = {};      // the records of the slab that used output set i are on the host
+    bool ev_out_set[2] = {false, false};
+    DevBuf ctx_d;
+    char *ctx_h = nullptr;           // pinned, NCTX blocks
+    long long slab_seq = 0;
+    struct Rates {                   // records per sample seen so far (maxima, slowly decaying): sizes the next slab's buffers
+        bool have = false;
+        double R = 0, M = 0, sym = 0, b0 = 0, b1 = 0, em = 0;
+    } rates;
 
     // stream state
     int64_t pos = 0;
@@ -159,9 +178,11 @@ struct Stream {
 
     // device scratch
     DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
-        seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, events_d, maps_d, prefix_d, cnts_d, cprefix_d,
-        line_scr, totals_d, sym_d, bits0_d, bits1_d, em_d, carry_d, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
+        seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, maps_d, prefix_d, cnts_d, cprefix_d,
+        line_scr, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
         redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr, summ_d;
+    // outputs of a slab's chain, two sets: the records of slab k travel to the host while the chain of slab k+1 writes the other
+    DevBuf events_d[2], sym_d[2], bits0_d[2], bits1_d[2], em_d[2];
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     // results come back into one of three pinned buffers.  The carries of a slab (256 bytes) are copied first and are all
     // the next slab waits for; the records behind them are awaited by a worker thread, which turns them into the output
@@ -183,20 +204,27 @@ struct Stream {
     }
     int set_wait_mode(bool blocking);
     std::atomic<int> marshal_err{0};
-    // a slab whose records are on their way to the host: completed (carries taken over, marshalling started) right
-    // before the next slab needs its carries, or when the caller looks at results
-    struct Pending {
-        bool active = false;
-        char *hp = nullptr;
-        size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, off_c = 0, total = 0;
-        uint32_t M = 0, nsym = 0, nbit0 = 0, nbit1 = 0, nemit = 0;
+    // a slab whose chain is queued and whose context the host has not looked at yet
+    struct SlabJob {
+        long long seq = 0;
         int64_t a = 0, b = 0;
+        uint32_t cap_R = 0, cap_M = 0, cap_sym = 0, cap_b0 = 0, cap_b1 = 0, cap_em = 0;
+        bool exact = false;      // sizes were read while queuing: cannot overflow
+        bool from_bitmap = false;
         bool want_ev = false, want_sym = false, want_fr = false, have_line = false;
         double t0 = 0, t1 = 0, t2 = 0;
-        int ei = 0, pi = 0;
-    } pend;
+    };
+    std::deque<SlabJob> jobs;
     cudaEvent_t ev_d[NPIN] = {nullptr, nullptr, nullptr};  // all records of the slab that used pinned[i] have arrived
-    cudaEvent_t ev_carry = nullptr;                         // the carries of the pending slab have arrived
+    int post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1);
+    int finalize_front();
+    int finalize_all() {
+        while (!jobs.empty())
+            if (finalize_front()) return -1;
+        return 0;
+    }
+    int marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t off_b0, size_t off_b1, uint32_t M,
+                uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit);
 
     // results
     std::vector<nfc_event> out_events;
@@ -216,8 +244,8 @@ struct Stream {
     void destroy();
     int ensure_pinned(int idx, size_t bytes);
     int join_marshal();
-    int finish_pending();
-    int settle() { return finish_pending() || join_marshal() ? -1 : 0; }
+    int finish_pending() { return finalize_all(); }
+    int settle() { return finalize_all() || join_marshal() ? -1 : 0; }
     int64_t push(const void *items, int64_t n, int mem, int *called_back);
     int64_t push_batch(const void *items, int mem, int64_t n_cap, int64_t cap_len, int64_t stride_items, const double *lo_vals,
                        const double *hi_vals, int64_t *pitch_out);
@@ -228,9 +256,7 @@ struct Stream {
     int process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, int64_t slicer_end);
     int run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool serial, uint32_t *R_out,
                    bool *fell_back);
-    int run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b_post, int64_t b,
-                      uint32_t *R_out, bool *fell_back);
-    int extract_only(int64_t a, int64_t b, uint32_t *R_out);
+    int run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool *fell_back);
     // the class bitmap holds stream positions [bm_lo, bm_hi) (chunk 0 at bm_origin): the streaming slicer may run ahead of the
     // slab that is being turned into events
     int64_t bm_lo = 0, bm_hi = 0, bm_origin = 0;
@@ -279,13 +305,17 @@ int Stream::init(const nfc_params *p) {
     for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_h[i], cudaEventDisableTiming));
     NFC_CUDA_CHECK(cudaEventCreate(&ev_k0));
     NFC_CUDA_CHECK(cudaEventCreate(&ev_k1));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NCTX; i++) {
         NFC_CUDA_CHECK(cudaEventCreate(&ev_a[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_c[i]));
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ctx[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
     for (int i = 0; i < NPIN; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming));
-    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_carry, cudaEventDisableTiming));
+    NFC_CUDA_CHECK(cudaMallocHost((void **)&ctx_h, (size_t)NCTX * 256));
+    if (ctx_d.ensure((size_t)NCTX * 256)) return -1;
+    NFC_CUDA_CHECK(cudaMemset(ctx_d.p, 0, (size_t)NCTX * 256));
     factor = 1e6 / p->samp_rate;  // transition_sink.py:21
     sp.lo = p->lo_val;
     sp.hi = p->hi_val;
@@ -334,8 +364,6 @@ int Stream::init(const nfc_params *p) {
 
     warm.reserve((size_t)sp.L);
     if (state.ensure(state_block_bytes(sp.L))) return -1;
-    if (carry_d.ensure(256)) return -1;
-    if (totals_d.ensure(256)) return -1;
     resident_ctas = parallel_ok() ? slicer_resident_ctas(sp.L, vec_ok(), sp.input_kind) : 1;
     if (const char *e = getenv("NFC_SUPER_SLAB")) super_slab = std::max(1, std::min(8, atoi(e)));
     if (const char *e = getenv("NFC_SUPER_BALANCE")) super_balance = atoi(e) != 0;
@@ -344,20 +372,28 @@ int Stream::init(const nfc_params *p) {
 
 void Stream::destroy() {
     DevBuf *all[] = {&batch_states, &batch_stage, &params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
-                     &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &events_d, &maps_d,
-                     &prefix_d, &cnts_d, &cprefix_d, &line_scr, &totals_d, &sym_d, &bits0_d, &bits1_d, &em_d, &carry_d,
+                     &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &maps_d,
+                     &prefix_d, &cnts_d, &cprefix_d, &line_scr, &ctx_d, &events_d[0], &events_d[1], &sym_d[0], &sym_d[1], &bits0_d[0],
+                     &bits0_d[1], &bits1_d[0], &bits1_d[1], &em_d[0], &em_d[1],
                      &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
                      &ex_counts, &ex_offsets, &ex_scr, &summ_d};
-    for (DevBuf *b : all) b->release();
-    finish_pending();
+    finalize_all();
     if (marshal_thr.joinable()) marshal_thr.join();
+    if (cs) cudaStreamSynchronize(cs);
+    if (cs2) cudaStreamSynchronize(cs2);
+    for (DevBuf *b : all) b->release();
+    if (ctx_h) cudaFreeHost(ctx_h);
+    ctx_h = nullptr;
     for (int i = 0; i < NPIN; i++)
         if (pinned[i]) cudaFreeHost(pinned[i]);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NCTX; i++) {
         if (ev_a[i]) cudaEventDestroy(ev_a[i]);
         if (ev_b[i]) cudaEventDestroy(ev_b[i]);
         if (ev_c[i]) cudaEventDestroy(ev_c[i]);
+        if (ev_ctx[i]) cudaEventDestroy(ev_ctx[i]);
     }
+    for (int i = 0; i < 2; i++)
+        if (ev_out[i]) cudaEventDestroy(ev_out[i]);
     if (cs2) cudaStreamDestroy(cs2);
     if (cs3) cudaStreamDestroy(cs3);
     if (ev_k0) cudaEventDestroy(ev_k0);
@@ -368,7 +404,6 @@ void Stream::destroy() {
     }
     for (int i = 0; i < NPIN; i++)
         if (ev_d[i]) cudaEventDestroy(ev_d[i]);
-    if (ev_carry) cudaEventDestroy(ev_carry);
     if (ev_blk) cudaEventDestroy(ev_blk);
     if (cs) cudaStreamDestroy(cs);
 }
@@ -405,9 +440,11 @@ int Stream::set_wait_mode(bool blocking) {
         ev_d[i] = nullptr;
         NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], flags));
     }
-    if (ev_carry) cudaEventDestroy(ev_carry);
-    ev_carry = nullptr;
-    NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_carry, flags));
+    for (int i = 0; i < NCTX; i++) {
+        if (ev_ctx[i]) cudaEventDestroy(ev_ctx[i]);
+        ev_ctx[i] = nullptr;
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ctx[i], flags));
+    }
     if (blocking && !ev_blk) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming | cudaEventBlockingSync));
     blocking_wait = blocking;
     return 0;
@@ -1016,8 +1053,10 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
 // The streaming kernel over [a, b): class bitmap (fixed-rate output, no per-segment lists), seams verified and repaired like
 // run_slicer, then the dense ordered transitions of [a, b_post) extracted from the bitmap (b_post <= b: the slicer may cover
 // several slabs at once -- longer segments, relatively shorter speculative starts; extract_only serves the rest).
-int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b_post, int64_t b,
-                          uint32_t *R_out, bool *fell_back) {
+int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b, bool *fell_back) {
+    // the slabs whose chains are still queued read the bitmap this launch is about to overwrite; should one of them have to be
+    // done again, its bitmap must still be there: look at them first (their chains end within a fraction of a millisecond)
+    if (finalize_all()) return -1;
     bm_hi = bm_lo = 0;
     const int L = sp.L;
     const int T = tile();
@@ -1135,22 +1174,6 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         if (compare(nseg)) return -1;
     }
     NFC_CUDA_CHECK(cudaMemcpyAsync(status.data(), seg_status.p, sizeof(int32_t) * (size_t)nseg, cudaMemcpyDeviceToHost, cs));
-    // The transition count of the bitmap is queued behind the seam check so that one synchronisation serves both; it
-    // stands when no segment has to be redone (the usual case).  The previous slab's carries are needed for it: its
-    // records were copied back beside this slab's kernel.
-    if (finish_pending()) return -1;
-    const size_t nblk = extract_blocks(bm_pos0, a, b_post);
-    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
-    uint32_t R = 0;
-    auto count_transitions = [&]() -> int {
-        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_pos0, a, b_post, run_carry.last_bit, ex_counts.as<uint32_t>(),
-                                 ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
-            return -1;
-        stats.launches += 4;
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
-        return 0;
-    };
-    if (count_transitions()) return -1;
     NFC_CUDA_CHECK(sync_cs());
     kernel_time();
     int st_all = 0;
@@ -1159,8 +1182,6 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         *fell_back = true;  // caller redoes the slab with the sequential kernel
         return 0;
     }
-    bool bitmap_changed = false;
-
     // ---- repair: redo a wrong segment from its predecessor's true final state, checkpoint by checkpoint; the
     // redo overwrites the bitmap in place and stops at the first checkpoint of the speculative run it reproduces
     std::vector<char> bad((size_t)nseg, 0);
@@ -1170,7 +1191,6 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
         nbad += bad[(size_t)k];
     }
     for (int guard = 0; nbad > 0 && guard < nseg + 2; guard++) {
-        bitmap_changed = true;
         std::vector<int> ks;
         for (int k = 1; k < nseg; k++)
             if (bad[(size_t)k] && !bad[(size_t)k - 1]) ks.push_back(k);
@@ -1282,42 +1302,10 @@ int Stream::run_slicer_bm(const void *d_in, int64_t in_pos0, int64_t in_begin, i
             kc[(size_t)best] = 0;
         }
     }
-    // ---- bitmap -> dense ordered transitions (the first sample is compared with the previous slab's last val)
-    if (bitmap_changed) {  // segments were redone: count again
-        if (count_transitions()) return -1;
-        NFC_CUDA_CHECK(sync_cs());
-    }
-    if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
-    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_pos0, a, b_post, run_carry.last_bit, ex_offsets.as<uint32_t>(),
-                             trans_dense.as<TransRec>(), R, cs))
-        return -1;
-    stats.launches++;
     NFC_CUDA_CHECK(cudaMemcpyAsync(state.p, st_out(nseg - 1), sblk, cudaMemcpyDeviceToDevice, cs));
     bm_lo = a;
     bm_hi = b;
     bm_origin = bm_pos0;
-    *R_out = R;
-    return 0;
-}
-
-// Transitions of [a, b) from a bitmap the slicer has already filled.
-int Stream::extract_only(int64_t a, int64_t b, uint32_t *R_out) {
-    if (finish_pending()) return -1;  // run_carry.last_bit: the val before sample a
-    const size_t nblk = extract_blocks(bm_origin, a, b);
-    if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
-    if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_origin, a, b, run_carry.last_bit, ex_counts.as<uint32_t>(),
-                             ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), totals_d.as<uint32_t>() + 48, cs))
-        return -1;
-    stats.launches += 4;
-    uint32_t R = 0;
-    NFC_CUDA_CHECK(cudaMemcpyAsync(&R, totals_d.as<uint32_t>() + 48, 4, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(sync_cs());
-    if (trans_dense.ensure(((size_t)R + 16) * sizeof(TransRec))) return -1;
-    if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, run_carry.last_bit, ex_offsets.as<uint32_t>(),
-                             trans_dense.as<TransRec>(), R, cs))
-        return -1;
-    stats.launches++;
-    *R_out = R;
     return 0;
 }
 
@@ -1325,187 +1313,294 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- a slab's context block in device memory (256 bytes; ring of NCTX): counts and flags of the slab's chain, and the
+// carries it leaves for the next slab (the reference's cur_state / last_bit / dur, decoder and PacketProcessor state)
+struct PostCtx {
+    uint32_t M, R, flags, pad0[5];
+    uint32_t tot[8];      // ChunkCnt: nsym, nbit0, nbit1, nemit, has0, tail0, has1, tail1
+    RunCarry rc_out;
+    DecCarry dc_out;
+    uint32_t pend_out[2];
+    uint32_t pad1[38];
+};
+static_assert(sizeof(PostCtx) == 256, "context blocks are 256 bytes apart");
+
 int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b,
                          int64_t slicer_end) {
-    static const bool timing = getenv("NFC_TIMING") != nullptr;
     const double t0 = now_ms();
-    double t1 = t0, t2 = t0;
-    ev_idx ^= 1;
-    const int ei = ev_idx;
-    NFC_CUDA_CHECK(cudaEventRecord(ev_a[ei], cs));
+    const int ci = (int)(slab_seq % NCTX);
+    NFC_CUDA_CHECK(cudaEventRecord(ev_a[ci], cs));
     uint32_t R = 0;
-    bool fell_back = false;
+    bool fell_back = false, from_bitmap = false;
     const bool par = parallel_ok();
     if (streaming_ok() && a >= bm_lo && b <= bm_hi) {
-        if (extract_only(a, b, &R)) return -1;  // the slicer ran over this slab together with the one before
+        from_bitmap = true;  // the slicer ran over this slab together with the one before
     } else if (streaming_ok()) {
-        if (run_slicer_bm(d_in, in_pos0, in_begin, in_end, a, b, std::max(b, slicer_end), &R, &fell_back)) return -1;
-    } else if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) {
-        return -1;
+        if (run_slicer_bm(d_in, in_pos0, in_begin, in_end, a, std::max(b, slicer_end), &fell_back)) return -1;
+        from_bitmap = !fell_back;
+    } else {
+        if (finalize_all()) return -1;  // trans_dense is written by this slab's slicer while an older chain may still read it
+        if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, !par, &R, &fell_back)) return -1;
     }
     if (fell_back) {
+        if (finalize_all()) return -1;
         bm_lo = bm_hi = 0;
         serial_mode = true;  // sums are no longer exactly representable: stay on the sequential kernel
         if (run_slicer(d_in, in_pos0, in_begin, in_end, a, b, true, &R, &fell_back)) return -1;
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_b[ei], cs));
-    t1 = now_ms();
-    if (finish_pending()) return -1;  // the previous slab's carries (its records arrived while the slicer ran)
+    return post_chain(a, b, from_bitmap, R, false, t0, now_ms());
+}
+
+// Queues extraction (from the bitmap; else the slicer left R_host transitions in trans_dense) -> runs -> line code of slab
+// [a, b) and the copy of its context block to the host.  Sizes: from the slabs before; exact (read while queuing, with a
+// synchronisation each) for the first slab of a stream and for a slab that is done again.
+int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1) {
+    static const bool no_async = getenv("NFC_POST_SYNC") != nullptr;
+    const int64_t n = b - a;
+    SlabJob j;
+    j.seq = slab_seq++;
+    j.a = a; j.b = b;
+    j.from_bitmap = from_bitmap;
+    j.t0 = t0; j.t1 = t1;
+    const int ci = (int)(j.seq % NCTX), pv = (int)((j.seq + NCTX - 1) % NCTX), oi = (int)(j.seq & 1);
+    PostCtx *cx = ctx_d.as<PostCtx>() + ci, *cp = ctx_d.as<PostCtx>() + pv;
+    if (force_exact) NFC_CUDA_CHECK(cudaEventRecord(ev_a[ci], cs));  // a slab done again: not through process_slab
+    if (jobs.empty()) {
+        // nothing is queued: the host's copy of the carries is the current one (reset, warm-up, set_state, the slab before)
+        PostCtx up;
+        memset(&up, 0, sizeof(up));
+        up.rc_out = run_carry;
+        up.dc_out = dec_carry;
+        up.pend_out[0] = pending[0];
+        up.pend_out[1] = pending[1];
+        NFC_CUDA_CHECK(cudaMemcpyAsync(cp, &up, sizeof(up), cudaMemcpyHostToDevice, cs));
+    }
+    NFC_CUDA_CHECK(cudaMemsetAsync(cx, 0, 64, cs));  // counts, flags, totals
+    const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
+    const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
+    const int keep_dropped = (prm.outputs & NFC_OUT_DROPPED_EVENTS) ? 1 : 0;
+    j.exact = force_exact || no_async || !rates.have || !from_bitmap;
+    auto cap_of = [&](double rate) -> uint32_t {
+        const double c = rate * (double)n * 1.5 + 65536.0;
+        return (uint32_t)std::min(c, 4.0e9);
+    };
+    // the records of the slab before last have left the output set this slab writes
+    if (ev_out_set[oi]) NFC_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_out[oi], 0));
+
+    // ---- transitions
+    if (from_bitmap) {
+        const size_t nblk = extract_blocks(bm_origin, a, b);
+        if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
+        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, ex_counts.as<uint32_t>(), ex_offsets.as<uint32_t>(),
+                                 ex_scr.as<uint32_t>(), &cx->R, cs))
+            return -1;
+        stats.launches += 4;
+        if (j.exact) {
+            uint32_t R = 0;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(&R, &cx->R, 4, cudaMemcpyDeviceToHost, cs));
+            NFC_CUDA_CHECK(sync_cs());
+            j.cap_R = R;
+        } else {
+            j.cap_R = cap_of(rates.R);
+        }
+        if (trans_dense.ensure(((size_t)j.cap_R + 16) * sizeof(TransRec))) return -1;
+        if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, ex_offsets.as<uint32_t>(), trans_dense.as<TransRec>(),
+                                 j.cap_R, cs))
+            return -1;
+        stats.launches++;
+    } else {
+        j.cap_R = R_host;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->R, &R_host, 4, cudaMemcpyHostToDevice, cs));
+    }
+    NFC_CUDA_CHECK(cudaEventRecord(ev_b[ci], cs));
 
     // ---- runs -> events
-    const int keep_dropped = (prm.outputs & NFC_OUT_DROPPED_EVENTS) ? 1 : 0;
-    const size_t nrun = (size_t)R + 1;
+    const size_t nrun = (size_t)j.cap_R + 1;
     if (run_counts.ensure(nrun * 4) || run_offsets.ensure(nrun * 4) || scan_scr.ensure((nrun / 256 + 1024) * 4 * 4)) return -1;
-    if (launch_run_count(trans_dense.as<TransRec>(), R, 0, b - a, run_carry, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
-                         run_offsets.as<uint32_t>(), scan_scr.as<uint32_t>(), totals_d.as<uint32_t>(), cs))
+    if (launch_run_count(trans_dense.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
+                         run_offsets.as<uint32_t>(), scan_scr.as<uint32_t>(), &cx->M, &cx->flags, cs))
         return -1;
     stats.launches += 3;
-    uint32_t M = 0;
-    NFC_CUDA_CHECK(cudaMemcpyAsync(&M, totals_d.p, 4, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(sync_cs());
-    if (events_d.ensure(((size_t)M + 16) * sizeof(EventRec))) return -1;
-    RunCarry *d_rc = carry_d.as<RunCarry>();
-    if (launch_run_write(trans_dense.as<TransRec>(), R, 0, b - a, run_carry, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
-                         events_d.as<EventRec>(), M, d_rc, cs))
+    if (j.exact) {
+        uint32_t M = 0;
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&M, &cx->M, 4, cudaMemcpyDeviceToHost, cs));
+        NFC_CUDA_CHECK(sync_cs());
+        j.cap_M = M;
+    } else {
+        j.cap_M = cap_of(rates.M);
+    }
+    if (events_d[oi].ensure(((size_t)j.cap_M + 16) * sizeof(EventRec))) return -1;
+    if (launch_run_write(trans_dense.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
+                         events_d[oi].as<EventRec>(), j.cap_M, &cx->M, &cx->rc_out, &cx->flags, cs))
         return -1;
     stats.launches++;
 
     // ---- events -> symbols, frame bits, frame closings
-    const uint32_t nc = linecode_chunks(M);
-    struct Totals {
-        uint32_t nsym, nbit0, nbit1, nemit, has0, tail0, has1, tail1;
-    } tot = {0, 0, 0, 0, 0, 0, 0, 0};
-    DecCarry *d_dc = reinterpret_cast<DecCarry *>(carry_d.as<char>() + 64);
-    uint32_t *d_pend = reinterpret_cast<uint32_t *>(carry_d.as<char>() + 128);
-    const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
-    if (nc > 0 && want_line) {
+    j.have_line = want_line;
+    if (want_line) {
+        const uint32_t nc = std::max(1u, linecode_chunks(j.cap_M));
         if (start_d.ensure((size_t)nc * 2 + 64) || summ_d.ensure((size_t)nc * 2 + 64) || cnts_d.ensure((size_t)nc * linecode_cnt_bytes()) ||
             cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) || line_scr.ensure(linecode_scratch_bytes(nc) + 256))
             return -1;
-        int *d_unres = reinterpret_cast<int *>(totals_d.as<char>() + 128);
-        if (launch_linecode_start(events_d.as<EventRec>(), M, lt, dec_carry, summ_d.as<uint16_t>(), start_d.as<uint16_t>(), d_unres,
-                                  cs))
-            return -1;
-        if (launch_linecode_count(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p,
-                                  totals_d.as<char>() + 64, cs))
-            return -1;
+        const EventRec *ev = events_d[oi].as<EventRec>();
+        if (launch_linecode_start(ev, &cx->M, j.cap_M, lt, &cp->dc_out, summ_d.as<uint16_t>(), start_d.as<uint16_t>(), &cx->flags, cs)) return -1;
+        if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, cs)) return -1;
         stats.launches += 6;
-        int unres = 0;
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&unres, d_unres, sizeof(int), cudaMemcpyDeviceToHost, cs));
-        NFC_CUDA_CHECK(sync_cs());
-        if (unres) {
-            // some chunk saw no decoder reset within the search limit: compose chunk transfer functions instead
-            stats.linecode_scan_fallbacks++;
-            if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes())) return -1;
-            if (launch_linecode_start_scan(events_d.as<EventRec>(), M, lt, dec_carry, maps_d.p, prefix_d.p, line_scr.p,
-                                           start_d.as<uint16_t>(), cs))
-                return -1;
-            if (launch_linecode_count(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p,
-                                      line_scr.p, totals_d.as<char>() + 64, cs))
-                return -1;
-            stats.launches += 9;
-            NFC_CUDA_CHECK(cudaMemcpyAsync(&tot, totals_d.as<char>() + 64, sizeof(tot), cudaMemcpyDeviceToHost, cs));
+        if (j.exact) {
+            PostCtx hx;
+            NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, cs));
             NFC_CUDA_CHECK(sync_cs());
+            if (hx.flags & POST_UNRESOLVED) {
+                // some chunk saw no decoder reset within the search limit: compose chunk transfer functions instead
+                stats.linecode_scan_fallbacks++;
+                if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes())) return -1;
+                if (launch_linecode_start_scan(ev, &cx->M, j.cap_M, lt, &cp->dc_out, maps_d.p, prefix_d.p, line_scr.p, start_d.as<uint16_t>(), cs))
+                    return -1;
+                if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, cs)) return -1;
+                stats.launches += 9;
+                NFC_CUDA_CHECK(cudaMemsetAsync(&cx->flags, 0, 4, cs));
+                NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, cs));
+                NFC_CUDA_CHECK(sync_cs());
+            }
+            j.cap_sym = hx.tot[0]; j.cap_b0 = hx.tot[1]; j.cap_b1 = hx.tot[2]; j.cap_em = hx.tot[3];
+        } else {
+            j.cap_sym = cap_of(rates.sym); j.cap_b0 = cap_of(rates.b0); j.cap_b1 = cap_of(rates.b1); j.cap_em = cap_of(rates.em);
         }
-        const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
-        if ((want_sym && sym_d.ensure(((size_t)tot.nsym + 16) * sizeof(SymbolRec))) || bits0_d.ensure((size_t)tot.nbit0 + 16) ||
-            bits1_d.ensure((size_t)tot.nbit1 + 16) || em_d.ensure(((size_t)tot.nemit + 16) * linecode_emission_bytes()))
+        if ((want_sym && sym_d[oi].ensure(((size_t)j.cap_sym + 16) * sizeof(SymbolRec))) || bits0_d[oi].ensure((size_t)j.cap_b0 + 16) ||
+            bits1_d[oi].ensure((size_t)j.cap_b1 + 16) || em_d[oi].ensure(((size_t)j.cap_em + 16) * linecode_emission_bytes()))
             return -1;
-        if (launch_linecode_write(events_d.as<EventRec>(), M, lt, start_d.as<uint16_t>(), cprefix_d.p,
-                                  want_sym ? sym_d.as<SymbolRec>() : nullptr, want_sym ? tot.nsym : 0, bits0_d.as<uint8_t>(),
-                                  tot.nbit0, bits1_d.as<uint8_t>(), tot.nbit1, em_d.p, tot.nemit, pending[0], pending[1], d_dc,
-                                  d_pend, cs))
+        if (launch_linecode_write(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cprefix_d.p, want_sym ? sym_d[oi].as<SymbolRec>() : nullptr,
+                                  want_sym ? j.cap_sym : 0, bits0_d[oi].as<uint8_t>(), j.cap_b0, bits1_d[oi].as<uint8_t>(), j.cap_b1, em_d[oi].p,
+                                  j.cap_em, cp->pend_out, &cp->dc_out, &cx->dc_out, cx->pend_out, cs))
             return -1;
         stats.launches++;
+    } else {
+        // no decoder runs: its state passes through
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->dc_out, &cp->dc_out, sizeof(DecCarry) + 8, cudaMemcpyDeviceToDevice, cs));
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_c[ei], cs));
-    t2 = now_ms();
+    NFC_CUDA_CHECK(cudaEventRecord(ev_c[ci], cs));
+    NFC_CUDA_CHECK(cudaMemcpyAsync(ctx_h + (size_t)ci * 256, cx, 256, cudaMemcpyDeviceToHost, cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_ctx[ci], cs));
+    j.want_ev = (prm.outputs & NFC_OUT_EVENTS) != 0;
+    j.want_sym = want_sym && want_line;
+    j.want_fr = (prm.outputs & NFC_OUT_FRAMES) != 0 && want_line;
+    j.t2 = now_ms();
+    jobs.push_back(j);
+    // the slab before this one: its chain has run (or is about to end) while this one was queued
+    while (jobs.size() > 1)
+        if (finalize_front()) return -1;
+    return 0;
+}
 
-    // ---- records back to the host
-    const bool want_ev = (prm.outputs & NFC_OUT_EVENTS) != 0;
-    const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0 && nc > 0;
-    const bool want_fr = (prm.outputs & NFC_OUT_FRAMES) != 0 && nc > 0;
-    size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, off_c = 0, total = 0;
+// The context block of the oldest queued slab has arrived: take over its carries, put its records on their way to the
+// host and hand them to the worker thread -- or, if a buffer was too small for it, do it (and whatever was queued behind
+// it) again with exact sizes.
+int Stream::finalize_front() {
+    if (jobs.empty()) return 0;
+    static const bool timing = getenv("NFC_TIMING") != nullptr;
+    const SlabJob j = jobs.front();
+    const int ci = (int)(j.seq % NCTX), oi = (int)(j.seq & 1);
+    NFC_CUDA_CHECK(cudaEventSynchronize(ev_ctx[ci]));
+    const double t3 = now_ms();
+    PostCtx hx;
+    memcpy(&hx, ctx_h + (size_t)ci * 256, sizeof(hx));
+    bool bad = false;
+    if (!j.exact) {
+        bad = (hx.flags & (POST_OVF_TRANS | POST_OVF_EVENTS | POST_UNRESOLVED)) != 0 || hx.R > j.cap_R || hx.M > j.cap_M;
+        if (j.have_line)
+            bad = bad || (j.want_sym && hx.tot[0] > j.cap_sym) || hx.tot[1] > j.cap_b0 || hx.tot[2] > j.cap_b1 || hx.tot[3] > j.cap_em;
+    } else if (hx.flags & (POST_OVF_TRANS | POST_OVF_EVENTS | POST_UNRESOLVED)) {
+        set_error("internal: a slab sized exactly reports flags %u", hx.flags);
+        return -1;
+    }
+    if (bad) {
+        // sizes taken from the slabs before did not hold (or the frame-boundary search needs the scan): this slab and the
+        // ones queued behind it (they started from its carries) again, sized exactly; their bitmap is still in place
+        std::vector<SlabJob> again(jobs.begin(), jobs.end());
+        jobs.clear();
+        NFC_CUDA_CHECK(sync_cs());
+        stats.overflow_retries++;
+        slab_seq = j.seq;
+        for (const SlabJob &r : again) {
+            if (!r.from_bitmap) {
+                set_error("internal: a slab without bitmap cannot be done again");
+                return -1;
+            }
+            if (post_chain(r.a, r.b, true, 0, true, r.t0, r.t1)) return -1;  // finalizes the one before it
+        }
+        return 0;
+    }
+    jobs.pop_front();
+    const uint32_t M = hx.M, nsym = hx.tot[0], nbit0 = hx.tot[1], nbit1 = hx.tot[2], nemit = hx.tot[3];
+    // ---- carries and sizes
+    run_carry = hx.rc_out;
+    dec_carry = hx.dc_out;
+    pending[0] = hx.pend_out[0];
+    pending[1] = hx.pend_out[1];
+    {
+        const double n = (double)std::max<int64_t>(1, j.b - j.a);
+        auto upd = [&](double &r, uint32_t v) { r = std::max(r * 0.98, (double)v / n); };
+        upd(rates.R, hx.R); upd(rates.M, M); upd(rates.sym, nsym); upd(rates.b0, nbit0); upd(rates.b1, nbit1); upd(rates.em, nemit);
+        rates.have = true;
+    }
+    float ms_ab = 0, ms_ac = 0;
+    cudaEventElapsedTime(&ms_ab, ev_a[ci], ev_b[ci]);
+    cudaEventElapsedTime(&ms_ac, ev_a[ci], ev_c[ci]);
+    stats.slicer_ms += ms_ab;
+    stats.kernel_ms += ms_ac;
+
+    // ---- records back to the host (cs2; the chain has completed: the host has seen its context block)
+    const bool want_ev = j.want_ev, want_sym = j.want_sym, want_fr = j.want_fr;
+    size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, total = 0;
     auto place = [&](size_t bytes) {
         size_t o = total;
         total += (bytes + 63) / 64 * 64;
         return o;
     };
-    off_c = place(256);
+    place(64);
     if (want_ev) off_ev = place((size_t)M * sizeof(EventRec));
-    if (want_sym) off_sym = place((size_t)tot.nsym * sizeof(SymbolRec));
+    if (want_sym) off_sym = place((size_t)nsym * sizeof(SymbolRec));
     if (want_fr) {
-        off_em = place((size_t)tot.nemit * sizeof(EmissionHost));
-        off_b0 = place(tot.nbit0);
-        off_b1 = place(tot.nbit1);
+        off_em = place((size_t)nemit * sizeof(EmissionHost));
+        off_b0 = place(nbit0);
+        off_b1 = place(nbit1);
     }
     const int pi = (int)(slabs_enqueued % NPIN);
     // the slab that used this buffer last (three slabs ago) must be in the output vectors: long done, normally
     while (slabs_marshalled.load(std::memory_order_acquire) < slabs_enqueued - (NPIN - 1)) std::this_thread::yield();
     if (ensure_pinned(pi, total)) return -1;
     char *hp = (char *)pinned[pi];
-    NFC_CUDA_CHECK(cudaStreamWaitEvent(cs2, ev_c[ei], 0));
-    NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_c, carry_d.p, 256, cudaMemcpyDeviceToHost, cs2));
-    NFC_CUDA_CHECK(cudaEventRecord(ev_carry, cs2));
-    if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d.p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
-    if (want_sym && tot.nsym)
-        NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d.p, (size_t)tot.nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
+    if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d[oi].p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
+    if (want_sym && nsym)
+        NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d[oi].p, (size_t)nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
     if (want_fr) {
-        if (tot.nemit)
-            NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d.p, (size_t)tot.nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs2));
-        if (tot.nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d.p, tot.nbit0, cudaMemcpyDeviceToHost, cs2));
-        if (tot.nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d.p, tot.nbit1, cudaMemcpyDeviceToHost, cs2));
+        if (nemit) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d[oi].p, (size_t)nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs2));
+        if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
+        if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
     }
     NFC_CUDA_CHECK(cudaEventRecord(ev_d[pi], cs2));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_out[oi], cs2));
+    ev_out_set[oi] = true;
     slabs_enqueued++;
-    pend.pi = pi;
-    pend.active = true;
-    pend.hp = hp;
-    pend.off_ev = off_ev; pend.off_sym = off_sym; pend.off_em = off_em; pend.off_b0 = off_b0; pend.off_b1 = off_b1;
-    pend.off_c = off_c; pend.total = total;
-    pend.M = M; pend.nsym = tot.nsym; pend.nbit0 = tot.nbit0; pend.nbit1 = tot.nbit1; pend.nemit = tot.nemit;
-    pend.a = a; pend.b = b;
-    pend.want_ev = want_ev; pend.want_sym = want_sym; pend.want_fr = want_fr; pend.have_line = nc > 0 && want_line;
-    pend.t0 = t0; pend.t1 = t1; pend.t2 = t2;
-    pend.ei = ei;
-    return 0;
+    stats.d2h_bytes += (int64_t)total + 256;
+    if (timing)
+        fprintf(stderr, "slab %lld..%lld%s: slicer %.2f ms (dev %.2f), chain queued in %.2f (dev %.2f), context seen %.2f ms after queuing\n",
+                (long long)j.a, (long long)j.b, j.exact ? " (exact sizes)" : "", j.t1 - j.t0, ms_ab, j.t2 - j.t1, ms_ac - ms_ab, t3 - j.t2);
+    return marshal(j, pi, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, nsym, nbit0, nbit1, nemit);
 }
 
-// The records of the last slab have arrived: take over its carries and hand the records to the worker thread.
-int Stream::finish_pending() {
-    if (!pend.active) return 0;
-    static const bool timing = getenv("NFC_TIMING") != nullptr;
-    pend.active = false;
-    NFC_CUDA_CHECK(cudaEventSynchronize(ev_carry));  // the carries only: the records behind them are the worker's business
-    const double t3 = now_ms();
-    char *hp = pend.hp;
-    const size_t off_ev = pend.off_ev, off_sym = pend.off_sym, off_em = pend.off_em, off_b0 = pend.off_b0, off_b1 = pend.off_b1,
-                 off_c = pend.off_c;
-    const uint32_t M = pend.M;
-    const int64_t a = pend.a;
-    const bool want_ev = pend.want_ev, want_sym = pend.want_sym, want_fr = pend.want_fr;
+// Records of a slab -> output vectors (absolute positions) on a worker thread: it waits for its predecessor (the vectors
+// are filled in slab order), then for the slab's records to arrive.
+int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t off_b0, size_t off_b1,
+                    uint32_t M, uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit) {
     struct Totals {
         uint32_t nsym, nbit0, nbit1, nemit;
-    } totc = {pend.nsym, pend.nbit0, pend.nbit1, pend.nemit};
-    stats.d2h_bytes += (int64_t)pend.total;
-    float ms_ab = 0, ms_ac = 0;
-    cudaEventElapsedTime(&ms_ab, ev_a[pend.ei], ev_b[pend.ei]);
-    cudaEventElapsedTime(&ms_ac, ev_a[pend.ei], ev_c[pend.ei]);
-    stats.slicer_ms += ms_ab;
-    stats.kernel_ms += ms_ac;
-    // ---- carries
-    run_carry = *reinterpret_cast<RunCarry *>(hp + off_c);
-    if (pend.have_line) {
-        dec_carry = *reinterpret_cast<DecCarry *>(hp + off_c + 64);
-        pending[0] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[0];
-        pending[1] = reinterpret_cast<uint32_t *>(hp + off_c + 128)[1];
-    }
-    // ---- marshal records (absolute positions) on a worker thread: it waits for its predecessor (the output vectors are
-    // filled in slab order), then for the slab's records to arrive
+    } totc = {nsym, nbit0, nbit1, nemit};
+    const int64_t a = j.a;
+    const bool want_ev = j.want_ev, want_sym = j.want_sym, want_fr = j.want_fr;
     if (marshal_err.load()) return join_marshal();
     auto prev = std::make_shared<std::thread>(std::move(marshal_thr));
-    const cudaEvent_t evd = ev_d[pend.pi];
+    const cudaEvent_t evd = ev_d[pi];
     const int dev = prm.device;
     marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, totc, a, want_ev, want_sym,
                                want_fr]() {
@@ -1514,10 +1609,13 @@ int Stream::finish_pending() {
       if (cudaEventSynchronize(evd) != cudaSuccess) marshal_err = 2;
       else [&]() {
         const Totals &tot = totc;
+        auto grow = [](auto &v, size_t more) {  // geometric: an exact reserve per slab would copy the vector every slab
+            if (v.capacity() < v.size() + more) v.reserve(std::max(v.size() + more, v.capacity() * 2));
+        };
         // ---- marshal records (absolute positions)
         if (want_ev) {
             const EventRec *e = reinterpret_cast<const EventRec *>(hp + off_ev);
-            out_events.reserve(out_events.size() + M);
+            grow(out_events, M);
             for (uint32_t i = 0; i < M; i++) {
                 nfc_event o;
                 o.pos = a + (int64_t)e[i].rel_pos;
@@ -1530,6 +1628,7 @@ int Stream::finish_pending() {
         }
         if (want_sym) {
             const SymbolRec *s = reinterpret_cast<const SymbolRec *>(hp + off_sym);
+            grow(out_symbols, tot.nsym);
             for (uint32_t i = 0; i < tot.nsym; i++) {
                 nfc_symbol o;
                 o.pos = a + (int64_t)s[i].rel_pos;
@@ -1579,7 +1678,7 @@ int Stream::finish_pending() {
             if (tot.nemit > 20000) helper = std::thread(copy_bits);
             else copy_bits();
             bool bad_frame = false;
-            out_frames.reserve(out_frames.size() + tot.nemit);
+            grow(out_frames, tot.nemit);
             for (uint32_t i = 0; i < tot.nemit; i++) {
                 const int t = em[i].type;
                 const size_t end = old[t] + em[i].bit_end;
@@ -1604,9 +1703,6 @@ int Stream::finish_pending() {
       }();
       slabs_marshalled.fetch_add(1, std::memory_order_release);
     });
-    if (timing)
-        fprintf(stderr, "slab %lld..%lld: slicer %.2f ms (dev %.2f), runs+linecode %.2f (dev %.2f), completed %.2f ms after enqueue\n",
-                (long long)a, (long long)pend.b, pend.t1 - pend.t0, ms_ab, pend.t2 - pend.t1, ms_ac - ms_ab, t3 - pend.t2);
     return 0;
 }
 

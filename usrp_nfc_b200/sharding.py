@@ -153,8 +153,20 @@ def _discard(engine):
         engine.drain_frames()
 
 
+def _push_range(engine, fetch, a, b, piece):
+    """Samples [a, b) into the engine, at most `piece` at a time (a capture larger than the memory of the device is rendered
+    or loaded piece by piece: fetch may reuse one buffer, the engine has consumed a piece when push_all returns)."""
+    if not piece or piece >= b - a:
+        engine.push_all(fetch(a, b))
+        return
+    while a < b:
+        m = min(piece, b - a)
+        engine.push_all(fetch(a, a + m))
+        a += m
+
+
 def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, group=None, device="cpu",
-                        halo_windows=16, strict_dur=False, flat=False):
+                        halo_windows=16, strict_dur=False, flat=False, piece=None):
     """Decode this rank's time shard of a `total`-sample capture.
 
     fetch(a, b) returns samples [a, b) (numpy array, or a CUDA tensor for a device-resident capture).
@@ -162,6 +174,7 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
     With flat=True the frames stay in the engine's bulk form: dict(records, bits, pos_offset, n_frames); with
     flat="view" they are not even copied: bits = (bits_tag, bits_reader) as Stream.view_frames returns them, valid until
     the caller's engine.release_frames().
+    piece: samples per fetch (None: the whole shard at once).
     """
     rank = dist.get_rank(group) if dist is not None else 0
     world = dist.get_world_size(group) if dist is not None else 1
@@ -180,7 +193,7 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
         _discard(engine)
     assumed = SeamState.from_engine(engine, base, L) if rank > 0 else None
     if end > begin:
-        engine.push_all(fetch(begin, end))
+        _push_range(engine, fetch, begin, end, piece)
     rec, bits, is_flat = _drain(engine, flat)
     pos_offset = base
     frames = None if is_flat else [(int(r["pos"]) + base, int(r["type"]), b) for r, b in zip(rec, bits)]
@@ -204,7 +217,7 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
                 engine.reset()
                 finals[k - 1].apply(engine, state_cls)
                 if end > begin:
-                    engine.push_all(fetch(begin, end))
+                    _push_range(engine, fetch, begin, end, piece)
                 rec, bits, is_flat = _drain(engine, flat)
                 pos_offset = 0
                 frames = None if is_flat else [(int(r["pos"]), int(r["type"]), b) for r, b in zip(rec, bits)]
