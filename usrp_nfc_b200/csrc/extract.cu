@@ -64,13 +64,24 @@ __device__ __forceinline__ void load_chunk(const uint32_t *__restrict__ bm, int6
     }
 }
 
+// val of the sample before the slab: the carry the slab before left on the device (its `_last_bit`), or -- when that slab's
+// run kernels may not have finished yet and the sample is covered by the same bitmap -- the val bits of sample a - 1
+__device__ __forceinline__ int carry_in(const uint32_t *__restrict__ bm, int64_t bm_pos0, int64_t a, const RunCarry *__restrict__ rc_in,
+                                        int carry_from_bm) {
+    if (!carry_from_bm) return rc_in->last_bit;
+    const int64_t q = a - 1 - bm_pos0;
+    const int64_t k = q >> 7;
+    const int off = (int)(q & 127), l = off >> 2, jj = off & 3;
+    return (int)((__ldg(bm + k * 8 + jj) >> l) & 1u) + (int)((__ldg(bm + k * 8 + 4 + jj) >> l) & 1u) - 1;
+}
+
 // block_counts[blockIdx] = transitions in this block's chunks
 __global__ void __launch_bounds__(EX_BLOCK) extract_count_kernel(const uint32_t *__restrict__ bm, int64_t k0, int64_t nchunks,
                                                                  int64_t bm_pos0, int64_t a, int64_t b,
-                                                                 const RunCarry *__restrict__ rc_in,
+                                                                 const RunCarry *__restrict__ rc_in, int carry_from_bm,
                                                                  uint32_t *__restrict__ block_counts) {
     const int64_t i = (int64_t)blockIdx.x * EX_BLOCK + threadIdx.x;
-    const int carry_val = rc_in->last_bit;  // val of the sample before the slab (left on the device by the slab before)
+    const int carry_val = carry_in(bm, bm_pos0, a, rc_in, carry_from_bm);
     int cnt = 0;
     if (i < nchunks) {
         ChunkMaps m;
@@ -92,11 +103,11 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_count_kernel(const uint32_t 
 
 __global__ void __launch_bounds__(EX_BLOCK) extract_write_kernel(const uint32_t *__restrict__ bm, int64_t k0, int64_t nchunks,
                                                                  int64_t bm_pos0, int64_t a, int64_t b,
-                                                                 const RunCarry *__restrict__ rc_in,
+                                                                 const RunCarry *__restrict__ rc_in, int carry_from_bm,
                                                                  const uint32_t *__restrict__ block_offsets,
                                                                  TransRec *__restrict__ out, uint32_t out_cap) {
     const int64_t i = (int64_t)blockIdx.x * EX_BLOCK + threadIdx.x;
-    const int carry_val = rc_in->last_bit;
+    const int carry_val = carry_in(bm, bm_pos0, a, rc_in, carry_from_bm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ChunkMaps m;
     m.T[0] = m.T[1] = m.T[2] = m.T[3] = 0u;
@@ -139,24 +150,25 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_write_kernel(const uint32_t 
 
 // Counts the transitions of [a, b) (device total in *d_total) and leaves per-block offsets in d_block_offsets.
 // d_rc_in: the carry the slab before left on the device (its last_bit is compared with the slab's first sample).
-int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, uint32_t *d_block_counts,
+int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, int carry_from_bm,
+                         uint32_t *d_block_counts,
                          uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total, cudaStream_t stream) {
     if (b <= a) return 0;
     const int64_t k0 = (a - bm_pos0) >> 7, k1 = (b - 1 - bm_pos0) >> 7;
     const int64_t nchunks = k1 - k0 + 1;
     const unsigned nblk = (unsigned)((nchunks + EX_BLOCK - 1) / EX_BLOCK);
-    extract_count_kernel<<<nblk, EX_BLOCK, 0, stream>>>(d_bm, k0, nchunks, bm_pos0, a, b, d_rc_in, d_block_counts);
+    extract_count_kernel<<<nblk, EX_BLOCK, 0, stream>>>(d_bm, k0, nchunks, bm_pos0, a, b, d_rc_in, carry_from_bm, d_block_counts);
     NFC_CUDA_CHECK(cudaGetLastError());
     return device_exclusive_scan<uint32_t, AddU32>(d_block_counts, d_block_offsets, nblk, 0u, AddU32(), d_scan_scratch, d_total, stream);
 }
 
-int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in,
+int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, int carry_from_bm,
                          const uint32_t *d_block_offsets, TransRec *d_out, uint32_t out_cap, cudaStream_t stream) {
     if (b <= a) return 0;
     const int64_t k0 = (a - bm_pos0) >> 7, k1 = (b - 1 - bm_pos0) >> 7;
     const int64_t nchunks = k1 - k0 + 1;
     const unsigned nblk = (unsigned)((nchunks + EX_BLOCK - 1) / EX_BLOCK);
-    extract_write_kernel<<<nblk, EX_BLOCK, 0, stream>>>(d_bm, k0, nchunks, bm_pos0, a, b, d_rc_in, d_block_offsets, d_out, out_cap);
+    extract_write_kernel<<<nblk, EX_BLOCK, 0, stream>>>(d_bm, k0, nchunks, bm_pos0, a, b, d_rc_in, carry_from_bm, d_block_offsets, d_out, out_cap);
     NFC_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -28,9 +28,10 @@ namespace nfc {
 int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, bool vec_ok, cudaStream_t);
 bool slicer_streaming_ok(int L, bool vec_ok);
 int launch_slicer_streaming(const SegWork *d_works, int n_works, const SlicerParams *d_params, int L, int kind, cudaStream_t);
-int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, uint32_t *d_block_counts,
-                         uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total, cudaStream_t stream);
-int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in,
+int launch_extract_count(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, int carry_from_bm,
+                         uint32_t *d_block_counts, uint32_t *d_block_offsets, uint32_t *d_scan_scratch, uint32_t *d_total,
+                         cudaStream_t stream);
+int launch_extract_write(const uint32_t *d_bm, int64_t bm_pos0, int64_t a, int64_t b, const RunCarry *d_rc_in, int carry_from_bm,
                          const uint32_t *d_block_offsets, TransRec *d_out, uint32_t out_cap, cudaStream_t stream);
 size_t extract_blocks(int64_t bm_pos0, int64_t a, int64_t b);
 int launch_slicer_serial(const SegWork *d_works, int n_works, const SlicerParams *d_params, float *d_ring_scratch,
@@ -150,6 +151,13 @@ struct Stream {
     // records on their way to the host.  A slab whose buffers turn out too small is done again with exact sizes.
     static const int NCTX = 4;
     cudaEvent_t ev_a[NCTX] = {}, ev_b[NCTX] = {}, ev_c[NCTX] = {};  // timing: slab begins, transitions ready, chain done
+    // The three stages of a chain run on three streams: extraction on `cs` (behind the slicer), runs on csR, line code on csL;
+    // stage X of slab k waits for the stage before it (event) and, being queued behind it, for stage X of slab k-1 -- so the
+    // extraction of slab k+1 runs beside the runs of slab k and the line code of slab k-1.
+    cudaStream_t csR = nullptr, csL = nullptr;
+    cudaEvent_t evE[NCTX] = {}, evR[NCTX] = {}, evL[NCTX] = {};
+    long long chain_first_seq = 0;   // slabs from this one on were queued since the streams were last idle (their events are valid)
+    long long last_final_seq = -1;
     cudaEvent_t ev_ctx[NCTX] = {};   // the slab's context block has arrived in ctx_h
     cudaEvent_t ev_out[2] = {};      // the records of the slab that used output set i are on the host
     bool ev_out_set[2] = {false, false};
@@ -177,12 +185,13 @@ struct Stream {
     int force_serial = 0;
 
     // device scratch
-    DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, trans_dense, seg_counts, seg_offsets, seg_status,
+    DevBuf params_d, tab_d, staging, works_d, states_d, trans_seg, seg_counts, seg_offsets, seg_status,
         seam_ptrs, mismatch_d, run_counts, run_offsets, scan_scr, maps_d, prefix_d, cnts_d, cprefix_d,
         line_scr, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
         redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr, summ_d;
     // outputs of a slab's chain, two sets: the records of slab k travel to the host while the chain of slab k+1 writes the other
     DevBuf events_d[2], sym_d[2], bits0_d[2], bits1_d[2], em_d[2];
+    DevBuf trans_dense[2];  // transitions of slab k in [k & 1]: the extraction of slab k+1 runs beside the runs of slab k
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     // results come back into one of three pinned buffers.  The carries of a slab (256 bytes) are copied first and are all
     // the next slab waits for; the records behind them are awaited by a worker thread, which turns them into the output
@@ -302,6 +311,8 @@ int Stream::init(const nfc_params *p) {
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
     NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs3, cudaStreamNonBlocking));
+    NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&csR, cudaStreamNonBlocking));
+    NFC_CUDA_CHECK(cudaStreamCreateWithFlags(&csL, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_h[i], cudaEventDisableTiming));
     NFC_CUDA_CHECK(cudaEventCreate(&ev_k0));
     NFC_CUDA_CHECK(cudaEventCreate(&ev_k1));
@@ -310,6 +321,9 @@ int Stream::init(const nfc_params *p) {
         NFC_CUDA_CHECK(cudaEventCreate(&ev_b[i]));
         NFC_CUDA_CHECK(cudaEventCreate(&ev_c[i]));
         NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ctx[i], cudaEventDisableTiming));
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&evE[i], cudaEventDisableTiming));
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&evR[i], cudaEventDisableTiming));
+        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&evL[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
     for (int i = 0; i < NPIN; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming));
@@ -371,7 +385,7 @@ int Stream::init(const nfc_params *p) {
 }
 
 void Stream::destroy() {
-    DevBuf *all[] = {&batch_states, &batch_stage, &params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense, &seg_counts, &seg_offsets,
+    DevBuf *all[] = {&batch_states, &batch_stage, &params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense[0], &trans_dense[1], &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &ctx_d, &events_d[0], &events_d[1], &sym_d[0], &sym_d[1], &bits0_d[0],
                      &bits0_d[1], &bits1_d[0], &bits1_d[1], &em_d[0], &em_d[1],
@@ -380,6 +394,8 @@ void Stream::destroy() {
     finalize_all();
     if (marshal_thr.joinable()) marshal_thr.join();
     if (cs) cudaStreamSynchronize(cs);
+    if (csR) cudaStreamSynchronize(csR);
+    if (csL) cudaStreamSynchronize(csL);
     if (cs2) cudaStreamSynchronize(cs2);
     for (DevBuf *b : all) b->release();
     if (ctx_h) cudaFreeHost(ctx_h);
@@ -391,9 +407,14 @@ void Stream::destroy() {
         if (ev_b[i]) cudaEventDestroy(ev_b[i]);
         if (ev_c[i]) cudaEventDestroy(ev_c[i]);
         if (ev_ctx[i]) cudaEventDestroy(ev_ctx[i]);
+        if (evE[i]) cudaEventDestroy(evE[i]);
+        if (evR[i]) cudaEventDestroy(evR[i]);
+        if (evL[i]) cudaEventDestroy(evL[i]);
     }
     for (int i = 0; i < 2; i++)
         if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+    if (csR) cudaStreamDestroy(csR);
+    if (csL) cudaStreamDestroy(csL);
     if (cs2) cudaStreamDestroy(cs2);
     if (cs3) cudaStreamDestroy(cs3);
     if (ev_k0) cudaEventDestroy(ev_k0);
@@ -1029,13 +1050,14 @@ int Stream::run_slicer(const void *d_in, int64_t in_pos0, int64_t in_begin, int6
                 R += pc.n;
             }
         const size_t np = psrc.size();
-        if (trans_dense.ensure((R + 16) * sizeof(TransRec)) || pieces_d.ensure(np * (sizeof(void *) + 8) + 64)) return -1;
+        DevBuf &td = trans_dense[slab_seq & 1];  // the chain of this slab (post_chain) reads the set of its sequence number
+        if (td.ensure((R + 16) * sizeof(TransRec)) || pieces_d.ensure(np * (sizeof(void *) + 8) + 64)) return -1;
         char *pb = pieces_d.as<char>();
         NFC_CUDA_CHECK(cudaMemcpyAsync(pb, psrc.data(), np * sizeof(void *), cudaMemcpyHostToDevice, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(pb + np * sizeof(void *), pn.data(), np * 4, cudaMemcpyHostToDevice, cs));
         NFC_CUDA_CHECK(cudaMemcpyAsync(pb + np * (sizeof(void *) + 4), poff.data(), np * 4, cudaMemcpyHostToDevice, cs));
         if (launch_gather_pieces((const TransRec *const *)pb, (const uint32_t *)(pb + np * sizeof(void *)),
-                                 (const uint32_t *)(pb + np * (sizeof(void *) + 4)), (int)np, trans_dense.as<TransRec>(), cs))
+                                 (const uint32_t *)(pb + np * (sizeof(void *) + 4)), (int)np, td.as<TransRec>(), cs))
             return -1;
         stats.launches++;
         // the slab's final state becomes the stream's state
@@ -1365,8 +1387,10 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
     const int ci = (int)(j.seq % NCTX), pv = (int)((j.seq + NCTX - 1) % NCTX), oi = (int)(j.seq & 1);
     PostCtx *cx = ctx_d.as<PostCtx>() + ci, *cp = ctx_d.as<PostCtx>() + pv;
     if (force_exact) NFC_CUDA_CHECK(cudaEventRecord(ev_a[ci], cs));  // a slab done again: not through process_slab
-    if (jobs.empty()) {
+    const bool fresh = jobs.empty();
+    if (fresh) {
         // nothing is queued: the host's copy of the carries is the current one (reset, warm-up, set_state, the slab before)
+        // and all three streams are idle
         PostCtx up;
         memset(&up, 0, sizeof(up));
         up.rc_out = run_carry;
@@ -1374,7 +1398,9 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
         up.pend_out[0] = pending[0];
         up.pend_out[1] = pending[1];
         NFC_CUDA_CHECK(cudaMemcpyAsync(cp, &up, sizeof(up), cudaMemcpyHostToDevice, cs));
+        chain_first_seq = j.seq;
     }
+    auto queued = [&](long long seq) { return seq >= chain_first_seq && seq >= 0; };  // its events were recorded since the streams idled
     NFC_CUDA_CHECK(cudaMemsetAsync(cx, 0, 64, cs));  // counts, flags, totals
     const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
     const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
@@ -1384,28 +1410,38 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
         const double c = rate * (double)n * 1.5 + 65536.0;
         return (uint32_t)std::min(c, 4.0e9);
     };
-    // the records of the slab before last have left the output set this slab writes
-    if (ev_out_set[oi]) NFC_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_out[oi], 0));
+    auto sync_on = [&](cudaStream_t st) -> cudaError_t {
+        if (!blocking_wait) return cudaStreamSynchronize(st);
+        const cudaError_t e = cudaEventRecord(ev_blk, st);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_blk);
+    };
+    DevBuf &td = trans_dense[oi];
 
-    // ---- transitions
+    // ---------------------------------------------------------------- extraction (cs, behind the slicer)
     if (from_bitmap) {
+        // the transitions of slab k-2 (same set) have been read by its run kernels
+        if (queued(j.seq - 2)) NFC_CUDA_CHECK(cudaStreamWaitEvent(cs, evR[(j.seq - 2) % NCTX], 0));
         const size_t nblk = extract_blocks(bm_origin, a, b);
         if (ex_counts.ensure((nblk + 16) * 4) || ex_offsets.ensure((nblk + 16) * 4) || ex_scr.ensure((nblk / 256 + 1024) * 4 * 4)) return -1;
-        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, ex_counts.as<uint32_t>(), ex_offsets.as<uint32_t>(),
-                                 ex_scr.as<uint32_t>(), &cx->R, cs))
+        // the val before the slab's first sample: the slab before may still be in its run kernels -- its last val is in the
+        // bitmap as well (the same launch of the slicer filled it); a fresh chain takes the carry just uploaded
+        const int carry_from_bm = (!fresh && a > bm_lo) ? 1 : 0;
+        if (!fresh && !carry_from_bm) NFC_CUDA_CHECK(cudaStreamWaitEvent(cs, evR[pv], 0));
+        if (launch_extract_count(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, carry_from_bm, ex_counts.as<uint32_t>(),
+                                 ex_offsets.as<uint32_t>(), ex_scr.as<uint32_t>(), &cx->R, cs))
             return -1;
         stats.launches += 4;
         if (j.exact) {
             uint32_t R = 0;
             NFC_CUDA_CHECK(cudaMemcpyAsync(&R, &cx->R, 4, cudaMemcpyDeviceToHost, cs));
-            NFC_CUDA_CHECK(sync_cs());
+            NFC_CUDA_CHECK(sync_on(cs));
             j.cap_R = R;
         } else {
             j.cap_R = cap_of(rates.R);
         }
-        if (trans_dense.ensure(((size_t)j.cap_R + 16) * sizeof(TransRec))) return -1;
-        if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, ex_offsets.as<uint32_t>(), trans_dense.as<TransRec>(),
-                                 j.cap_R, cs))
+        if (td.ensure(((size_t)j.cap_R + 16) * sizeof(TransRec))) return -1;
+        if (launch_extract_write(bitmap_d.as<uint32_t>(), bm_origin, a, b, &cp->rc_out, carry_from_bm, ex_offsets.as<uint32_t>(),
+                                 td.as<TransRec>(), j.cap_R, cs))
             return -1;
         stats.launches++;
     } else {
@@ -1413,29 +1449,36 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
         NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->R, &R_host, 4, cudaMemcpyHostToDevice, cs));
     }
     NFC_CUDA_CHECK(cudaEventRecord(ev_b[ci], cs));
+    NFC_CUDA_CHECK(cudaEventRecord(evE[ci], cs));
 
-    // ---- runs -> events
+    // ---------------------------------------------------------------- runs -> events (csR)
+    NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, evE[ci], 0));
+    if (queued(j.seq - 2)) NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, evL[(j.seq - 2) % NCTX], 0));  // the events of slab k-2 have been decoded
+    if (ev_out_set[oi]) NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, ev_out[oi], 0));                  // ... and have left for the host
     const size_t nrun = (size_t)j.cap_R + 1;
     if (run_counts.ensure(nrun * 4) || run_offsets.ensure(nrun * 4) || scan_scr.ensure((nrun / 256 + 1024) * 4 * 4)) return -1;
-    if (launch_run_count(trans_dense.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
-                         run_offsets.as<uint32_t>(), scan_scr.as<uint32_t>(), &cx->M, &cx->flags, cs))
+    if (launch_run_count(td.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
+                         run_offsets.as<uint32_t>(), scan_scr.as<uint32_t>(), &cx->M, &cx->flags, csR))
         return -1;
     stats.launches += 3;
     if (j.exact) {
         uint32_t M = 0;
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&M, &cx->M, 4, cudaMemcpyDeviceToHost, cs));
-        NFC_CUDA_CHECK(sync_cs());
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&M, &cx->M, 4, cudaMemcpyDeviceToHost, csR));
+        NFC_CUDA_CHECK(sync_on(csR));
         j.cap_M = M;
     } else {
         j.cap_M = cap_of(rates.M);
     }
     if (events_d[oi].ensure(((size_t)j.cap_M + 16) * sizeof(EventRec))) return -1;
-    if (launch_run_write(trans_dense.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
-                         events_d[oi].as<EventRec>(), j.cap_M, &cx->M, &cx->rc_out, &cx->flags, cs))
+    if (launch_run_write(td.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_offsets.as<uint32_t>(),
+                         events_d[oi].as<EventRec>(), j.cap_M, &cx->M, &cx->rc_out, &cx->flags, csR))
         return -1;
     stats.launches++;
+    NFC_CUDA_CHECK(cudaEventRecord(evR[ci], csR));
 
-    // ---- events -> symbols, frame bits, frame closings
+    // ---------------------------------------------------------------- events -> symbols, frame bits, frame closings (csL)
+    NFC_CUDA_CHECK(cudaStreamWaitEvent(csL, evR[ci], 0));
+    if (ev_out_set[oi]) NFC_CUDA_CHECK(cudaStreamWaitEvent(csL, ev_out[oi], 0));  // the records of slab k-2 have left this output set
     j.have_line = want_line;
     if (want_line) {
         const uint32_t nc = std::max(1u, linecode_chunks(j.cap_M));
@@ -1443,24 +1486,24 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
             cprefix_d.ensure((size_t)nc * linecode_cnt_bytes()) || line_scr.ensure(linecode_scratch_bytes(nc) + 256))
             return -1;
         const EventRec *ev = events_d[oi].as<EventRec>();
-        if (launch_linecode_start(ev, &cx->M, j.cap_M, lt, &cp->dc_out, summ_d.as<uint16_t>(), start_d.as<uint16_t>(), &cx->flags, cs)) return -1;
-        if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, cs)) return -1;
+        if (launch_linecode_start(ev, &cx->M, j.cap_M, lt, &cp->dc_out, summ_d.as<uint16_t>(), start_d.as<uint16_t>(), &cx->flags, csL)) return -1;
+        if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, csL)) return -1;
         stats.launches += 6;
         if (j.exact) {
             PostCtx hx;
-            NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, cs));
-            NFC_CUDA_CHECK(sync_cs());
+            NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, csL));
+            NFC_CUDA_CHECK(sync_on(csL));
             if (hx.flags & POST_UNRESOLVED) {
                 // some chunk saw no decoder reset within the search limit: compose chunk transfer functions instead
                 stats.linecode_scan_fallbacks++;
                 if (maps_d.ensure((size_t)nc * linecode_map_bytes()) || prefix_d.ensure((size_t)nc * linecode_map_bytes())) return -1;
-                if (launch_linecode_start_scan(ev, &cx->M, j.cap_M, lt, &cp->dc_out, maps_d.p, prefix_d.p, line_scr.p, start_d.as<uint16_t>(), cs))
+                if (launch_linecode_start_scan(ev, &cx->M, j.cap_M, lt, &cp->dc_out, maps_d.p, prefix_d.p, line_scr.p, start_d.as<uint16_t>(), csL))
                     return -1;
-                if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, cs)) return -1;
+                if (launch_linecode_count(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cnts_d.p, cprefix_d.p, line_scr.p, cx->tot, csL)) return -1;
                 stats.launches += 9;
-                NFC_CUDA_CHECK(cudaMemsetAsync(&cx->flags, 0, 4, cs));
-                NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, cs));
-                NFC_CUDA_CHECK(sync_cs());
+                NFC_CUDA_CHECK(cudaMemsetAsync(&cx->flags, 0, 4, csL));
+                NFC_CUDA_CHECK(cudaMemcpyAsync(&hx, cx, 64, cudaMemcpyDeviceToHost, csL));
+                NFC_CUDA_CHECK(sync_on(csL));
             }
             j.cap_sym = hx.tot[0]; j.cap_b0 = hx.tot[1]; j.cap_b1 = hx.tot[2]; j.cap_em = hx.tot[3];
         } else {
@@ -1471,16 +1514,17 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
             return -1;
         if (launch_linecode_write(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cprefix_d.p, want_sym ? sym_d[oi].as<SymbolRec>() : nullptr,
                                   want_sym ? j.cap_sym : 0, bits0_d[oi].as<uint8_t>(), j.cap_b0, bits1_d[oi].as<uint8_t>(), j.cap_b1, em_d[oi].p,
-                                  j.cap_em, cp->pend_out, &cp->dc_out, &cx->dc_out, cx->pend_out, cs))
+                                  j.cap_em, cp->pend_out, &cp->dc_out, &cx->dc_out, cx->pend_out, csL))
             return -1;
         stats.launches++;
     } else {
         // no decoder runs: its state passes through
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->dc_out, &cp->dc_out, sizeof(DecCarry) + 8, cudaMemcpyDeviceToDevice, cs));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->dc_out, &cp->dc_out, sizeof(DecCarry) + 8, cudaMemcpyDeviceToDevice, csL));
     }
-    NFC_CUDA_CHECK(cudaEventRecord(ev_c[ci], cs));
-    NFC_CUDA_CHECK(cudaMemcpyAsync(ctx_h + (size_t)ci * 256, cx, 256, cudaMemcpyDeviceToHost, cs));
-    NFC_CUDA_CHECK(cudaEventRecord(ev_ctx[ci], cs));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_c[ci], csL));
+    NFC_CUDA_CHECK(cudaMemcpyAsync(ctx_h + (size_t)ci * 256, cx, 256, cudaMemcpyDeviceToHost, csL));
+    NFC_CUDA_CHECK(cudaEventRecord(ev_ctx[ci], csL));
+    NFC_CUDA_CHECK(cudaEventRecord(evL[ci], csL));
     j.want_ev = (prm.outputs & NFC_OUT_EVENTS) != 0;
     j.want_sym = want_sym && want_line;
     j.want_fr = (prm.outputs & NFC_OUT_FRAMES) != 0 && want_line;
@@ -1518,7 +1562,9 @@ int Stream::finalize_front() {
         // ones queued behind it (they started from its carries) again, sized exactly; their bitmap is still in place
         std::vector<SlabJob> again(jobs.begin(), jobs.end());
         jobs.clear();
-        NFC_CUDA_CHECK(sync_cs());
+        NFC_CUDA_CHECK(cudaStreamSynchronize(cs));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(csR));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(csL));
         stats.overflow_retries++;
         slab_seq = j.seq;
         for (const SlabJob &r : again) {
@@ -1543,9 +1589,15 @@ int Stream::finalize_front() {
         upd(rates.R, hx.R); upd(rates.M, M); upd(rates.sym, nsym); upd(rates.b0, nbit0); upd(rates.b1, nbit1); upd(rates.em, nemit);
         rates.have = true;
     }
-    float ms_ab = 0, ms_ac = 0;
+    float ms_ab = 0, ms_ac = 0, ms_cc = 0;
     cudaEventElapsedTime(&ms_ab, ev_a[ci], ev_b[ci]);
     cudaEventElapsedTime(&ms_ac, ev_a[ci], ev_c[ci]);
+    // chains of consecutive slabs overlap: the device time this slab adds ends at its chain's end and begins at the end of
+    // the chain before it, if that came later than this slab's own begin
+    if (last_final_seq == j.seq - 1 && j.seq > chain_first_seq &&
+        cudaEventElapsedTime(&ms_cc, ev_c[(j.seq + NCTX - 1) % NCTX], ev_c[ci]) == cudaSuccess && ms_cc > 0 && ms_cc < ms_ac)
+        ms_ac = ms_cc;
+    last_final_seq = j.seq;
     stats.slicer_ms += ms_ab;
     stats.kernel_ms += ms_ac;
 
