@@ -191,6 +191,7 @@ def leg_stream(torch, _cabi, rate, n, local_rank, args, peak, steps=2, warmup=2)
     _cabi.synth_render(x, codes, lens, seed=99, as_envelope=True, device=local_rank, first_index=0, **chan_for(rate, args))
     torch.cuda.synchronize()
     s = _cabi.Stream(rate, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
+    s.set_tuning(slab_len=1 << 30)
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_running()
@@ -323,10 +324,10 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
         clock["on"] = time.perf_counter()
         clock["render"] += clock["on"] - t
         return buf[: b - a]
-    # warm-up: the first piece of rank 0's shard (allocations, first launches), untimed
-    s.reset()
-    s.push_all(fetch(0, min(piece, total // world)))
-    s.view_frames()
+    s.set_tuning(slab_len=1 << 30)
+    # warm-up: the whole pass once, untimed (device buffers and the host's output vectors reach their sizes)
+    res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
+                                       halo_windows=args.halo_windows, flat="view", piece=piece)
     s.release_frames()
     torch.cuda.synchronize()
     if world > 1:
@@ -341,8 +342,7 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     t_begin = clock["on"]
     res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
                                        halo_windows=args.halo_windows, flat="view", piece=piece)
-    index = sharding.gather_frame_records(res["records"], res["pos_offset"], res["bounds"][0], dist if world > 1 else None,
-                                          device="cuda", state=gstate)
+    index = sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate)
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     clock["sum"] += t_end - clock["on"]
@@ -362,7 +362,7 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     return {"workload": "ONE synthetic capture of %.3g samples at %.2f MS/s, time shards of %.3g samples with a halo of %d av_windows, "
                         "rendered and decoded in pieces of %.3g samples (400 GB never resident)" % (
                             total, rate / 1e6, per_gpu, args.halo_windows, piece),
-            "samp_rate": rate, **params, "n_gpus": world, "scaling": "strong", "steps": 1, "warmup": "one piece",
+            "samp_rate": rate, **params, "n_gpus": world, "scaling": "strong", "steps": 1, "warmup": 1,
             "ms": ms, "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "frac": step_frac(per_gpu, ms, peak),
             "kernel_ms": kern, "kernel_frac": step_frac(per_gpu, kern, peak) if kern > 0 else None,
             "render_ms_untimed": render_ms, "frames": int(len(index)) if index is not None else n_frames_rank,
@@ -585,11 +585,12 @@ def main():
                                            device="cuda", halo_windows=args.halo_windows, flat="view")
         shard_info.update(repaired=res["repaired"], seam_ok=res["seam_ok"])
         nfr = res["n_frames"]
+        tg = time.perf_counter()
         # the frame offsets of all shards on rank 0, in stream order (packets.py:94-98): fixed 8-byte records over NCCL
-        index = sharding.gather_frame_records(res["records"], res["pos_offset"], res["bounds"][0], dist, device="cuda", state=gather_state)
+        index = sharding.gather_frame_records(s, res["pos_offset"], dist, device="cuda", state=gather_state)
         if index is not None:
-            shard_info.update(gathered_frames=int(len(index)), gathered_bytes=int(len(index)) * 8,
-                              in_order=bool((np.diff(index["pos"]) >= 0).all()) if len(index) > 1 else True)
+            shard_info.update(gathered_frames=int(len(index)), gathered_bytes=int(len(index)) * 8, index=index)
+        shard_info["phases_ms"] = dict(res["phases_ms"], gather_offsets=(time.perf_counter() - tg) * 1e3)
         s.release_frames()
         return nfr
 
@@ -641,6 +642,10 @@ def main():
         frames_total, launches, mism = frames, int(st["launches"]), int(st["seam_mismatches"])
     value = world * n / (wall_ms * 1e-3) / 1e6  # whole job, wall clock around the synchronous ABI calls (>= device time)
     repaired_ranks = 0
+    if world > 1 and rank == 0 and shard_info.get("index") is not None:  # untimed: the gathered offsets are in stream order
+        pos_all = shard_info.pop("index").positions()
+        shard_info["in_order"] = bool((np.diff(pos_all) >= 0).all()) if len(pos_all) > 1 else True
+    shard_info.pop("index", None)
     if world > 1:
         rp = torch.tensor([1.0 if shard_info.get("repaired") else 0.0], device="cuda")
         dist.all_reduce(rp)
@@ -837,7 +842,8 @@ def main():
             "sharding": {"kind": "time shards of one capture, halo %d av_windows, seam states all_gathered and verified, frame "
                                  "offsets gathered to rank 0 inside the timed step" % args.halo_windows,
                          "ranks_redone_last_step": repaired_ranks, "frame_offsets_gathered": shard_info.get("gathered_frames"),
-                         "gathered_bytes_per_step": shard_info.get("gathered_bytes"), "gathered_in_stream_order": shard_info.get("in_order")} if world > 1 else None,
+                         "gathered_bytes_per_step": shard_info.get("gathered_bytes"), "gathered_in_stream_order": shard_info.get("in_order"),
+                         "rank0_phases_ms_last_step": shard_info.get("phases_ms")} if world > 1 else None,
             "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
             "selfcheck": selfcheck, "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments", "pipe_tiles", "pipe_runs", "pipe_aborts")},

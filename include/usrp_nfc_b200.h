@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 4
+#define NFC_ABI_VERSION 5
 
 /* what a pushed item is */
 enum {
@@ -127,6 +127,13 @@ int64_t nfc_stream_pending_frame_bits(nfc_stream *s); /* bytes the next full dra
 int64_t nfc_stream_view_frames(nfc_stream *s, const nfc_frame **frames, const uint8_t **bits_tag, int64_t *n_bits_tag,
                                const uint8_t **bits_reader, int64_t *n_bits_reader);
 int nfc_stream_release_frames(nfc_stream *s);
+/* The frame offsets alone, eight bytes per frame, in page-locked host memory: what a time shard sends to the rank that
+ * merges the shards (the order contract of CombinedPacketProcessor.append_bit, packets.py:94-98: frames reach
+ * fsm.process_bits in closing order).  index[i] = pos << 24 | nbits << 8 | type of frame i of nfc_stream_view_frames
+ * (pos < 2^40, nbits < 2^16); maintained beside the frame records while slabs are decoded, so viewing it costs nothing.
+ * Valid until the next push / drain / reset / release on this stream.  Returns the frame count, -1 on error (a frame that
+ * does not fit the packing). */
+int64_t nfc_stream_view_frame_index(nfc_stream *s, const uint64_t **index);
 
 /* What fsm.process_bits does to a frame before any protocol logic, for a batch of frames on the device:
  * fsm._fix_ending (fsm.py:51-66), fsm._check_parity (fsm.py:28-49), fsm._print_enc (fsm.py:114-131) and

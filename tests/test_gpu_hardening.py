@@ -131,3 +131,28 @@ def test_queued_slab_chain_is_done_again_when_its_buffers_are_too_small():
     check_against_oracle(got, want)
     st = got["stream"].stats()
     assert st["fast_tiles"] > 0 and st["overflow_retries"] > 0
+
+
+def test_frame_index_is_the_frames_in_eight_bytes():
+    """nfc_stream_view_frame_index: one packed record per frame of view_frames (pos << 24 | nbits << 8 | type), kept in step
+    with the frame records over several pushes, emptied by release."""
+    from usrp_nfc_b200 import sharding
+    rate = 13.56e6
+    p = synth.rate_params(rate)
+    frames = synth.load_sessions()["classic1k"]
+    pcm = synth.capture(frames, rate, 9, av_window=p["av_window"], sessions=2)
+    x = synth.envelope(synth.pcm_to_float(pcm))
+    s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_FRAMES, **p)
+    s.set_tuning(slab_len=1 << 20)
+    half = x.size // 2
+    s.push_all(x[:half])
+    s.push_all(x[half:])
+    fr, b0, b1 = s.view_frames()
+    idx = s.view_frame_index()
+    assert len(fr) == len(idx) > 100
+    back = sharding.unpack_records([idx], [0])
+    assert np.array_equal(back["pos"], fr["pos"]) and np.array_equal(back["nbits"], fr["nbits"]) and np.array_equal(back["type"], fr["type"])
+    assert np.array_equal(sharding.pack_records(fr), idx)
+    s.release_frames()
+    assert len(s.view_frame_index()) == 0 and len(s.view_frames()[0]) == 0
+    s.close()

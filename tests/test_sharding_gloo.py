@@ -114,7 +114,8 @@ def _worker(rank, world, port, halo_windows, q):
     mine = np.zeros(len(res["frames"]), dtype=_cabi.FRAME_DTYPE)
     for i, (pp, tt, bb) in enumerate(res["frames"]):
         mine[i] = (pp, 0, len(bb), tt)
-    index = sharding.gather_frame_records(mine, 0, res["bounds"][0], dist)
+    index = sharding.gather_frame_records(mine, 0, dist)
+    index = index.unpack() if index is not None else None
     if rank == 0:
         want = oracle.decode_capture(x, 2e6, hi_val=1.09)
         ok = len(merged) == len(want["frames"])
@@ -165,10 +166,13 @@ def test_plan_alignment():
 def test_packed_records_round_trip():
     from usrp_nfc_b200 import _cabi, sharding
     rec = np.zeros(5, dtype=_cabi.FRAME_DTYPE)
-    rec["pos"], rec["nbits"], rec["type"] = [10, 10, 4000000000, 4000000007, 2 ** 33], [7, 163, 9, 0, 18], [1, 0, 1, 0, 1]
-    packed = sharding.pack_records(rec[:4], 100, 50)
-    assert packed.dtype.itemsize == 8
-    back = sharding.unpack_records([packed, sharding.pack_records(rec[:0], 0, 0)], [50, 999])
-    assert back["pos"].tolist() == (rec["pos"][:4] + 100).tolist() and back["nbits"].tolist() == [7, 163, 9, 0]
+    rec["pos"], rec["nbits"], rec["type"] = [10, 10, 4000000000, (1 << 40) - 1, 2 ** 41], [7, 163, 9, 0, 18], [1, 0, 1, 0, 1]
+    packed = sharding.pack_records(rec[:4])
+    assert packed.dtype == np.uint64 and packed.dtype.itemsize == 8
+    back = sharding.unpack_records([packed, sharding.pack_records(rec[:0])], [50, 999])
+    assert back["pos"].tolist() == (rec["pos"][:4] + 50).tolist() and back["nbits"].tolist() == [7, 163, 9, 0]
+    assert back["type"].tolist() == [1, 0, 1, 0] and back["shard"].tolist() == [0, 0, 0, 0]
+    idx = sharding.FrameIndex([packed, packed[:2]], [50, 1 << 41])
+    assert len(idx) == 6 and idx.positions().tolist() == (rec["pos"][:4] + 50).tolist() + [10 + (1 << 41), 10 + (1 << 41)]
     with pytest.raises(ValueError):
-        sharding.pack_records(rec, 0, 0)  # a gap of more than 2^32 samples between two frames of one shard
+        sharding.pack_records(rec)  # a position beyond 2^40 samples from the start of the shard's stream

@@ -68,6 +68,7 @@ SIGNATURES = {
     "nfc_stream_view_frames": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "nfc_stream_release_frames": (C.c_int, [C.c_void_p]),
+    "nfc_stream_view_frame_index": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "nfc_stream_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_tuning": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
@@ -314,6 +315,18 @@ class Stream(object):
             return np.frombuffer(buf, dtype=dtype, count=count)
 
         return arr(fp, n, FRAME_DTYPE), arr(b0, n0.value, np.uint8), arr(b1, n1.value, np.uint8)
+
+    def view_frame_index(self):
+        """The frame offsets alone (nfc_stream_view_frame_index): a uint64 numpy view of page-locked memory owned by the
+        stream, one record per frame of view_frames: pos << 24 | nbits << 8 | type.  Valid like view_frames."""
+        p = C.c_void_p()
+        n = lib().nfc_stream_view_frame_index(self._h, C.byref(p))
+        if n < 0:
+            raise NfcError(last_error())
+        if not n or not p.value:
+            return np.zeros(0, dtype=np.uint64)
+        buf = (C.c_char * (n * 8)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint64, count=n)
 
     def release_frames(self):
         if lib().nfc_stream_release_frames(self._h) != 0:

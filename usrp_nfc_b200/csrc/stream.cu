@@ -239,6 +239,21 @@ struct Stream {
     std::vector<nfc_event> out_events;
     std::vector<nfc_symbol> out_symbols;
     std::vector<nfc_frame> out_frames;   // bit_off is relative to out_fbits[type]
+    // packed frame offsets (pos << 24 | nbits << 8 | type) of out_frames in page-locked memory (nfc_stream_view_frame_index)
+    uint64_t *findex = nullptr;
+    size_t findex_n = 0, findex_cap = 0;
+    bool findex_bad = false;
+    int findex_reserve(size_t n) {  // worker thread or settled stream only
+        if (n <= findex_cap) return 0;
+        const size_t cap = std::max(n, findex_cap * 2 + 4096);
+        uint64_t *p = nullptr;
+        if (cudaMallocHost((void **)&p, cap * sizeof(uint64_t)) != cudaSuccess) return -1;
+        if (findex_n) memcpy(p, findex, findex_n * sizeof(uint64_t));
+        if (findex) cudaFreeHost(findex);
+        findex = p;
+        findex_cap = cap;
+        return 0;
+    }
     std::vector<uint8_t> out_fbits[2];   // forwarded frame bits per type, frames back to back
     int resident_ctas = 0;
     size_t ev_head = 0, sym_head = 0, fr_head = 0;
@@ -326,7 +341,9 @@ int Stream::init(const nfc_params *p) {
         NFC_CUDA_CHECK(cudaEventCreateWithFlags(&evL[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    for (int i = 0; i < NPIN; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming));
+    // the worker thread that turns a slab's records into the output vectors is off the critical path: it sleeps while it waits
+    // (spinning waiters of eight ranks crowd the host's cores)
+    for (int i = 0; i < NPIN; i++) NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], cudaEventDisableTiming | cudaEventBlockingSync));
     NFC_CUDA_CHECK(cudaMallocHost((void **)&ctx_h, (size_t)NCTX * 256));
     if (ctx_d.ensure((size_t)NCTX * 256)) return -1;
     NFC_CUDA_CHECK(cudaMemset(ctx_d.p, 0, (size_t)NCTX * 256));
@@ -400,6 +417,9 @@ void Stream::destroy() {
     for (DevBuf *b : all) b->release();
     if (ctx_h) cudaFreeHost(ctx_h);
     ctx_h = nullptr;
+    if (findex) cudaFreeHost(findex);
+    findex = nullptr;
+    findex_cap = findex_n = 0;
     for (int i = 0; i < NPIN; i++)
         if (pinned[i]) cudaFreeHost(pinned[i]);
     for (int i = 0; i < NCTX; i++) {
@@ -456,11 +476,6 @@ int Stream::set_wait_mode(bool blocking) {
     if (settle()) return -1;
     NFC_CUDA_CHECK(cudaSetDevice(prm.device));
     const unsigned flags = cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0);
-    for (int i = 0; i < NPIN; i++) {
-        if (ev_d[i]) cudaEventDestroy(ev_d[i]);
-        ev_d[i] = nullptr;
-        NFC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_d[i], flags));
-    }
     for (int i = 0; i < NCTX; i++) {
         if (ev_ctx[i]) cudaEventDestroy(ev_ctx[i]);
         ev_ctx[i] = nullptr;
@@ -1658,8 +1673,12 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                                want_fr]() {
       if (prev->joinable()) prev->join();
       cudaSetDevice(dev);
+      static const bool timing = getenv("NFC_TIMING") != nullptr;
+      const double tm0 = timing ? now_ms() : 0.0;
+      double tm1 = tm0;
       if (cudaEventSynchronize(evd) != cudaSuccess) marshal_err = 2;
       else [&]() {
+        if (timing) tm1 = now_ms();
         const Totals &tot = totc;
         auto grow = [](auto &v, size_t more) {  // geometric: an exact reserve per slab would copy the vector every slab
             if (v.capacity() < v.size() + more) v.reserve(std::max(v.size() + more, v.capacity() * 2));
@@ -1714,23 +1733,36 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                     marshal_err = 1;
                     return;
                 }
-            auto copy_bits = [&]() {
-                for (int t = 0; t < 2; t++) {
-                    if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
-                        const size_t used_new = last_end[t] - old[t];
-                        out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
-                        out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
-                        hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
-                    } else {
-                        hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
-                    }
+            auto copy_bits = [&](int t) {
+                if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
+                    const size_t used_new = last_end[t] - old[t];
+                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
+                    out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
+                    hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
+                } else {
+                    hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
                 }
             };
-            std::thread helper;
-            if (tot.nemit > 20000) helper = std::thread(copy_bits);
-            else copy_bits();
+            // large slabs: one helper thread per type copies the bits while this one walks the frames
+            std::thread helper, helper1;
+            if (tot.nemit > 20000) {
+                helper = std::thread(copy_bits, 0);
+                helper1 = std::thread(copy_bits, 1);
+            } else {
+                copy_bits(0);
+                copy_bits(1);
+            }
             bool bad_frame = false;
+            const size_t f0 = out_frames.size();
             grow(out_frames, tot.nemit);
+            out_frames.resize(f0 + tot.nemit);
+            nfc_frame *fo = out_frames.data() + f0;
+            size_t nf = 0;
+            if (findex_reserve(f0 + tot.nemit)) {
+                marshal_err = 2;
+                return;
+            }
+            uint64_t *fx = findex + f0;
             for (uint32_t i = 0; i < tot.nemit; i++) {
                 const int t = em[i].type;
                 const size_t end = old[t] + em[i].bit_end;
@@ -1739,13 +1771,17 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                     bad_frame = true;
                     break;
                 }
-                nfc_frame f;
+                nfc_frame &f = fo[nf++];
                 f.pos = a + (int64_t)em[i].rel_pos;
                 f.bit_off = (int64_t)(fbase[t] + end - em[i].nbits);  // frames of one type are back to back
                 f.nbits = (int32_t)em[i].nbits;
                 f.type = t;
-                out_frames.push_back(f);
+                if (((uint64_t)f.pos >> 40) || em[i].nbits >= 65536u) findex_bad = true;
+                fx[nf - 1] = ((uint64_t)f.pos << 24) | ((uint64_t)em[i].nbits << 8) | (uint64_t)t;
             }
+            out_frames.resize(f0 + nf);
+            findex_n = f0 + nf;
+            if (helper1.joinable()) helper1.join();
             if (helper.joinable()) helper.join();
             if (bad_frame) {
                 marshal_err = 1;
@@ -1753,6 +1789,7 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
             }
         }
       }();
+      if (timing) fprintf(stderr, "  records of slab at %lld: waited %.2f ms for them, into the output vectors in %.2f ms\n", (long long)a, tm1 - tm0, now_ms() - tm1);
       slabs_marshalled.fetch_add(1, std::memory_order_release);
     });
     return 0;
@@ -1846,6 +1883,8 @@ int nfc_stream_reset(nfc_stream *h) {
     s.out_events.clear();
     s.out_symbols.clear();
     s.out_frames.clear();
+    s.findex_n = 0;
+    s.findex_bad = false;
     s.out_fbits[0].clear();
     s.out_fbits[1].clear();
     s.ev_head = s.sym_head = s.fr_head = 0;
@@ -1939,6 +1978,8 @@ int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint
         copy_frames(0, avail);
     }
     s.out_frames.clear();
+    s.findex_n = 0;
+    s.findex_bad = false;
     s.out_fbits[0].clear();
     s.out_fbits[1].clear();
     s.fr_head = 0;
@@ -1968,10 +2009,27 @@ int64_t nfc_stream_view_frames(nfc_stream *h, const nfc_frame **frames, const ui
     return (int64_t)s.out_frames.size();
 }
 
+int64_t nfc_stream_view_frame_index(nfc_stream *h, const uint64_t **index) {
+    if (!h || !index) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    if (h->s.settle()) return -1;
+    Stream &s = h->s;
+    if (s.findex_bad || s.findex_n != s.out_frames.size()) {
+        nfc::set_error("view_frame_index: a frame does not fit the packing (position >= 2^40 or more than 65535 bits)");
+        return -1;
+    }
+    *index = s.findex;
+    return (int64_t)s.findex_n;
+}
+
 int nfc_stream_release_frames(nfc_stream *h) {
     if (!h || h->s.settle()) return -1;
     Stream &s = h->s;
     s.out_frames.clear();
+    s.findex_n = 0;
+    s.findex_bad = false;
     s.out_fbits[0].clear();
     s.out_fbits[1].clear();
     s.fr_head = 0;

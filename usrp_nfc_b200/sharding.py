@@ -178,10 +178,12 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
     """
     rank = dist.get_rank(group) if dist is not None else 0
     world = dist.get_world_size(group) if dist is not None else 1
+    import time
     L = av_window
     bounds, halo = plan(total, world, L, halo_windows)
     begin, end = bounds[rank]
     base = 0
+    tp = [time.perf_counter()]
     engine.reset()
     if rank > 0 and begin - halo - L > 0:
         base = begin - halo - L
@@ -192,9 +194,11 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
         engine.push_all(fetch(0, begin))  # shard too close to the stream start: decode from the true start
         _discard(engine)
     assumed = SeamState.from_engine(engine, base, L) if rank > 0 else None
+    tp.append(time.perf_counter())  # halo decoded, state at the seam taken
     if end > begin:
         _push_range(engine, fetch, begin, end, piece)
     rec, bits, is_flat = _drain(engine, flat)
+    tp.append(time.perf_counter())  # shard decoded, frames on the host
     pos_offset = base
     frames = None if is_flat else [(int(r["pos"]) + base, int(r["type"]), b) for r, b in zip(rec, bits)]
     final = SeamState.from_engine(engine, base, L) if begin < end or rank == 0 else assumed
@@ -227,82 +231,106 @@ def decode_time_sharded(engine, fetch, total, av_window, state_cls, dist=None, g
             else:
                 vec = SeamState.zeros(L).vec
             finals[k] = SeamState(_broadcast(vec, k, dist, group, device), L)
-    out = dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo, n_frames=len(rec))
+    tp.append(time.perf_counter())  # seams verified (and a wrong shard done again)
+    out = dict(frames=frames, repaired=repaired, seam_ok=seam_ok, bounds=(begin, end), halo=halo, n_frames=len(rec),
+               phases_ms=dict(halo=(tp[1] - tp[0]) * 1e3, shard=(tp[2] - tp[1]) * 1e3, seams=(tp[3] - tp[2]) * 1e3))
     if frames is None:
         out.update(records=rec, bits=bits, pos_offset=pos_offset)
     return out
 
 
-REC_DTYPE = np.dtype([("dpos", "<u4"), ("nbits", "<u2"), ("type", "u1"), ("pad", "u1")])
+# A frame offset in eight bytes (the layout of nfc_stream_view_frame_index, include/usrp_nfc_b200.h): position relative to the
+# stream the shard was decoded as << 24 | length in bits << 8 | type.  The absolute closing position is pos_offset + position.
+def pack_records(rec):
+    """Frame records (fields pos, nbits, type) -> uint64 array, one packed offset per frame."""
+    pos = np.asarray(rec["pos"], dtype=np.int64)
+    nb = np.asarray(rec["nbits"], dtype=np.int64)
+    if len(pos) and (pos.min() < 0 or pos.max() >= 1 << 40 or nb.min() < 0 or nb.max() >= 1 << 16):
+        raise ValueError("a frame does not fit the packing (position >= 2^40 or more than 65535 bits)")
+    u = np.uint64
+    return (pos.astype(u) << u(24)) | (nb.astype(u) << u(8)) | np.asarray(rec["type"], dtype=np.int64).astype(u)
 
 
-def pack_records(rec, pos_offset, begin):
-    """Frame records of one shard as 8 bytes each: closing position as the distance from the frame before (the first from
-    the shard's first sample), length, type.  bit_off is not sent: frames of one type are back to back."""
-    out = np.zeros(len(rec), dtype=REC_DTYPE)
-    if len(rec):
-        pos = rec["pos"].astype(np.int64) + pos_offset
-        d = np.diff(np.concatenate(([begin], pos)))
-        if (d < 0).any() or (d >= 1 << 32).any():
-            raise ValueError("frame positions of a shard must ascend within 2^32 samples of each other")
-        out["dpos"], out["nbits"], out["type"] = d, rec["nbits"], rec["type"]
+FRAME_INDEX_DTYPE = np.dtype([("pos", "<i8"), ("nbits", "<i4"), ("type", "i1"), ("shard", "i1"), ("pad", "<i2")])
+
+
+def unpack_records(parts, pos_offsets):
+    """Packed offsets of the shards (in shard order) -> one array with absolute closing position, length, type, shard."""
+    out = np.zeros(sum(len(p) for p in parts), dtype=FRAME_INDEX_DTYPE)
+    o = 0
+    for r, (p, off) in enumerate(zip(parts, pos_offsets)):
+        n = len(p)
+        if n:
+            v = np.asarray(p).view(np.uint64)
+            out["pos"][o: o + n] = (v >> np.uint64(24)).astype(np.int64) + int(off)
+            out["nbits"][o: o + n] = ((v >> np.uint64(8)) & np.uint64(0xffff)).astype(np.int32)
+            out["type"][o: o + n] = (v & np.uint64(0xff)).astype(np.int8)
+            out["shard"][o: o + n] = r
+        o += n
     return out
 
 
-def gather_frame_records(rec, pos_offset, begin, dist=None, group=None, device="cpu", state=None):
+class FrameIndex(object):
+    """The frame offsets of all shards on rank 0, in stream order (shard order = closing order, packets.py:94-98): the packed
+    records as they arrived (one uint64 array per shard, views of page-locked memory when they came over NCCL) and the
+    position offset of every shard.  len(), positions() and unpack() decode them; nothing is decoded before it is asked for."""
+
+    def __init__(self, parts, pos_offsets):
+        self.parts, self.pos_offsets = parts, [int(o) for o in pos_offsets]
+
+    def __len__(self):
+        return sum(len(p) for p in self.parts)
+
+    def positions(self):
+        return np.concatenate([(np.asarray(p).view(np.uint64) >> np.uint64(24)).astype(np.int64) + o for p, o in zip(self.parts, self.pos_offsets)]) \
+            if self.parts else np.zeros(0, dtype=np.int64)
+
+    def unpack(self):
+        return unpack_records(self.parts, self.pos_offsets)
+
+
+def gather_frame_records(engine_or_rec, pos_offset, dist=None, group=None, device="cpu", state=None):
     """The frame offsets of all shards on rank 0 in stream order (the order the reference hands frames to fsm.process_bits,
-    packets.py:94-98): one all_gather of the counts, one gather of the packed records (8 bytes per frame, device tensors
-    over NCCL or host tensors over gloo), read back into host memory on rank 0.  Returns on rank 0 an array with absolute
-    closing position, length, type and shard of every frame; None elsewhere.  `state`: a dict that keeps the staging
-    tensors between calls."""
+    packets.py:94-98): one all_gather of (count, position offset), one gather of the packed records (8 bytes per frame; device
+    tensors over NCCL, fed from and read back into page-locked memory, or host tensors over gloo).  engine_or_rec: a Stream
+    (its packed index is used as it lies in page-locked memory: nfc_stream_view_frame_index) or an array of frame records.
+    Returns a FrameIndex on rank 0, None elsewhere.  `state`: a dict that keeps the staging tensors between calls."""
     import torch
+    if hasattr(engine_or_rec, "view_frame_index"):
+        packed = engine_or_rec.view_frame_index()
+    else:
+        packed = pack_records(engine_or_rec)
     if dist is None or dist.get_world_size(group) == 1:
-        return unpack_records([pack_records(rec, pos_offset, begin)], [begin])
+        return FrameIndex([packed], [pos_offset])
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    packed = pack_records(rec, pos_offset, begin)
     state = state if state is not None else {}
-    cnt = torch.tensor([len(packed), begin], dtype=torch.int64, device=device)
+    on_gpu = str(device) != "cpu"
+    cnt = torch.tensor([len(packed), int(pos_offset)], dtype=torch.int64, device=device)
     cnts = [torch.empty_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt, group=group)
     meta = torch.stack(cnts).cpu().numpy()
-    nmax = int(meta[:, 0].max())
-    cap = max(1, nmax)
+    cap = max(1, int(meta[:, 0].max()))
     if state.get("cap", 0) < cap:
         state["cap"] = int(cap * 1.25) + 16
         state["send"] = torch.zeros(state["cap"], dtype=torch.int64, device=device)
         state["recv"] = [torch.zeros(state["cap"], dtype=torch.int64, device=device) for _ in range(world)] if rank == 0 else None
-        state["host"] = torch.zeros((world, state["cap"]), dtype=torch.int64).pin_memory() if (rank == 0 and str(device) != "cpu") else None
+        state["host"] = torch.zeros((world, state["cap"]), dtype=torch.int64).pin_memory() if (rank == 0 and on_gpu) else None
     send = state["send"]
     if len(packed):
         send[: len(packed)].copy_(torch.from_numpy(packed.view(np.int64)), non_blocking=True)
     dist.gather(send, state["recv"] if rank == 0 else None, dst=0, group=group)
+    if on_gpu:
+        torch.cuda.current_stream().synchronize()  # the engine may reuse its index once this returns
     if rank != 0:
         return None
     if state["host"] is not None:
         for r in range(world):
             state["host"][r, : int(meta[r, 0])].copy_(state["recv"][r][: int(meta[r, 0])], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        parts = [state["host"][r, : int(meta[r, 0])].numpy().view(REC_DTYPE) for r in range(world)]
+        parts = [state["host"][r, : int(meta[r, 0])].numpy().view(np.uint64) for r in range(world)]
     else:
-        parts = [state["recv"][r][: int(meta[r, 0])].numpy().view(REC_DTYPE) for r in range(world)]
-    return unpack_records(parts, [int(b) for b in meta[:, 1]])
-
-
-FRAME_INDEX_DTYPE = np.dtype([("pos", "<i8"), ("nbits", "<i4"), ("type", "i1"), ("shard", "i1"), ("pad", "<i2")])
-
-
-def unpack_records(parts, begins):
-    out = np.zeros(sum(len(p) for p in parts), dtype=FRAME_INDEX_DTYPE)
-    o = 0
-    for r, (p, b) in enumerate(zip(parts, begins)):
-        n = len(p)
-        if n:
-            out["pos"][o: o + n] = b + np.cumsum(p["dpos"].astype(np.int64))
-            out["nbits"][o: o + n] = p["nbits"]
-            out["type"][o: o + n] = p["type"]
-            out["shard"][o: o + n] = r
-        o += n
-    return out
+        parts = [state["recv"][r][: int(meta[r, 0])].numpy().view(np.uint64).copy() for r in range(world)]
+    return FrameIndex(parts, meta[:, 1])
 
 
 def gather_frames(frames, dist=None, group=None):
