@@ -226,6 +226,7 @@ def leg_stream(torch, _cabi, rate, n, local_rank, args, peak, steps=2, warmup=2)
             "kernel_ms": kern, "kernel_frac": step_frac(n, kern, peak) if kern > 0 else None,
             "slicer_stage_ms": st["slicer_ms"] / steps, "device_ms": st["kernel_ms"] / steps, "frames": int(frames),
             "streaming_tiles": int(st["fast_tiles"]), "pipelined_tiles": int(st["pipe_tiles"]), "exact_tiles": int(st["exact_tiles"]),
+            "tiles": {k: int(st[k]) for k in ("repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "pipe_runs", "pipe_aborts", "segments")},
             "clocks": clocks}
 
 

@@ -29,16 +29,17 @@ def test_line_code_scan_fallback_is_taken():
 
 def test_transition_buffer_overflow_is_retried():
     """A stretch where val changes with every sample: the segments' transition lists outgrow their first estimate
-    (one per eight samples) and the launch is repeated with larger buffers."""
+    (one per eight samples) and the launch is repeated with larger buffers.  (A window below 1024 samples: the
+    first-generation kernel with transition lists; larger windows write the class bitmap.)"""
     rate = 2e6
     frames = synth.load_sessions()["ultralight"]
-    pcm = synth.capture(frames, rate, 5, av_window=2000)
+    pcm = synth.capture(frames, rate, 5, av_window=1000)
     x = synth.envelope(synth.pcm_to_float(pcm)).copy()
-    lvl = float(np.median(x[:2000]))
+    lvl = float(np.median(x[:1000]))
     a = 2000 + 9000
     x[a: a + 20000: 2] = np.float32(lvl * 1.3)  # HIGH on every other sample, the carrier level between
-    want = oracle.decode_capture(x, rate, hi_val=1.09)
-    got = gpu_decode(x, rate, hi_val=1.09, tuning=dict(seg_len=8192, halo=4096))
+    want = oracle.decode_capture(x, rate, hi_val=1.09, av_window=1000)
+    got = gpu_decode(x, rate, hi_val=1.09, av_window=1000, tuning=dict(seg_len=8192, halo=4096))
     check_against_oracle(got, want)
     assert got["stream"].stats()["overflow_retries"] > 0
 

@@ -1279,7 +1279,12 @@ __global__ void seam_compare_kernel(const SlicerHdr *const *__restrict__ truth, 
 // ---------------------------------------------------------------- host launchers
 // rows per tile of the vector kernel for a given window: a tile must fit twice into the ring
 int slicer_rows(int L) { return L >= 8192 ? 4 : (L >= 4096 ? 2 : 1); }
-int slicer_tile(int L, bool vec_ok) { return (vec_ok && L >= 1024) ? 1024 * slicer_rows(L) : 256; }
+bool slicer_streaming_ok(int L, bool vec_ok);
+// tile of the kernel a window takes: segment boundaries and halos are whole tiles
+int slicer_tile(int L, bool vec_ok) {
+    if (slicer_streaming_ok(L, vec_ok)) return L >= 8192 ? 4096 : 512;
+    return (vec_ok && L >= 1024) ? 1024 * slicer_rows(L) : 256;
+}
 
 static int raise_dynamic_smem(const void *fn, size_t smem);
 
@@ -1312,15 +1317,31 @@ static size_t smem_optin_limit() {
 }
 static const size_t FAST_STATIC_SMEM = 10 * 1024;  // upper bound of the kernels' static shared memory
 
+// Windows below two tiles of 4096 samples (the reference's own default: av_window = 2000, transition_sink.py:12) take the
+// same kernel with tiles of 512 samples: four worker warps, one chunk of 128 samples each.
+static const int FAST_SMALL_MIN_L = 1024, FAST_BIG_MIN_L = 8192;
 template <int KIND>
 static FastVariant fast_variant(int L) {
     static const int pipe = env_int("NFC_SLICER_PIPE", 1), stages = env_int("NFC_SLICER_STAGES", 3);
     const size_t ring = ((size_t)L * 4 + 15) / 16 * 16;
     const size_t item = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
-    const size_t one = KIND == IN_IQ_F32 ? 0 : 4096 * item;  // staging buffer of the synchronous loop (IQ tiles are not staged)
-    const size_t stg = KIND == IN_PCM_S16 ? 4096 * 6 : 4096 * 4;  // a stage of the pipelined mode (PipeStage): samples, undo log
+    const size_t T = L >= FAST_BIG_MIN_L ? 4096 : 512;
+    const size_t one = KIND == IN_IQ_F32 ? 0 : T * item;  // staging buffer of the synchronous loop (IQ tiles are not staged)
+    const size_t stg = KIND == IN_PCM_S16 ? T * 6 : T * 4;  // a stage of the pipelined mode (PipeStage): samples, undo log
     const size_t half = smem_optin_limit() / 2;               // two CTAs per SM
     FastVariant v;
+    if (L < FAST_BIG_MIN_L) {
+        if (pipe && KIND != IN_IQ_F32) {
+            v.fn = (const void *)slicer_fast_kernel<128, 1, 5, KIND, 3>;
+            v.threads = 192;
+            v.smem = ring + 3 * stg;
+        } else {
+            v.fn = (const void *)slicer_fast_kernel<128, 1, 6, KIND, 0>;
+            v.threads = 128;
+            v.smem = ring + one;
+        }
+        return v;
+    }
     if (pipe && KIND != IN_IQ_F32) {
         if (stages >= 3 && ring + 3 * stg + FAST_STATIC_SMEM <= half) {
             v.fn = (const void *)slicer_fast_kernel<256, 4, 2, KIND, 3>;
@@ -1371,7 +1392,8 @@ static int raise_dynamic_smem(const void *fn, size_t smem) {
 // own scratch into one CTA's shared memory); NFC_SLICER_OLD=1 keeps the first-generation kernel
 bool slicer_streaming_ok(int L, bool vec_ok) {
     static const bool old = getenv("NFC_SLICER_OLD") && getenv("NFC_SLICER_OLD")[0] == '1';
-    if (!(vec_ok && L >= 8192 && !old)) return false;
+    static const bool no_small = getenv("NFC_SLICER_SMALL") && getenv("NFC_SLICER_SMALL")[0] == '0';
+    if (!(vec_ok && L >= (no_small ? FAST_BIG_MIN_L : FAST_SMALL_MIN_L) && !old)) return false;
     return fast_variant_of(L, IN_IQ_F32).smem + 16384 + FAST_STATIC_SMEM <= smem_optin_limit();
 }
 

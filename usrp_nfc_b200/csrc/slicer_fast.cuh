@@ -143,6 +143,47 @@ struct FastShared {
     double vtot[32];  // exact verification: sum of the admitted steps of each chunk
 };
 
+// The hysteresis of transition_sink.py:67-73 matters only where a HIGH sample comes within max_len + 1 samples after a LOW
+// sample (cur_state == 2 holds it back: val != class there).  Lane = chunk of 128 samples of a tile (nl / hh: its "not LOW" /
+// "HIGH" words; lanes beyond the tile hold no LOW and no HIGH sample); relC: the last LOW sample before the tile, relative
+// to the tile's first sample (very negative: none in reach).  Exact to the sample for the first HIGH sample of a chunk
+// against the nearest LOW sample before it; a chunk with a LOW sample behind its first HIGH sample counts as a risk.
+__device__ __forceinline__ bool hysteresis_risk(const uint4 &nl, const uint4 &hh, bool hasL, bool hasH, int lane, int mx, int relC) {
+    const unsigned NLw[4] = {nl.x, nl.y, nl.z, nl.w}, Hw[4] = {hh.x, hh.y, hh.z, hh.w};
+    int firstH = 1 << 20, lastLany = -1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (Hw[j]) firstH = min(firstH, ((__ffs(Hw[j]) - 1) << 2) | j);
+        const unsigned lw = ~NLw[j];
+        if (lw) lastLany = max(lastLany, ((31 - __clz(lw)) << 2) | j);
+    }
+    // the last LOW sample of the chunks before this one (or before the tile)
+    int v = hasL ? lane * FAST_CH + lastLany : -(1 << 29);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v = max(v, u);
+    }
+    int prevL = __shfl_up_sync(FULL, v, 1);
+    if (lane == 0) prevL = -(1 << 29);
+    prevL = max(prevL, relC);
+    bool risk = false;
+    if (hasH) {
+        int nearest = prevL;
+        if (hasL) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int cnt = (firstH - j + 3) >> 2;  // lanes l with 4l + j < firstH
+                const unsigned m = cnt >= 32 ? FULL : (cnt <= 0 ? 0u : ((1u << cnt) - 1u));
+                const unsigned lw = ~NLw[j] & m;
+                if (lw) nearest = max(nearest, lane * FAST_CH + (((31 - __clz(lw)) << 2) | j));
+            }
+        }
+        risk = (lane * FAST_CH + firstH - nearest <= mx + 1) || (hasL && lastLany > firstH);
+    }
+    return __any_sync(FULL, risk);
+}
+
 }  // namespace nfc
 #include "slicer_pipe.cuh"
 namespace nfc {
@@ -180,6 +221,8 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     bool ok = ss_lo > 0.0 && ssf < 1.0e30f && ssf > 1.0e-30f;
     if (!(a_est > 0.0f)) a_est = ssf * 0x1p-7f;
     const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;  // fixed-point step: a power of two near a_est * 2^-31
+    // (smaller tiles: a lane's share of the tile's steps is larger, the step coarser by as much)
+    constexpr unsigned QEXP = NC >= 32 ? 30u : (NC >= 16 ? 29u : (NC >= 8 ? 28u : 27u));
     ok = ok && ae > 45u && ae < 250u;
     const float TLb = __double2float_rn(ssm * loL), THb = __double2float_rn(ssm * hiL);
     const float srel = ok ? __fdividef(tot_prev * (1.0f / NC), ssf) : 0.0f;  // predicted relative change of ss per chunk (a guess)
@@ -189,7 +232,7 @@ __device__ __forceinline__ void fast_prepare(FastUni &u, double ss_lo, double ss
     u.gMid[lane] = ssf * (f - 1.0f);
     __syncwarp();  // every lane has read the values of `u` its arguments were computed from
     if (lane == 0) {
-        const unsigned qe = ok ? ae - 30u : 127u;
+        const unsigned qe = ok ? ae - QEXP : 127u;
         u.q = __uint_as_float(qe << 23);
         u.invq = __uint_as_float((254u - qe) << 23);
         u.invqA = u.invq * (1.0f + 0x1p-20f);
@@ -287,14 +330,15 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     constexpr int XR = T / SUB;           // exact_tile rows per tile
     constexpr int ITEM = KIND == IN_IQ_F32 ? 8 : (KIND == IN_PCM_S16 ? 2 : 4);
     constexpr int tile_bytes = T * ITEM;
-    static_assert(NC == 32, "one lane per chunk record");
+    static_assert(NC <= 32 && NC >= 4, "one lane per chunk record");
     static_assert(T % SUB == 0, "tile is a whole number of exact rows");
-    static_assert(R == 4 || R == 2, "bitmap words of a warp are written by its first R * 8 lanes");
-    static_assert(NW >= 8, "warps 0 and 1 share the verification, another keeps the carries");
-#ifndef NFC_CARRY_THREAD
-#define NFC_CARRY_THREAD 128
-#endif
-    constexpr int CARRY_THREAD = NFC_CARRY_THREAD;  // not in warp 0: that one has the longest way to the next barrier already
+    static_assert(R == 4 || R == 2 || R == 1, "bitmap words of a warp are written by its first R * 8 lanes");
+    static_assert(NW >= 4, "warps 0 and 1 share the verification, others write the bitmap, another keeps the carries");
+    // Small windows (the reference's default: av_window = 2000 at 2 MS/s, transition_sink.py:12) take tiles of 512 samples:
+    // four warps, one chunk each; the lanes of the verifying warps beyond the tile's chunks see empty chunks.
+    constexpr int BM_FIRST = NW >= 8 ? NW - 4 : 2;  // warps BM_FIRST.. store the tile's bitmap words while warps 0 and 1 judge it
+    constexpr int BM_WARPS = NW - BM_FIRST;
+    constexpr int CARRY_THREAD = NT >= 256 ? 128 : 96;  // not in warp 0: that one has the longest way to the next barrier already
     extern __shared__ __align__(16) float ring[];
     __shared__ BlockShared<NT, 1> sh;  // exact_tile's scratch
     __shared__ FastShared<NT, R> fs;
@@ -318,6 +362,12 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     }
     if (threadIdx.x < FS_N) fs.uni.stats[threadIdx.x] = 0u;
     if (threadIdx.x == 0) ps.inited = 0;
+    if (NC < 32 && threadIdx.x >= NC && threadIdx.x < 32) {  // chunks a smaller tile does not have: no steps, no samples near a guess
+        FastRec e;
+        e.S = 0; e.A = 0; e.mL = INFINITY; e.mH = INFINITY;
+        fs.recs[threadIdx.x] = e;
+        fs.vtot[threadIdx.x] = 0.0;
+    }
     cta_sync<NT>();
     const SegWork &w = w_s;
     const SlicerParams &p = p_s;
@@ -540,8 +590,11 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
 
     // phase 2b (warp 1): the class maps of the tile, lane = chunk: hysteresis risk and the carries the tile would leave
     auto maps_phase = [&](int t) {
-            const uint4 nl = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8]);
-            const uint4 hh = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8 + 4]);
+            uint4 nl = make_uint4(FULL, FULL, FULL, FULL), hh = make_uint4(0u, 0u, 0u, 0u);
+            if (NC == 32 || lane < NC) {
+                nl = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8]);
+                hh = *reinterpret_cast<const uint4 *>(&fs.bm[lane * 8 + 4]);
+            }
             const bool hasL = (nl.x & nl.y & nl.z & nl.w) != FULL, hasH = (hh.x | hh.y | hh.z | hh.w) != 0u;
             const int firstc = (int)((nl.x & 1u) + (hh.x & 1u)), lastc = (int)((nl.w >> 31) + (hh.w >> 31));
             const unsigned Lmask = __ballot_sync(FULL, hasL), Hmask = __ballot_sync(FULL, hasH);
@@ -549,16 +602,17 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
             bool st2 = false;
             if (Hmask) {
+                // cheap test by chunks first; only if it fires, to the sample
                 const int nb = plan.nb;
                 const int lo_c = max(lane - nb, 0);
                 const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
                 bool risk = hasH && win != 0u;
                 const int64_t cl = c_s.lastL;
-                if (hasH && cl != NO_POS) {
-                    const int64_t dist = P0 + (int64_t)lane * FAST_CH - cl;  // first sample of the chunk to the carried LOW
-                    if (dist <= (int64_t)p.mx + 1) risk = true;
+                if (hasH && cl != NO_POS && P0 + (int64_t)lane * FAST_CH - cl <= (int64_t)p.mx + 1) risk = true;
+                if (__any_sync(FULL, risk)) {
+                    const int relC = (cl != NO_POS && P0 - cl < (int64_t)(1 << 28)) ? (int)(cl - P0) : -(1 << 29);
+                    st2 = hysteresis_risk(nl, hh, hasL, hasH, lane, p.mx, relC);
                 }
-                st2 = __any_sync(FULL, risk);
             }
             // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
             int newL = -1, newS = -1;
@@ -601,11 +655,14 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     // tile (a tile that is repeated or settled another way simply overwrites them).
     auto bitmap_out = [&](int t, int first_warp) {  // between the two barriers of a pass
         if (t >= plan.t_emit) {
-            static_assert(NC * 8 == 4 * 64, "four warps, two words per lane");
             uint32_t *dst = plan.bm_base + (size_t)t * (NC * 8);
-            const int i = (warp - first_warp) * 64 + lane;
-            dst[i] = fs.bm[i];
-            dst[i + 32] = fs.bm[i + 32];
+            if (NC * 8 == BM_WARPS * 64) {  // two words per lane
+                const int i = (warp - first_warp) * 64 + lane;
+                dst[i] = fs.bm[i];
+                dst[i + 32] = fs.bm[i + 32];
+            } else {
+                for (int i = (warp - first_warp) * 32 + lane; i < NC * 8; i += BM_WARPS * 32) dst[i] = fs.bm[i];
+            }
         }
     };
     // ring update and carries of an accepted tile
@@ -787,10 +844,11 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                             if (bad && redo) {  // a lane's sum did not fit: coarser fixed-point step
                                 const float ae = uni.a_est * 16.0f;
                                 const unsigned e = (__float_as_uint(ae) >> 23) & 0xffu;
+                                constexpr unsigned QEXP = NC >= 32 ? 30u : (NC >= 16 ? 29u : (NC >= 8 ? 28u : 27u));
                                 if (e > 45u && e < 250u) {
                                     uni.a_est = ae;
-                                    uni.q = __uint_as_float((e - 30u) << 23);
-                                    uni.invq = __uint_as_float((254u - (e - 30u)) << 23);
+                                    uni.q = __uint_as_float((e - QEXP) << 23);
+                                    uni.invq = __uint_as_float((254u - (e - QEXP)) << 23);
                                     uni.invqA = uni.invq * (1.0f + 0x1p-20f);
                                 } else {
                                     v = FV_SLOW;
@@ -816,8 +874,8 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                     }
                 } else if (warp == 1) {
                     maps_phase(t);
-                } else if (warp >= NW - 4) {
-                    bitmap_out(t, NW - 4);
+                } else if (warp >= BM_FIRST) {
+                    bitmap_out(t, BM_FIRST);
                 }
                 cta_sync<NT>();
                 verdict = uni.verdict;
@@ -958,7 +1016,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                     if (lane >= o) cinc += v;
                 }
                 const double chunk_ex = cinc - ct;
-                total = __shfl_sync(FULL, cinc, 31);
+                total = __shfl_sync(FULL, cinc, NC - 1);
                 unsigned ncls = 0u;
                 s0 = slot_w;
 #pragma unroll

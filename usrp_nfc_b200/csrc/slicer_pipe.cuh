@@ -308,10 +308,12 @@ __device__ __noinline__ int pipe_worker(PipeShared<NW, R, S> &ps, float *ring, c
 // ---------------------------------------------------------------- judge
 // fixed-point step: a power of two near a_est * 2^-27.  A lane's sum must stay below 2^22 steps (a_est / 32, a_est being an
 // upper bound of the tile's sum of |x - prev| of late: 128 times the lane's share), so that the sums of a tile's chunks fit int32.
+template <int NTHREADS>
 __device__ __forceinline__ bool pipe_step(float a_est, float &q, float &invq) {
     const unsigned ae = (__float_as_uint(a_est) >> 23) & 0xffu;
     const bool ok = ae > 45u && ae < 250u;
-    const unsigned qe = ok ? ae - 27u : 127u;
+    constexpr unsigned QEXP = NTHREADS >= 256 ? 27u : 24u;  // fewer threads: a lane's share of the tile's steps is larger
+    const unsigned qe = ok ? ae - QEXP : 127u;
     q = __uint_as_float(qe << 23);
     invq = __uint_as_float((254u - qe) << 23);
     return ok;
@@ -376,7 +378,7 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
     // to see that window sum + dr * (ofs + fc)
     auto prepare = [&](int b, float TLm, float THm, float dr, float ofs, float a_e, bool sane) {
         float q, invq;
-        const bool stepok = pipe_step(a_e, q, invq);
+        const bool stepok = pipe_step<NW * 32>(a_e, q, invq);
         const float go = dr * (ofs + fc);
         const float TL = fmaf(go, loLf, TLm), TH = fmaf(go, hiLf, THm);
         const float cg = 0.5f * (TL + TH), rg = 0.5f * (TH - TL);
@@ -527,15 +529,16 @@ __device__ __noinline__ void pipe_mapper(PipeShared<NW, R, S> &ps, SegCarry &cs,
         // hysteresis can matter only if a HIGH sample comes within max_len + 1 samples after a LOW sample
         bool st2 = false;
         if (Hmask) {
+            // cheap test by chunks first; only if it fires, to the sample
             const int nb = plan.nb;
             const int lo_c = max(lane - nb, 0);
             const unsigned win = (Lmask >> lo_c) & ((2u << (lane - lo_c)) - 1u);
             bool risk = hasH && win != 0u;
-            if (hasH && lastL != NO_POS) {
-                const int64_t dist = P0 + (int64_t)lane * FAST_CH - lastL;  // first sample of the chunk to the carried LOW
-                if (dist <= (int64_t)mx + 1) risk = true;
+            if (hasH && lastL != NO_POS && P0 + (int64_t)lane * FAST_CH - lastL <= (int64_t)mx + 1) risk = true;
+            if (__any_sync(FULL, risk)) {
+                const int relC = (lastL != NO_POS && P0 - lastL < (int64_t)(1 << 28)) ? (int)(lastL - P0) : -(1 << 29);
+                st2 = hysteresis_risk(nl, hh, hasL, hasH, lane, mx, relC);
             }
-            st2 = __any_sync(FULL, risk);
         }
         // the carries the tile would leave: val of its last sample, last LOW sample and the start of its run
         int newL = -1, newS = -1;

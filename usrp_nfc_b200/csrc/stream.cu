@@ -617,7 +617,7 @@ int64_t Stream::push_batch(const void *items, int mem, int64_t n_cap, int64_t ca
         return -1;
     }
     if (!streaming_ok()) {
-        set_error("push_batch: needs the streaming slicer (av_window >= 8192, a multiple of 4)");
+        set_error("push_batch: needs the streaming slicer (av_window >= 1024, a multiple of 4)");
         return -1;
     }
     if (n_cap <= 0 || cap_len <= (int64_t)L + 2 * sp.mx || stride_items < cap_len || L <= sp.mx + 1) {
