@@ -132,6 +132,38 @@ static int classify_ratio_host(double ratio, double lo, double hi) {  // transit
     return 0;
 }
 
+// All frame bits of one type in the order they were appended (cpp.append_bit), in page-locked memory: a slab's bits are
+// copied from the device straight to their final place behind the bits of the slabs before, frames refer to them by offset.
+// [0, closed): bits of the frames handed out so far (up to the last frame closing); [closed, len): bits of a frame still open.
+struct BitArena {
+    uint8_t *p = nullptr;
+    size_t cap = 0, len = 0, closed = 0;
+    // May move the arena: the caller guarantees that no copy into it is in flight and that nobody reads it.
+    int reserve(size_t need) {
+        if (need <= cap) return 0;
+        const size_t ncap = std::max(need + need / 2 + 65536, cap * 2);
+        uint8_t *q = nullptr;
+        if (cudaMallocHost((void **)&q, ncap) != cudaSuccess) return -1;
+        if (len) memcpy(q, p, len);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = ncap;
+        return 0;
+    }
+    void consume() {  // the frames were handed out: the open bits move to the front
+        const size_t open = len - closed;
+        if (open && closed) memmove(p, p + closed, open);
+        len = open;
+        closed = 0;
+    }
+    void clear() { len = closed = 0; }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = len = closed = 0;
+    }
+};
+
 struct Stream {
     nfc_params prm;
     SlicerParams sp;
@@ -178,7 +210,6 @@ struct Stream {
     RunCarry run_carry{0, 0, 0, 0};
     DecCarry dec_carry{0, 0, {0, 0}};
     uint32_t pending[2] = {0, 0};
-    std::vector<uint8_t> hbits[2];  // bits appended and not yet forwarded, per type
 
     // tuning
     int64_t seg_len = 0, halo = 0, slab_len = 0;
@@ -232,13 +263,13 @@ struct Stream {
             if (finalize_front()) return -1;
         return 0;
     }
-    int marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t off_b0, size_t off_b1, uint32_t M,
+    int marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t base0, size_t base1, uint32_t M,
                 uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit);
 
     // results
     std::vector<nfc_event> out_events;
     std::vector<nfc_symbol> out_symbols;
-    std::vector<nfc_frame> out_frames;   // bit_off is relative to out_fbits[type]
+    std::vector<nfc_frame> out_frames;   // bit_off is relative to fb[type].p
     // packed frame offsets (pos << 24 | nbits << 8 | type) of out_frames in page-locked memory (nfc_stream_view_frame_index)
     uint64_t *findex = nullptr;
     size_t findex_n = 0, findex_cap = 0;
@@ -254,7 +285,7 @@ struct Stream {
         findex_cap = cap;
         return 0;
     }
-    std::vector<uint8_t> out_fbits[2];   // forwarded frame bits per type, frames back to back
+    BitArena fb[2];                      // frame bits per type, frames back to back
     int resident_ctas = 0;
     size_t ev_head = 0, sym_head = 0, fr_head = 0;
 
@@ -417,6 +448,8 @@ void Stream::destroy() {
     for (DevBuf *b : all) b->release();
     if (ctx_h) cudaFreeHost(ctx_h);
     ctx_h = nullptr;
+    fb[0].release();
+    fb[1].release();
     if (findex) cudaFreeHost(findex);
     findex = nullptr;
     findex_cap = findex_n = 0;
@@ -1618,7 +1651,7 @@ int Stream::finalize_front() {
 
     // ---- records back to the host (cs2; the chain has completed: the host has seen its context block)
     const bool want_ev = j.want_ev, want_sym = j.want_sym, want_fr = j.want_fr;
-    size_t off_ev = 0, off_sym = 0, off_em = 0, off_b0 = 0, off_b1 = 0, total = 0;
+    size_t off_ev = 0, off_sym = 0, off_em = 0, total = 0;
     auto place = [&](size_t bytes) {
         size_t o = total;
         total += (bytes + 63) / 64 * 64;
@@ -1627,23 +1660,37 @@ int Stream::finalize_front() {
     place(64);
     if (want_ev) off_ev = place((size_t)M * sizeof(EventRec));
     if (want_sym) off_sym = place((size_t)nsym * sizeof(SymbolRec));
-    if (want_fr) {
-        off_em = place((size_t)nemit * sizeof(EmissionHost));
-        off_b0 = place(nbit0);
-        off_b1 = place(nbit1);
-    }
+    if (want_fr) off_em = place((size_t)nemit * sizeof(EmissionHost));
     const int pi = (int)(slabs_enqueued % NPIN);
     // the slab that used this buffer last (three slabs ago) must be in the output vectors: long done, normally
     while (slabs_marshalled.load(std::memory_order_acquire) < slabs_enqueued - (NPIN - 1)) std::this_thread::yield();
     if (ensure_pinned(pi, total)) return -1;
     char *hp = (char *)pinned[pi];
+    size_t base[2] = {fb[0].len, fb[1].len};
+    if (want_fr) {
+        // the slab's frame bits go straight behind the bits of the slabs before; an arena that has to grow moves: no copy
+        // into it may be in flight then, and the worker threads must be done with what they were given
+        const uint32_t nb[2] = {nbit0, nbit1};
+        for (int t = 0; t < 2; t++)
+            if (fb[t].len + nb[t] > fb[t].cap) {
+                if (join_marshal()) return -1;
+                NFC_CUDA_CHECK(cudaStreamSynchronize(cs2));
+                if (fb[t].reserve(fb[t].len + nb[t])) {
+                    set_error("out of page-locked memory for %zu frame bits", fb[t].len + nb[t]);
+                    return -1;
+                }
+            }
+    }
     if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d[oi].p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
     if (want_sym && nsym)
         NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d[oi].p, (size_t)nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
     if (want_fr) {
         if (nemit) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d[oi].p, (size_t)nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs2));
-        if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b0, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
-        if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_b1, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
+        if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[0].p + fb[0].len, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
+        if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[1].p + fb[1].len, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
+        fb[0].len += nbit0;
+        fb[1].len += nbit1;
+        total += (size_t)nbit0 + nbit1;
     }
     NFC_CUDA_CHECK(cudaEventRecord(ev_d[pi], cs2));
     NFC_CUDA_CHECK(cudaEventRecord(ev_out[oi], cs2));
@@ -1653,12 +1700,12 @@ int Stream::finalize_front() {
     if (timing)
         fprintf(stderr, "slab %lld..%lld%s: slicer %.2f ms (dev %.2f), chain queued in %.2f (dev %.2f), context seen %.2f ms after queuing\n",
                 (long long)j.a, (long long)j.b, j.exact ? " (exact sizes)" : "", j.t1 - j.t0, ms_ab, j.t2 - j.t1, ms_ac - ms_ab, t3 - j.t2);
-    return marshal(j, pi, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, nsym, nbit0, nbit1, nemit);
+    return marshal(j, pi, hp, off_ev, off_sym, off_em, base[0], base[1], M, nsym, nbit0, nbit1, nemit);
 }
 
 // Records of a slab -> output vectors (absolute positions) on a worker thread: it waits for its predecessor (the vectors
 // are filled in slab order), then for the slab's records to arrive.
-int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t off_b0, size_t off_b1,
+int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t base0, size_t base1,
                     uint32_t M, uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit) {
     struct Totals {
         uint32_t nsym, nbit0, nbit1, nemit;
@@ -1669,7 +1716,7 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
     auto prev = std::make_shared<std::thread>(std::move(marshal_thr));
     const cudaEvent_t evd = ev_d[pi];
     const int dev = prm.device;
-    marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, off_em, off_b0, off_b1, M, totc, a, want_ev, want_sym,
+    marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, off_em, base0, base1, M, totc, a, want_ev, want_sym,
                                want_fr]() {
       if (prev->joinable()) prev->join();
       cudaSetDevice(dev);
@@ -1712,46 +1759,11 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
         }
         if (want_fr) {
             const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
-            const uint8_t *nb[2] = {(const uint8_t *)(hp + off_b0), (const uint8_t *)(hp + off_b1)};
+            // the slab's bits lie in the arenas at base[t] (finalize_front put them there); a frame ends bit_end bits behind
+            // that and begins nbits before its end (possibly among the bits of earlier slabs)
+            const size_t base[2] = {base0, base1};
             const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
-            // hbits[t]: bits of a frame still open at the end of the previous slab; the slab's new bits follow them
-            const size_t old[2] = {hbits[0].size(), hbits[1].size()};
-            size_t last_end[2] = {0, 0};
-            bool any[2] = {false, false};
-            const size_t fbase[2] = {out_fbits[0].size(), out_fbits[1].size()};
-            // the last closing of each type says how many of the new bits go out: known before the frames are walked, so the
-            // bits can be copied by a helper thread meanwhile (different containers)
-            for (uint32_t i = tot.nemit; i > 0 && !(any[0] && any[1]); i--) {
-                const int t = em[i - 1].type;
-                if (!any[t]) {
-                    any[t] = true;
-                    last_end[t] = old[t] + em[i - 1].bit_end;  // index into (open bits ++ new bits)
-                }
-            }
-            for (int t = 0; t < 2; t++)
-                if (any[t] && last_end[t] - old[t] > nnew[t]) {
-                    marshal_err = 1;
-                    return;
-                }
-            auto copy_bits = [&](int t) {
-                if (any[t]) {  // everything up to the last closing goes out (one copy), the rest stays open
-                    const size_t used_new = last_end[t] - old[t];
-                    out_fbits[t].insert(out_fbits[t].end(), hbits[t].begin(), hbits[t].end());
-                    out_fbits[t].insert(out_fbits[t].end(), nb[t], nb[t] + used_new);
-                    hbits[t].assign(nb[t] + used_new, nb[t] + nnew[t]);
-                } else {
-                    hbits[t].insert(hbits[t].end(), nb[t], nb[t] + nnew[t]);
-                }
-            };
-            // large slabs: one helper thread per type copies the bits while this one walks the frames
-            std::thread helper, helper1;
-            if (tot.nemit > 20000) {
-                helper = std::thread(copy_bits, 0);
-                helper1 = std::thread(copy_bits, 1);
-            } else {
-                copy_bits(0);
-                copy_bits(1);
-            }
+            size_t closed[2] = {0, 0};
             bool bad_frame = false;
             const size_t f0 = out_frames.size();
             grow(out_frames, tot.nemit);
@@ -1765,7 +1777,12 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
             uint64_t *fx = findex + f0;
             for (uint32_t i = 0; i < tot.nemit; i++) {
                 const int t = em[i].type;
-                const size_t end = old[t] + em[i].bit_end;
+                if (em[i].bit_end > nnew[t]) {
+                    bad_frame = true;
+                    break;
+                }
+                const size_t end = base[t] + em[i].bit_end;
+                closed[t] = end;  // closings of a type come in order
                 if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
                 if (em[i].nbits > end) {
                     bad_frame = true;
@@ -1773,7 +1790,7 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                 }
                 nfc_frame &f = fo[nf++];
                 f.pos = a + (int64_t)em[i].rel_pos;
-                f.bit_off = (int64_t)(fbase[t] + end - em[i].nbits);  // frames of one type are back to back
+                f.bit_off = (int64_t)(end - em[i].nbits);  // frames of one type are back to back
                 f.nbits = (int32_t)em[i].nbits;
                 f.type = t;
                 if (((uint64_t)f.pos >> 40) || em[i].nbits >= 65536u) findex_bad = true;
@@ -1781,8 +1798,8 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
             }
             out_frames.resize(f0 + nf);
             findex_n = f0 + nf;
-            if (helper1.joinable()) helper1.join();
-            if (helper.joinable()) helper.join();
+            for (int t = 0; t < 2; t++)
+                if (closed[t] > fb[t].closed) fb[t].closed = closed[t];
             if (bad_frame) {
                 marshal_err = 1;
                 return;
@@ -1878,15 +1895,13 @@ int nfc_stream_reset(nfc_stream *h) {
     s.run_carry = nfc::RunCarry{0, 0, 0, 0};
     s.dec_carry = nfc::DecCarry{0, 0, {0, 0}};
     s.pending[0] = s.pending[1] = 0;
-    s.hbits[0].clear();
-    s.hbits[1].clear();
+    s.fb[0].clear();
+    s.fb[1].clear();
     s.out_events.clear();
     s.out_symbols.clear();
     s.out_frames.clear();
     s.findex_n = 0;
     s.findex_bad = false;
-    s.out_fbits[0].clear();
-    s.out_fbits[1].clear();
     s.ev_head = s.sym_head = s.fr_head = 0;
     return 0;
 }
@@ -1943,7 +1958,7 @@ int64_t nfc_stream_drain_symbols(nfc_stream *h, nfc_symbol *out, int64_t cap) {
 
 int64_t nfc_stream_pending_frame_bits(nfc_stream *h) {
     if (!h || h->s.settle()) return -1;
-    return (int64_t)(h->s.out_fbits[0].size() + h->s.out_fbits[1].size());
+    return (int64_t)(h->s.fb[0].closed + h->s.fb[1].closed);
 }
 
 int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint8_t *bits, int64_t bits_cap) {
@@ -1951,7 +1966,7 @@ int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint
     Stream &s = h->s;
     const int64_t avail = (int64_t)s.out_frames.size();
     if (cap <= 0 || !out) return avail;
-    const int64_t nb0 = (int64_t)s.out_fbits[0].size(), nb1 = (int64_t)s.out_fbits[1].size();
+    const int64_t nb0 = (int64_t)s.fb[0].closed, nb1 = (int64_t)s.fb[1].closed;
     if (cap < avail || bits_cap < nb0 + nb1 || (!bits && nb0 + nb1 > 0)) {
         nfc::set_error("drain_frames: buffers too small (%lld frames, %lld bits pending)", (long long)avail,
                        (long long)(nb0 + nb1));
@@ -1965,23 +1980,23 @@ int64_t nfc_stream_drain_frames(nfc_stream *h, nfc_frame *out, int64_t cap, uint
         }
     };
     if (nb0 + nb1 > (4 << 20)) {
-        std::thread t0([&] { if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0); });
-        std::thread t1([&] { if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1); });
+        std::thread t0([&] { if (nb0) memcpy(bits, s.fb[0].p, (size_t)nb0); });
+        std::thread t1([&] { if (nb1) memcpy(bits + nb0, s.fb[1].p, (size_t)nb1); });
         std::thread t2([&] { copy_frames(0, avail / 2); });
         copy_frames(avail / 2, avail);
         t0.join();
         t1.join();
         t2.join();
     } else {
-        if (nb0) memcpy(bits, s.out_fbits[0].data(), (size_t)nb0);
-        if (nb1) memcpy(bits + nb0, s.out_fbits[1].data(), (size_t)nb1);
+        if (nb0) memcpy(bits, s.fb[0].p, (size_t)nb0);
+        if (nb1) memcpy(bits + nb0, s.fb[1].p, (size_t)nb1);
         copy_frames(0, avail);
     }
     s.out_frames.clear();
     s.findex_n = 0;
     s.findex_bad = false;
-    s.out_fbits[0].clear();
-    s.out_fbits[1].clear();
+    s.fb[0].consume();
+    s.fb[1].consume();
     s.fr_head = 0;
     return avail;
 }
@@ -2002,10 +2017,10 @@ int64_t nfc_stream_view_frames(nfc_stream *h, const nfc_frame **frames, const ui
     if (h->s.settle()) return -1;
     Stream &s = h->s;
     *frames = s.out_frames.data();
-    *bits_tag = s.out_fbits[0].data();
-    *n_bits_tag = (int64_t)s.out_fbits[0].size();
-    *bits_reader = s.out_fbits[1].data();
-    *n_bits_reader = (int64_t)s.out_fbits[1].size();
+    *bits_tag = s.fb[0].p;
+    *n_bits_tag = (int64_t)s.fb[0].closed;
+    *bits_reader = s.fb[1].p;
+    *n_bits_reader = (int64_t)s.fb[1].closed;
     return (int64_t)s.out_frames.size();
 }
 
@@ -2030,8 +2045,8 @@ int nfc_stream_release_frames(nfc_stream *h) {
     s.out_frames.clear();
     s.findex_n = 0;
     s.findex_bad = false;
-    s.out_fbits[0].clear();
-    s.out_fbits[1].clear();
+    s.fb[0].consume();
+    s.fb[1].consume();
     s.fr_head = 0;
     return 0;
 }
@@ -2078,8 +2093,9 @@ int nfc_stream_get_state(nfc_stream *h, nfc_state *st, float *ring, uint8_t *pen
     if (pending_bits) {
         size_t o = 0;
         for (int t = 0; t < 2; t++) {
-            if (s.hbits[t].size()) memcpy(pending_bits + o, s.hbits[t].data(), s.hbits[t].size());
-            o += s.hbits[t].size();
+            const size_t open = s.fb[t].len - s.fb[t].closed;
+            if (open) memcpy(pending_bits + o, s.fb[t].p + s.fb[t].closed, open);
+            o += open;
         }
     }
     return 0;
@@ -2138,9 +2154,15 @@ int nfc_stream_set_state(nfc_stream *h, const nfc_state *st, const float *ring, 
     for (int t = 0; t < 2; t++) {
         s.dec_carry.started[t] = st->started[t];
         s.pending[t] = (uint32_t)st->pending[t];
-        s.hbits[t].clear();
-        if (pending_bits) s.hbits[t].assign(pending_bits + o, pending_bits + o + st->pending[t]);
-        else s.hbits[t].assign((size_t)st->pending[t], 0);
+        // the open bits behind whatever has not been handed out yet
+        s.fb[t].len = s.fb[t].closed;
+        if (s.fb[t].reserve(s.fb[t].len + (size_t)st->pending[t] + 64)) {
+            nfc::set_error("out of page-locked memory");
+            return -1;
+        }
+        if (pending_bits) memcpy(s.fb[t].p + s.fb[t].len, pending_bits + o, (size_t)st->pending[t]);
+        else memset(s.fb[t].p + s.fb[t].len, 0, (size_t)st->pending[t]);
+        s.fb[t].len += (size_t)st->pending[t];
         o += (size_t)st->pending[t];
     }
     return 0;
