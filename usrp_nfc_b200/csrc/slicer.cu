@@ -1351,10 +1351,14 @@ static FastVariant fast_variant(int L) {
             v.fn = (const void *)slicer_fast_kernel<256, 4, 2, KIND, 2>;
             v.threads = 320;
             v.smem = ring + 2 * stg;
-        } else {
+        } else if (ring + 3 * stg + FAST_STATIC_SMEM <= smem_optin_limit()) {
             v.fn = (const void *)slicer_fast_kernel<512, 2, 1, KIND, 3>;
             v.threads = 576;
             v.smem = ring + 3 * stg;
+        } else {  // a window that leaves no room for the stages beside its ring: the synchronous loop
+            v.fn = (const void *)slicer_fast_kernel<256, 4, 3, KIND, 0>;
+            v.threads = 256;
+            v.smem = ring + one;
         }
     } else {
         v.fn = (const void *)slicer_fast_kernel<256, 4, 3, KIND, 0>;

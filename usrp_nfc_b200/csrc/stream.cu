@@ -293,7 +293,8 @@ struct Stream {
 
     int tile() const { return slicer_tile(sp.L, vec_ok()); }
     bool vec_ok() const { return (sp.L % 4) == 0; }
-    bool parallel_ok() const { return sp.L >= 256 && sp.L <= 56000 && !force_serial && !serial_mode; }
+    // (windows whose ring does not fit a CTA's shared memory beside the kernels' own scratch take the sequential kernel)
+    bool parallel_ok() const { return sp.L >= 256 && sp.L <= 52000 && !force_serial && !serial_mode; }
 
     int init(const nfc_params *p);
     void destroy();

@@ -99,8 +99,14 @@ class decoder(gr.hier_block2):
                                  device=device, on_frame_bytes=on_frame_bytes, **sink_kwargs)
         if HAVE_GNURADIO and isinstance(src, str):  # pragma: no cover - needs GNU Radio
             if src == "uhd":
-                import usrp_src  # the reference's own source wrapper (usrp_src.py), minus its mag^2 block
-                self._src = usrp_src.usrp_src(samp_rate=samp_rate, dst=dst)
+                # the source of usrp_src.py:19-30 itself, complex items: the reference's wrapper squares them on the host
+                # (usrp_src.py:31-33) and has a float output, this sink takes IN_IQ_F32 and computes the envelope on the device
+                from gnuradio import uhd
+                self._src = uhd.usrp_source(device_addr="", stream_args=uhd.stream_args(cpu_format="fc32", channels=range(1)))
+                self._src.set_samp_rate(samp_rate)
+                self._src.set_center_freq(13.57e6, 0)  # usrp_src.py:14 defaults: freq, rx_gain
+                self._src.set_gain(6.5, 0)
+                self._src.set_antenna("RX", 0)
             else:
                 self._src = blocks.wavfile_source(src, repeat)
             self.connect(self._src, self._trans)
