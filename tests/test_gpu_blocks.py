@@ -46,6 +46,17 @@ def test_decoder_block_hands_frames_to_fsm():
     assert [t for t, _ in got] == case["ftype"].tolist()
 
 
+def test_decoder_block_coalesces_small_work_calls():
+    """coalesce: the items of successive work() calls go to the device together; the same frames in the same order."""
+    from usrp_nfc_b200.decoder import decoder
+    case = H.load_case("surrogate_classic1k")
+    got = []
+    d = decoder(src=case["pcm"], samp_rate=2e6, on_frame=lambda bits, t: got.append((t, bits)), coalesce=50000)
+    assert d.run(chunk=8192) == len(case["pcm"])
+    assert len(got) == len(case["fpos"]) and [t for t, _ in got] == case["ftype"].tolist()
+    assert np.array_equal(np.array([b for _, bits in got for b in bits], dtype=np.uint8), case["fbits"])
+
+
 def test_decoder_block_hands_frame_bytes_from_the_device_tail():
     """on_frame_bytes: what fsm.process_bits derives first (fsm.py:28-66,114-131; utilities.py:26-46), per frame, next to
     the bit lists of the same frames."""

@@ -21,17 +21,42 @@ class frame_sink(gr.sync_block):
     path (raw samples, squared on the device) and complex64 for UHD."""
 
     def __init__(self, samp_rate, on_frame, reader=True, tag=True, hi_val=1.1, lo_val=0.1, av_window=2000, max_len=50,
-                 input_kind=_cabi.IN_REAL_F32, device=0, on_frame_bytes=None):
+                 input_kind=_cabi.IN_REAL_F32, device=0, on_frame_bytes=None, coalesce=0):
+        """coalesce: GNU Radio hands a sync block a few thousand items per work() call; a call costs about a millisecond of
+        launches whatever its size.  With coalesce > 0 the items of successive calls are collected (every call still consumes
+        all it is offered) and go to the device once at least that many are there: the same frames in the same order, at
+        most `coalesce` items later.  0: every call is pushed as it comes."""
         in_type = {_cabi.IN_IQ_F32: numpy.complex64, _cabi.IN_PCM_S16: numpy.int16}.get(input_kind, numpy.float32)
         gr.sync_block.__init__(self, name="nfc_frame_sink", in_sig=[in_type], out_sig=None)
         self._on_frame = on_frame
         self._on_frame_bytes = on_frame_bytes
         self._device = device
+        self._coalesce = int(coalesce)
+        self._held, self._held_n = [], 0
         self._stream = _cabi.Stream(samp_rate, lo_val, hi_val, av_window, max_len, reader=reader, tag=tag,
                                     input_kind=input_kind, outputs=_cabi.OUT_FRAMES, device=device)
 
     def work(self, input_items, output_items):
-        consumed, _ = self._stream.push(input_items[0])
+        items = input_items[0]
+        if self._coalesce > 0:
+            self._held.append(numpy.array(items, copy=True))  # the view is only valid during the call
+            self._held_n += len(items)
+            if self._held_n >= self._coalesce:
+                self.flush()
+            return len(items)
+        consumed, _ = self._stream.push(items)
+        self._forward()
+        return consumed
+
+    def flush(self):
+        """Push what coalescing holds back (end of the source)."""
+        if self._held_n:
+            block = self._held[0] if len(self._held) == 1 else numpy.concatenate(self._held)
+            self._held, self._held_n = [], 0
+            self._stream.push_all(block)
+            self._forward()
+
+    def _forward(self):
         records, flat = self._stream.drain_frames_flat()
         if self._on_frame is not None:
             for rec in records:
@@ -44,7 +69,6 @@ class frame_sink(gr.sync_block):
             for rec, tl in zip(records, tails):
                 o, n = int(tl["byte_off"]), int(tl["nbytes"])
                 self._on_frame_bytes(by[o: o + n].tolist(), fl[o: o + n].tolist(), tl, int(rec["type"]))
-        return consumed
 
     def stream(self):
         return self._stream
@@ -131,6 +155,7 @@ class decoder(gr.hier_block2):
             off += used
             if used == 0:
                 break
+        self._trans.flush()
         return off
 
     def stream(self):
