@@ -45,3 +45,40 @@ ev = s.drain_events(); fr, bits = s.drain_frames()
 st = s.stats()
 print("corner events", len(ev), "frames", len(fr), {k: st[k] for k in ("segments", "seam_mismatches", "fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles")})
 s.close()
+
+# the small-window variant of the streaming kernel (tiles of 512 samples): the reference's defaults at 2 MS/s, several
+# slabs (queued chains), and a corner stream with its hysteresis cases
+rate = 2e6
+frames = synth.load_sessions()["classic1k"]
+pcm = synth.capture(frames, rate, 7, channel=synth.Channel(pause=0.015, tag_high=1.07, fade=0.05), av_window=2000, sessions=2)
+x = synth.envelope(synth.pcm_to_float(pcm))
+s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_ALL)
+s.set_tuning(seg_len=40000, halo=8000, slab_len=1 << 18)
+s.push_all(x)
+ev = s.drain_events(); fr, bits = s.drain_frames()
+st = s.stats()
+print("small kind 0 events", len(ev), "frames", len(fr), {k: st[k] for k in ("segments", "seam_mismatches", "fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "pipe_tiles", "overflow_retries")})
+s.close()
+L, n = 2000, 120000
+y = (0.25 * (1 + 0.01 * rng.standard_normal(n))).astype(np.float32)
+i = L + 10
+while i < n - 4 * mx - 10:
+    kind = rng.integers(0, 5)
+    ln = min(int(rng.choice([1, 2, mx, 2 * mx + 1, 6, 700])), n - i - 1)
+    if kind == 0:
+        y[i:i + ln] = 1e-4
+        i += ln
+        if rng.random() < 0.7:
+            k = int(rng.integers(0, mx + 4))
+            y[i + k: i + k + 2] = 0.4
+    elif kind == 2:
+        y[i:i + ln] = 0.2725 * (1 + 0.002 * rng.standard_normal(ln))
+        i += ln
+    i += int(rng.integers(1, 6 * mx))
+s = _cabi.Stream(2e6, hi_val=1.09, outputs=_cabi.OUT_ALL, av_window=L, max_len=mx)
+s.set_tuning(seg_len=16384, halo=4 * L)
+s.push_all(y)
+ev = s.drain_events(); fr, bits = s.drain_frames()
+st = s.stats()
+print("small corner events", len(ev), "frames", len(fr), {k: st[k] for k in ("segments", "seam_mismatches", "fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles")})
+s.close()

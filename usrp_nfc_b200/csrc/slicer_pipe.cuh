@@ -475,6 +475,9 @@ __device__ __noinline__ void pipe_judge(PipeShared<NW, R, S> &ps, FastUni &uni, 
         // tile k stands: its stage (the undo log by now) is free for tile k + S
         if (issued < K) {
             if (lane == 0) {
+                // the workers' undo log (generic proxy) lies in this stage: it is ordered before this thread by the mbarriers,
+                // the bulk copy (async proxy) behind it by the proxy fence
+                fence_proxy_async();
                 mbar_expect_tx(&ps.x_full[st], tile_bytes);
                 bulk_g2s(stage0 + (size_t)st * stage_bytes, src0 + (size_t)issued * tile_bytes, tile_bytes, &ps.x_full[st]);
             }

@@ -1776,26 +1776,70 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                 return;
             }
             uint64_t *fx = findex + f0;
-            for (uint32_t i = 0; i < tot.nemit; i++) {
-                const int t = em[i].type;
-                if (em[i].bit_end > nnew[t]) {
-                    bad_frame = true;
-                    break;
+            // slabs with many closings: the walk is bound by memory latency, so it is cut into parts that run on threads of
+            // their own (first pass: how many frames each part forwards; second pass: the records)
+            const int parts = tot.nemit > 60000 ? 4 : 1;
+            size_t part_n[4] = {0, 0, 0, 0}, part_closed[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            bool part_bad[4] = {false, false, false, false}, part_fx_bad[4] = {false, false, false, false};
+            auto range = [&](int q, uint32_t &i0, uint32_t &i1) {
+                i0 = (uint32_t)((uint64_t)tot.nemit * (uint64_t)q / (uint64_t)parts);
+                i1 = (uint32_t)((uint64_t)tot.nemit * (uint64_t)(q + 1) / (uint64_t)parts);
+            };
+            auto count_part = [&](int q) {
+                uint32_t i0, i1;
+                range(q, i0, i1);
+                size_t c = 0;
+                for (uint32_t i = i0; i < i1; i++) c += em[i].nbits != 0;
+                part_n[q] = c;
+            };
+            auto write_part = [&](int q, size_t o) {
+                uint32_t i0, i1;
+                range(q, i0, i1);
+                for (uint32_t i = i0; i < i1; i++) {
+                    const int t = em[i].type;
+                    if (em[i].bit_end > nnew[t]) {
+                        part_bad[q] = true;
+                        return;
+                    }
+                    const size_t end = base[t] + em[i].bit_end;
+                    part_closed[q][t] = end;  // closings of a type come in order
+                    if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
+                    if (em[i].nbits > end) {
+                        part_bad[q] = true;
+                        return;
+                    }
+                    nfc_frame &f = fo[o];
+                    f.pos = a + (int64_t)em[i].rel_pos;
+                    f.bit_off = (int64_t)(end - em[i].nbits);  // frames of one type are back to back
+                    f.nbits = (int32_t)em[i].nbits;
+                    f.type = t;
+                    if (((uint64_t)f.pos >> 40) || em[i].nbits >= 65536u) part_fx_bad[q] = true;
+                    fx[o] = ((uint64_t)f.pos << 24) | ((uint64_t)em[i].nbits << 8) | (uint64_t)t;
+                    o++;
                 }
-                const size_t end = base[t] + em[i].bit_end;
-                closed[t] = end;  // closings of a type come in order
-                if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
-                if (em[i].nbits > end) {
-                    bad_frame = true;
-                    break;
+            };
+            if (parts == 1) {
+                count_part(0);
+                write_part(0, 0);
+            } else {
+                std::thread th[3];
+                for (int q = 1; q < parts; q++) th[q - 1] = std::thread(count_part, q);
+                count_part(0);
+                for (int q = 1; q < parts; q++) th[q - 1].join();
+                size_t o = part_n[0];
+                for (int q = 1; q < parts; q++) {
+                    th[q - 1] = std::thread(write_part, q, o);
+                    o += part_n[q];
                 }
-                nfc_frame &f = fo[nf++];
-                f.pos = a + (int64_t)em[i].rel_pos;
-                f.bit_off = (int64_t)(end - em[i].nbits);  // frames of one type are back to back
-                f.nbits = (int32_t)em[i].nbits;
-                f.type = t;
-                if (((uint64_t)f.pos >> 40) || em[i].nbits >= 65536u) findex_bad = true;
-                fx[nf - 1] = ((uint64_t)f.pos << 24) | ((uint64_t)em[i].nbits << 8) | (uint64_t)t;
+                write_part(0, 0);
+                for (int q = 1; q < parts; q++) th[q - 1].join();
+            }
+            for (int q = 0; q < parts; q++) {
+                nf += part_n[q];
+                bad_frame = bad_frame || part_bad[q];
+                findex_bad = findex_bad || part_fx_bad[q];
+                for (int t = 0; t < 2; t++)
+                    if (part_closed[q][t] > closed[t]) closed[t] = part_closed[q][t];
             }
             out_frames.resize(f0 + nf);
             findex_n = f0 + nf;
