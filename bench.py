@@ -171,6 +171,15 @@ def cpu_baseline(x_host_pieces, params, threads):
     return n / dt / 1e6, dt, res
 
 
+def shm_room():
+    """Free bytes in /dev/shm (a segment larger than that kills the process that touches it)."""
+    try:
+        st = os.statvfs("/dev/shm")
+        return st.f_bavail * st.f_frsize
+    except Exception:
+        return 0
+
+
 def chan_for(rate, args):
     """Amplitude model of SURVEY.md 8(d) at a sample rate (the fade period is 20 ms of samples)."""
     return dict(carrier=0.5, pause=0.015, tag_high=args.tag_high, noise=0.003, fade=args.fade, fade_period=round(rate * 0.02))
@@ -317,6 +326,7 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     clock = {"on": None, "sum": 0.0, "render": 0.0}
 
     def fetch(a, b):
+        torch.cuda.synchronize()  # the decode of the piece before is still on the device: that is decode time, not rendering
         t = time.perf_counter()
         if clock["on"] is not None:
             clock["sum"] += t - clock["on"]
@@ -328,9 +338,13 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     s.set_tuning(slab_len=1 << 30)
     # warm-up: the whole pass once, untimed (device buffers and the host's output vectors reach their sizes)
     gstate = {}
+    shared = None
+    if world > 1:
+        want_recs = int(total // world * 2.5e-4) + (1 << 16)
+        shared = sharding.SharedFrameIndex(s, want_recs if shm_room() > 4 * world * want_recs * 8 else 0, dist)
     res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
                                        halo_windows=args.halo_windows, flat="view", piece=piece)
-    sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate)
+    sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate, shared=shared)
     s.release_frames()
     torch.cuda.synchronize()
     if world > 1:
@@ -344,13 +358,18 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     t_begin = clock["on"]
     res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
                                        halo_windows=args.halo_windows, flat="view", piece=piece)
-    index = sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate)
+    index = sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate, shared=shared)
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     clock["sum"] += t_end - clock["on"]
     st = s.stats()
     n_frames_rank = int(res["n_frames"])
+    n_index = int(len(index)) if index is not None else 0
+    via = "shared memory of the node (no copy)" if (shared is not None and shared.ok) else ("NCCL gather" if world > 1 else "local")
+    index = None
     s.release_frames()
+    if shared is not None:
+        shared.close()
     s.close()
     clocks = sampler.stop(t_begin, t_begin, t_end) if rank == 0 else None
     t = torch.tensor([clock["sum"] * 1e3, clock["render"] * 1e3, float(res["repaired"]), st["slicer_kernel_ms"]], dtype=torch.float64, device="cuda")
@@ -367,8 +386,8 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
             "samp_rate": rate, **params, "n_gpus": world, "scaling": "strong", "steps": 1, "warmup": 1,
             "ms": ms, "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "frac": step_frac(per_gpu, ms, peak),
             "kernel_ms": kern, "kernel_frac": step_frac(per_gpu, kern, peak) if kern > 0 else None,
-            "render_ms_untimed": render_ms, "frames": int(len(index)) if index is not None else n_frames_rank,
-            "frame_offsets_gathered_bytes": int(len(index)) * 8 if index is not None else 0,
+            "render_ms_untimed": render_ms, "frames": n_index if rank == 0 else n_frames_rank,
+            "frame_offsets_gathered_bytes": n_index * 8, "gathered_via": via,
             "ranks_redone": repaired, "clocks": clocks}
 
 
@@ -605,6 +624,13 @@ def main():
     s.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(args.slab))
     shard_info = {}
     gather_state = {}
+    shared = None
+    if world > 1:
+        # the ranks of the node keep their packed frame indexes in shared memory that rank 0 maps (falls back to the NCCL
+        # gather when /dev/shm has no room)
+        want_recs = int(n * 2.5e-4) + (1 << 16)
+        room = shm_room()
+        shared = sharding.SharedFrameIndex(s, want_recs if room > 4 * world * want_recs * 8 else 0, dist)
 
     def step():
         if world == 1:
@@ -620,9 +646,10 @@ def main():
         nfr = res["n_frames"]
         tg = time.perf_counter()
         # the frame offsets of all shards on rank 0, in stream order (packets.py:94-98): fixed 8-byte records over NCCL
-        index = sharding.gather_frame_records(s, res["pos_offset"], dist, device="cuda", state=gather_state)
+        index = sharding.gather_frame_records(s, res["pos_offset"], dist, device="cuda", state=gather_state, shared=shared)
         if index is not None:
-            shard_info.update(gathered_frames=int(len(index)), gathered_bytes=int(len(index)) * 8, index=index)
+            shard_info.update(gathered_frames=int(len(index)), gathered_bytes=int(len(index)) * 8, index=index,
+                              gather_via="shared memory of the node (no copy)" if (shared is not None and shared.ok) else "NCCL gather")
         shard_info["phases_ms"] = dict(res["phases_ms"], gather_offsets=(time.perf_counter() - tg) * 1e3)
         s.release_frames()
         return nfr
@@ -810,6 +837,8 @@ def main():
         host = x[: piece * threads].cpu().numpy()
         cpu_pieces = [host[i * piece: (i + 1) * piece] for i in range(threads)]
 
+    if shared is not None:
+        shared.close()
     # ---- the other BASELINE.json configs, each with its own timing, roofline fractions and clocks (none of them enters `value`)
     configs = None
     if not args.no_configs:
@@ -879,6 +908,7 @@ def main():
                                  "offsets gathered to rank 0 inside the timed step" % args.halo_windows,
                          "ranks_redone_last_step": repaired_ranks, "frame_offsets_gathered": shard_info.get("gathered_frames"),
                          "gathered_bytes_per_step": shard_info.get("gathered_bytes"), "gathered_in_stream_order": shard_info.get("in_order"),
+                         "gathered_via": shard_info.get("gather_via"),
                          "rank0_phases_ms_last_step": shard_info.get("phases_ms")} if world > 1 else None,
             "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,

@@ -134,6 +134,11 @@ int nfc_stream_release_frames(nfc_stream *s);
  * Valid until the next push / drain / reset / release on this stream.  Returns the frame count, -1 on error (a frame that
  * does not fit the packing). */
 int64_t nfc_stream_view_frame_index(nfc_stream *s, const uint64_t **index);
+/* Keep the packed frame index in memory of the caller's (room for cap records; NULL: the stream's own buffer again) -- e.g. a
+ * shared-memory segment that the process merging the time shards of one node maps, so that "gathering" the frame offsets
+ * moves no data at all.  The stream must hold no frames (right after create / reset / release).  More frames than cap make
+ * nfc_stream_view_frame_index fail. */
+int nfc_stream_set_frame_index_buffer(nfc_stream *s, uint64_t *buf, int64_t cap);
 
 /* What fsm.process_bits does to a frame before any protocol logic, for a batch of frames on the device:
  * fsm._fix_ending (fsm.py:51-66), fsm._check_parity (fsm.py:28-49), fsm._print_enc (fsm.py:114-131) and

@@ -25,6 +25,9 @@ def _worker(rank, world, port, halo_windows, rate, q, view=False):
     x = synth.envelope(synth.pcm_to_float(pcm))
     eng = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_FRAMES, **p)
     eng.set_tuning(seg_len=16 * p["av_window"], halo=4 * p["av_window"])
+    # the frame offsets alone: in shared memory of the node when the view form is used (what bench.py does), else over the
+    # process group
+    shared = sharding.SharedFrameIndex(eng, 4096, dist) if view else None
     res = sharding.decode_time_sharded(eng, lambda a, b: x[a:b], x.size, p["av_window"], _cabi.State, dist=dist,
                                        halo_windows=halo_windows, flat="view" if view else False)
     if view:  # zero-copy bulk form (what bench.py uses): records + the engine's own bit buffers, released by the caller
@@ -35,13 +38,24 @@ def _worker(rank, world, port, halo_windows, rate, q, view=False):
             mine.append((int(r["pos"]) + res["pos_offset"], int(r["type"]),
                          buf[int(r["bit_off"]): int(r["bit_off"]) + int(r["nbits"])].copy()))
         assert len(mine) == res["n_frames"]
+        index = sharding.gather_frame_records(eng, res["pos_offset"], dist, shared=shared)
+        idx = index.unpack() if index is not None else None  # (a copy: the segments are unmapped below)
+        assert shared.ok
         eng.release_frames()
+        shared.close()
     else:
         mine = res["frames"]
+        rec = np.zeros(len(mine), dtype=_cabi.FRAME_DTYPE)
+        for i, (pp, tt, bb) in enumerate(mine):
+            rec[i] = (pp, 0, len(bb), tt)
+        index = sharding.gather_frame_records(rec, 0, dist)
+        idx = index.unpack() if index is not None else None
     merged = sharding.gather_frames(mine, dist)
     if rank == 0:
         want = oracle.decode_capture(x, rate, hi_val=1.09, **p)
         ok = len(merged) == len(want["frames"])
+        ok = ok and len(idx) == len(want["frames"]) and np.array_equal(idx["pos"], want["frames"]["pos"])
+        ok = ok and np.array_equal(idx["nbits"], want["frames"]["nbits"]) and np.array_equal(idx["type"], want["frames"]["type"])
         ok = ok and all(pp == int(w["pos"]) and t == int(w["type"]) and np.array_equal(b, wb)
                         for (pp, t, b), w, wb in zip(merged, want["frames"], want["frame_bits"]))
         q.put((ok, len(merged), len(want["frames"])))

@@ -69,6 +69,7 @@ SIGNATURES = {
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "nfc_stream_release_frames": (C.c_int, [C.c_void_p]),
     "nfc_stream_view_frame_index": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nfc_stream_set_frame_index_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "nfc_stream_set_tuning": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
@@ -327,6 +328,12 @@ class Stream(object):
             return np.zeros(0, dtype=np.uint64)
         buf = (C.c_char * (n * 8)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.uint64, count=n)
+
+    def set_frame_index_buffer(self, address, cap):
+        """Keep the packed frame index in the caller's memory (address of room for cap uint64 records; None: the stream's
+        own buffer again): nfc_stream_set_frame_index_buffer."""
+        if lib().nfc_stream_set_frame_index_buffer(self._h, C.c_void_p(address) if address else None, int(cap)) != 0:
+            raise NfcError(last_error())
 
     def release_frames(self):
         if lib().nfc_stream_release_frames(self._h) != 0:

@@ -274,8 +274,10 @@ struct Stream {
     uint64_t *findex = nullptr;
     size_t findex_n = 0, findex_cap = 0;
     bool findex_bad = false;
+    bool findex_ext = false;  // the caller's memory (nfc_stream_set_frame_index_buffer): never reallocated
     int findex_reserve(size_t n) {  // worker thread or settled stream only
         if (n <= findex_cap) return 0;
+        if (findex_ext) return -1;
         const size_t cap = std::max(n, findex_cap * 2 + 4096);
         uint64_t *p = nullptr;
         if (cudaMallocHost((void **)&p, cap * sizeof(uint64_t)) != cudaSuccess) return -1;
@@ -337,7 +339,8 @@ int Stream::ensure_pinned(int idx, size_t bytes) {
 int Stream::join_marshal() {
     if (marshal_thr.joinable()) marshal_thr.join();
     if (const int err = marshal_err.exchange(0)) {
-        set_error(err == 2 ? "copying a slab's records to the host failed" : "internal: frame longer than the retained bits");
+        set_error(err == 3 ? "more frames than the caller's frame index buffer holds (nfc_stream_set_frame_index_buffer)"
+                           : (err == 2 ? "copying a slab's records to the host failed" : "internal: frame longer than the retained bits"));
         return -1;
     }
     return 0;
@@ -451,7 +454,7 @@ void Stream::destroy() {
     ctx_h = nullptr;
     fb[0].release();
     fb[1].release();
-    if (findex) cudaFreeHost(findex);
+    if (findex && !findex_ext) cudaFreeHost(findex);
     findex = nullptr;
     findex_cap = findex_n = 0;
     for (int i = 0; i < NPIN; i++)
@@ -1772,7 +1775,7 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
             nfc_frame *fo = out_frames.data() + f0;
             size_t nf = 0;
             if (findex_reserve(f0 + tot.nemit)) {
-                marshal_err = 2;
+                marshal_err = findex_ext ? 3 : 2;
                 return;
             }
             uint64_t *fx = findex + f0;
@@ -2082,6 +2085,27 @@ int64_t nfc_stream_view_frame_index(nfc_stream *h, const uint64_t **index) {
     }
     *index = s.findex;
     return (int64_t)s.findex_n;
+}
+
+int nfc_stream_set_frame_index_buffer(nfc_stream *h, uint64_t *buf, int64_t cap) {
+    if (!h || (buf && cap <= 0)) {
+        nfc::set_error("bad argument");
+        return -1;
+    }
+    if (h->s.settle()) return -1;
+    Stream &s = h->s;
+    if (!s.out_frames.empty()) {
+        nfc::set_error("set_frame_index_buffer: the stream holds frames; release them first");
+        return -1;
+    }
+    cudaSetDevice(s.prm.device);
+    if (s.findex && !s.findex_ext) cudaFreeHost(s.findex);
+    s.findex = buf;
+    s.findex_ext = buf != nullptr;
+    s.findex_cap = buf ? (size_t)cap : 0;
+    s.findex_n = 0;
+    s.findex_bad = false;
+    return 0;
 }
 
 int nfc_stream_release_frames(nfc_stream *h) {

@@ -289,11 +289,84 @@ class FrameIndex(object):
         return unpack_records(self.parts, self.pos_offsets)
 
 
-def gather_frame_records(engine_or_rec, pos_offset, dist=None, group=None, device="cpu", state=None):
+class SharedFrameIndex(object):
+    """The packed frame indexes of the ranks of ONE node in shared memory: every rank's stream writes its index straight into
+    a segment of its own (nfc_stream_set_frame_index_buffer) that rank 0 maps, so that gathering the frame offsets moves no
+    data -- only the counts travel (one small all_gather).  Collective: all ranks construct it with the same capacity
+    (records per rank) and close() it together; it fails over to the NCCL / gloo gather when shared memory or the stream's
+    call is not available (ok is False then)."""
+
+    def __init__(self, engine, capacity, dist, group=None):
+        from multiprocessing import shared_memory
+        import ctypes
+        self.engine, self.dist, self.group = engine, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.capacity = int(capacity)
+        self.mine, self.others, self.ok = None, [], False
+        name = None
+        try:
+            if hasattr(engine, "set_frame_index_buffer"):
+                self.mine = shared_memory.SharedMemory(create=True, size=self.capacity * 8)
+                self._addr = ctypes.addressof(ctypes.c_char.from_buffer(self.mine.buf))
+                engine.release_frames()
+                engine.set_frame_index_buffer(self._addr, self.capacity)
+                name = self.mine.name
+        except Exception:
+            name = None
+        names = [None] * self.world
+        dist.all_gather_object(names, name, group=group)
+        self.ok = all(n is not None for n in names)
+        if self.ok and self.rank == 0:
+            try:
+                self.others = [self.mine if r == 0 else shared_memory.SharedMemory(name=names[r]) for r in range(self.world)]
+            except Exception:
+                self.ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, self.ok, group=group)
+        self.ok = all(flags)
+        if not self.ok:
+            self._detach()
+
+    def parts(self, counts):
+        """rank 0: the ranks' packed indexes as uint64 views of the shared segments (valid until a rank decodes again)."""
+        return [np.frombuffer(self.others[r].buf, dtype=np.uint64, count=int(counts[r])) for r in range(self.world)]
+
+    def _detach(self):
+        if self.mine is not None:
+            try:
+                self.engine.release_frames()
+                self.engine.set_frame_index_buffer(None, 0)
+            except Exception:
+                pass
+        for m in self.others:
+            if m is not self.mine:
+                try:
+                    m.close()
+                except Exception:
+                    pass
+        self.others = []
+        if self.mine is not None:
+            try:
+                del self._addr
+                self.mine.close()
+                self.mine.unlink()
+            except Exception:
+                pass
+            self.mine = None
+
+    def close(self):
+        if self.dist is not None and self.ok:
+            self.dist.barrier(group=self.group)  # rank 0 is done reading
+        self.ok = False
+        self._detach()
+
+
+def gather_frame_records(engine_or_rec, pos_offset, dist=None, group=None, device="cpu", state=None, shared=None):
     """The frame offsets of all shards on rank 0 in stream order (the order the reference hands frames to fsm.process_bits,
-    packets.py:94-98): one all_gather of (count, position offset), one gather of the packed records (8 bytes per frame; device
-    tensors over NCCL, fed from and read back into page-locked memory, or host tensors over gloo).  engine_or_rec: a Stream
-    (its packed index is used as it lies in page-locked memory: nfc_stream_view_frame_index) or an array of frame records.
+    packets.py:94-98).  One all_gather of (count, position offset); then either nothing more -- `shared`: a SharedFrameIndex,
+    the ranks of one node keep their packed indexes in shared memory that rank 0 maps -- or one gather of the packed records
+    (8 bytes per frame; device tensors over NCCL, fed from and read back into page-locked memory, or host tensors over gloo).
+    engine_or_rec: a Stream (its packed index is used as it lies: nfc_stream_view_frame_index) or an array of frame records.
     Returns a FrameIndex on rank 0, None elsewhere.  `state`: a dict that keeps the staging tensors between calls."""
     import torch
     if hasattr(engine_or_rec, "view_frame_index"):
@@ -309,6 +382,9 @@ def gather_frame_records(engine_or_rec, pos_offset, dist=None, group=None, devic
     cnts = [torch.empty_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt, group=group)
     meta = torch.stack(cnts).cpu().numpy()
+    if shared is not None and shared.ok:
+        # every rank's index is complete in its segment (view_frame_index settled the stream before the all_gather)
+        return FrameIndex(shared.parts(meta[:, 0]), meta[:, 1]) if rank == 0 else None
     cap = max(1, int(meta[:, 0].max()))
     if state.get("cap", 0) < cap:
         state["cap"] = int(cap * 1.25) + 16
