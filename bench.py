@@ -544,6 +544,9 @@ def main():
     ap.add_argument("--c5-piece", type=float, default=1e10, help="configs[4]: samples rendered and pushed at a time")
     ap.add_argument("--c4-per-gpu", type=int, default=512, help="configs[3] leg: captures per GPU (4096 over eight GPUs)")
     ap.add_argument("--parity-windows", type=int, default=4, help="windows of the timed capture decoded again by the oracle (untimed)")
+    ap.add_argument("--wait", default="auto", choices=["auto", "spin", "blocking"],
+                    help="how host threads wait for the device: blocking sleeps in the driver (auto = spin: at eight ranks "
+                         "blocking waits were no faster)")
     ap.add_argument("--fade", type=float, default=0.05, help="channel: slow amplitude fade depth (experiments)")
     ap.add_argument("--tag-high", type=float, default=1.07, help="channel: tag load-modulation amplitude ratio (experiments)")
     args = ap.parse_args()
@@ -622,6 +625,10 @@ def main():
 
     s = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
     s.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(args.slab))
+    blocking = args.wait == "blocking"  # (A/B at eight ranks: spinning 31.1 ms per step, blocking 32.0)
+    if blocking:
+        s.set_wait_mode(True)
+    config["host_waits"] = "blocking" if blocking else "spinning"
     shard_info = {}
     gather_state = {}
     shared = None

@@ -37,7 +37,7 @@ static const unsigned FULL = 0xffffffffu;
 __device__ unsigned long long g_tile_stats[16];
 // pipelined mode of the streaming kernel: shortest run worth entering (tiles), tiles the synchronous loop must prove at the
 // first attempt before the pipeline is entered again (NFC_PIPE_MIN / NFC_PIPE_COOL set them per process, for experiments)
-__device__ int g_pipe_tune[4] = {6, 2, 0, 0};
+__device__ int g_pipe_tune[4] = {6, 3, 2, 18};  // NFC_PIPE_MIN, NFC_PIPE_COOL, NFC_MEAS_MAX, NFC_RESUM_BITS (slicer_fast.cuh)
 enum { CLS_LOW = -1, CLS_MID = 0, CLS_HIGH = 1 };
 
 // Barrier over the first NT threads of the CTA (named barrier 1).  The streaming kernel's CTAs carry two more warps
@@ -1409,10 +1409,11 @@ static int apply_pipe_tuning() {
     std::lock_guard<std::mutex> lock(mu);
     if (done[dev & 63]) return 0;
     done[dev & 63] = true;
-    if (getenv("NFC_PIPE_MIN") || getenv("NFC_PIPE_COOL")) {
-        int t[4] = {env_int("NFC_PIPE_MIN", 6), env_int("NFC_PIPE_COOL", 2), 0, 0};
+    if (getenv("NFC_PIPE_MIN") || getenv("NFC_PIPE_COOL") || getenv("NFC_MEAS_MAX") || getenv("NFC_RESUM_BITS")) {
+        int t[4] = {env_int("NFC_PIPE_MIN", 6), env_int("NFC_PIPE_COOL", 3), env_int("NFC_MEAS_MAX", 2), env_int("NFC_RESUM_BITS", 18)};
         if (t[0] < 3) t[0] = 3;
         if (t[1] < 0) t[1] = 0;
+        if (t[2] < 1) t[2] = 1;
         NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_pipe_tune, t, sizeof(t)));
     }
     return 0;

@@ -269,37 +269,47 @@ __device__ __forceinline__ void fast_row(const float4 x4, const float4 pv4, floa
             const float v = __shfl_up_sync(FULL, incA, o);
             if (lane >= o) incA += v;
         }
-        const float PA = incA - ssum;
+        float Pprev = incA - ssum;
         // ... give every sample its own guessed ss: (chunk start the repeat assumes) + (steps before it).  Classify again,
-        // in order inside the lane; the margins are now against per-sample thresholds, in ss units.
-        const float base = c0g + PA;
-        const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
+        // in order inside the lane; the margins are now against per-sample thresholds, in ss units.  The steps before a lane
+        // were taken from the classes of the pass before: where samples hover around a threshold many of them change class,
+        // and what the lanes' slack has to cover is how far that moved the prefix -- so go round (at most three times) with
+        // the prefix of the classes just found until nothing moves any more.
         const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
         const float ps[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
-        float run = 0.0f, wmin = INFINITY;
-        a = 0.0f;
+#pragma unroll 1
+        for (int it = 0; it < 3; it++) {
+            const float base = c0g + Pprev;
+            const float tl0 = fmaf(base, loLf, TLb), th0 = fmaf(base, hiLf, THb);
+            float run = 0.0f, wmin = INFINITY;
+            a = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
-            const bool pnl = xs[j] > tl, ph = xs[j] > th;
-            NLm[j] = __ballot_sync(FULL, pnl);
-            Hm[j] = __ballot_sync(FULL, ph);
-            const float nn = (pnl && !ph) ? xs[j] : ps[j];
-            const float d = nn - ps[j];
-            n[j] = nn;
-            run += d;
-            a += fabsf(d);
-            wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
-        }
-        ssum = run;
-        float incB = ssum;
+            for (int j = 0; j < 4; j++) {
+                const float tl = fmaf(run, loLf, tl0), th = fmaf(run, hiLf, th0);
+                const bool pnl = xs[j] > tl, ph = xs[j] > th;
+                NLm[j] = __ballot_sync(FULL, pnl);
+                Hm[j] = __ballot_sync(FULL, ph);
+                const float nn = (pnl && !ph) ? xs[j] : ps[j];
+                const float d = nn - ps[j];
+                n[j] = nn;
+                run += d;
+                a += fabsf(d);
+                wmin = fmin_nan(wmin, fmin_nan(fabsf(xs[j] - tl) * invLo, fabsf(xs[j] - th) * invHi));
+            }
+            ssum = run;
+            float incB = ssum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float v = __shfl_up_sync(FULL, incB, o);
-            if (lane >= o) incB += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(FULL, incB, o);
+                if (lane >= o) incB += v;
+            }
+            const float Pnew = incB - ssum;
+            // slack of the lane, in ss units: margin less what this classification moved the steps before it by
+            const float moved = fabsf(Pnew - Pprev);
+            mL = wmin - moved * 1.001f;
+            if (!__any_sync(FULL, moved != 0.0f)) break;  // self-consistent: the thresholds used are the ones these classes give
+            Pprev = Pnew;
         }
-        // slack of the lane, in ss units: margin less what the second classification moved the steps before it by
-        mL = wmin - fabsf((incB - ssum) - PA) * 1.001f;
         mH = INFINITY;
     }
     const float af = a * invqA;
@@ -694,6 +704,8 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     // 16-byte aligned tiles; entered when a run of PIPE_MIN tiles can be streamed and the last PIPE_COOL tiles of the
     // synchronous loop were proven at the first attempt (bursts of tiles that need the precise passes stay with it)
     const int PIPE_MIN = g_pipe_tune[0], PIPE_COOL = g_pipe_tune[1];
+    const int MEAS_MAX = g_pipe_tune[2];
+    const int RESUM_BITS = g_pipe_tune[3];  // after a refused tile: sum the ring anew when the interval is wider than 2^-bits of the sum (0: never)  // passes with measured guesses before the exact fix-point takes a tile
     char *const stage0 = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16;
     const bool pipe_can = PIPED && L >= 3 * T && ((reinterpret_cast<uintptr_t>(plan.xbase) & 15u) == 0u) && plan.bm_base != nullptr;
     int cool = 0, pipe_K = 0;
@@ -827,7 +839,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                     const bool all_fine = failing == 0u;
                     if (!all_fine || bad) {
                         // first the failing chunks alone, then (if that does not settle it) every chunk
-                        const bool redo = bad ? n_coarse < 3 : n_meas < 2;
+                        const bool redo = bad ? n_coarse < 3 : n_meas < MEAS_MAX;
                         const unsigned again = n_meas == 0 ? failing : FULL;
                         if (redo && !bad && ((again >> lane) & 1u)) {  // go round again with the measured window sums as the guess
                             const float mid = c0 + 0.5f * Sf;  // measured window sum at the chunk's middle
@@ -952,6 +964,13 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             if (done < pipe_K) {
                 cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
                 if (threadIdx.x == 0) uni.stats[FS_PIPE_AB]++;
+                // A refused tile usually holds samples close to a threshold: what the precise pass can prove there is limited
+                // by the width of the window sum's interval, which has grown with every streamed tile.  Summing the ring anew
+                // (exact) is much cheaper than the exact fix-point a tile that cannot be proven falls back to.
+                if (RESUM_BITS > 0) {
+                    const double lo = uni.ss_lo, hi = uni.ss_hi;
+                    if ((hi - lo) > ldexp(hi, -RESUM_BITS)) make_exact();  // block-uniform
+                }
             }
             if (warp == 0) {  // the coming tile's constants for the synchronous loop
                 const double lo = uni.ss_lo, hi = uni.ss_hi;
