@@ -27,6 +27,7 @@
 #include <mutex>
 #include <utility>
 #include "common.cuh"
+#include <cstdio>
 #include <stdlib.h>
 
 namespace nfc {
@@ -35,6 +36,9 @@ static const unsigned FULL = 0xffffffffu;
 // tile counters (device-wide): 0 streamed, 1 exact path, 2 coarse-step retries exhausted, 3 exact fix-point pass, 4 ring resums,
 // 5 repeated passes, 6 hysteresis risk, 7 fix-point pass gave up, 8 exact-path rounds, 9/10 first-generation kernel: refined / refine failed
 __device__ unsigned long long g_tile_stats[16];
+#ifdef NFC_CYCLES
+__device__ unsigned long long g_cyc[8];  // diagnostics build: see slicer_fast.cuh
+#endif
 // pipelined mode of the streaming kernel: shortest run worth entering (tiles), tiles the synchronous loop must prove at the
 // first attempt before the pipeline is entered again (NFC_PIPE_MIN / NFC_PIPE_COOL set them per process, for experiments)
 __device__ int g_pipe_tune[4] = {6, 3, 2, 18};  // NFC_PIPE_MIN, NFC_PIPE_COOL, NFC_MEAS_MAX, NFC_RESUM_BITS (slicer_fast.cuh)
@@ -1445,6 +1449,18 @@ int launch_slicer(const SegWork *d_works, int n_works, const SlicerParams *d_par
 
 int slicer_tile_stats(unsigned long long *out4, bool reset) {
     NFC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 16));
+#ifdef NFC_CYCLES
+    {
+        unsigned long long c[8];
+        NFC_CUDA_CHECK(cudaMemcpyFromSymbol(c, g_cyc, sizeof(c)));
+        fprintf(stderr, "cycles: tile passes %llu in %llu calls (%llu repeats), ring sums after refused tiles %llu, fix-point path %llu, exact path %llu\n",
+                c[0], c[1], c[5], c[2], c[3], c[4]);
+        if (reset) {
+            unsigned long long z[8] = {0};
+            NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_cyc, z, sizeof(z)));
+        }
+    }
+#endif
     if (reset) {
         unsigned long long z[16] = {0};
         NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z)));

@@ -709,6 +709,13 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     char *const stage0 = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16;
     const bool pipe_can = PIPED && L >= 3 * T && ((reinterpret_cast<uintptr_t>(plan.xbase) & 15u) == 0u) && plan.bm_base != nullptr;
     int cool = 0, pipe_K = 0;
+    long long pipe_cycles = 0;  // diagnostics: cycles spent inside pipelined runs (thread 0)
+#ifdef NFC_CYCLES
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};  // tile passes (cycles, calls), ring sums after refused tiles, fix-point path, exact path, repeats (calls)
+#define NFC_CYC(i, expr) do { const long long c0_ = clock64(); expr; cyc[i] += clock64() - c0_; } while (0)
+#else
+#define NFC_CYC(i, expr) do { expr; } while (0)
+#endif
     int t = 0;
     while (t < ntiles) {
         const int t_entry = t;
@@ -912,7 +919,11 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 }
                 const int x_ready = have_x;
                 have_x = 0;
-                int verdict = tile_pass(x_ready, 0, 0);
+                int verdict;
+                NFC_CYC(0, verdict = tile_pass(x_ready, 0, 0));
+#ifdef NFC_CYCLES
+                cyc[1]++;
+#endif
                 if (verdict == FV_ACCEPT) {
                     if (cool > 0) cool--;
                 } else {
@@ -930,7 +941,10 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                         } else {
                             break;
                         }
-                        verdict = tile_pass(0, n_meas, n_coarse);
+                        NFC_CYC(0, verdict = tile_pass(0, n_meas, n_coarse));
+#ifdef NFC_CYCLES
+                        cyc[1]++; cyc[5]++;
+#endif
                         if (verdict == FV_ACCEPT) break;
                     }
                     if (verdict != FV_ACCEPT) {
@@ -949,6 +963,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
         if (PIPED && why == WHY_PIPE) {
             // ------------------------------------------------------------------------ pipelined run over tiles [t, t + pipe_K)
             asm volatile("cp.async.wait_group 0;" ::: "memory");  // a tile requested by the synchronous loop is dropped
+            const long long clk_p0 = clock64();
             if (threadIdx.x == 0) {
                 ps.cmd = PIPE_CMD_ENTER;
                 ps.t0 = t;
@@ -960,6 +975,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // barriers and first guesses are set up
             const int done = pipe_worker<NW, R, (PIPE > 0 ? PIPE : 1), KIND>(ps, ring, stage0, plan, L, p.pcm_scale, warp, lane);
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
+            if (threadIdx.x == 0) pipe_cycles += clock64() - clk_p0;
             t += done;
             if (done < pipe_K) {
                 cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
@@ -969,7 +985,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 // (exact) is much cheaper than the exact fix-point a tile that cannot be proven falls back to.
                 if (RESUM_BITS > 0) {
                     const double lo = uni.ss_lo, hi = uni.ss_hi;
-                    if ((hi - lo) > ldexp(hi, -RESUM_BITS)) make_exact();  // block-uniform
+                    if ((hi - lo) > ldexp(hi, -RESUM_BITS)) NFC_CYC(2, make_exact());  // block-uniform
                 }
             }
             if (warp == 0) {  // the coming tile's constants for the synchronous loop
@@ -984,6 +1000,10 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
 
         // ---------------------------------------------------------------------------- tile t the hard way (rare)
         bool done = false;
+#ifdef NFC_CYCLES
+        const long long c_hard = clock64();
+        const int why_hard = why;
+#endif
         if (why == WHY_VERIFY) {
             // ---------------------------------------------------------------- exact fix-point from the precise pass
             // Every sample's class is recomputed from its own exact window sum under the current classes, until
@@ -1134,6 +1154,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             }
             cta_sync<NT>();
         }
+#ifdef NFC_CYCLES
+        cyc[why_hard == WHY_VERIFY ? 3 : 4] += clock64() - c_hard;
+#endif
         t++;
     }
 
@@ -1183,6 +1206,11 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
         atomicAdd(&g_tile_stats[11], (unsigned long long)uni.stats[FS_PIPE_T]);
         atomicAdd(&g_tile_stats[12], (unsigned long long)uni.stats[FS_PIPE_IN]);
         atomicAdd(&g_tile_stats[13], (unsigned long long)uni.stats[FS_PIPE_AB]);
+        atomicAdd(&g_tile_stats[14], (unsigned long long)pipe_cycles);
+        atomicAdd(&g_tile_stats[15], (unsigned long long)(clock64() - clk0));
+#ifdef NFC_CYCLES
+        for (int i = 0; i < 6; i++) atomicAdd(&g_cyc[i], (unsigned long long)cyc[i]);
+#endif
     }
 }
 

@@ -2268,6 +2268,8 @@ int nfc_stream_get_stats(nfc_stream *h, nfc_stats *st) {
         h->s.stats.pipe_tiles = (int64_t)ts[11];
         h->s.stats.pipe_runs = (int64_t)ts[12];
         h->s.stats.pipe_aborts = (int64_t)ts[13];
+        if (getenv("NFC_TIMING"))
+            fprintf(stderr, "slicer segments: %llu cycles in all, %llu of them inside pipelined runs (%llu tiles of %llu)\n", ts[15], ts[14], ts[11], ts[0]);
     }
     *st = h->s.stats;
     return 0;
