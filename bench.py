@@ -889,7 +889,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic,
-                "kernel": "nfc::slicer_fast_kernel<256,4,3,IN_ENVELOPE_F32>", "peak_source": peak_src,
+                "kernel": "nfc::slicer_fast_kernel<256,4,2,IN_ENVELOPE_F32,3> (pipelined mode: slicer_pipe.cuh)", "peak_source": peak_src,
                 "algorithmic_bytes_per_sample": 4, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": kern_ms * args.steps / k_launches, "launches_per_step": k_launches / args.steps,
                 "slicer_stage_ms_per_step": slicer_ms,
