@@ -323,7 +323,8 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     if buf is None or buf.numel() < piece:
         buf = torch.empty(piece, dtype=torch.float32, device="cuda")
     s = _cabi.Stream(rate, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, **params)
-    clock = {"on": None, "sum": 0.0, "render": 0.0}
+    clock = {"on": None, "sum": 0.0, "render": 0.0, "calls": 0}
+    n_fetches = 1 + -(-(total // world) // piece)  # per pass and rank: the halo (rank 0: a barrier in its place), then the pieces
 
     def fetch(a, b):
         torch.cuda.synchronize()  # the decode of the piece before is still on the device: that is decode time, not rendering
@@ -332,6 +333,9 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
             clock["sum"] += t - clock["on"]
         _cabi.synth_render(buf[: b - a], codes, lens, seed=99, as_envelope=True, device=local_rank, first_index=a, **chan)
         torch.cuda.synchronize()
+        clock["calls"] += 1
+        if world > 1 and clock["calls"] <= n_fetches:  # (a shard that is decoded again after a seam mismatch fetches alone)
+            dist.barrier()  # every rank has rendered: nobody's decode clock runs while it waits for another rank's rendering
         clock["on"] = time.perf_counter()
         clock["render"] += clock["on"] - t
         return buf[: b - a]
@@ -342,6 +346,9 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
     if world > 1:
         want_recs = int(total // world * 2.5e-4) + (1 << 16)
         shared = sharding.SharedFrameIndex(s, want_recs if shm_room() > 4 * world * want_recs * 8 else 0, dist)
+        if rank == 0:
+            clock["calls"] += 1
+            dist.barrier()  # (pairs with the other ranks' halo fetch, see below)
     res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
                                        halo_windows=args.halo_windows, flat="view", piece=piece)
     sharding.gather_frame_records(s, res["pos_offset"], dist if world > 1 else None, device="cuda", state=gstate, shared=shared)
@@ -354,6 +361,10 @@ def leg_c5(torch, _cabi, dist, rank, world, local_rank, args, peak, total, rate,
         sampler.start()
         sampler.wait_running()
     s.reset_stats()
+    clock["calls"] = 0
+    if world > 1 and rank == 0:
+        clock["calls"] += 1
+        dist.barrier()  # the other ranks fetch (render) a halo first: the barrier of that fetch
     clock.update(on=time.perf_counter(), sum=0.0, render=0.0)
     t_begin = clock["on"]
     res = sharding.decode_time_sharded(s, fetch, total, L, _cabi.State, dist=dist if world > 1 else None, device="cuda",
