@@ -83,7 +83,9 @@ def test_batch_one_pass_matches_oracle_per_capture():
     assert (res["frames"]["pos"] % res["pitch"] >= p["av_window"]).all() and (res["frames"]["pos"] % res["pitch"] < n_items).all()
     assert _check_batch(x2d, rate, p, los, his, res) > 500
     st = res["stream"].stats()
-    assert st["slicer_kernel_launches"] == 1 and st["pipe_tiles"] > 0  # one launch of the streaming slicer for the whole batch
+    assert st["slicer_kernel_launches"] == 1  # one launch of the streaming slicer for the whole batch
+    import os
+    assert st["pipe_tiles"] > 0 or os.environ.get("NFC_SLICER_PIPE") == "0"  # (the pipelined mode, unless it is switched off)
     # the same stream again, device-resident input, other thresholds
     import torch
     xd = torch.from_numpy(x2d).cuda()
