@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 5
+#define NFC_ABI_VERSION 6
 
 /* what a pushed item is */
 enum {
@@ -112,6 +112,12 @@ int64_t nfc_stream_push(nfc_stream *s, const void *items, int64_t n, int mem, in
  * spread samples): decode the captures one by one with nfc_stream_push then.  The stream takes no further items until reset. */
 int64_t nfc_stream_push_batch(nfc_stream *s, const void *items, int mem, int64_t n_captures, int64_t items_per_capture,
                               int64_t stride_items, const double *lo_vals, const double *hi_vals, int64_t *pitch);
+
+/* background.append(transitions) (background.py:27-29): the list transition_sink hands to its callback, fed directly -- the
+ * decoders, PacketProcessors and everything behind them run on the device as for pushed samples; decoder and framer state
+ * carry on from whatever was pushed before.  ev[i].pos: positions the symbols and frames are reported at (ascending, less
+ * than 2^32 apart from ev[0].pos); d in 1..max_len.  Returns n, or -1. */
+int64_t nfc_stream_push_events(nfc_stream *s, const nfc_event *ev, int64_t n);
 
 /* Results accumulated since the last drain, in stream order.  Each call copies up to cap records
  * and removes them from the stream.  Pass cap = 0 to query the number available. */

@@ -408,3 +408,43 @@ def test_streaming_kernel_falls_back_on_inexact_or_insane_samples():
     want = oracle.decode_capture(z, 13.56e6, av_window=L, max_len=mx)
     got = gpu_decode(z, 13.56e6, av_window=L, max_len=mx)
     check_against_oracle(got, want)
+
+
+def test_decoder_kats_through_the_device_line_code():
+    """The 40 known-answer event streams of the reference's decoders (tests/golden/decoder_kat.npz: miller_decoder,
+    manchester_decoder and PacketProcessor driven on adversarial event lists) through nfc_stream_push_events -- the
+    background.append boundary (background.py:27-29): symbols and frames of the device's line-code kernels, fed whole and in
+    two parts (decoder and framer state carry over)."""
+    z = H.load_case("decoder_kat")
+    for ci in range(40):
+        evs = z["ev%d" % ci]
+        ev = np.zeros(len(evs), dtype=_cabi.EVENT_DTYPE)
+        ev["v"], ev["d"], ev["type"], ev["pos"] = evs[:, 0], evs[:, 1], evs[:, 2], np.arange(len(evs)) * 3 + 7
+        for cut in (len(ev), len(ev) // 3):
+            s = _cabi.Stream(2e6, outputs=_cabi.OUT_SYMBOLS | _cabi.OUT_FRAMES)
+            s.push_events(ev[:cut])
+            if cut < len(ev):
+                s.push_events(ev[cut:])
+            sym = s.drain_symbols()
+            fr, bits = s.drain_frames()
+            s.close()
+            want = z["sym%d" % ci]
+            assert len(sym) == len(want), (ci, cut)
+            assert np.array_equal(sym["type"], want[:, 0]) and np.array_equal(sym["val"], want[:, 1]), (ci, cut)
+            assert np.array_equal(fr["type"], z["ftype%d" % ci]) and np.array_equal(fr["nbits"], z["flen%d" % ci]), (ci, cut)
+            got_bits = np.concatenate(bits) if len(bits) else np.zeros(0, dtype=np.uint8)
+            assert np.array_equal(got_bits, z["fbits%d" % ci]), (ci, cut)
+            # symbols are reported at the positions of the events that produced them
+            assert set(sym["pos"].tolist()) <= set(ev["pos"].tolist())
+
+
+def test_push_events_rejects_what_transition_sink_cannot_emit():
+    s = _cabi.Stream(2e6, outputs=_cabi.OUT_SYMBOLS)
+    ev = np.zeros(3, dtype=_cabi.EVENT_DTYPE)
+    ev["d"], ev["pos"] = [5, 51, 5], [0, 1, 2]
+    with pytest.raises(_cabi.NfcError):
+        s.push_events(ev)  # d beyond max_len
+    ev["d"], ev["pos"] = [5, 5, 5], [5, 4, 6]
+    with pytest.raises(_cabi.NfcError):
+        s.push_events(ev)  # positions do not ascend
+    s.close()

@@ -61,6 +61,7 @@ SIGNATURES = {
     "nfc_stream_push": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
     "nfc_stream_push_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_int64)]),
+    "nfc_stream_push_events": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_events": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_symbols": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "nfc_stream_drain_frames": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
@@ -228,6 +229,15 @@ class Stream(object):
         if rc < 0:
             raise NfcError("nfc_stream_push_batch: " + last_error())
         return int(pitch.value)
+
+    def push_events(self, events):
+        """background.append (background.py:27-29): transition_sink's events (EVENT_DTYPE array: pos, d, v, type) straight
+        into the decoders on the device."""
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        n = lib().nfc_stream_push_events(self._h, ev.ctypes.data, len(ev))
+        if n < 0:
+            raise NfcError("nfc_stream_push_events: " + last_error())
+        return int(n)
 
     def push_all(self, items, chunk=None):
         """Feed everything, re-offering what a call did not consume (the GNU Radio scheduler's job)."""

@@ -250,13 +250,16 @@ struct Stream {
         int64_t a = 0, b = 0;
         uint32_t cap_R = 0, cap_M = 0, cap_sym = 0, cap_b0 = 0, cap_b1 = 0, cap_em = 0;
         bool exact = false;      // sizes were read while queuing: cannot overflow
+        bool events_only = false;  // events from the caller (push_events): says nothing about records per sample
         bool from_bitmap = false;
         bool want_ev = false, want_sym = false, want_fr = false, have_line = false;
         double t0 = 0, t1 = 0, t2 = 0;
     };
     std::deque<SlabJob> jobs;
     cudaEvent_t ev_d[NPIN] = {nullptr, nullptr, nullptr};  // all records of the slab that used pinned[i] have arrived
-    int post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1);
+    int post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1,
+                   const EventRec *host_events = nullptr, uint32_t n_host_events = 0);
+    int64_t push_events(const nfc_event *ev, int64_t n);
     int finalize_front();
     int finalize_all() {
         while (!jobs.empty())
@@ -1399,6 +1402,42 @@ struct PostCtx {
 };
 static_assert(sizeof(PostCtx) == 256, "context blocks are 256 bytes apart");
 
+// background.append (background.py:27-29): a list of transition_sink's events straight into the line-code stage.
+int64_t Stream::push_events(const nfc_event *ev, int64_t n) {
+    if (n < 0 || (n > 0 && !ev) || n >= ((int64_t)1 << 31)) {
+        set_error("push_events: bad arguments");
+        return -1;
+    }
+    NFC_CUDA_CHECK(cudaSetDevice(prm.device));
+    if (finalize_all()) return -1;
+    if (n == 0) return 0;
+    const int64_t a = ev[0].pos;
+    std::vector<EventRec> recs((size_t)n);
+    int64_t prev = a;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t rel = ev[i].pos - a;
+        if (ev[i].pos < prev || rel >= ((int64_t)1 << 32) || ev[i].d < 1 || ev[i].d > sp.mx || ev[i].v < -1 || ev[i].v > 2 ||
+            ev[i].type < -1 || ev[i].type > 1) {
+            set_error("push_events: event %lld out of range (positions ascend within 2^32, d in 1..max_len, v in -1..2, type in -1..1)",
+                      (long long)i);
+            return -1;
+        }
+        prev = ev[i].pos;
+        EventRec r;
+        r.rel_pos = (uint32_t)rel;
+        r.d = (uint16_t)ev[i].d;
+        r.v = ev[i].v;
+        r.type = ev[i].type;
+        recs[(size_t)i] = r;
+    }
+    const double t0 = now_ms();
+    const int ci = (int)(slab_seq % NCTX);
+    NFC_CUDA_CHECK(cudaEventRecord(ev_a[ci], cs));
+    if (post_chain(a, a + 1, false, 0, false, t0, t0, recs.data(), (uint32_t)n)) return -1;
+    if (finalize_all()) return -1;
+    return n;
+}
+
 int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, int64_t in_end, int64_t a, int64_t b,
                          int64_t slicer_end) {
     const double t0 = now_ms();
@@ -1428,7 +1467,8 @@ int Stream::process_slab(const void *d_in, int64_t in_pos0, int64_t in_begin, in
 // Queues extraction (from the bitmap; else the slicer left R_host transitions in trans_dense) -> runs -> line code of slab
 // [a, b) and the copy of its context block to the host.  Sizes: from the slabs before; exact (read while queuing, with a
 // synchronisation each) for the first slab of a stream and for a slab that is done again.
-int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1) {
+int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, bool force_exact, double t0, double t1,
+                       const EventRec *host_events, uint32_t n_host_events) {
     static const bool no_async = getenv("NFC_POST_SYNC") != nullptr;
     const int64_t n = b - a;
     SlabJob j;
@@ -1457,7 +1497,8 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
     const bool want_line = (prm.outputs & (NFC_OUT_SYMBOLS | NFC_OUT_FRAMES)) != 0;
     const bool want_sym = (prm.outputs & NFC_OUT_SYMBOLS) != 0;
     const int keep_dropped = (prm.outputs & NFC_OUT_DROPPED_EVENTS) ? 1 : 0;
-    j.exact = force_exact || no_async || !rates.have || !from_bitmap;
+    j.exact = force_exact || no_async || !rates.have || !from_bitmap || host_events != nullptr;
+    j.events_only = host_events != nullptr;
     auto cap_of = [&](double rate) -> uint32_t {
         const double c = rate * (double)n * 1.5 + 65536.0;
         return (uint32_t)std::min(c, 4.0e9);
@@ -1507,6 +1548,16 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
     NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, evE[ci], 0));
     if (queued(j.seq - 2)) NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, evL[(j.seq - 2) % NCTX], 0));  // the events of slab k-2 have been decoded
     if (ev_out_set[oi]) NFC_CUDA_CHECK(cudaStreamWaitEvent(csR, ev_out[oi], 0));                  // ... and have left for the host
+    if (host_events) {
+        // the events come from the caller (nfc_stream_push_events): no runs to turn into events, the run carry passes through
+        j.cap_M = n_host_events;
+        if (events_d[oi].ensure(((size_t)j.cap_M + 16) * sizeof(EventRec))) return -1;
+        if (n_host_events)
+            NFC_CUDA_CHECK(cudaMemcpyAsync(events_d[oi].p, host_events, (size_t)n_host_events * sizeof(EventRec), cudaMemcpyHostToDevice, csR));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->M, &n_host_events, 4, cudaMemcpyHostToDevice, csR));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->rc_out, &cp->rc_out, sizeof(RunCarry), cudaMemcpyDeviceToDevice, csR));
+        NFC_CUDA_CHECK(cudaStreamSynchronize(csR));  // host_events is the caller's memory
+    } else {
     const size_t nrun = (size_t)j.cap_R + 1;
     if (run_counts.ensure(nrun * 4) || run_offsets.ensure(nrun * 4) || scan_scr.ensure((nrun / 256 + 1024) * 4 * 4)) return -1;
     if (launch_run_count(td.as<TransRec>(), &cx->R, j.cap_R, 0, n, &cp->rc_out, sp.mx, keep_dropped, run_counts.as<uint32_t>(),
@@ -1526,6 +1577,7 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
                          events_d[oi].as<EventRec>(), j.cap_M, &cx->M, &cx->rc_out, &cx->flags, csR))
         return -1;
     stats.launches++;
+    }
     NFC_CUDA_CHECK(cudaEventRecord(evR[ci], csR));
 
     // ---------------------------------------------------------------- events -> symbols, frame bits, frame closings (csL)
@@ -1635,7 +1687,7 @@ int Stream::finalize_front() {
     dec_carry = hx.dc_out;
     pending[0] = hx.pend_out[0];
     pending[1] = hx.pend_out[1];
-    {
+    if (!j.events_only) {
         const double n = (double)std::max<int64_t>(1, j.b - j.a);
         auto upd = [&](double &r, uint32_t v) { r = std::max(r * 0.98, (double)v / n); };
         upd(rates.R, hx.R); upd(rates.M, M); upd(rates.sym, nsym); upd(rates.b0, nbit0); upd(rates.b1, nbit1); upd(rates.em, nemit);
@@ -1992,6 +2044,14 @@ int64_t nfc_stream_push_batch(nfc_stream *h, const void *items, int mem, int64_t
     }
     if (h->s.settle()) return -1;
     return h->s.push_batch(items, mem, n_captures, items_per_capture, stride_items, lo_vals, hi_vals, pitch);
+}
+
+int64_t nfc_stream_push_events(nfc_stream *h, const nfc_event *ev, int64_t n) {
+    if (!h) {
+        nfc::set_error("null argument");
+        return -1;
+    }
+    return h->s.push_events(ev, n);
 }
 
 int64_t nfc_stream_drain_events(nfc_stream *h, nfc_event *out, int64_t cap) {
