@@ -159,3 +159,32 @@ def test_frame_index_is_the_frames_in_eight_bytes():
     s.release_frames()
     assert len(s.view_frame_index()) == 0 and len(s.view_frames()[0]) == 0
     s.close()
+
+
+def test_frame_index_in_the_callers_memory():
+    """nfc_stream_set_frame_index_buffer: the packed index is written into memory of the caller's (what the ranks of a node
+    share); a buffer that is too small is reported, not overrun."""
+    import ctypes
+    rate = 2e6
+    frames = synth.load_sessions()["ultralight"]
+    x = synth.envelope(synth.pcm_to_float(synth.capture(frames, rate, 3)))
+    buf = (ctypes.c_uint64 * 64)()
+    guard = 0xdeadbeefdeadbeef
+    for i in range(64):
+        buf[i] = guard
+    s = _cabi.Stream(rate, hi_val=1.09, outputs=_cabi.OUT_FRAMES)
+    s.set_frame_index_buffer(ctypes.addressof(buf), 32)
+    s.push_all(x)
+    fr = s.view_frames()[0]
+    idx = s.view_frame_index()
+    assert len(fr) == len(frames) == len(idx) <= 32
+    assert idx.ctypes.data == ctypes.addressof(buf) and all(buf[i] == guard for i in range(32, 64))
+    assert np.array_equal(idx >> np.uint64(24), fr["pos"].astype(np.uint64))
+    s.release_frames()
+    s.reset()
+    s.set_frame_index_buffer(ctypes.addressof(buf), 4)  # fewer records than the capture has frames
+    with pytest.raises(_cabi.NfcError):
+        s.push_all(x)
+        s.view_frame_index()
+    assert all(buf[i] == guard for i in range(32, 64))
+    s.close()

@@ -37,7 +37,7 @@ static const unsigned FULL = 0xffffffffu;
 // 5 repeated passes, 6 hysteresis risk, 7 fix-point pass gave up, 8 exact-path rounds, 9/10 first-generation kernel: refined / refine failed
 __device__ unsigned long long g_tile_stats[16];
 #ifdef NFC_CYCLES
-__device__ unsigned long long g_cyc[8];  // diagnostics build: see slicer_fast.cuh
+__device__ unsigned long long g_cyc[12];  // diagnostics build: see slicer_fast.cuh
 #endif
 // pipelined mode of the streaming kernel: shortest run worth entering (tiles), tiles the synchronous loop must prove at the
 // first attempt before the pipeline is entered again (NFC_PIPE_MIN / NFC_PIPE_COOL set them per process, for experiments)
@@ -1451,12 +1451,12 @@ int slicer_tile_stats(unsigned long long *out4, bool reset) {
     NFC_CUDA_CHECK(cudaMemcpyFromSymbol(out4, g_tile_stats, sizeof(unsigned long long) * 16));
 #ifdef NFC_CYCLES
     {
-        unsigned long long c[8];
+        unsigned long long c[12];
         NFC_CUDA_CHECK(cudaMemcpyFromSymbol(c, g_cyc, sizeof(c)));
-        fprintf(stderr, "cycles: tile passes %llu in %llu calls (%llu repeats), ring sums after refused tiles %llu, fix-point path %llu, exact path %llu\n",
-                c[0], c[1], c[5], c[2], c[3], c[4]);
+        fprintf(stderr, "cycles: tile passes %llu in %llu calls (%llu repeats), ring sums after refused tiles %llu, fix-point path %llu, exact path %llu, segment set-up %llu, snapshots %llu, after pipelined runs %llu, loop top %llu, commits %llu\n",
+                c[0], c[1], c[5], c[2], c[3], c[4], c[6], c[7], c[8], c[9], c[10]);
         if (reset) {
-            unsigned long long z[8] = {0};
+            unsigned long long z[12] = {0};
             NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_cyc, z, sizeof(z)));
         }
     }

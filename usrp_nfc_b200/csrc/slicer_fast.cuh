@@ -711,19 +711,27 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     int cool = 0, pipe_K = 0;
     long long pipe_cycles = 0;  // diagnostics: cycles spent inside pipelined runs (thread 0)
 #ifdef NFC_CYCLES
-    long long cyc[6] = {0, 0, 0, 0, 0, 0};  // tile passes (cycles, calls), ring sums after refused tiles, fix-point path, exact path, repeats (calls)
+    long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ... [8] after a pipelined run until the loop goes on, [9] loop top until the first pass / run, [10] commits  // tile passes (cycles, calls), ring sums after refused tiles, fix-point path, exact path, repeats (calls), segment set-up, snapshots
+    cyc[6] = clock64() - clk0;
 #define NFC_CYC(i, expr) do { const long long c0_ = clock64(); expr; cyc[i] += clock64() - c0_; } while (0)
 #else
 #define NFC_CYC(i, expr) do { expr; } while (0)
 #endif
     int t = 0;
     while (t < ntiles) {
+#ifdef NFC_CYCLES
+        const long long c_top = clock64();
+        bool top_open = true;
+#endif
         const int t_entry = t;
         {
             bool snap = false;
 #pragma unroll
             for (int j = 0; j < 4; j++) snap = snap || (t == plan.t_snap[j]);
             if (snap) {
+#ifdef NFC_CYCLES
+                const long long c_sn = clock64();
+#endif
                 if (t == plan.t_snap[0]) snapshot(w.seam_in, w.begin);
                 for (int j = 1; j < 4; j++)
                     if (t == plan.t_snap[j]) snapshot(w.ckpt_state[j - 1], tile0_pos + (int64_t)t * T);
@@ -735,6 +743,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                     fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
                 }
                 cta_sync<NT>();
+#ifdef NFC_CYCLES
+                cyc[7] += clock64() - c_sn;
+#endif
             }
         }
         int why = WHY_NONE;
@@ -792,8 +803,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                         }
                     }
                 }
-                // next tile's samples on their way while this one is settled
-                if (t + 1 < t_stop) {
+                // next tile's samples on their way while this one is settled -- unless the pipelined mode takes over with the
+                // next tile (its own bulk copies fetch it; a copy requested here would only have to be waited for)
+                if (t + 1 < t_stop && !(pipe_can && cool <= 1 && t_stop - (t + 1) >= PIPE_MIN)) {
                     request_tile(t + 1);
                     have_x = STAGED ? 1 : 0;
                 }
@@ -920,6 +932,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 const int x_ready = have_x;
                 have_x = 0;
                 int verdict;
+#ifdef NFC_CYCLES
+                if (top_open) { cyc[9] += clock64() - c_top; top_open = false; }
+#endif
                 NFC_CYC(0, verdict = tile_pass(x_ready, 0, 0));
 #ifdef NFC_CYCLES
                 cyc[1]++;
@@ -952,7 +967,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                         break;
                     }
                 }
-                commit(n, t, slot_w);
+                NFC_CYC(10, commit(n, t, slot_w));
                 slot_w += slot_step;
                 if (slot_w >= L) slot_w -= L;
                 t++;
@@ -963,6 +978,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
         if (PIPED && why == WHY_PIPE) {
             // ------------------------------------------------------------------------ pipelined run over tiles [t, t + pipe_K)
             asm volatile("cp.async.wait_group 0;" ::: "memory");  // a tile requested by the synchronous loop is dropped
+#ifdef NFC_CYCLES
+            if (top_open) { cyc[9] += clock64() - c_top; top_open = false; }
+#endif
             const long long clk_p0 = clock64();
             if (threadIdx.x == 0) {
                 ps.cmd = PIPE_CMD_ENTER;
@@ -976,6 +994,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
             const int done = pipe_worker<NW, R, (PIPE > 0 ? PIPE : 1), KIND>(ps, ring, stage0, plan, L, p.pcm_scale, warp, lane);
             named_bar_sync<PIPE_BAR_RUN, NT_ALL>();   // interval and carries are handed back
             if (threadIdx.x == 0) pipe_cycles += clock64() - clk_p0;
+#ifdef NFC_CYCLES
+            const long long c_post = clock64();
+#endif
             t += done;
             if (done < pipe_K) {
                 cool = PIPE_COOL > 1 ? PIPE_COOL : 1;  // at least the refused tile goes through the synchronous loop
@@ -995,6 +1016,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
             }
             cta_sync<NT>();
+#ifdef NFC_CYCLES
+            cyc[8] += clock64() - c_post;
+#endif
             continue;
         }
 
@@ -1209,7 +1233,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
         atomicAdd(&g_tile_stats[14], (unsigned long long)pipe_cycles);
         atomicAdd(&g_tile_stats[15], (unsigned long long)(clock64() - clk0));
 #ifdef NFC_CYCLES
-        for (int i = 0; i < 6; i++) atomicAdd(&g_cyc[i], (unsigned long long)cyc[i]);
+        for (int i = 0; i < 12; i++) atomicAdd(&g_cyc[i], (unsigned long long)cyc[i]);
 #endif
     }
 }
