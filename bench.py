@@ -639,7 +639,7 @@ def main():
     blocking = args.wait == "blocking"  # (A/B at eight ranks: spinning 31.1 ms per step, blocking 32.0)
     if blocking:
         s.set_wait_mode(True)
-    config["host_waits"] = "blocking" if blocking else "spinning"
+    host_waits = "blocking" if blocking else "spinning"  # (not part of `config`: the reference arm has no such thing)
     shard_info = {}
     gather_state = {}
     shared = None
@@ -931,7 +931,8 @@ def main():
             "per_rank": per_rank,
             "device_ms_per_step": dev_ms, "frames_per_step": frames_total, "seam_mismatches": mism,
             "selfcheck": selfcheck, "slicer_ms_per_step": slicer_ms, "tiles": {k: st[k] for k in ("fast_tiles", "exact_tiles", "repeated_passes", "fixpoint_tiles", "st2_tiles", "unproven_tiles", "ring_resums", "segments", "pipe_tiles", "pipe_runs", "pipe_aborts")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "configs": configs}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
+            "host_waits": host_waits}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
