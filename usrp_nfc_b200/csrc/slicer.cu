@@ -1284,9 +1284,10 @@ __global__ void seam_compare_kernel(const SlicerHdr *const *__restrict__ truth, 
 // rows per tile of the vector kernel for a given window: a tile must fit twice into the ring
 int slicer_rows(int L) { return L >= 8192 ? 4 : (L >= 4096 ? 2 : 1); }
 bool slicer_streaming_ok(int L, bool vec_ok);
+int slicer_streaming_tile(int L, int kind);
 // tile of the kernel a window takes: segment boundaries and halos are whole tiles
-int slicer_tile(int L, bool vec_ok) {
-    if (slicer_streaming_ok(L, vec_ok)) return L >= 8192 ? 4096 : 512;
+int slicer_tile(int L, bool vec_ok, int kind) {
+    if (slicer_streaming_ok(L, vec_ok)) return slicer_streaming_tile(L, kind);
     return (vec_ok && L >= 1024) ? 1024 * slicer_rows(L) : 256;
 }
 
@@ -1308,6 +1309,7 @@ struct FastVariant {
     const void *fn;
     int threads;
     size_t smem;  // dynamic: the ring, then the stages (or the one staging buffer of the synchronous loop)
+    int tile;     // samples per tile: segment boundaries and halos are whole tiles
 };
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -1334,6 +1336,7 @@ static FastVariant fast_variant(int L) {
     const size_t stg = KIND == IN_PCM_S16 ? T * 6 : T * 4;  // a stage of the pipelined mode (PipeStage): samples, undo log
     const size_t half = smem_optin_limit() / 2;               // two CTAs per SM
     FastVariant v;
+    v.tile = (int)T;
     if (L < FAST_BIG_MIN_L) {
         if (pipe && KIND != IN_IQ_F32) {
             v.fn = (const void *)slicer_fast_kernel<128, 1, 5, KIND, 3>;
@@ -1355,6 +1358,13 @@ static FastVariant fast_variant(int L) {
             v.fn = (const void *)slicer_fast_kernel<256, 4, 2, KIND, 2>;
             v.threads = 320;
             v.smem = ring + 2 * stg;
+        } else if (env_int("NFC_SLICER_HALF_TILE", 1) && ring + 3 * (stg / 2) + FAST_STATIC_SMEM <= half) {
+            // a window too long for two CTAs with tiles of 4096 samples beside their rings (20 MS/s: 80 KB): tiles of 2048 samples
+            // (two chunks per warp) keep two CTAs per SM
+            v.fn = (const void *)slicer_fast_kernel<256, 2, 2, KIND, 3>;
+            v.threads = 320;
+            v.smem = ring + 3 * (stg / 2);
+            v.tile = 2048;
         } else if (ring + 3 * stg + FAST_STATIC_SMEM <= smem_optin_limit()) {
             v.fn = (const void *)slicer_fast_kernel<512, 2, 1, KIND, 3>;
             v.threads = 576;
@@ -1379,6 +1389,8 @@ static FastVariant fast_variant_of(int L, int kind) {
         default: return fast_variant<IN_PCM_S16>(L);
     }
 }
+
+int slicer_streaming_tile(int L, int kind) { return fast_variant_of(L, kind).tile; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel is only ever raised (streams with different windows share the
 // kernels, and setting the attribute before every launch serialises the launching threads)

@@ -64,7 +64,7 @@ int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, const uint32_t *d_pending_in,
                           const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream);
-int slicer_tile(int L, bool vec_ok);
+int slicer_tile(int L, bool vec_ok, int kind);
 int slicer_resident_ctas(int L, bool vec_ok, int kind);
 int slicer_tile_stats(unsigned long long *out4, bool reset);
 int launch_batch_warm(const void *d_items, int64_t stride_bytes, int64_t pitch, int n_cap, int L, const SlicerParams *d_params,
@@ -296,7 +296,7 @@ struct Stream {
 
     nfc_stats stats;
 
-    int tile() const { return slicer_tile(sp.L, vec_ok()); }
+    int tile() const { return slicer_tile(sp.L, vec_ok(), sp.input_kind); }
     bool vec_ok() const { return (sp.L % 4) == 0; }
     // (windows whose ring does not fit a CTA's shared memory beside the kernels' own scratch take the sequential kernel)
     bool parallel_ok() const { return sp.L >= 256 && sp.L <= 52000 && !force_serial && !serial_mode; }
