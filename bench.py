@@ -767,30 +767,26 @@ def main():
     e2e = None
     ne = int(min(args.e2e_samples, n))
     try:
-        xa = torch.empty(ne, dtype=torch.float32, device="cuda")
-        _cabi.synth_render(xa, codes, lens, seed=99, as_envelope=False, device=local_rank, first_index=base, **chan)
-        pcm_d = torch.round(xa * 32767.0).to(torch.int16)
-        del xa
-        xh = torch.empty(ne, dtype=torch.int16, pin_memory=True)
-        xh.copy_(pcm_d)
-        del pcm_d
-        torch.cuda.synchronize()
-        # the host -> device ceiling of this box for the same pinned buffer: rank 0 alone, then all ranks at once (the e2e
-        # number cannot exceed samples = bytes / 2 over these)
+        # ---- the host -> device ceiling of this box, measured first: rank 0 alone, then all ranks at once (the e2e number
+        # cannot exceed samples = bytes / 2 over these).  The GPUs of a node share PCIe roots unevenly (eight at once: 24 to
+        # 35 GB/s each): every rank's host buffer is sized in proportion to the rate its GPU gets, so that the ranks finish
+        # together (the job is as fast as its slowest rank); the sizes are in the line.
         h2d = {}
+        per = [1.0] * world
         try:
-            dev_buf = torch.empty_like(xh, device="cuda")
+            scratch = torch.empty(min(ne, 1 << 27), dtype=torch.int16, pin_memory=True)
+            dev_buf = torch.empty_like(scratch, device="cuda")
 
             def copy_gbs():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                dev_buf.copy_(xh, non_blocking=True)
+                dev_buf.copy_(scratch, non_blocking=True)
                 torch.cuda.synchronize()
                 e0.record()
-                for _ in range(3):
-                    dev_buf.copy_(xh, non_blocking=True)
+                for _ in range(4):
+                    dev_buf.copy_(scratch, non_blocking=True)
                 e1.record()
                 torch.cuda.synchronize()
-                return 3 * xh.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+                return 4 * scratch.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
             if world > 1:
                 dist.barrier()
                 alone = copy_gbs() if rank == 0 else 0.0
@@ -808,10 +804,24 @@ def main():
                 per = [mine_gbs]
             h2d = {"one_gpu_alone_gbs": alone, "all_gpus_at_once_gbs_per_rank": per, "all_gpus_at_once_gbs_sum": float(sum(per)),
                    "e2e_ceiling_msamples_per_s": float(sum(per)) * 1e3 / 2.0,
-                   "note": "pinned int16 host buffer -> device, torch copy, 3 repetitions; all ranks copy at the same time"}
-            del dev_buf
+                   "note": "pinned int16 host buffer -> device, torch copy, 4 repetitions of %d MB; all ranks copy at the same time" % (scratch.numel() * 2 >> 20)}
+            del dev_buf, scratch
         except Exception as exc:
             h2d = {"error": str(exc)[:200]}
+            per = [1.0] * world
+        ne_r = ne
+        if world > 1 and min(per) > 0:
+            share = per[rank] / (sum(per) / world)
+            ne_r = int(ne * min(max(share, 0.5), 1.6))
+            ne_r -= ne_r % 4
+        xa = torch.empty(ne_r, dtype=torch.float32, device="cuda")
+        _cabi.synth_render(xa, codes, lens, seed=99, as_envelope=False, device=local_rank, first_index=base, **chan)
+        pcm_d = torch.round(xa * 32767.0).to(torch.int16)
+        del xa
+        xh = torch.empty(ne_r, dtype=torch.int16, pin_memory=True)
+        xh.copy_(pcm_d)
+        del pcm_d
+        torch.cuda.synchronize()
         se = _cabi.Stream(RATE, hi_val=HI_VAL, outputs=_cabi.OUT_FRAMES, device=local_rank, input_kind=_cabi.IN_PCM_S16, **params)
         se.set_tuning(seg_len=args.seg_len, halo=args.halo, slab_len=int(min(args.slab, 1 << 28)))
         xh_np = xh.numpy()
@@ -834,12 +844,20 @@ def main():
         e_wall = (time.perf_counter() - t0) / esteps
         est = se.stats()
         tt = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        tot = torch.tensor([float(ne_r), est["h2d_bytes"] / esteps, est["d2h_bytes"] / esteps, float(n_fr_e)], dtype=torch.float64, device="cuda")
+        sizes = [ne_r]
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * ne / float(tt[0]) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(est["h2d_bytes"] / esteps), "d2h_bytes_per_step": int(est["d2h_bytes"] / esteps),
-               "samples_per_step_per_gpu": ne, "ms_per_step": float(tt[0]) * 1e3, "frames_per_step": int(n_fr_e),
-               "host_buffer": "int16 PCM (pinned), what wavfile_source reads; normalised and squared on the device",
+            alls = [torch.empty_like(tot) for _ in range(world)]
+            dist.all_gather(alls, tot)
+            sizes = [int(a[0]) for a in alls]
+            tot = torch.stack(alls).sum(0)
+        e2e = {"value": float(tot[0]) / float(tt[0]) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(tot[1]), "d2h_bytes_per_step": int(tot[2]),
+               "samples_per_step_per_gpu": sizes if world > 1 else ne_r, "samples_per_step": int(tot[0]),
+               "ms_per_step": float(tt[0]) * 1e3, "frames_per_step": int(tot[3]),
+               "host_buffer": "int16 PCM (pinned), what wavfile_source reads; normalised and squared on the device; bytes and frames "
+                              "are the whole job's" + ("; buffer sizes in proportion to the host -> device rate every GPU gets" if world > 1 else ""),
                "h2d_ceiling": h2d}
         se.close()
         del xh
