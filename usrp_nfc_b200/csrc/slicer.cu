@@ -1465,8 +1465,8 @@ int slicer_tile_stats(unsigned long long *out4, bool reset) {
     {
         unsigned long long c[12];
         NFC_CUDA_CHECK(cudaMemcpyFromSymbol(c, g_cyc, sizeof(c)));
-        fprintf(stderr, "cycles: tile passes %llu in %llu calls (%llu repeats), ring sums after refused tiles %llu, fix-point path %llu, exact path %llu, segment set-up %llu, snapshots %llu, after pipelined runs %llu, loop top %llu, commits %llu\n",
-                c[0], c[1], c[5], c[2], c[3], c[4], c[6], c[7], c[8], c[9], c[10]);
+        fprintf(stderr, "cycles: tile passes %llu in %llu calls (%llu repeats), ring sums after refused tiles %llu, fix-point path %llu, exact path %llu, segment set-up %llu, snapshots %llu, after pipelined runs %llu (its last barrier %llu), loop top %llu, commits %llu\n",
+                c[0], c[1], c[5], c[2], c[3], c[4], c[6], c[7], c[8], c[11], c[9], c[10]);
         if (reset) {
             unsigned long long z[12] = {0};
             NFC_CUDA_CHECK(cudaMemcpyToSymbol(g_cyc, z, sizeof(z)));

@@ -705,7 +705,9 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
     // synchronous loop were proven at the first attempt (bursts of tiles that need the precise passes stay with it)
     const int PIPE_MIN = g_pipe_tune[0], PIPE_COOL = g_pipe_tune[1];
     const int MEAS_MAX = g_pipe_tune[2];
-    const int RESUM_BITS = g_pipe_tune[3];  // after a refused tile: sum the ring anew when the interval is wider than 2^-bits of the sum (0: never)  // passes with measured guesses before the exact fix-point takes a tile
+    const int RESUM_BITS = g_pipe_tune[3];
+    const double resum_eps = __longlong_as_double((long long)(1023 - (RESUM_BITS > 0 ? RESUM_BITS : 0)) << 52);  // 2^-RESUM_BITS
+     // after a refused tile: sum the ring anew when the interval is wider than 2^-bits of the sum (0: never)  // passes with measured guesses before the exact fix-point takes a tile
     char *const stage0 = reinterpret_cast<char *>(ring) + (((size_t)L * 4 + 15) / 16) * 16;
     const bool pipe_can = PIPED && L >= 3 * T && ((reinterpret_cast<uintptr_t>(plan.xbase) & 15u) == 0u) && plan.bm_base != nullptr;
     int cool = 0, pipe_K = 0;
@@ -1006,7 +1008,7 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 // (exact) is much cheaper than the exact fix-point a tile that cannot be proven falls back to.
                 if (RESUM_BITS > 0) {
                     const double lo = uni.ss_lo, hi = uni.ss_hi;
-                    if ((hi - lo) > ldexp(hi, -RESUM_BITS)) NFC_CYC(2, make_exact());  // block-uniform
+                    if ((hi - lo) > hi * resum_eps) NFC_CYC(2, make_exact());  // block-uniform
                 }
             }
             if (warp == 0) {  // the coming tile's constants for the synchronous loop
@@ -1015,8 +1017,12 @@ __global__ void __launch_bounds__(NT + (PIPE ? 64 : 0), MINB) slicer_fast_kernel
                 __syncwarp();
                 fast_prepare<NC>(uni, lo, hi, tp, ae, p.loL, p.hiL, lane);
             }
+#ifdef NFC_CYCLES
+            const long long c_bar = clock64();
+#endif
             cta_sync<NT>();
 #ifdef NFC_CYCLES
+            cyc[11] += clock64() - c_bar;
             cyc[8] += clock64() - c_post;
 #endif
             continue;
