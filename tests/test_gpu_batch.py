@@ -115,3 +115,20 @@ def test_batch_one_pass_refuses_what_needs_the_sequential_path():
         want = oracle.decode_capture(x2d[i], rate, lo_val=float(los[i]), hi_val=float(his[i]), **p)
         assert len(fr) == len(want["frames"]) and np.array_equal(fr["pos"], want["frames"]["pos"]), i
     res["stream"].close()
+
+
+def test_batch_in_several_slabs_matches_oracle_per_capture():
+    """The batch's extraction / runs / line code in slabs of a few captures each (slab_len shortens them), their chains queued
+    back to back: what a slab inherits from the one before must not show in any capture's frames."""
+    rate, n, n_items = 13.56e6, 23, 262144 + 1000
+    x2d, los, his, p = _uniform_captures(rate, n, n_items, 9100)
+    s = _cabi.Stream(rate, outputs=_cabi.OUT_FRAMES, **p)
+    res0 = batch.decode_batch_onepass(x2d, rate, p, lo_vals=los, hi_vals=his, stream=s)  # one slab: also sets the sizing rates
+    pitch = res0["pitch"]
+    total0 = _check_batch(x2d, rate, p, los, his, res0)
+    s.release_frames()
+    s.set_tuning(slab_len=3 * pitch)  # eight slabs
+    res = batch.decode_batch_onepass(x2d, rate, p, lo_vals=los, hi_vals=his, stream=s)
+    assert res["pitch"] == pitch
+    assert _check_batch(x2d, rate, p, los, his, res) == total0 > 150
+    s.close()

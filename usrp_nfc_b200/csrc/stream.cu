@@ -724,9 +724,16 @@ int64_t Stream::push_batch(const void *items, int mem, int64_t n_cap, int64_t ca
                           sblk, cs))
         return -1;
     stats.launches++;
+    // Captures take different times (the closer hi_val lies to the tag's HIGH level, the more of a capture's tiles need the
+    // precise passes) and there are more of them than CTAs fit on the device at once: the ones expected to take longest go
+    // first, so that the last wave is made of short ones.
+    std::vector<int64_t> order((size_t)n_cap);
+    for (int64_t c = 0; c < n_cap; c++) order[(size_t)c] = c;
+    if (hi_vals) std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return hi_vals[a] > hi_vals[b]; });
     std::vector<SegWork> works((size_t)n_cap);
-    for (int64_t c = 0; c < n_cap; c++) {
-        SegWork &w = works[(size_t)c];
+    for (int64_t k = 0; k < n_cap; k++) {
+        const int64_t c = order[(size_t)k];
+        SegWork &w = works[(size_t)k];
         memset(&w, 0, sizeof(w));
         const int64_t B = c * pitch;
         w.in = (const char *)d_items + (size_t)c * (size_t)stride_items * ib;
@@ -774,12 +781,17 @@ int64_t Stream::push_batch(const void *items, int mem, int64_t n_cap, int64_t ca
     lt.batch_pitch = (uint32_t)pitch;
     lt.batch_skip = (uint32_t)L;
     lt.batch_len = (uint32_t)cap_len;
-    const int64_t per_slab = std::max<int64_t>(1, ((int64_t)1 << 30) / pitch);
+    // slabs of whole captures (nfc_stream_set_tuning's slab_len shortens them: tests)
+    const int64_t slab_max = slab_len > 0 ? std::min<int64_t>(slab_len, (int64_t)1 << 30) : (int64_t)1 << 30;
+    const int64_t per_slab = std::max<int64_t>(1, slab_max / pitch);  // (more, shorter slabs were slower: 10.5 against 9.6 ms)
     int rc = 0;
+    if (finish_pending()) return -1;
+    // What a slab's chain inherits from the slab before (run carry, decoder state, the val before its first sample) does
+    // not matter: a capture's warm-up flushes it, and its first event finds decoders and PacketProcessors as new.  So the
+    // chains of the batch's slabs are queued back to back like those of one stream.
+    run_carry = RunCarry{0, 0, L % sp.mx, 0};
     for (int64_t c0 = 0; c0 < n_cap && !rc; c0 += per_slab) {
         const int64_t c1 = std::min(n_cap, c0 + per_slab);
-        if (finish_pending()) { rc = -1; break; }
-        run_carry = RunCarry{0, 0, L % sp.mx, 0};  // whatever the slab before left: the first capture's warm-up flushes it
         if (process_slab(nullptr, c0 * pitch, c0 * pitch, c1 * pitch, c0 * pitch, c1 * pitch, c1 * pitch)) rc = -1;
         pos = c1 * pitch;
         stats.samples += (c1 - c0) * cap_len;
