@@ -1845,7 +1845,7 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
             uint64_t *fx = findex + f0;
             // slabs with many closings: the walk is bound by memory latency, so it is cut into parts that run on threads of
             // their own (first pass: how many frames each part forwards; second pass: the records)
-            const int parts = tot.nemit > 60000 ? 4 : 1;
+            const int parts = tot.nemit > 300000 ? 4 : 1;  // (below that the threads cost more than they save)
             size_t part_n[4] = {0, 0, 0, 0}, part_closed[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
             bool part_bad[4] = {false, false, false, false}, part_fx_bad[4] = {false, false, false, false};
             auto range = [&](int q, uint32_t &i0, uint32_t &i1) {
