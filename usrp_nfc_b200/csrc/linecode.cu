@@ -419,18 +419,19 @@ __global__ void chunk_count_kernel(const EventRec *__restrict__ ev, EvCount evc,
     cnts[c] = sink.c;
 }
 
-// ---- pass C: write symbols, frame bits and frame-closing records --------------------------------
-struct EmissionRec {
-    uint32_t rel_pos;   // closing event
-    int32_t type;
-    uint32_t nbits;     // len(self._cur) when the frame closed; 0 = nothing forwarded (packets.py:97)
-    uint32_t bit_end;   // bits of this type appended in this slab before the frame closed
-};
-
+// ---- pass C: write symbols, frame bits and frame records --------------------------------
+// A frame record is final as the device writes it (the layout of nfc_frame): closing position in stream coordinates, offset of
+// the frame's first bit in the stream's bit arena of its type (all bits of a type in append order: bits_base[t] of them before
+// this slab), length, type.  An empty frame (packets.py:97: not forwarded) still gets a record, with nbits == 0, and is
+// counted in *n_empty: the host drops such records (rare), otherwise the records go to their final place by DMA alone.
 struct WriteSink {
     SymbolRec *sym;
     uint8_t *bits0, *bits1;
-    EmissionRec *em;
+    FrameRec *fr;
+    unsigned long long *fx;
+    uint32_t *n_empty;
+    int64_t a;
+    unsigned long long base0, base1;
     uint32_t isym, ib0, ib1, iem;
     uint32_t pend0, pend1;
     uint32_t cap_sym, cap_b0, cap_b1, cap_em;
@@ -443,13 +444,18 @@ struct WriteSink {
         isym++;
     }
     __device__ __forceinline__ void emission(uint32_t pos, int type) {
+        const uint32_t nbits = type == 0 ? pend0 : pend1;
         if (iem < cap_em) {
-            EmissionRec e;
-            e.rel_pos = pos; e.type = type;
-            e.nbits = type == 0 ? pend0 : pend1;
-            e.bit_end = type == 0 ? ib0 : ib1;
-            em[iem] = e;
+            FrameRec f;
+            f.pos = a + (int64_t)pos;
+            f.bit_off = (int64_t)((type == 0 ? base0 + ib0 : base1 + ib1) - nbits);  // frames of one type are back to back
+            f.nbits = (int32_t)nbits;
+            f.type = type;
+            fr[iem] = f;
+            fx[iem] = ((unsigned long long)f.pos << 24) | ((unsigned long long)nbits << 8) | (unsigned long long)type;
         }
+        if (nbits == 0) atomicAdd(n_empty, 1u);
+        if ((((unsigned long long)(a + (int64_t)pos)) >> 40) || nbits >= 65536u) atomicOr(n_empty, 0x80000000u);  // does not fit the packed index
         iem++;
         if (type == 0) pend0 = 0; else pend1 = 0;
     }
@@ -463,9 +469,14 @@ struct WriteSink {
 struct LineOut {
     SymbolRec *sym;
     uint8_t *bits0, *bits1;
-    EmissionRec *em;
+    FrameRec *fr;
+    unsigned long long *fx;       // packed frame index beside the records: pos << 24 | nbits << 8 | type
     uint32_t cap_sym, cap_b0, cap_b1, cap_em;
     const uint32_t *pending_in;   // len(_cur) of each PacketProcessor at the slab start (device memory: [2])
+    int64_t a;                    // stream position of the slab's first sample
+    const unsigned long long *bits_in;  // bits of each type appended before this slab (device memory: [2]) ...
+    unsigned long long *bits_out;       // ... and behind it
+    uint32_t *n_empty;
 };
 
 __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
@@ -479,12 +490,15 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc,
         *carry_out = *carry_in;
         pending_out[0] = out.pending_in[0];
         pending_out[1] = out.pending_in[1];
+        out.bits_out[0] = out.bits_in[0];
+        out.bits_out[1] = out.bits_in[1];
     }
     if (c >= n_chunks) return;
     int rs = start[c] & 31, gs = (start[c] >> 8) & 15;
     const ChunkCnt pc = cnt_prefix[c];
     WriteSink sink;
-    sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.em = out.em;
+    sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.fr = out.fr; sink.fx = out.fx;
+    sink.n_empty = out.n_empty; sink.a = out.a; sink.base0 = out.bits_in[0]; sink.base1 = out.bits_in[1];
     sink.cap_sym = out.cap_sym; sink.cap_b0 = out.cap_b0; sink.cap_b1 = out.cap_b1; sink.cap_em = out.cap_em;
     sink.isym = pc.nsym; sink.ib0 = pc.nbit0; sink.ib1 = pc.nbit1; sink.iem = pc.nemit;
     sink.pend0 = pc.has0 ? pc.tail0 : out.pending_in[0] + pc.tail0;
@@ -505,6 +519,8 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc,
         *carry_out = co;
         pending_out[0] = sink.pend0;
         pending_out[1] = sink.pend1;
+        out.bits_out[0] = sink.base0 + sink.ib0;  // the last chunk's counters are the slab's totals
+        out.bits_out[1] = sink.base1 + sink.ib1;
     }
 }
 
@@ -512,7 +528,7 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc,
 uint32_t linecode_chunks(uint32_t n_ev) { return (n_ev + CHUNK - 1) / CHUNK; }
 size_t linecode_map_bytes() { return sizeof(ChunkMap); }
 size_t linecode_cnt_bytes() { return sizeof(ChunkCnt); }
-size_t linecode_emission_bytes() { return sizeof(EmissionRec); }
+size_t linecode_emission_bytes() { return sizeof(FrameRec); }
 size_t linecode_scratch_bytes(uint32_t n_chunks) {
     return scan_scratch_elems(n_chunks) * sizeof(ChunkMap) + scan_scratch_elems(n_chunks) * sizeof(ChunkCnt);
 }
@@ -565,13 +581,18 @@ int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
 
 int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
-                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, const uint32_t *d_pending_in,
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_frames, void *d_findex, uint32_t cap_em, int64_t a,
+                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, const uint32_t *d_pending_in,
                           const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
     const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
     LineOut out;
-    out.sym = d_sym; out.bits0 = d_bits0; out.bits1 = d_bits1; out.em = (EmissionRec *)d_em;
+    out.sym = d_sym; out.bits0 = d_bits0; out.bits1 = d_bits1; out.fr = (FrameRec *)d_frames; out.fx = (unsigned long long *)d_findex;
     out.cap_sym = cap_sym; out.cap_b0 = cap_b0; out.cap_b1 = cap_b1; out.cap_em = cap_em;
     out.pending_in = d_pending_in;
+    out.a = a;
+    out.bits_in = (const unsigned long long *)d_bits_in;
+    out.bits_out = (unsigned long long *)d_bits_out;
+    out.n_empty = d_n_empty;
     const EvCount evc{d_M, cap_ev};
     chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_start, (const ChunkCnt *)d_cnt_prefix, out,
                                                              d_carry_in, d_carry_out, d_pending_out);

@@ -62,7 +62,8 @@ int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
                           void *d_cnts, void *d_cnt_prefix, void *d_scratch, void *d_total, cudaStream_t stream);
 int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
-                          uint8_t *d_bits1, uint32_t cap_b1, void *d_em, uint32_t cap_em, const uint32_t *d_pending_in,
+                          uint8_t *d_bits1, uint32_t cap_b1, void *d_frames, void *d_findex, uint32_t cap_em, int64_t a,
+                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, const uint32_t *d_pending_in,
                           const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream);
 int slicer_tile(int L, bool vec_ok, int kind);
 int slicer_resident_ctas(int L, bool vec_ok, int kind);
@@ -131,6 +132,35 @@ static int classify_ratio_host(double ratio, double lo, double hi) {  // transit
     if (ratio > hi) return 1;
     return 0;
 }
+
+// The frame records of a stream in page-locked memory: the device writes them final (linecode.cu: WriteSink::emission), a
+// slab's records are copied straight behind those of the slabs before.
+struct FrameArena {
+    nfc_frame *p = nullptr;
+    size_t n = 0, cap = 0;
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    nfc_frame *data() { return p; }
+    const nfc_frame &operator[](size_t i) const { return p[i]; }
+    void clear() { n = 0; }
+    int reserve(size_t need) {  // may move the arena: no copy into it in flight, nobody reading
+        if (need <= cap) return 0;
+        const size_t ncap = std::max(need + need / 2 + 4096, cap * 2);
+        nfc_frame *q = nullptr;
+        if (cudaMallocHost((void **)&q, ncap * sizeof(nfc_frame)) != cudaSuccess) return -1;
+        if (n) memcpy(q, p, n * sizeof(nfc_frame));
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = ncap;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+};
+static_assert(sizeof(nfc_frame) == sizeof(FrameRec), "the device writes nfc_frame records");
 
 // All frame bits of one type in the order they were appended (cpp.append_bit), in page-locked memory: a slab's bits are
 // copied from the device straight to their final place behind the bits of the slabs before, frames refer to them by offset.
@@ -221,7 +251,7 @@ struct Stream {
         line_scr, serial_ring, start_d, ckpt_d, redo_states, redo_trans,
         redo_counts, pieces_d, bitmap_d, ex_counts, ex_offsets, ex_scr, summ_d;
     // outputs of a slab's chain, two sets: the records of slab k travel to the host while the chain of slab k+1 writes the other
-    DevBuf events_d[2], sym_d[2], bits0_d[2], bits1_d[2], em_d[2];
+    DevBuf events_d[2], sym_d[2], bits0_d[2], bits1_d[2], em_d[2], fx_d[2];  // em_d: frame records (FrameRec), fx_d: their packed index
     DevBuf trans_dense[2];  // transitions of slab k in [k & 1]: the extraction of slab k+1 runs beside the runs of slab k
     std::vector<DevBuf> kept_bufs;  // redo buffers whose contents are still referenced by transition pieces
     // results come back into one of three pinned buffers.  The carries of a slab (256 bytes) are copied first and are all
@@ -272,7 +302,11 @@ struct Stream {
     // results
     std::vector<nfc_event> out_events;
     std::vector<nfc_symbol> out_symbols;
-    std::vector<nfc_frame> out_frames;   // bit_off is relative to fb[type].p
+    FrameArena out_frames;               // bit_off is relative to fb[type].p
+    bool frames_have_empty = false;      // some records have nbits == 0 (packets.py:97: not forwarded): dropped when the stream settles
+    cudaEvent_t ev_last_records = nullptr;  // the copy of the last finalized slab's records (a slab no worker thread waits for)
+    bool have_last_records = false;
+    int settle_frames();
     // packed frame offsets (pos << 24 | nbits << 8 | type) of out_frames in page-locked memory (nfc_stream_view_frame_index)
     uint64_t *findex = nullptr;
     size_t findex_n = 0, findex_cap = 0;
@@ -306,7 +340,7 @@ struct Stream {
     int ensure_pinned(int idx, size_t bytes);
     int join_marshal();
     int finish_pending() { return finalize_all(); }
-    int settle() { return finalize_all() || join_marshal() ? -1 : 0; }
+    int settle() { return finalize_all() || join_marshal() || settle_frames() ? -1 : 0; }
     int64_t push(const void *items, int64_t n, int mem, int *called_back);
     int64_t push_batch(const void *items, int mem, int64_t n_cap, int64_t cap_len, int64_t stride_items, const double *lo_vals,
                        const double *hi_vals, int64_t *pitch_out);
@@ -443,7 +477,7 @@ void Stream::destroy() {
     DevBuf *all[] = {&batch_states, &batch_stage, &params_d, &tab_d, &staging, &works_d, &states_d, &trans_seg, &trans_dense[0], &trans_dense[1], &seg_counts, &seg_offsets,
                      &seg_status, &seam_ptrs, &mismatch_d, &run_counts, &run_offsets, &scan_scr, &maps_d,
                      &prefix_d, &cnts_d, &cprefix_d, &line_scr, &ctx_d, &events_d[0], &events_d[1], &sym_d[0], &sym_d[1], &bits0_d[0],
-                     &bits0_d[1], &bits1_d[0], &bits1_d[1], &em_d[0], &em_d[1],
+                     &bits0_d[1], &bits1_d[0], &bits1_d[1], &em_d[0], &em_d[1], &fx_d[0], &fx_d[1],
                      &serial_ring, &start_d, &ckpt_d, &redo_states, &redo_trans, &redo_counts, &pieces_d, &state, &bitmap_d,
                      &ex_counts, &ex_offsets, &ex_scr, &summ_d};
     finalize_all();
@@ -457,6 +491,7 @@ void Stream::destroy() {
     ctx_h = nullptr;
     fb[0].release();
     fb[1].release();
+    out_frames.release();
     if (findex && !findex_ext) cudaFreeHost(findex);
     findex = nullptr;
     findex_cap = findex_n = 0;
@@ -1405,12 +1440,14 @@ static double now_ms() {
 // ---- a slab's context block in device memory (256 bytes; ring of NCTX): counts and flags of the slab's chain, and the
 // carries it leaves for the next slab (the reference's cur_state / last_bit / dur, decoder and PacketProcessor state)
 struct PostCtx {
-    uint32_t M, R, flags, pad0[5];
+    uint32_t M, R, flags, n_empty, pad0[4];
     uint32_t tot[8];      // ChunkCnt: nsym, nbit0, nbit1, nemit, has0, tail0, has1, tail1
     RunCarry rc_out;
     DecCarry dc_out;
     uint32_t pend_out[2];
-    uint32_t pad1[38];
+    uint32_t pad1[2];
+    unsigned long long bits_out[2];  // bits of each type appended so far (offsets into the stream's bit arenas)
+    uint32_t pad2[32];
 };
 static_assert(sizeof(PostCtx) == 256, "context blocks are 256 bytes apart");
 
@@ -1501,6 +1538,8 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
         up.dc_out = dec_carry;
         up.pend_out[0] = pending[0];
         up.pend_out[1] = pending[1];
+        up.bits_out[0] = fb[0].len;
+        up.bits_out[1] = fb[1].len;
         NFC_CUDA_CHECK(cudaMemcpyAsync(cp, &up, sizeof(up), cudaMemcpyHostToDevice, cs));
         chain_first_seq = j.seq;
     }
@@ -1626,16 +1665,18 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
             j.cap_sym = cap_of(rates.sym); j.cap_b0 = cap_of(rates.b0); j.cap_b1 = cap_of(rates.b1); j.cap_em = cap_of(rates.em);
         }
         if ((want_sym && sym_d[oi].ensure(((size_t)j.cap_sym + 16) * sizeof(SymbolRec))) || bits0_d[oi].ensure((size_t)j.cap_b0 + 16) ||
-            bits1_d[oi].ensure((size_t)j.cap_b1 + 16) || em_d[oi].ensure(((size_t)j.cap_em + 16) * linecode_emission_bytes()))
+            bits1_d[oi].ensure((size_t)j.cap_b1 + 16) || em_d[oi].ensure(((size_t)j.cap_em + 16) * linecode_emission_bytes()) ||
+            fx_d[oi].ensure(((size_t)j.cap_em + 16) * 8))
             return -1;
         if (launch_linecode_write(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cprefix_d.p, want_sym ? sym_d[oi].as<SymbolRec>() : nullptr,
                                   want_sym ? j.cap_sym : 0, bits0_d[oi].as<uint8_t>(), j.cap_b0, bits1_d[oi].as<uint8_t>(), j.cap_b1, em_d[oi].p,
-                                  j.cap_em, cp->pend_out, &cp->dc_out, &cx->dc_out, cx->pend_out, csL))
+                                  fx_d[oi].p, j.cap_em, a, cp->bits_out, cx->bits_out, &cx->n_empty, cp->pend_out, &cp->dc_out, &cx->dc_out,
+                                  cx->pend_out, csL))
             return -1;
         stats.launches++;
     } else {
         // no decoder runs: its state passes through
-        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->dc_out, &cp->dc_out, sizeof(DecCarry) + 8, cudaMemcpyDeviceToDevice, csL));
+        NFC_CUDA_CHECK(cudaMemcpyAsync(&cx->dc_out, &cp->dc_out, sizeof(DecCarry) + 8 + 8 + 16, cudaMemcpyDeviceToDevice, csL));  // dc_out .. bits_out
     }
     NFC_CUDA_CHECK(cudaEventRecord(ev_c[ci], csL));
     NFC_CUDA_CHECK(cudaMemcpyAsync(ctx_h + (size_t)ci * 256, cx, 256, cudaMemcpyDeviceToHost, csL));
@@ -1649,6 +1690,30 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
     // the slab before this one: its chain has run (or is about to end) while this one was queued
     while (jobs.size() > 1)
         if (finalize_front()) return -1;
+    return 0;
+}
+
+// Everything queued has been looked at: wait for the last records to arrive, and drop the records of empty frames (rare;
+// packets.py:97 does not forward them) from the frame arena and its index.
+int Stream::settle_frames() {
+    if (have_last_records) {
+        NFC_CUDA_CHECK(cudaEventSynchronize(ev_last_records));
+        have_last_records = false;
+    }
+    if (frames_have_empty) {
+        size_t o = 0;
+        for (size_t i = 0; i < out_frames.n; i++)
+            if (out_frames.p[i].nbits != 0) {
+                if (o != i) {
+                    out_frames.p[o] = out_frames.p[i];
+                    findex[o] = findex[i];
+                }
+                o++;
+            }
+        out_frames.n = o;
+        findex_n = o;
+        frames_have_empty = false;
+    }
     return 0;
 }
 
@@ -1719,7 +1784,7 @@ int Stream::finalize_front() {
 
     // ---- records back to the host (cs2; the chain has completed: the host has seen its context block)
     const bool want_ev = j.want_ev, want_sym = j.want_sym, want_fr = j.want_fr;
-    size_t off_ev = 0, off_sym = 0, off_em = 0, total = 0;
+    size_t off_ev = 0, off_sym = 0, total = 0;
     auto place = [&](size_t bytes) {
         size_t o = total;
         total += (bytes + 63) / 64 * 64;
@@ -1728,38 +1793,56 @@ int Stream::finalize_front() {
     place(64);
     if (want_ev) off_ev = place((size_t)M * sizeof(EventRec));
     if (want_sym) off_sym = place((size_t)nsym * sizeof(SymbolRec));
-    if (want_fr) off_em = place((size_t)nemit * sizeof(EmissionHost));
     const int pi = (int)(slabs_enqueued % NPIN);
     // the slab that used this buffer last (three slabs ago) must be in the output vectors: long done, normally
     while (slabs_marshalled.load(std::memory_order_acquire) < slabs_enqueued - (NPIN - 1)) std::this_thread::yield();
     if (ensure_pinned(pi, total)) return -1;
     char *hp = (char *)pinned[pi];
-    size_t base[2] = {fb[0].len, fb[1].len};
     if (want_fr) {
-        // the slab's frame bits go straight behind the bits of the slabs before; an arena that has to grow moves: no copy
-        // into it may be in flight then, and the worker threads must be done with what they were given
+        // The slab's frame records, their packed index and the frame bits go straight behind those of the slabs before, in
+        // page-locked memory; an arena that has to grow moves: no copy into it may be in flight then, and the worker threads
+        // must be done with what they were given.
         const uint32_t nb[2] = {nbit0, nbit1};
-        for (int t = 0; t < 2; t++)
-            if (fb[t].len + nb[t] > fb[t].cap) {
-                if (join_marshal()) return -1;
-                NFC_CUDA_CHECK(cudaStreamSynchronize(cs2));
-                if (fb[t].reserve(fb[t].len + nb[t])) {
-                    set_error("out of page-locked memory for %zu frame bits", fb[t].len + nb[t]);
-                    return -1;
-                }
+        const size_t f0 = out_frames.size();
+        const bool grow_any = fb[0].len + nb[0] > fb[0].cap || fb[1].len + nb[1] > fb[1].cap || f0 + nemit > out_frames.cap ||
+                              f0 + nemit > findex_cap;
+        if (grow_any) {
+            if (join_marshal()) return -1;
+            NFC_CUDA_CHECK(cudaStreamSynchronize(cs2));
+            if (findex_n != f0) {
+                set_error("internal: frame index out of step");
+                return -1;
             }
+            if (fb[0].reserve(fb[0].len + nb[0]) || fb[1].reserve(fb[1].len + nb[1]) || out_frames.reserve(f0 + nemit)) {
+                set_error("out of page-locked memory for the frames of a slab");
+                return -1;
+            }
+            if (findex_reserve(f0 + nemit)) {
+                set_error(findex_ext ? "more frames than the caller's frame index buffer holds (nfc_stream_set_frame_index_buffer)"
+                                     : "out of page-locked memory for the frame index");
+                return -1;
+            }
+        }
+        if (nemit) {
+            NFC_CUDA_CHECK(cudaMemcpyAsync(out_frames.p + f0, em_d[oi].p, (size_t)nemit * sizeof(nfc_frame), cudaMemcpyDeviceToHost, cs2));
+            NFC_CUDA_CHECK(cudaMemcpyAsync(findex + f0, fx_d[oi].p, (size_t)nemit * 8, cudaMemcpyDeviceToHost, cs2));
+        }
+        if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[0].p + fb[0].len, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
+        if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[1].p + fb[1].len, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
+        // bits up to the last closing of a type are handed out with the frames (the line-code totals know where that is)
+        if (hx.tot[4]) fb[0].closed = fb[0].len + nbit0 - hx.tot[5];
+        if (hx.tot[6]) fb[1].closed = fb[1].len + nbit1 - hx.tot[7];
+        fb[0].len += nbit0;
+        fb[1].len += nbit1;
+        out_frames.n = f0 + nemit;
+        findex_n = f0 + nemit;
+        if (hx.n_empty & 0x7fffffffu) frames_have_empty = true;
+        if (hx.n_empty >> 31) findex_bad = true;  // a position or a length that the packed index cannot hold
+        total += (size_t)nbit0 + nbit1 + (size_t)nemit * (sizeof(nfc_frame) + 8);
     }
     if (want_ev && M) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_ev, events_d[oi].p, (size_t)M * sizeof(EventRec), cudaMemcpyDeviceToHost, cs2));
     if (want_sym && nsym)
         NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_sym, sym_d[oi].p, (size_t)nsym * sizeof(SymbolRec), cudaMemcpyDeviceToHost, cs2));
-    if (want_fr) {
-        if (nemit) NFC_CUDA_CHECK(cudaMemcpyAsync(hp + off_em, em_d[oi].p, (size_t)nemit * sizeof(EmissionHost), cudaMemcpyDeviceToHost, cs2));
-        if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[0].p + fb[0].len, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
-        if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[1].p + fb[1].len, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
-        fb[0].len += nbit0;
-        fb[1].len += nbit1;
-        total += (size_t)nbit0 + nbit1;
-    }
     NFC_CUDA_CHECK(cudaEventRecord(ev_d[pi], cs2));
     NFC_CUDA_CHECK(cudaEventRecord(ev_out[oi], cs2));
     ev_out_set[oi] = true;
@@ -1768,7 +1851,13 @@ int Stream::finalize_front() {
     if (timing)
         fprintf(stderr, "slab %lld..%lld%s: slicer %.2f ms (dev %.2f), chain queued in %.2f (dev %.2f), context seen %.2f ms after queuing\n",
                 (long long)j.a, (long long)j.b, j.exact ? " (exact sizes)" : "", j.t1 - j.t0, ms_ab, j.t2 - j.t1, ms_ac - ms_ab, t3 - j.t2);
-    return marshal(j, pi, hp, off_ev, off_sym, off_em, base[0], base[1], M, nsym, nbit0, nbit1, nemit);
+    if (!want_ev && !want_sym) {  // nothing for a worker thread to do: the frames arrive where they belong by DMA
+        ev_last_records = ev_d[pi];
+        have_last_records = true;
+        slabs_marshalled.fetch_add(1, std::memory_order_release);
+        return 0;
+    }
+    return marshal(j, pi, hp, off_ev, off_sym, 0, 0, 0, M, nsym, nbit0, nbit1, nemit);
 }
 
 // Records of a slab -> output vectors (absolute positions) on a worker thread: it waits for its predecessor (the vectors
@@ -1823,98 +1912,6 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
                 o.pad = 0;
                 o.pad2 = 0;
                 out_symbols.push_back(o);
-            }
-        }
-        if (want_fr) {
-            const EmissionHost *em = reinterpret_cast<const EmissionHost *>(hp + off_em);
-            // the slab's bits lie in the arenas at base[t] (finalize_front put them there); a frame ends bit_end bits behind
-            // that and begins nbits before its end (possibly among the bits of earlier slabs)
-            const size_t base[2] = {base0, base1};
-            const uint32_t nnew[2] = {tot.nbit0, tot.nbit1};
-            size_t closed[2] = {0, 0};
-            bool bad_frame = false;
-            const size_t f0 = out_frames.size();
-            grow(out_frames, tot.nemit);
-            out_frames.resize(f0 + tot.nemit);
-            nfc_frame *fo = out_frames.data() + f0;
-            size_t nf = 0;
-            if (findex_reserve(f0 + tot.nemit)) {
-                marshal_err = findex_ext ? 3 : 2;
-                return;
-            }
-            uint64_t *fx = findex + f0;
-            // slabs with many closings: the walk is bound by memory latency, so it is cut into parts that run on threads of
-            // their own (first pass: how many frames each part forwards; second pass: the records)
-            const int parts = tot.nemit > 300000 ? 4 : 1;  // (below that the threads cost more than they save)
-            size_t part_n[4] = {0, 0, 0, 0}, part_closed[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            bool part_bad[4] = {false, false, false, false}, part_fx_bad[4] = {false, false, false, false};
-            auto range = [&](int q, uint32_t &i0, uint32_t &i1) {
-                i0 = (uint32_t)((uint64_t)tot.nemit * (uint64_t)q / (uint64_t)parts);
-                i1 = (uint32_t)((uint64_t)tot.nemit * (uint64_t)(q + 1) / (uint64_t)parts);
-            };
-            auto count_part = [&](int q) {
-                uint32_t i0, i1;
-                range(q, i0, i1);
-                size_t c = 0;
-                for (uint32_t i = i0; i < i1; i++) c += em[i].nbits != 0;
-                part_n[q] = c;
-            };
-            auto write_part = [&](int q, size_t o) {
-                uint32_t i0, i1;
-                range(q, i0, i1);
-                for (uint32_t i = i0; i < i1; i++) {
-                    const int t = em[i].type;
-                    if (em[i].bit_end > nnew[t]) {
-                        part_bad[q] = true;
-                        return;
-                    }
-                    const size_t end = base[t] + em[i].bit_end;
-                    part_closed[q][t] = end;  // closings of a type come in order
-                    if (em[i].nbits == 0) continue;  // empty frame: not forwarded (packets.py:97)
-                    if (em[i].nbits > end) {
-                        part_bad[q] = true;
-                        return;
-                    }
-                    nfc_frame &f = fo[o];
-                    f.pos = a + (int64_t)em[i].rel_pos;
-                    f.bit_off = (int64_t)(end - em[i].nbits);  // frames of one type are back to back
-                    f.nbits = (int32_t)em[i].nbits;
-                    f.type = t;
-                    if (((uint64_t)f.pos >> 40) || em[i].nbits >= 65536u) part_fx_bad[q] = true;
-                    fx[o] = ((uint64_t)f.pos << 24) | ((uint64_t)em[i].nbits << 8) | (uint64_t)t;
-                    o++;
-                }
-            };
-            if (parts == 1) {
-                count_part(0);
-                write_part(0, 0);
-            } else {
-                std::thread th[3];
-                for (int q = 1; q < parts; q++) th[q - 1] = std::thread(count_part, q);
-                count_part(0);
-                for (int q = 1; q < parts; q++) th[q - 1].join();
-                size_t o = part_n[0];
-                for (int q = 1; q < parts; q++) {
-                    th[q - 1] = std::thread(write_part, q, o);
-                    o += part_n[q];
-                }
-                write_part(0, 0);
-                for (int q = 1; q < parts; q++) th[q - 1].join();
-            }
-            for (int q = 0; q < parts; q++) {
-                nf += part_n[q];
-                bad_frame = bad_frame || part_bad[q];
-                findex_bad = findex_bad || part_fx_bad[q];
-                for (int t = 0; t < 2; t++)
-                    if (part_closed[q][t] > closed[t]) closed[t] = part_closed[q][t];
-            }
-            out_frames.resize(f0 + nf);
-            findex_n = f0 + nf;
-            for (int t = 0; t < 2; t++)
-                if (closed[t] > fb[t].closed) fb[t].closed = closed[t];
-            if (bad_frame) {
-                marshal_err = 1;
-                return;
             }
         }
       }();
