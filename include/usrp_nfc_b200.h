@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NFC_ABI_VERSION 6
+#define NFC_ABI_VERSION 7
 
 /* what a pushed item is */
 enum {
@@ -220,6 +220,7 @@ typedef struct {
     int64_t pipe_tiles;       /* tiles proven while the workers ran ahead of the verdicts (subset of fast_tiles) */
     int64_t pipe_runs;        /* runs of consecutive tiles entered in that mode */
     int64_t pipe_aborts;      /* runs ended by a tile the pipelined mode could not prove (settled by the synchronous loop) */
+    int64_t empty_frames;     /* frames closed without a bit: the reference does not forward them (packets.py:97), nor are they handed out */
 } nfc_stats;
 int nfc_stream_get_stats(nfc_stream *s, nfc_stats *st);
 int nfc_stream_reset_stats(nfc_stream *s);

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_cabi.LIB_PATH)
     for name in _declared():
         assert hasattr(raw, name), name
-    assert L.nfc_abi_version() == 6
+    assert L.nfc_abi_version() == 7
 
 
 def test_default_params_match_reference_constructors():

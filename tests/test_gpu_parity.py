@@ -410,12 +410,29 @@ def test_streaming_kernel_falls_back_on_inexact_or_insane_samples():
     check_against_oracle(got, want)
 
 
+def _empty_closings(symbols):
+    """PacketProcessor.append_bit (packets.py:67-79) on a symbol list [(type, val, ...)]: how many frames close empty."""
+    started, cur, empty = [False, False], [0, 0], 0
+    for row in symbols:
+        t, v = int(row[0]), int(row[1])
+        if v != 0 and v != 1:
+            if started[t]:
+                empty += cur[t] == 0
+                started[t], cur[t] = False, 0
+        elif not started[t] and v == (1 if t == 0 else 0):  # PacketType.start_bit (packets.py:24-28)
+            started[t] = True
+        else:
+            cur[t] += 1
+    return empty
+
+
 def test_decoder_kats_through_the_device_line_code():
     """The 40 known-answer event streams of the reference's decoders (tests/golden/decoder_kat.npz: miller_decoder,
     manchester_decoder and PacketProcessor driven on adversarial event lists) through nfc_stream_push_events -- the
     background.append boundary (background.py:27-29): symbols and frames of the device's line-code kernels, fed whole and in
     two parts (decoder and framer state carry over)."""
     z = H.load_case("decoder_kat")
+    empties = 0
     for ci in range(40):
         evs = z["ev%d" % ci]
         ev = np.zeros(len(evs), dtype=_cabi.EVENT_DTYPE)
@@ -427,8 +444,12 @@ def test_decoder_kats_through_the_device_line_code():
                 s.push_events(ev[cut:])
             sym = s.drain_symbols()
             fr, bits = s.drain_frames()
+            n_empty = s.stats()["empty_frames"]
             s.close()
             want = z["sym%d" % ci]
+            # frames closed without a bit (packets.py:67-79: started, then a symbol that is no bit) are counted, not handed out
+            assert n_empty == _empty_closings(want), (ci, cut)
+            empties += n_empty
             assert len(sym) == len(want), (ci, cut)
             assert np.array_equal(sym["type"], want[:, 0]) and np.array_equal(sym["val"], want[:, 1]), (ci, cut)
             assert np.array_equal(fr["type"], z["ftype%d" % ci]) and np.array_equal(fr["nbits"], z["flen%d" % ci]), (ci, cut)
@@ -436,6 +457,7 @@ def test_decoder_kats_through_the_device_line_code():
             assert np.array_equal(got_bits, z["fbits%d" % ci]), (ci, cut)
             # symbols are reported at the positions of the events that produced them
             assert set(sym["pos"].tolist()) <= set(ev["pos"].tolist())
+    assert empties > 0  # the known answers do hold such closings
 
 
 def test_push_events_rejects_what_transition_sink_cannot_emit():

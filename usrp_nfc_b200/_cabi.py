@@ -48,7 +48,8 @@ class Stats(C.Structure):
                 ("exact_tiles", C.c_int64), ("repeated_passes", C.c_int64), ("fixpoint_tiles", C.c_int64),
                 ("st2_tiles", C.c_int64), ("unproven_tiles", C.c_int64), ("ring_resums", C.c_int64),
                 ("exact_rounds", C.c_int64), ("slicer_kernel_ms", C.c_double), ("slicer_kernel_launches", C.c_int64),
-                ("pipe_tiles", C.c_int64), ("pipe_runs", C.c_int64), ("pipe_aborts", C.c_int64)]
+                ("pipe_tiles", C.c_int64), ("pipe_runs", C.c_int64), ("pipe_aborts", C.c_int64),
+                ("empty_frames", C.c_int64)]
 
 
 # every symbol include/usrp_nfc_b200.h declares: (restype, argtypes)

@@ -1837,6 +1837,7 @@ int Stream::finalize_front() {
         out_frames.n = f0 + nemit;
         findex_n = f0 + nemit;
         if (hx.n_empty & 0x7fffffffu) frames_have_empty = true;
+        stats.empty_frames += hx.n_empty & 0x7fffffffu;
         if (hx.n_empty >> 31) findex_bad = true;  // a position or a length that the packed index cannot hold
         total += (size_t)nbit0 + nbit1 + (size_t)nemit * (sizeof(nfc_frame) + 8);
     }
