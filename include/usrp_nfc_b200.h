@@ -143,7 +143,8 @@ int64_t nfc_stream_view_frame_index(nfc_stream *s, const uint64_t **index);
 /* Keep the packed frame index in memory of the caller's (room for cap records; NULL: the stream's own buffer again) -- e.g. a
  * shared-memory segment that the process merging the time shards of one node maps, so that "gathering" the frame offsets
  * moves no data at all.  The stream must hold no frames (right after create / reset / release).  More frames than cap make
- * nfc_stream_view_frame_index fail. */
+ * the push that produces them fail.  The device writes the index there by DMA: the library page-locks the buffer
+ * (cudaHostRegister) for as long as it is set -- set NULL (or destroy the stream) before freeing or unmapping it. */
 int nfc_stream_set_frame_index_buffer(nfc_stream *s, uint64_t *buf, int64_t cap);
 
 /* What fsm.process_bits does to a frame before any protocol logic, for a batch of frames on the device:

@@ -169,3 +169,85 @@ def events_from_transitions(tpos, tval, w0, w1, st0, last_bit0, dur0, mx, keep_d
     else:
         st1, dur1, lb1 = st0, dur0, last_bit0
     return ev, (st1, lb1, dur1)
+
+
+# ---- frame counts of the line-code kernels (linecode.cu: ChunkCnt, CountSink, CombineCnt, resolved_records) ----------------
+# A symbol is (type, val): val 0/1 a bit, anything else closes the frame of that type if one has started
+# (PacketProcessor.append_bit, packets.py:67-79); "cap" marks a capture boundary of a batch (nothing pending behind it).
+def framer_items(symbols, started):
+    """[(kind, type)]: the calls the device's sinks see -- 'bit' and 'close' per symbol (framer_put), given the framers'
+    started flags at the beginning."""
+    st = list(started)
+    out = []
+    for t, v in symbols:
+        if t == "cap":
+            out.append(("cap", 0))
+            st = [False, False]
+            continue
+        if v in (0, 1):
+            if not st[t] and v == (1 if t == 0 else 0):
+                st[t] = True
+            else:
+                out.append(("bit", t))
+        elif st[t]:
+            out.append(("close", t))
+            st[t] = False
+    return out
+
+
+def chunk_cnt(items):
+    """CountSink over one chunk: nemit, has[2] (bit 0: closes / capture end, bit 1: first closing depends on what is pending
+    before the chunk), tail[2]."""
+    c = dict(nemit=0, has=[0, 0], tail=[0, 0], nbit=[0, 0])
+    for kind, t in items:
+        if kind == "bit":
+            c["nbit"][t] += 1
+            c["tail"][t] += 1
+        elif kind == "close":
+            if c["tail"][t] != 0:
+                c["nemit"] += 1
+            elif not (c["has"][t] & 1):
+                c["nemit"] += 1
+                c["has"][t] |= 2
+            c["has"][t] |= 1
+            c["tail"][t] = 0
+        else:
+            for u in (0, 1):
+                c["has"][u] |= 1
+                c["tail"][u] = 0
+    return c
+
+
+def combine_cnt(a, b):
+    c = dict(nemit=a["nemit"] + b["nemit"], has=[0, 0], tail=[0, 0], nbit=[a["nbit"][0] + b["nbit"][0], a["nbit"][1] + b["nbit"][1]])
+    for t in (0, 1):
+        if a["has"][t] & 1:
+            if (b["has"][t] & 2) and a["tail"][t] == 0:
+                c["nemit"] -= 1
+            c["has"][t] = a["has"][t]
+        else:
+            c["has"][t] = (b["has"][t] & 1) | (2 if (b["has"][t] & 2) and a["tail"][t] == 0 else 0)
+        c["tail"][t] = b["tail"][t] if (b["has"][t] & 1) else a["tail"][t] + b["tail"][t]
+    return c
+
+
+def resolved_records(pc, pending):
+    return pc["nemit"] - sum(1 for t in (0, 1) if (pc["has"][t] & 2) and pending[t] == 0)
+
+
+def frames_sequential(items, pending):
+    """What the write pass does: lengths of the frames that get a record, closings without a bit, bits pending at the end."""
+    pend = list(pending)
+    lens, empty = [], 0
+    for kind, t in items:
+        if kind == "bit":
+            pend[t] += 1
+        elif kind == "close":
+            if pend[t] == 0:
+                empty += 1
+            else:
+                lens.append((t, pend[t]))
+            pend[t] = 0
+        else:
+            pend = [0, 0]
+    return lens, empty, pend

@@ -101,3 +101,45 @@ def test_model_hysteresis_corner_cases():
                 i += ln
             i += int(rng.integers(1, 3 * mx))
         _compare(x, L, 0.1, 1.1, mx, rng.integers(1, n, 3))
+
+
+def test_frame_record_counts_leave_out_empty_frames():
+    """linecode.cu ChunkCnt / CombineCnt: the scanned counts give every chunk the index of its first frame record with the
+    frames that close without a bit left out (packets.py:97 does not forward them) -- whatever the chunking, whatever is
+    pending when the slab begins, with capture boundaries of a batch in between.  Model of the device code, checked against
+    the sequential rule on random symbol streams (the device kernels themselves: tests/test_gpu_parity.py, decoder KATs)."""
+    import functools
+    rng = np.random.default_rng(11)
+    zero = dict(nemit=0, has=[0, 0], tail=[0, 0], nbit=[0, 0])
+    for trial in range(300):
+        n = int(rng.integers(0, 120))
+        syms = []
+        for _ in range(n):
+            r = rng.random()
+            if r < 0.03:
+                syms.append(("cap", 0))
+            else:
+                syms.append((int(rng.integers(0, 2)), int(rng.choice([0, 1, 2], p=[0.35, 0.35, 0.3]))))
+        started = [bool(rng.integers(0, 2)), bool(rng.integers(0, 2))]
+        pending = [int(rng.integers(0, 3)) * int(rng.integers(0, 2)), int(rng.integers(0, 3)) * int(rng.integers(0, 2))]
+        items = M.framer_items(syms, started)
+        lens, empty, pend_end = M.frames_sequential(items, pending)
+        chunk = int(rng.integers(1, 9))
+        chunks = [items[i:i + chunk] for i in range(0, len(items), chunk)]
+        cnts = [M.chunk_cnt(c) for c in chunks]
+        prefix = zero
+        written = 0
+        for c, items_c in zip(cnts, chunks):
+            assert M.resolved_records(prefix, pending) == written, (trial, chunk)
+            pend_c = [prefix["tail"][t] if (prefix["has"][t] & 1) else pending[t] + prefix["tail"][t] for t in (0, 1)]
+            lens_c, _, _ = M.frames_sequential(items_c, pend_c)
+            written += len(lens_c)
+            prefix = M.combine_cnt(prefix, c)
+        assert written == len(lens) and M.resolved_records(prefix, pending) == len(lens)
+        assert M.resolved_records(prefix, pending) <= prefix["nemit"] <= len(lens) + 2  # the scan's total is an upper bound
+        # associativity: any bracketing of the chunks gives the same total
+        if len(cnts) >= 3:
+            k = int(rng.integers(1, len(cnts) - 1))
+            left = functools.reduce(M.combine_cnt, cnts[:k], zero)
+            right = functools.reduce(M.combine_cnt, cnts[k:])
+            assert M.combine_cnt(left, right) == prefix

@@ -42,9 +42,15 @@ struct ComposeMap {  // (a then b)
     }
 };
 
+// Counts of a run of events.  nemit counts the frame closings that get a record: a frame that closes without a bit is not
+// forwarded (packets.py:97) and gets none.  Whether the FIRST closing of a type in the run is such a frame can depend on the
+// bits pending before the run: hasT bit 0 = the run closes a frame of type T (or a capture ends in it: nothing pending
+// behind that), bit 1 = its first closing has no bit of the run before it and no capture end -- it is counted in nemit
+// and is empty if and only if nothing is pending when the run begins (resolved when runs are combined, and against the
+// slab's pending_in at last).
 struct __align__(16) ChunkCnt {
     uint32_t nsym, nbit0, nbit1, nemit;
-    uint32_t has0, tail0, has1, tail1;  // bits appended after the chunk's last emission (or all, if none)
+    uint32_t has0, tail0, has1, tail1;  // tailT: bits appended after the run's last closing (or all, if none)
 };
 struct CombineCnt {
     __device__ __forceinline__ ChunkCnt operator()(const ChunkCnt &a, const ChunkCnt &b) const {
@@ -53,13 +59,27 @@ struct CombineCnt {
         c.nbit0 = a.nbit0 + b.nbit0;
         c.nbit1 = a.nbit1 + b.nbit1;
         c.nemit = a.nemit + b.nemit;
-        c.has0 = a.has0 | b.has0;
-        c.tail0 = b.has0 ? b.tail0 : a.tail0 + b.tail0;
-        c.has1 = a.has1 | b.has1;
-        c.tail1 = b.has1 ? b.tail1 : a.tail1 + b.tail1;
+        if (a.has0 & 1) {
+            if ((b.has0 & 2) && a.tail0 == 0) c.nemit--;  // b's first closing of type 0 is empty
+            c.has0 = a.has0;
+        } else {
+            c.has0 = (b.has0 & 1) | (((b.has0 & 2) && a.tail0 == 0) ? 2u : 0u);
+        }
+        if (a.has1 & 1) {
+            if ((b.has1 & 2) && a.tail1 == 0) c.nemit--;
+            c.has1 = a.has1;
+        } else {
+            c.has1 = (b.has1 & 1) | (((b.has1 & 2) && a.tail1 == 0) ? 2u : 0u);
+        }
+        c.tail0 = (b.has0 & 1) ? b.tail0 : a.tail0 + b.tail0;
+        c.tail1 = (b.has1 & 1) ? b.tail1 : a.tail1 + b.tail1;
         return c;
     }
 };
+// records before a run whose counts are pc, in a slab that begins with pending[] bits pending
+__device__ __forceinline__ uint32_t resolved_records(const ChunkCnt &pc, const uint32_t *pending) {
+    return pc.nemit - (((pc.has0 & 2) && pending[0] == 0) ? 1u : 0u) - (((pc.has1 & 2) && pending[1] == 0) ? 1u : 0u);
+}
 
 // The number of events of a slab is read from device memory (left there by the run kernels' scan), so that the host can
 // queue the line-code kernels without waiting for it; cap sizes grids and buffers (more events than that: POST_OVF_EVENTS,
@@ -260,15 +280,19 @@ struct CountSink {
     ChunkCnt c;
     __device__ __forceinline__ void symbol(uint32_t, int, int) { c.nsym++; }
     __device__ __forceinline__ void emission(uint32_t, int type) {
-        c.nemit++;
-        if (type == 0) { c.has0 = 1; c.tail0 = 0; } else { c.has1 = 1; c.tail1 = 0; }
+        uint32_t &has = type == 0 ? c.has0 : c.has1;
+        uint32_t &tail = type == 0 ? c.tail0 : c.tail1;
+        if (tail != 0) c.nemit++;                      // a frame with bits
+        else if (!(has & 1)) { c.nemit++; has |= 2; }  // empty if nothing is pending before the chunk (ChunkCnt)
+        has |= 1;                                      // (else: empty for certain -- no record)
+        tail = 0;
     }
     __device__ __forceinline__ void bit(int type, int) {
         if (type == 0) { c.nbit0++; c.tail0++; } else { c.nbit1++; c.tail1++; }
     }
     __device__ __forceinline__ void new_capture() {  // the bits appended so far belong to no later frame
-        c.has0 = 1; c.tail0 = 0;
-        c.has1 = 1; c.tail1 = 0;
+        c.has0 |= 1; c.tail0 = 0;
+        c.has1 |= 1; c.tail1 = 0;
     }
 };
 
@@ -422,8 +446,8 @@ __global__ void chunk_count_kernel(const EventRec *__restrict__ ev, EvCount evc,
 // ---- pass C: write symbols, frame bits and frame records --------------------------------
 // A frame record is final as the device writes it (the layout of nfc_frame): closing position in stream coordinates, offset of
 // the frame's first bit in the stream's bit arena of its type (all bits of a type in append order: bits_base[t] of them before
-// this slab), length, type.  An empty frame (packets.py:97: not forwarded) still gets a record, with nbits == 0, and is
-// counted in *n_empty: the host drops such records (rare), otherwise the records go to their final place by DMA alone.
+// this slab), length, type.  An empty frame (packets.py:97: not forwarded) gets no record (the counts of pass B leave it out:
+// ChunkCnt) and is counted in *n_empty; the records go to their final place in host memory by DMA alone.
 struct WriteSink {
     SymbolRec *sym;
     uint8_t *bits0, *bits1;
@@ -445,6 +469,10 @@ struct WriteSink {
     }
     __device__ __forceinline__ void emission(uint32_t pos, int type) {
         const uint32_t nbits = type == 0 ? pend0 : pend1;
+        if (nbits == 0) {  // not forwarded (packets.py:97): no record -- the counts knew (ChunkCnt)
+            atomicAdd(n_empty, 1u);
+            return;
+        }
         if (iem < cap_em) {
             FrameRec f;
             f.pos = a + (int64_t)pos;
@@ -454,7 +482,6 @@ struct WriteSink {
             fr[iem] = f;
             fx[iem] = ((unsigned long long)f.pos << 24) | ((unsigned long long)nbits << 8) | (unsigned long long)type;
         }
-        if (nbits == 0) atomicAdd(n_empty, 1u);
         if ((((unsigned long long)(a + (int64_t)pos)) >> 40) || nbits >= 65536u) atomicOr(n_empty, 0x80000000u);  // does not fit the packed index
         iem++;
         if (type == 0) pend0 = 0; else pend1 = 0;
@@ -477,6 +504,7 @@ struct LineOut {
     const unsigned long long *bits_in;  // bits of each type appended before this slab (device memory: [2]) ...
     unsigned long long *bits_out;       // ... and behind it
     uint32_t *n_empty;
+    uint32_t *n_frames;                 // records written (the scan's total may count one more per type: ChunkCnt)
 };
 
 __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc, LineTables lt,
@@ -500,9 +528,9 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc,
     sink.sym = out.sym; sink.bits0 = out.bits0; sink.bits1 = out.bits1; sink.fr = out.fr; sink.fx = out.fx;
     sink.n_empty = out.n_empty; sink.a = out.a; sink.base0 = out.bits_in[0]; sink.base1 = out.bits_in[1];
     sink.cap_sym = out.cap_sym; sink.cap_b0 = out.cap_b0; sink.cap_b1 = out.cap_b1; sink.cap_em = out.cap_em;
-    sink.isym = pc.nsym; sink.ib0 = pc.nbit0; sink.ib1 = pc.nbit1; sink.iem = pc.nemit;
-    sink.pend0 = pc.has0 ? pc.tail0 : out.pending_in[0] + pc.tail0;
-    sink.pend1 = pc.has1 ? pc.tail1 : out.pending_in[1] + pc.tail1;
+    sink.isym = pc.nsym; sink.ib0 = pc.nbit0; sink.ib1 = pc.nbit1; sink.iem = resolved_records(pc, out.pending_in);
+    sink.pend0 = (pc.has0 & 1) ? pc.tail0 : out.pending_in[0] + pc.tail0;
+    sink.pend1 = (pc.has1 & 1) ? pc.tail1 : out.pending_in[1] + pc.tail1;
     const uint32_t i0 = c * CHUNK, i1 = min(n_ev, i0 + CHUNK);
     uint32_t cap_prev = tv.pitch ? batch_capture_before(tv, ev, (int64_t)i0) : 0u;
     for (uint32_t i = i0; i < i1; i += 8) {
@@ -521,6 +549,7 @@ __global__ void chunk_write_kernel(const EventRec *__restrict__ ev, EvCount evc,
         pending_out[1] = sink.pend1;
         out.bits_out[0] = sink.base0 + sink.ib0;  // the last chunk's counters are the slab's totals
         out.bits_out[1] = sink.base1 + sink.ib1;
+        *out.n_frames = sink.iem;
     }
 }
 
@@ -582,7 +611,7 @@ int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
 int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_frames, void *d_findex, uint32_t cap_em, int64_t a,
-                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, const uint32_t *d_pending_in,
+                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, uint32_t *d_n_frames, const uint32_t *d_pending_in,
                           const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream) {
     const uint32_t nc = std::max(1u, linecode_chunks(cap_ev));
     LineOut out;
@@ -593,6 +622,7 @@ int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
     out.bits_in = (const unsigned long long *)d_bits_in;
     out.bits_out = (unsigned long long *)d_bits_out;
     out.n_empty = d_n_empty;
+    out.n_frames = d_n_frames;
     const EvCount evc{d_M, cap_ev};
     chunk_write_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_ev, evc, lt, d_start, (const ChunkCnt *)d_cnt_prefix, out,
                                                              d_carry_in, d_carry_out, d_pending_out);

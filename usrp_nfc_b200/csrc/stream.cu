@@ -63,7 +63,7 @@ int launch_linecode_count(const EventRec *d_ev, const uint32_t *d_M, uint32_t ca
 int launch_linecode_write(const EventRec *d_ev, const uint32_t *d_M, uint32_t cap_ev, const LineTables &lt, const uint16_t *d_start,
                           const void *d_cnt_prefix, SymbolRec *d_sym, uint32_t cap_sym, uint8_t *d_bits0, uint32_t cap_b0,
                           uint8_t *d_bits1, uint32_t cap_b1, void *d_frames, void *d_findex, uint32_t cap_em, int64_t a,
-                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, const uint32_t *d_pending_in,
+                          const void *d_bits_in, void *d_bits_out, uint32_t *d_n_empty, uint32_t *d_n_frames, const uint32_t *d_pending_in,
                           const DecCarry *d_carry_in, DecCarry *d_carry_out, uint32_t *d_pending_out, cudaStream_t stream);
 int slicer_tile(int L, bool vec_ok, int kind);
 int slicer_resident_ctas(int L, bool vec_ok, int kind);
@@ -303,7 +303,6 @@ struct Stream {
     std::vector<nfc_event> out_events;
     std::vector<nfc_symbol> out_symbols;
     FrameArena out_frames;               // bit_off is relative to fb[type].p
-    bool frames_have_empty = false;      // some records have nbits == 0 (packets.py:97: not forwarded): dropped when the stream settles
     cudaEvent_t ev_last_records = nullptr;  // the copy of the last finalized slab's records (a slab no worker thread waits for)
     bool have_last_records = false;
     int settle_frames();
@@ -312,6 +311,14 @@ struct Stream {
     size_t findex_n = 0, findex_cap = 0;
     bool findex_bad = false;
     bool findex_ext = false;  // the caller's memory (nfc_stream_set_frame_index_buffer): never reallocated
+    bool findex_ext_locked = false;  // ... page-locked by this library for the time it is in use (cudaHostRegister), so that the copies into it stay asynchronous
+    void findex_drop() {
+        if (findex && findex_ext && findex_ext_locked) cudaHostUnregister(findex);
+        if (findex && !findex_ext) cudaFreeHost(findex);
+        findex = nullptr;
+        findex_ext = findex_ext_locked = false;
+        findex_cap = findex_n = 0;
+    }
     int findex_reserve(size_t n) {  // worker thread or settled stream only
         if (n <= findex_cap) return 0;
         if (findex_ext) return -1;
@@ -492,9 +499,7 @@ void Stream::destroy() {
     fb[0].release();
     fb[1].release();
     out_frames.release();
-    if (findex && !findex_ext) cudaFreeHost(findex);
-    findex = nullptr;
-    findex_cap = findex_n = 0;
+    findex_drop();
     for (int i = 0; i < NPIN; i++)
         if (pinned[i]) cudaFreeHost(pinned[i]);
     for (int i = 0; i < NCTX; i++) {
@@ -1440,7 +1445,7 @@ static double now_ms() {
 // ---- a slab's context block in device memory (256 bytes; ring of NCTX): counts and flags of the slab's chain, and the
 // carries it leaves for the next slab (the reference's cur_state / last_bit / dur, decoder and PacketProcessor state)
 struct PostCtx {
-    uint32_t M, R, flags, n_empty, pad0[4];
+    uint32_t M, R, flags, n_empty, n_frames, pad0[3];
     uint32_t tot[8];      // ChunkCnt: nsym, nbit0, nbit1, nemit, has0, tail0, has1, tail1
     RunCarry rc_out;
     DecCarry dc_out;
@@ -1670,7 +1675,7 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
             return -1;
         if (launch_linecode_write(ev, &cx->M, j.cap_M, lt, start_d.as<uint16_t>(), cprefix_d.p, want_sym ? sym_d[oi].as<SymbolRec>() : nullptr,
                                   want_sym ? j.cap_sym : 0, bits0_d[oi].as<uint8_t>(), j.cap_b0, bits1_d[oi].as<uint8_t>(), j.cap_b1, em_d[oi].p,
-                                  fx_d[oi].p, j.cap_em, a, cp->bits_out, cx->bits_out, &cx->n_empty, cp->pend_out, &cp->dc_out, &cx->dc_out,
+                                  fx_d[oi].p, j.cap_em, a, cp->bits_out, cx->bits_out, &cx->n_empty, &cx->n_frames, cp->pend_out, &cp->dc_out, &cx->dc_out,
                                   cx->pend_out, csL))
             return -1;
         stats.launches++;
@@ -1693,26 +1698,12 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
     return 0;
 }
 
-// Everything queued has been looked at: wait for the last records to arrive, and drop the records of empty frames (rare;
-// packets.py:97 does not forward them) from the frame arena and its index.
+// Everything queued has been looked at: wait for the last frame records to arrive (slabs without event or symbol output have
+// no worker thread that would).
 int Stream::settle_frames() {
     if (have_last_records) {
         NFC_CUDA_CHECK(cudaEventSynchronize(ev_last_records));
         have_last_records = false;
-    }
-    if (frames_have_empty) {
-        size_t o = 0;
-        for (size_t i = 0; i < out_frames.n; i++)
-            if (out_frames.p[i].nbits != 0) {
-                if (o != i) {
-                    out_frames.p[o] = out_frames.p[i];
-                    findex[o] = findex[i];
-                }
-                o++;
-            }
-        out_frames.n = o;
-        findex_n = o;
-        frames_have_empty = false;
     }
     return 0;
 }
@@ -1758,7 +1749,8 @@ int Stream::finalize_front() {
         return 0;
     }
     jobs.pop_front();
-    const uint32_t M = hx.M, nsym = hx.tot[0], nbit0 = hx.tot[1], nbit1 = hx.tot[2], nemit = hx.tot[3];
+    const uint32_t M = hx.M, nsym = hx.tot[0], nbit0 = hx.tot[1], nbit1 = hx.tot[2];
+    const uint32_t nemit = hx.n_frames;  // (tot[3] may count one frame per type more: an empty one, linecode.cu ChunkCnt)
     // ---- carries and sizes
     run_carry = hx.rc_out;
     dec_carry = hx.dc_out;
@@ -1830,13 +1822,12 @@ int Stream::finalize_front() {
         if (nbit0) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[0].p + fb[0].len, bits0_d[oi].p, nbit0, cudaMemcpyDeviceToHost, cs2));
         if (nbit1) NFC_CUDA_CHECK(cudaMemcpyAsync(fb[1].p + fb[1].len, bits1_d[oi].p, nbit1, cudaMemcpyDeviceToHost, cs2));
         // bits up to the last closing of a type are handed out with the frames (the line-code totals know where that is)
-        if (hx.tot[4]) fb[0].closed = fb[0].len + nbit0 - hx.tot[5];
-        if (hx.tot[6]) fb[1].closed = fb[1].len + nbit1 - hx.tot[7];
+        if (hx.tot[4] & 1) fb[0].closed = fb[0].len + nbit0 - hx.tot[5];
+        if (hx.tot[6] & 1) fb[1].closed = fb[1].len + nbit1 - hx.tot[7];
         fb[0].len += nbit0;
         fb[1].len += nbit1;
         out_frames.n = f0 + nemit;
         findex_n = f0 + nemit;
-        if (hx.n_empty & 0x7fffffffu) frames_have_empty = true;
         stats.empty_frames += hx.n_empty & 0x7fffffffu;
         if (hx.n_empty >> 31) findex_bad = true;  // a position or a length that the packed index cannot hold
         total += (size_t)nbit0 + nbit1 + (size_t)nemit * (sizeof(nfc_frame) + 8);
@@ -2169,10 +2160,15 @@ int nfc_stream_set_frame_index_buffer(nfc_stream *h, uint64_t *buf, int64_t cap)
         return -1;
     }
     cudaSetDevice(s.prm.device);
-    if (s.findex && !s.findex_ext) cudaFreeHost(s.findex);
+    s.findex_drop();
     s.findex = buf;
     s.findex_ext = buf != nullptr;
     s.findex_cap = buf ? (size_t)cap : 0;
+    if (buf) {
+        // memory that is page-locked already (or cannot be locked) is used as it is: the copies into it are then staged by the driver
+        s.findex_ext_locked = cudaHostRegister(buf, (size_t)cap * 8, cudaHostRegisterPortable) == cudaSuccess;
+        if (!s.findex_ext_locked) cudaGetLastError();
+    }
     s.findex_n = 0;
     s.findex_bad = false;
     return 0;
