@@ -1702,7 +1702,14 @@ int Stream::post_chain(int64_t a, int64_t b, bool from_bitmap, uint32_t R_host, 
 // no worker thread that would).
 int Stream::settle_frames() {
     if (have_last_records) {
-        NFC_CUDA_CHECK(cudaEventSynchronize(ev_last_records));
+        // the copy events sleep when waited for (worker threads wait on them); the caller's thread is about to read the
+        // records and polls instead, unless the stream was told to keep its waits off the cores (nfc_stream_set_wait_mode):
+        // waking up costs 0.25 ms, which a work()-sized call would pay every time
+        cudaError_t e;
+        if (blocking_wait) e = cudaEventSynchronize(ev_last_records);
+        else
+            while ((e = cudaEventQuery(ev_last_records)) == cudaErrorNotReady) {}
+        NFC_CUDA_CHECK(e);
         have_last_records = false;
     }
     return 0;
