@@ -106,13 +106,6 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct EmissionHost {
-    uint32_t rel_pos;
-    int32_t type;
-    uint32_t nbits;
-    uint32_t bit_end;
-};
-
 static size_t item_bytes(int kind) {
     switch (kind) {
         case IN_IQ_F32: return 8;
@@ -296,8 +289,7 @@ struct Stream {
             if (finalize_front()) return -1;
         return 0;
     }
-    int marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t base0, size_t base1, uint32_t M,
-                uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit);
+    int marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, uint32_t M, uint32_t nsym);
 
     // results
     std::vector<nfc_event> out_events;
@@ -1856,24 +1848,20 @@ int Stream::finalize_front() {
         slabs_marshalled.fetch_add(1, std::memory_order_release);
         return 0;
     }
-    return marshal(j, pi, hp, off_ev, off_sym, 0, 0, 0, M, nsym, nbit0, nbit1, nemit);
+    return marshal(j, pi, hp, off_ev, off_sym, M, nsym);
 }
 
-// Records of a slab -> output vectors (absolute positions) on a worker thread: it waits for its predecessor (the vectors
-// are filled in slab order), then for the slab's records to arrive.
-int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, size_t off_em, size_t base0, size_t base1,
-                    uint32_t M, uint32_t nsym, uint32_t nbit0, uint32_t nbit1, uint32_t nemit) {
-    struct Totals {
-        uint32_t nsym, nbit0, nbit1, nemit;
-    } totc = {nsym, nbit0, nbit1, nemit};
+// Event and symbol records of a slab -> output vectors (absolute positions) on a worker thread: it waits for its predecessor
+// (the vectors are filled in slab order), then for the slab's records to arrive (the slab's frames, copied before them on the
+// same stream, have arrived by then as well).
+int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t off_sym, uint32_t M, uint32_t nsym) {
     const int64_t a = j.a;
-    const bool want_ev = j.want_ev, want_sym = j.want_sym, want_fr = j.want_fr;
+    const bool want_ev = j.want_ev, want_sym = j.want_sym;
     if (marshal_err.load()) return join_marshal();
     auto prev = std::make_shared<std::thread>(std::move(marshal_thr));
     const cudaEvent_t evd = ev_d[pi];
     const int dev = prm.device;
-    marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, off_em, base0, base1, M, totc, a, want_ev, want_sym,
-                               want_fr]() {
+    marshal_thr = std::thread([this, prev, evd, dev, hp, off_ev, off_sym, M, nsym, a, want_ev, want_sym]() {
       if (prev->joinable()) prev->join();
       cudaSetDevice(dev);
       static const bool timing = getenv("NFC_TIMING") != nullptr;
@@ -1882,7 +1870,6 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
       if (cudaEventSynchronize(evd) != cudaSuccess) marshal_err = 2;
       else [&]() {
         if (timing) tm1 = now_ms();
-        const Totals &tot = totc;
         auto grow = [](auto &v, size_t more) {  // geometric: an exact reserve per slab would copy the vector every slab
             if (v.capacity() < v.size() + more) v.reserve(std::max(v.size() + more, v.capacity() * 2));
         };
@@ -1902,8 +1889,8 @@ int Stream::marshal(const SlabJob &j, int pi, char *hp, size_t off_ev, size_t of
         }
         if (want_sym) {
             const SymbolRec *s = reinterpret_cast<const SymbolRec *>(hp + off_sym);
-            grow(out_symbols, tot.nsym);
-            for (uint32_t i = 0; i < tot.nsym; i++) {
+            grow(out_symbols, nsym);
+            for (uint32_t i = 0; i < nsym; i++) {
                 nfc_symbol o;
                 o.pos = a + (int64_t)s[i].rel_pos;
                 o.type = s[i].type;
