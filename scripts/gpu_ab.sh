@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of two builds of the library on ONE box: the bench step alternately with build_variants/libold.so and the in-tree build
+# A/B of two builds of the library on ONE box: the bench step alternately with build_variants/libold.so and the in-tree build.
+# The other build (build_variants/ is not tracked):  mkdir -p build_variants/old && git archive <commit> usrp_nfc_b200/csrc include |
+#   tar -x -C build_variants/old && make -C build_variants/old/usrp_nfc_b200/csrc OUT=$PWD/build_variants/libold.so
 mkdir -p gpurun_out
 for r in 1 2; do
 for v in old new; do
